@@ -1,0 +1,73 @@
+"""TEST INFRASTRUCTURE ONLY -- driver for ``oracle/_ref/callsite_runner_*``.
+
+Those executables are the reference's unmodified ``src/common`` call site
+(``ProcessorProxy`` -> ``ProcessorCore2::Process``) compiled from
+``/root/reference`` by ``oracle/Makefile`` and linked against either the CPU
+oracle (``which="oracle"``) or the CUDA product library (``which="b200"``).
+They run as a separate process so the reference's C++ never shares a symbol
+namespace with Python extension modules (doing so crashed inside libstdc++).
+"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+# reference src/common/error.h:11-25
+ERROR_NAMES = ["kSuccess", "kFileOpenError", "kFileTooSmall", "kFileTooLarge", "kInvalidFileSize",
+               "kTOMLSyntaxError", "kInvalidModelConfig", "kSpeakerIDOutOfRange",
+               "kInvalidPitchCorrectionType", "kModelNotLoaded", "kResamplerNotReady", "kGainNotReady",
+               "kUnknownError"]
+
+
+def exe_path(which: str) -> str:
+    return os.path.join(_HERE, "_ref", f"callsite_runner_{which}")
+
+
+def available(which: str) -> bool:
+    return os.path.exists(exe_path(which))
+
+
+def run(which: str, toml_path, x: np.ndarray, sample_rate: float = 48000.0, block: int = 480,
+        events=(), timeout: float = 600.0):
+    """Feeds ``x`` through ProcessorCore::Process in ``block``-sample calls.
+
+    ``events``: iterable of ``(block_index, name, value)``; ``block_index`` -1 applies the
+    parameter before LoadModel, ``name="reset"`` calls ResetContext().  ``toml_path=None``
+    leaves the proxy unloaded.  Returns ``(y, info)`` with info = dict(load, last, version).
+    """
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.f32"), os.path.join(d, "out.f32")
+        np.ascontiguousarray(x, "<f4").tofile(fin)
+        cmd = [exe_path(which), "run", toml_path or "-", fin, fout, repr(float(sample_rate)), str(int(block))]
+        cmd += [f"{int(b)}:{n}={float(v)!r}" for b, n, v in events]
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        if p.returncode != 0:
+            raise RuntimeError(f"callsite_runner failed ({p.returncode}): {p.stderr[-2000:]}")
+        y = np.fromfile(fout, "<f4")
+    info = {}
+    for tok in p.stdout.split():
+        if "=" in tok:
+            k, v = tok.split("=")
+            info[k] = int(v)
+    return y, info
+
+
+def bench(which: str, toml_path: str, signal: np.ndarray, warmup: int = 10, timeout: float = 1800.0):
+    """signal [n_threads, n_frames, 480] -> dict(frames_per_s, threads, ...)."""
+    signal = np.ascontiguousarray(signal, "<f4")
+    nt, nf, hop = signal.shape
+    assert hop == 480
+    with tempfile.TemporaryDirectory() as d:
+        fsig = os.path.join(d, "sig.f32")
+        signal.tofile(fsig)
+        p = subprocess.run([exe_path(which), "bench", toml_path, fsig, str(nt), str(nf), str(warmup)],
+                           capture_output=True, text=True, timeout=timeout)
+    if p.returncode != 0:
+        raise RuntimeError(f"callsite_runner bench failed ({p.returncode}): {p.stderr[-2000:]}")
+    return json.loads(p.stdout.strip().splitlines()[-1])
