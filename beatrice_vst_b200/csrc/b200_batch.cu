@@ -1,0 +1,657 @@
+// Batched engine: N concurrent voice streams are the batch axis (BASELINE.json north_star).
+// Semantics = N independent ProcessorCore2 instances (reference
+// src/common/processor_core_2.cc) stepping in lock step; what the call site does on the host
+// between the three library calls -- the fp64 pitch transform (:190-252), the 4-hop key-value
+// embedding schedule (:179-181, processor_core_2.h:161-169) and, for the 48 kHz entry, gain and
+// AnyFreqInOut (gain.h:41-71, resample.h:401-438) -- is reproduced per stream on the device.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/beatrice_b200.h"
+#include "b200_common.h"
+#include "b200_engine.h"
+#include "b200_hostrate.h"
+#include "b200_kernels.h"
+
+using namespace b200;
+
+namespace {
+constexpr int kStageC[4] = {128, 64, 32, 16};
+
+struct StreamParams {  // host mirror; defaults = processor_core_2.h:103-113
+  int speaker = 0;
+  double formant_shift = 0.0;
+  double min_source_pitch = 33.125;
+  double max_source_pitch = 80.875;
+  int vq = 0;
+  int kv_set_count = kNBlocks;  // blocks 0..3 still to apply, one per hop (processor_core_2.h:161-169)
+};
+
+int NoteToBin(double note, int bins) {  // processor_core_2.cc:561-583
+  const int v = static_cast<int>(std::round((note - 33.0) * (96.0 / 12.0)));
+  return std::min(std::max(v, 1), bins - 1);
+}
+}  // namespace
+
+struct BeatriceB200_Engine {
+  int device = 0, B = 0, precision = 0;
+  cudaStream_t stream = nullptr, aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool loaded = false;
+  FamilyDims dims = kFamilies[2];
+
+  EncoderModel phone_m, pitch_m;
+  WaveModel wave_m;
+  SetterModel setter_m;
+  int n_speakers = 0;
+  DeviceBuffer codebooks, additive, formant_tab, kv;  // speaker tables in HBM
+
+  DeviceBuffer in16;  // [B][160] shared staging of both encoders
+  EncoderState phone_st, pitch_st;
+  WaveState wave_st;
+  DeviceBuffer q_raw, min_q, max_q, vq_n, codebook_ptrs, pitch_params, idx_a, idx_b;
+  HostRateState hostrate;  // 48 kHz adapter (gain + FIRs + FIFO), b200_hostrate.h
+
+  std::vector<StreamParams> sp;
+  std::vector<PitchParams> pp;
+  bool pitch_dirty = true, range_dirty = true, vq_dirty = true;
+  std::vector<int> pending_speaker, pending_formant;  // stream ids whose projection must be refreshed
+  std::vector<Op> hop_ops;                            // flat op list of one model-rate hop
+  std::vector<int> hop_lane;                          // 0 = main stream, 1 = aux (pitch branch)
+  GraphRunner graph16, graph48;
+  uint64_t launches = 0;
+  uint64_t hops = 0;
+
+  void* pin_in = nullptr;
+  void* pin_out = nullptr;
+  size_t pin_bytes = 0;
+};
+
+namespace {
+
+using Engine = BeatriceB200_Engine;
+
+bool StreamOk(const Engine* e, int stream) { return stream >= -1 && stream < e->B; }
+template <class F>
+void ForStreams(Engine* e, int stream, F f) {
+  if (stream < 0)
+    for (int b = 0; b < e->B; ++b) f(b);
+  else
+    f(stream);
+}
+
+void UploadInts(Engine* e, DeviceBuffer* dst, const std::vector<int>& v) {
+  B200_CHECK(cudaMemcpyAsync(dst->p, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+}
+
+// Applies everything the setters queued; runs on e->stream before the hop (outside the graph).
+void FlushPending(Engine* e) {
+  cudaStream_t s = e->stream;
+  if (e->pitch_dirty) {
+    B200_CHECK(cudaMemcpyAsync(e->pitch_params.p, e->pp.data(), e->pp.size() * sizeof(PitchParams),
+                               cudaMemcpyHostToDevice, s));
+    e->pitch_dirty = false;
+  }
+  if (e->range_dirty) {
+    std::vector<int> lo(e->B), hi(e->B);
+    for (int b = 0; b < e->B; ++b) {
+      lo[b] = NoteToBin(e->sp[b].min_source_pitch, e->dims.pitch_bins);
+      hi[b] = NoteToBin(e->sp[b].max_source_pitch, e->dims.pitch_bins);
+    }
+    UploadInts(e, &e->min_q, lo);
+    UploadInts(e, &e->max_q, hi);
+    e->range_dirty = false;
+  }
+  if (e->vq_dirty) {
+    std::vector<int> n(e->B);
+    std::vector<const float*> ptr(e->B);
+    const size_t cb = static_cast<size_t>(kCodebookSize) * e->dims.phone_channels;
+    for (int b = 0; b < e->B; ++b) {
+      n[b] = e->sp[b].vq;
+      ptr[b] = e->codebooks.as<float>() + cb * e->sp[b].speaker;
+    }
+    UploadInts(e, &e->vq_n, n);
+    B200_CHECK(cudaMemcpyAsync(e->codebook_ptrs.p, ptr.data(), ptr.size() * sizeof(float*), cudaMemcpyHostToDevice, s));
+    e->vq_dirty = false;
+  }
+  auto dedup = [](std::vector<int>* v) {
+    std::sort(v->begin(), v->end());
+    v->erase(std::unique(v->begin(), v->end()), v->end());
+  };
+  if (!e->pending_speaker.empty()) {  // SetAdditiveSpeakerEmbedding, processor_core_2.cc:451-455
+    dedup(&e->pending_speaker);
+    std::vector<int> src;
+    for (int b : e->pending_speaker) src.push_back(e->sp[b].speaker);
+    const int n = static_cast<int>(src.size());
+    UploadInts(e, &e->idx_a, src);
+    UploadInts(e, &e->idx_b, e->pending_speaker);
+    LaunchProject256(e->setter_m.add_w, e->setter_m.add_b, e->additive.as<float>(), kHidden, e->idx_a.as<int>(),
+                     e->wave_st.spk.as<float>(), e->idx_b.as<int>(), n, s);
+    ++e->launches;
+    e->pending_speaker.clear();
+  }
+  if (!e->pending_formant.empty()) {  // SetFormantShift, processor_core_2.cc:468-481
+    dedup(&e->pending_formant);
+    std::vector<int> src;
+    for (int b : e->pending_formant) {
+      const double f = std::min(std::max(e->sp[b].formant_shift, -2.0), 2.0);
+      src.push_back(static_cast<int>(std::round(f * 2.0 + 4.0)));
+    }
+    const int n = static_cast<int>(src.size());
+    // idx_a / idx_b are reused: stream order guarantees the previous launch consumed them
+    UploadInts(e, &e->idx_a, src);
+    UploadInts(e, &e->idx_b, e->pending_formant);
+    LaunchProject256(e->setter_m.for_w, e->setter_m.for_b, e->formant_tab.as<float>(), kHidden, e->idx_a.as<int>(),
+                     e->wave_st.formant.as<float>(), e->idx_b.as<int>(), n, s);
+    ++e->launches;
+    e->pending_formant.clear();
+  }
+  // key-value speaker embedding: one block per stream per hop until all four are applied
+  for (int blk = 0; blk < kNBlocks; ++blk) {
+    std::vector<int> streams, spk;
+    for (int b = 0; b < e->B; ++b)
+      if (e->sp[b].kv_set_count == blk) {
+        streams.push_back(b);
+        spk.push_back(e->sp[b].speaker);
+      }
+    if (streams.empty()) continue;
+    UploadInts(e, &e->idx_a, spk);
+    UploadInts(e, &e->idx_b, streams);
+    LaunchKvFilm(e->kv.as<float>(), e->idx_a.as<int>(), static_cast<size_t>(kKvLength) * kKvChannels,
+                 e->setter_m.query[blk], e->setter_m.film_w[blk], e->setter_m.film_b[blk], kStageC[blk],
+                 e->wave_st.film[blk].as<float>(), e->idx_b.as<int>(), static_cast<int>(streams.size()), s);
+    ++e->launches;
+    for (int b : streams) e->sp[b].kv_set_count = -(blk + 1);  // mark, bumped below
+  }
+  for (int b = 0; b < e->B; ++b)
+    if (e->sp[b].kv_set_count < 0) e->sp[b].kv_set_count = -e->sp[b].kv_set_count;
+}
+
+// Applies all remaining key-value blocks of `b` now (LoadModel / ResetContext do
+// `while (SetKeyValueSpeakerEmbedding());`, processor_core_2.cc:270, :414).
+void FlushAllKv(Engine* e) {
+  for (int round = 0; round < kNBlocks; ++round) FlushPending(e);
+}
+
+void BuildHop(Engine* e) {
+  e->hop_ops.clear();
+  e->hop_lane.clear();
+  const int B = e->B;
+  auto push = [&](const Op& op, int lane) {
+    e->hop_ops.push_back(op);
+    e->hop_lane.push_back(lane);
+  };
+  for (const Op& op : e->phone_st.program) push(op, 0);
+  {
+    Op op;
+    op.name = "phone.vq";
+    const float* in = e->phone_st.head_out.as<float>();
+    float* out = e->wave_st.phone_in.as<float>();
+    const float* const* cbs = e->codebook_ptrs.as<const float*>();
+    const int* n = e->vq_n.as<int>();
+    const int C = e->dims.phone_channels;
+    op.bytes = 8.0 * B * C;
+    op.launch = [=](cudaStream_t s) { LaunchVq(in, out, cbs, n, C, B, s); };
+    push(op, 0);
+  }
+  for (const Op& op : e->pitch_st.program) push(op, 1);
+  {
+    Op op;
+    op.name = "pitch.argmax";
+    const float* head = e->pitch_st.head_out.as<float>();
+    const int bins = e->dims.pitch_bins;
+    const int *lo = e->min_q.as<int>(), *hi = e->max_q.as<int>();
+    int* q = e->q_raw.as<int>();
+    float* feat = e->wave_st.feat_in.as<float>();
+    op.launch = [=](cudaStream_t s) { LaunchPitchArgmax(head, bins, lo, hi, q, feat, B, s); };
+    push(op, 1);
+    Op ot;
+    ot.name = "pitch.transform";
+    const PitchParams* pp = e->pitch_params.as<PitchParams>();
+    int* q_used = e->wave_st.q_in.as<int>();
+    ot.launch = [=](cudaStream_t s) { LaunchPitchTransform(q, pp, bins, q_used, B, s); };
+    push(ot, 1);
+  }
+  for (const Op& op : e->wave_st.program) push(op, 2);  // lane 2: main stream after the join
+}
+
+// Enqueues one model-rate hop (in16 staging already filled) with the two encoders as
+// concurrent branches.  Works both live and under stream capture.
+void EnqueueHop(Engine* e, cudaStream_t s) {
+  B200_CHECK(cudaEventRecord(e->ev_fork, s));
+  B200_CHECK(cudaStreamWaitEvent(e->aux, e->ev_fork, 0));
+  bool joined = false;
+  for (size_t i = 0; i < e->hop_ops.size(); ++i) {
+    const int lane = e->hop_lane[i];
+    if (lane == 2 && !joined) {
+      B200_CHECK(cudaEventRecord(e->ev_join, e->aux));
+      B200_CHECK(cudaStreamWaitEvent(s, e->ev_join, 0));
+      joined = true;
+    }
+    e->hop_ops[i].launch(lane == 1 ? e->aux : s);
+  }
+}
+
+void EnsurePinned(Engine* e) {
+  const size_t need = sizeof(float) * e->B * kHostHop48k;
+  if (e->pin_bytes >= need) return;
+  if (e->pin_in) cudaFreeHost(e->pin_in);
+  if (e->pin_out) cudaFreeHost(e->pin_out);
+  B200_CHECK(cudaMallocHost(&e->pin_in, need));
+  B200_CHECK(cudaMallocHost(&e->pin_out, need));
+  e->pin_bytes = need;
+}
+
+int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
+  B200_CHECK(cudaSetDevice(e->device));
+  B200_CHECK(cudaStreamSynchronize(e->stream));
+  e->loaded = false;
+  e->graph16.Reset();
+  e->graph48.Reset();
+  e->phone_m.dims = e->pitch_m.dims = e->wave_m.dims = e->setter_m.dims = e->dims;
+  e->pitch_m.is_pitch = true;
+  if (const int err = e->phone_m.LoadFromImage(images[0], sizes[0], e->device)) return err;
+  if (const int err = e->pitch_m.LoadFromImage(images[1], sizes[1], e->device)) return err;
+  if (const int err = e->wave_m.LoadFromImage(images[2], sizes[2], e->device)) return err;
+  if (const int err = e->setter_m.LoadFromImage(images[3], sizes[3], e->device)) return err;
+  FileImage img;
+  const FamilyDims d = e->dims;
+  if (const int err = ParseFileImage(images[4], sizes[4], d.family, kKindSpeakers, kKindSpeakers,
+                                     [&](uint32_t n) { return static_cast<long long>(SpeakerPayloadFloats(d, n)); }, &img))
+    return err;
+  const int n = static_cast<int>(img.count);
+  if (n <= 0) return 4;
+  e->n_speakers = n;
+  const size_t cb = static_cast<size_t>(kCodebookSize) * d.phone_channels;
+  const size_t kvn = static_cast<size_t>(kKvLength) * kKvChannels;
+  std::vector<float> h_cb(cb * n), h_add(static_cast<size_t>(kHidden) * n), h_kv(kvn * n);
+  const float* p = img.payload;
+  const float* h_formant = p;
+  p += kNFormant * kHidden;
+  for (int i = 0; i < n; ++i) {
+    std::memcpy(h_cb.data() + cb * i, p, cb * sizeof(float));
+    p += cb;
+    std::memcpy(h_add.data() + static_cast<size_t>(kHidden) * i, p, kHidden * sizeof(float));
+    p += kHidden;
+    std::memcpy(h_kv.data() + kvn * i, p, kvn * sizeof(float));
+    p += kvn;
+  }
+  auto up = [&](DeviceBuffer* b, const float* h, size_t count) {
+    b->Alloc(e->device, count * sizeof(float), false);
+    B200_CHECK(cudaMemcpy(b->p, h, count * sizeof(float), cudaMemcpyHostToDevice));
+  };
+  up(&e->codebooks, h_cb.data(), h_cb.size());
+  up(&e->additive, h_add.data(), h_add.size());
+  up(&e->formant_tab, h_formant, static_cast<size_t>(kNFormant) * kHidden);
+  up(&e->kv, h_kv.data(), h_kv.size());
+
+  const int B = e->B;
+  e->in16.Alloc(e->device, sizeof(float) * B * kInHop, true);
+  e->phone_st.Build(&e->phone_m, B, e->device, e->in16.as<float>());
+  e->pitch_st.Build(&e->pitch_m, B, e->device, e->in16.as<float>());
+  e->wave_st.cond_ready = false;
+  e->wave_st.Build(&e->wave_m, B, e->device);
+  e->q_raw.Alloc(e->device, sizeof(int) * B, true);
+  e->min_q.Alloc(e->device, sizeof(int) * B, true);
+  e->max_q.Alloc(e->device, sizeof(int) * B, true);
+  e->vq_n.Alloc(e->device, sizeof(int) * B, true);
+  e->codebook_ptrs.Alloc(e->device, sizeof(float*) * B, true);
+  e->pitch_params.Alloc(e->device, sizeof(PitchParams) * B, true);
+  e->idx_a.Alloc(e->device, sizeof(int) * B, true);
+  e->idx_b.Alloc(e->device, sizeof(int) * B, true);
+  e->hostrate.Init(e->device, B);
+
+  e->sp.assign(B, StreamParams());
+  PitchParams def;
+  def.average_source_pitch = 52.0;
+  def.intonation_intensity = 1.0;
+  def.pitch_shift = 0.0;
+  def.pitch_correction = 0.0;
+  def.pitch_correction_type = 0;
+  def.pad_ = 0;
+  e->pp.assign(B, def);
+  e->pitch_dirty = e->range_dirty = e->vq_dirty = true;
+  e->pending_speaker.clear();
+  e->pending_formant.clear();
+  for (int b = 0; b < B; ++b) {
+    e->sp[b].kv_set_count = 0;
+    e->pending_speaker.push_back(b);
+    e->pending_formant.push_back(b);
+  }
+  BuildHop(e);
+  e->loaded = true;
+  FlushAllKv(e);  // speaker 0 with all four key-value blocks, like LoadModel (:411-414)
+  B200_CHECK(cudaStreamSynchronize(e->stream));
+  e->hops = 0;
+  return 0;
+}
+
+void RunHop16(Engine* e, bool allow_graph) {
+  FlushPending(e);
+  e->graph16.Run(e->stream, [&](cudaStream_t s) { EnqueueHop(e, s); }, allow_graph && GraphsEnabled());
+  e->launches += e->hop_ops.size();
+  ++e->hops;
+}
+
+void RunHop48(Engine* e, bool allow_graph) {
+  FlushPending(e);
+  e->hostrate.PrepareHop(e->stream);
+  e->graph48.Run(
+      e->stream,
+      [&](cudaStream_t s) {
+        e->hostrate.EnqueueIn(e->in16.as<float>(), s);
+        EnqueueHop(e, s);
+        e->hostrate.EnqueueOut(e->wave_st.out.as<float>(), s);
+      },
+      allow_graph && GraphsEnabled());
+  e->launches += e->hop_ops.size() + HostRateState::kKernelsPerHop;
+  ++e->hops;
+}
+
+}  // namespace
+
+extern "C" {
+
+int BeatriceB200_DeviceCount(void) { return UsableDeviceCount(); }
+const char* BeatriceB200_Version(void) { return "beatrice-b200 0.1 (spec M0, sm_100a)"; }
+
+BeatriceB200_Engine* BeatriceB200_CreateEngine(int device, int n_streams, int precision) {
+  if (n_streams <= 0 || device < 0 || device >= UsableDeviceCount()) return nullptr;
+  if (precision != BEATRICE_B200_PRECISION_F32) return nullptr;  // no silent fallback for other modes
+  auto* e = new Engine();
+  e->device = device;
+  e->B = n_streams;
+  e->precision = precision;
+  B200_CHECK(cudaSetDevice(device));
+  B200_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  B200_CHECK(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
+  B200_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  B200_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  return e;
+}
+
+void BeatriceB200_DestroyEngine(BeatriceB200_Engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  cudaStreamSynchronize(e->aux);
+  e->graph16.Reset();
+  e->graph48.Reset();
+  if (e->pin_in) cudaFreeHost(e->pin_in);
+  if (e->pin_out) cudaFreeHost(e->pin_out);
+  cudaEventDestroy(e->ev_fork);
+  cudaEventDestroy(e->ev_join);
+  cudaStreamDestroy(e->stream);
+  cudaStreamDestroy(e->aux);
+  delete e;
+}
+
+int BeatriceB200_LoadModelFromMemory(BeatriceB200_Engine* e, const void* const images[5], const size_t sizes[5]) {
+  if (!e || !images || !sizes) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  return LoadImages(e, images, sizes);
+}
+
+int BeatriceB200_LoadModel(BeatriceB200_Engine* e, const char* utf8_model_dir) {
+  if (!e || !utf8_model_dir) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  static const char* kNames[5] = {"phone_extractor.bin", "pitch_estimator.bin", "waveform_generator.bin",
+                                  "embedding_setter.bin", "speaker_embeddings.bin"};
+  std::vector<uint8_t> bytes[5];
+  const void* images[5];
+  size_t sizes[5];
+  for (int i = 0; i < 5; ++i) {
+    const std::string path = std::string(utf8_model_dir) + "/" + kNames[i];
+    if (const int err = LoadFileBytes(path.c_str(), &bytes[i])) return err;
+    images[i] = bytes[i].data();
+    sizes[i] = bytes[i].size();
+  }
+  return LoadImages(e, images, sizes);
+}
+
+int BeatriceB200_NumSpeakers(const BeatriceB200_Engine* e) { return e ? e->n_speakers : 0; }
+int BeatriceB200_NumStreams(const BeatriceB200_Engine* e) { return e ? e->B : 0; }
+
+#define B200_SETTER_PROLOGUE()                                         \
+  if (!e || !StreamOk(e, stream)) return BEATRICE_B200_ERR_BAD_ARGUMENT; \
+  if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
+
+int BeatriceB200_SetTargetSpeaker(BeatriceB200_Engine* e, int stream, int speaker) {
+  B200_SETTER_PROLOGUE();
+  // the morph slot (id == n_speakers, processor_core_2.cc:51-177) is out of scope: SURVEY 8f-4
+  if (speaker < 0 || speaker >= e->n_speakers) return BEATRICE_B200_ERR_SPEAKER_RANGE;
+  ForStreams(e, stream, [&](int b) {
+    e->sp[b].speaker = speaker;
+    e->sp[b].kv_set_count = 0;  // :464 -- blocks are applied over the next four hops
+    e->pending_speaker.push_back(b);
+  });
+  e->vq_dirty = true;
+  return 0;
+}
+int BeatriceB200_SetFormantShift(BeatriceB200_Engine* e, int stream, double v) {
+  B200_SETTER_PROLOGUE();
+  ForStreams(e, stream, [&](int b) {
+    e->sp[b].formant_shift = std::min(std::max(v, -2.0), 2.0);
+    e->pending_formant.push_back(b);
+  });
+  return 0;
+}
+int BeatriceB200_SetPitchShift(BeatriceB200_Engine* e, int stream, double v) {
+  B200_SETTER_PROLOGUE();
+  ForStreams(e, stream, [&](int b) { e->pp[b].pitch_shift = std::min(std::max(v, -24.0), 24.0); });
+  e->pitch_dirty = true;
+  return 0;
+}
+int BeatriceB200_SetAverageSourcePitch(BeatriceB200_Engine* e, int stream, double v) {
+  B200_SETTER_PROLOGUE();
+  ForStreams(e, stream, [&](int b) { e->pp[b].average_source_pitch = std::min(std::max(v, 0.0), 128.0); });
+  e->pitch_dirty = true;
+  return 0;
+}
+int BeatriceB200_SetIntonationIntensity(BeatriceB200_Engine* e, int stream, double v) {
+  B200_SETTER_PROLOGUE();
+  ForStreams(e, stream, [&](int b) { e->pp[b].intonation_intensity = v; });
+  e->pitch_dirty = true;
+  return 0;
+}
+int BeatriceB200_SetPitchCorrection(BeatriceB200_Engine* e, int stream, double v) {
+  B200_SETTER_PROLOGUE();
+  ForStreams(e, stream, [&](int b) { e->pp[b].pitch_correction = std::min(std::max(v, 0.0), 1.0); });
+  e->pitch_dirty = true;
+  return 0;
+}
+int BeatriceB200_SetPitchCorrectionType(BeatriceB200_Engine* e, int stream, int type) {
+  B200_SETTER_PROLOGUE();
+  if (type < 0 || type > 1) return BEATRICE_B200_ERR_CORRECTION_TYPE;
+  ForStreams(e, stream, [&](int b) { e->pp[b].pitch_correction_type = type; });
+  e->pitch_dirty = true;
+  return 0;
+}
+int BeatriceB200_SetMinSourcePitch(BeatriceB200_Engine* e, int stream, double note) {
+  B200_SETTER_PROLOGUE();
+  ForStreams(e, stream, [&](int b) { e->sp[b].min_source_pitch = std::min(std::max(note, 0.0), 128.0); });
+  e->range_dirty = true;
+  return 0;
+}
+int BeatriceB200_SetMaxSourcePitch(BeatriceB200_Engine* e, int stream, double note) {
+  B200_SETTER_PROLOGUE();
+  ForStreams(e, stream, [&](int b) { e->sp[b].max_source_pitch = std::min(std::max(note, 0.0), 128.0); });
+  e->range_dirty = true;
+  return 0;
+}
+int BeatriceB200_SetVQNumNeighbors(BeatriceB200_Engine* e, int stream, int n) {
+  B200_SETTER_PROLOGUE();
+  ForStreams(e, stream, [&](int b) { e->sp[b].vq = std::min(std::max(n, 0), 8); });
+  e->vq_dirty = true;
+  return 0;
+}
+int BeatriceB200_SetInputGain(BeatriceB200_Engine* e, int stream, double db) {
+  B200_SETTER_PROLOGUE();
+  ForStreams(e, stream, [&](int b) { e->hostrate.SetTargetGain(b, true, db); });
+  return 0;
+}
+int BeatriceB200_SetOutputGain(BeatriceB200_Engine* e, int stream, double db) {
+  B200_SETTER_PROLOGUE();
+  ForStreams(e, stream, [&](int b) { e->hostrate.SetTargetGain(b, false, db); });
+  return 0;
+}
+
+// Like ResetContext: only the model contexts are re-created; the resampler / FIFO / gain state of
+// AnyFreqInOut persists (processor_core_2.cc:258-266 touches the four library contexts only).
+int BeatriceB200_ResetStream(BeatriceB200_Engine* e, int stream) {
+  B200_SETTER_PROLOGUE();
+  B200_CHECK(cudaSetDevice(e->device));
+  B200_CHECK(cudaStreamSynchronize(e->stream));
+  ForStreams(e, stream, [&](int b) {
+    e->phone_st.arena.ZeroStream(b, e->stream);
+    e->pitch_st.arena.ZeroStream(b, e->stream);
+    e->wave_st.arena.ZeroStream(b, e->stream);
+    e->sp[b].kv_set_count = 0;
+    e->pending_speaker.push_back(b);
+    e->pending_formant.push_back(b);
+  });
+  FlushAllKv(e);  // ResetContext re-applies the speaker with all four blocks at once (:269-270)
+  B200_CHECK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int BeatriceB200_ProcessFramesDevice(BeatriceB200_Engine* e, const float* in_dev, float* out_dev) {
+  if (!e || !in_dev || !out_dev) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
+  B200_CHECK(cudaSetDevice(e->device));
+  const size_t nin = sizeof(float) * e->B * kInHop, nout = sizeof(float) * e->B * kOutHop;
+  B200_CHECK(cudaMemcpyAsync(e->in16.p, in_dev, nin, cudaMemcpyDeviceToDevice, e->stream));
+  RunHop16(e, true);
+  B200_CHECK(cudaMemcpyAsync(out_dev, e->wave_st.out.p, nout, cudaMemcpyDeviceToDevice, e->stream));
+  return 0;
+}
+
+int BeatriceB200_ProcessFrames(BeatriceB200_Engine* e, const float* in_host, float* out_host) {
+  if (!e || !in_host || !out_host) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
+  B200_CHECK(cudaSetDevice(e->device));
+  const size_t nin = sizeof(float) * e->B * kInHop, nout = sizeof(float) * e->B * kOutHop;
+  B200_CHECK(cudaMemcpyAsync(e->in16.p, in_host, nin, cudaMemcpyHostToDevice, e->stream));
+  RunHop16(e, true);
+  B200_CHECK(cudaMemcpyAsync(out_host, e->wave_st.out.p, nout, cudaMemcpyDeviceToHost, e->stream));
+  B200_CHECK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int BeatriceB200_Process48kDevice(BeatriceB200_Engine* e, const float* in_dev, float* out_dev) {
+  if (!e || !in_dev || !out_dev) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
+  B200_CHECK(cudaSetDevice(e->device));
+  const size_t n = sizeof(float) * e->B * kHostHop48k;
+  B200_CHECK(cudaMemcpyAsync(e->hostrate.in48(), in_dev, n, cudaMemcpyDeviceToDevice, e->stream));
+  RunHop48(e, true);
+  B200_CHECK(cudaMemcpyAsync(out_dev, e->hostrate.out48(), n, cudaMemcpyDeviceToDevice, e->stream));
+  return 0;
+}
+
+int BeatriceB200_Process48k(BeatriceB200_Engine* e, const float* in_host, float* out_host) {
+  if (!e || !in_host || !out_host) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
+  B200_CHECK(cudaSetDevice(e->device));
+  const size_t n = sizeof(float) * e->B * kHostHop48k;
+  B200_CHECK(cudaMemcpyAsync(e->hostrate.in48(), in_host, n, cudaMemcpyHostToDevice, e->stream));
+  RunHop48(e, true);
+  B200_CHECK(cudaMemcpyAsync(out_host, e->hostrate.out48(), n, cudaMemcpyDeviceToHost, e->stream));
+  B200_CHECK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+void BeatriceB200_Synchronize(BeatriceB200_Engine* e) {
+  if (!e) return;
+  B200_CHECK(cudaSetDevice(e->device));
+  B200_CHECK(cudaStreamSynchronize(e->stream));
+}
+
+void* BeatriceB200_AllocPinned(size_t bytes) {
+  void* p = nullptr;
+  B200_CHECK(cudaMallocHost(&p, bytes ? bytes : 16));
+  return p;
+}
+void BeatriceB200_FreePinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+void* BeatriceB200_AllocDevice(BeatriceB200_Engine* e, size_t bytes) {
+  if (!e) return nullptr;
+  B200_CHECK(cudaSetDevice(e->device));
+  void* p = nullptr;
+  B200_CHECK(cudaMalloc(&p, bytes ? bytes : 16));
+  return p;
+}
+void BeatriceB200_FreeDevice(BeatriceB200_Engine* e, void* p) {
+  if (!e || !p) return;
+  cudaSetDevice(e->device);
+  cudaFree(p);
+}
+void BeatriceB200_CopyToDevice(BeatriceB200_Engine* e, void* dst_dev, const void* src_host, size_t bytes) {
+  B200_CHECK(cudaSetDevice(e->device));
+  B200_CHECK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, e->stream));
+  B200_CHECK(cudaStreamSynchronize(e->stream));
+}
+void BeatriceB200_CopyToHost(BeatriceB200_Engine* e, void* dst_host, const void* src_dev, size_t bytes) {
+  B200_CHECK(cudaSetDevice(e->device));
+  B200_CHECK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, e->stream));
+  B200_CHECK(cudaStreamSynchronize(e->stream));
+}
+void* BeatriceB200_Stream(BeatriceB200_Engine* e) { return e ? static_cast<void*>(e->stream) : nullptr; }
+
+int BeatriceB200_GetLastIntermediates(BeatriceB200_Engine* e, float* phone, int* bin_raw, int* bin_used,
+                                      float* feature4) {
+  if (!e) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
+  B200_CHECK(cudaSetDevice(e->device));
+  B200_CHECK(cudaStreamSynchronize(e->stream));
+  const int B = e->B;
+  if (phone)
+    B200_CHECK(cudaMemcpy(phone, e->wave_st.phone_in.p, sizeof(float) * B * e->dims.phone_channels, cudaMemcpyDeviceToHost));
+  if (bin_raw) B200_CHECK(cudaMemcpy(bin_raw, e->q_raw.p, sizeof(int) * B, cudaMemcpyDeviceToHost));
+  if (bin_used) B200_CHECK(cudaMemcpy(bin_used, e->wave_st.q_in.p, sizeof(int) * B, cudaMemcpyDeviceToHost));
+  if (feature4) B200_CHECK(cudaMemcpy(feature4, e->wave_st.feat_in.p, sizeof(float) * B * kPitchFeatures, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+uint64_t BeatriceB200_KernelLaunchCount(const BeatriceB200_Engine* e) { return e ? e->launches : 0; }
+
+int BeatriceB200_ProfileHop(BeatriceB200_Engine* e, const float* in_dev, float* out_dev,
+                            BeatriceB200_KernelRecord* records, int capacity) {
+  if (!e || !in_dev || !out_dev) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
+  B200_CHECK(cudaSetDevice(e->device));
+  cudaStream_t s = e->stream;
+  const size_t nin = sizeof(float) * e->B * kInHop, nout = sizeof(float) * e->B * kOutHop;
+  B200_CHECK(cudaMemcpyAsync(e->in16.p, in_dev, nin, cudaMemcpyDeviceToDevice, s));
+  FlushPending(e);
+  const size_t n = e->hop_ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& x : ev) B200_CHECK(cudaEventCreate(&x));
+  B200_CHECK(cudaEventRecord(ev[0], s));
+  for (size_t i = 0; i < n; ++i) {
+    e->hop_ops[i].launch(s);  // serialised on the main stream: each kernel timed alone
+    B200_CHECK(cudaEventRecord(ev[i + 1], s));
+  }
+  B200_CHECK(cudaMemcpyAsync(out_dev, e->wave_st.out.p, nout, cudaMemcpyDeviceToDevice, s));
+  B200_CHECK(cudaStreamSynchronize(s));
+  e->launches += n;
+  ++e->hops;
+  for (size_t i = 0; i < n; ++i) {
+    float ms = 0.f;
+    B200_CHECK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+    if (records && static_cast<int>(i) < capacity) {
+      BeatriceB200_KernelRecord& r = records[i];
+      std::memset(&r, 0, sizeof(r));
+      std::strncpy(r.name, e->hop_ops[i].name.c_str(), sizeof(r.name) - 1);
+      r.ms = ms;
+      r.flops = e->hop_ops[i].flops;
+      r.bytes = e->hop_ops[i].bytes;
+    }
+  }
+  for (auto& x : ev) cudaEventDestroy(x);
+  return static_cast<int>(n);
+}
+
+}  // extern "C"

@@ -1,0 +1,716 @@
+#include "b200_engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+namespace b200 {
+
+std::atomic<uint64_t> g_kernel_launches{0};
+
+// network spec "M0" (SURVEY.md App. B / beatrice_vst_b200/model_spec.py); the product's own
+// statement of it -- the oracle and the torch cross-check each carry an independent one.
+namespace spec {
+struct Front {
+  int k, cin, cout, stride;
+};
+constexpr Front kPhoneFront[6] = {{10, 1, 32, 5},   {3, 32, 64, 2},   {3, 64, 128, 2},
+                                  {3, 128, 256, 2}, {3, 256, 256, 2}, {2, 256, 256, 2}};
+constexpr int kPhoneDil[6] = {1, 2, 4, 1, 2, 4};
+constexpr Front kPitchFront[6] = {{10, 1, 16, 5},  {3, 16, 32, 2},   {3, 32, 64, 2},
+                                  {3, 64, 128, 2}, {3, 128, 128, 2}, {2, 128, 128, 2}};
+constexpr int kPitchDil[3] = {1, 2, 4};
+constexpr int kRates[4] = {5, 4, 4, 3};
+constexpr int kStageCh[5] = {256, 128, 64, 32, 16};
+constexpr int kMrfK[3] = {3, 7, 11};
+constexpr int kMrfD[3] = {1, 3, 5};
+constexpr int kPreK = 7, kPostK = 7;
+}  // namespace spec
+
+static size_t EncoderCount(const spec::Front* fs, int n_res, int width, int head_out) {
+  size_t n = 0;
+  for (int i = 0; i < 6; ++i) n += static_cast<size_t>(fs[i].k) * fs[i].cin * fs[i].cout + fs[i].cout;
+  n += static_cast<size_t>(n_res) * (2 * width + 3 * width * width + width);
+  n += static_cast<size_t>(width) * head_out + head_out;
+  return n;
+}
+size_t PhoneParamCount(const FamilyDims& d) { return EncoderCount(spec::kPhoneFront, 6, 256, d.phone_channels); }
+size_t PitchParamCount(const FamilyDims& d) {
+  return EncoderCount(spec::kPitchFront, 3, 128, d.pitch_bins + kPitchFeatures);
+}
+size_t WaveParamCount(const FamilyDims& d) {
+  size_t n = static_cast<size_t>(d.phone_channels) * kHidden + kHidden;
+  n += static_cast<size_t>(d.pitch_bins) * kHidden + kPitchFeatures * kHidden;
+  n += static_cast<size_t>(spec::kPreK) * kHidden * kHidden + kHidden;
+  for (int s = 0; s < 4; ++s) {
+    const int cin = spec::kStageCh[s], c = spec::kStageCh[s + 1];
+    n += 2u * cin * spec::kRates[s] * c + c;
+    for (int k : spec::kMrfK) n += 3u * 2u * (static_cast<size_t>(k) * c * c + c);
+  }
+  n += static_cast<size_t>(spec::kPostK) * 16 + 1;
+  return n;
+}
+size_t SetterParamCount() {
+  size_t n = 2u * (kHidden * kHidden + kHidden);
+  for (int b = 0; b < kNBlocks; ++b) {
+    const int c = spec::kStageCh[b + 1];
+    n += kKvChannels + static_cast<size_t>(kKvChannels) * 2 * c + 2 * c;
+  }
+  return n;
+}
+size_t SpeakerPayloadFloats(const FamilyDims& d, uint32_t n) {
+  if (d.has_setter)
+    return static_cast<size_t>(kNFormant) * kHidden +
+           static_cast<size_t>(n) * (static_cast<size_t>(kCodebookSize) * d.phone_channels + kHidden +
+                                     static_cast<size_t>(kKvLength) * kKvChannels);
+  return static_cast<size_t>(n) * kHidden;
+}
+
+int LoadFileBytes(const char* utf8_path, std::vector<uint8_t>* bytes) {
+  FILE* f = std::fopen(utf8_path, "rb");
+  if (!f) return 1;
+  std::fseek(f, 0, SEEK_END);
+  const long size = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  if (size < 0) {
+    std::fclose(f);
+    return 1;
+  }
+  bytes->resize(static_cast<size_t>(size));
+  const size_t got = size > 0 ? std::fread(bytes->data(), 1, static_cast<size_t>(size), f) : 0;
+  std::fclose(f);
+  return got == static_cast<size_t>(size) ? 0 : 1;
+}
+
+int ParseFileImage(const void* data, size_t size, int family, uint32_t kind_a, uint32_t kind_b,
+                   const std::function<long long(uint32_t)>& expected_floats, FileImage* out) {
+  if (size < 16) return 2;
+  uint32_t h[4];
+  std::memcpy(h, data, 16);
+  if (h[0] != kFileMagic || h[1] != static_cast<uint32_t>(family) || (h[2] != kind_a && h[2] != kind_b) ||
+      (size - 16) % 4 != 0)
+    return 4;
+  const long long expect = expected_floats(h[3]);
+  if (expect < 0) return 4;
+  const long long have = static_cast<long long>((size - 16) / 4);
+  if (have < expect) return 2;
+  if (have > expect) return 3;
+  out->family = h[1];
+  out->kind = h[2];
+  out->count = h[3];
+  out->payload = reinterpret_cast<const float*>(static_cast<const uint8_t*>(data) + 16);
+  out->n_floats = static_cast<size_t>(have);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// device plumbing
+// ---------------------------------------------------------------------------------------
+int UsableDeviceCount() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int DefaultDevice() {
+  static int dev = [] {
+    const int n = UsableDeviceCount();
+    if (n <= 0) {
+      std::fprintf(stderr,
+                   "[libbeatrice_b200] FATAL: no usable CUDA device; this library has no CPU fallback.\n");
+      std::abort();
+    }
+    const char* e = std::getenv("BEATRICE_B200_DEVICE");
+    int d = e ? std::atoi(e) : 0;
+    if (d < 0 || d >= n) d = 0;
+    return d;
+  }();
+  return dev;
+}
+
+bool GraphsEnabled() {
+  static bool on = [] {
+    const char* e = std::getenv("BEATRICE_B200_NO_GRAPH");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
+DeviceBuffer::~DeviceBuffer() { Free(); }
+void DeviceBuffer::Free() {
+  if (p) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (device >= 0 && device != cur) cudaSetDevice(device);
+    cudaFree(p);
+    if (device >= 0 && device != cur) cudaSetDevice(cur);
+  }
+  p = nullptr;
+  bytes = 0;
+}
+void DeviceBuffer::Alloc(int dev, size_t n_bytes, bool zero) {
+  Free();
+  device = dev;
+  B200_CHECK(cudaSetDevice(dev));
+  if (n_bytes == 0) n_bytes = 16;
+  B200_CHECK(cudaMalloc(&p, n_bytes));
+  bytes = n_bytes;
+  if (zero) B200_CHECK(cudaMemset(p, 0, n_bytes));
+}
+
+namespace {
+struct Cursor {
+  const float* host;
+  const float* dev;
+  size_t pos = 0;
+  const float* Take(size_t n) {
+    const float* r = dev + pos;
+    pos += n;
+    return r;
+  }
+  const float* HostAt(const float* dev_ptr) const { return host + (dev_ptr - dev); }
+};
+ConvW TakeConv(Cursor* c, int k, int cin, int cout) {
+  ConvW w;
+  w.k = k;
+  w.cin = cin;
+  w.cout = cout;
+  w.w = c->Take(static_cast<size_t>(k) * cin * cout);
+  w.b = c->Take(cout);
+  return w;
+}
+void Upload(DeviceBuffer* buf, int dev, const float* host, size_t n) {
+  buf->Alloc(dev, n * sizeof(float), false);
+  B200_CHECK(cudaMemcpy(buf->p, host, n * sizeof(float), cudaMemcpyHostToDevice));
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// models
+// ---------------------------------------------------------------------------------------
+int EncoderModel::LoadFromImage(const void* data, size_t size, int on_device) {
+  const size_t expect = is_pitch ? PitchParamCount(dims) : PhoneParamCount(dims);
+  FileImage img;
+  const int err = ParseFileImage(
+      data, size, dims.family, is_pitch ? kKindPitch : kKindPhone, is_pitch ? kKindPitch : kKindPhone,
+      [&](uint32_t cnt) { return cnt == expect ? static_cast<long long>(expect) : -1LL; }, &img);
+  if (err) return err;
+  device = on_device >= 0 ? on_device : DefaultDevice();
+  Upload(&blob, device, img.payload, img.n_floats);
+  Cursor c{img.payload, blob.as<float>()};
+  const spec::Front* fs = is_pitch ? spec::kPitchFront : spec::kPhoneFront;
+  const int* dl = is_pitch ? spec::kPitchDil : spec::kPhoneDil;
+  n_res = is_pitch ? 3 : 6;
+  width = is_pitch ? 128 : 256;
+  head_out = is_pitch ? dims.pitch_bins + kPitchFeatures : dims.phone_channels;
+  for (int i = 0; i < 6; ++i) {
+    front[i] = TakeConv(&c, fs[i].k, fs[i].cin, fs[i].cout);
+    stride[i] = fs[i].stride;
+  }
+  for (int i = 0; i < n_res; ++i) {
+    gamma[i] = c.Take(width);
+    beta[i] = c.Take(width);
+    res[i] = TakeConv(&c, 3, width, width);
+    dil[i] = dl[i];
+  }
+  head = TakeConv(&c, 1, width, head_out);
+  ++generation;
+  loaded = true;
+  return 0;
+}
+int EncoderModel::LoadFromFile(const char* path, int on_device) {
+  std::vector<uint8_t> bytes;
+  if (const int e = LoadFileBytes(path, &bytes)) return e;
+  return LoadFromImage(bytes.data(), bytes.size(), on_device);
+}
+
+int WaveModel::LoadFromImage(const void* data, size_t size, int on_device) {
+  const size_t expect = WaveParamCount(dims);
+  FileImage img;
+  const int err = ParseFileImage(data, size, dims.family, kKindWavegen, kKindWavegen,
+                                 [&](uint32_t cnt) { return cnt == expect ? static_cast<long long>(expect) : -1LL; },
+                                 &img);
+  if (err) return err;
+  device = on_device >= 0 ? on_device : DefaultDevice();
+  Upload(&blob, device, img.payload, img.n_floats);
+  Cursor c{img.payload, blob.as<float>()};
+  embed = TakeConv(&c, 1, dims.phone_channels, kHidden);
+  pitch_emb = c.Take(static_cast<size_t>(dims.pitch_bins) * kHidden);
+  feat_proj = c.Take(kPitchFeatures * kHidden);
+  pre = TakeConv(&c, spec::kPreK, kHidden, kHidden);
+  // ConvTranspose1d bias [C_out] is replicated per output phase for the 2-tap GEMM form
+  std::vector<float> rep;
+  size_t rep_off[4];
+  for (int s = 0; s < 4; ++s) {
+    const int cin = spec::kStageCh[s], co = spec::kStageCh[s + 1], r = spec::kRates[s];
+    ConvW u;
+    u.k = 2;
+    u.cin = cin;
+    u.cout = r * co;
+    u.w = c.Take(2u * cin * r * co);
+    const float* b_dev = c.Take(co);
+    const float* b_host = c.HostAt(b_dev);
+    rep_off[s] = rep.size();
+    for (int p = 0; p < r; ++p) rep.insert(rep.end(), b_host, b_host + co);
+    ups[s] = u;
+    for (int ki = 0; ki < 3; ++ki)
+      for (int di = 0; di < 3; ++di) {
+        c1[s][ki][di] = TakeConv(&c, spec::kMrfK[ki], co, co);
+        c2[s][ki][di] = TakeConv(&c, spec::kMrfK[ki], co, co);
+      }
+  }
+  post = TakeConv(&c, spec::kPostK, 16, 1);
+  Upload(&ups_bias, device, rep.data(), rep.size());
+  for (int s = 0; s < 4; ++s) ups[s].b = ups_bias.as<float>() + rep_off[s];
+  ++generation;
+  loaded = true;
+  return 0;
+}
+int WaveModel::LoadFromFile(const char* path, int on_device) {
+  std::vector<uint8_t> bytes;
+  if (const int e = LoadFileBytes(path, &bytes)) return e;
+  return LoadFromImage(bytes.data(), bytes.size(), on_device);
+}
+
+int SetterModel::LoadFromImage(const void* data, size_t size, int on_device) {
+  const size_t expect = SetterParamCount();
+  FileImage img;
+  const int err = ParseFileImage(data, size, dims.family, kKindSetter, kKindSetter,
+                                 [&](uint32_t cnt) { return cnt == expect ? static_cast<long long>(expect) : -1LL; },
+                                 &img);
+  if (err) return err;
+  device = on_device >= 0 ? on_device : DefaultDevice();
+  Upload(&blob, device, img.payload, img.n_floats);
+  Cursor c{img.payload, blob.as<float>()};
+  add_w = c.Take(kHidden * kHidden);
+  add_b = c.Take(kHidden);
+  for_w = c.Take(kHidden * kHidden);
+  for_b = c.Take(kHidden);
+  for (int b = 0; b < kNBlocks; ++b) {
+    const int ch = spec::kStageCh[b + 1];
+    query[b] = c.Take(kKvChannels);
+    film_w[b] = c.Take(static_cast<size_t>(kKvChannels) * 2 * ch);
+    film_b[b] = c.Take(2 * ch);
+  }
+  loaded = true;
+  return 0;
+}
+int SetterModel::LoadFromFile(const char* path, int on_device) {
+  std::vector<uint8_t> bytes;
+  if (const int e = LoadFileBytes(path, &bytes)) return e;
+  return LoadFromImage(bytes.data(), bytes.size(), on_device);
+}
+
+// ---------------------------------------------------------------------------------------
+// state arena
+// ---------------------------------------------------------------------------------------
+int StateArena::Plan(int history_rows, int T, int C) {
+  Ring r;
+  r.T = T;
+  r.C = C;
+  r.slots = history_rows > 0 ? (history_rows + T - 1) / T + 1 : 1;
+  if (r.slots > 16) {
+    std::fprintf(stderr, "[libbeatrice_b200] FATAL: ring needs %d slots (> 16)\n", r.slots);
+    std::abort();
+  }
+  rings_.push_back(r);
+  return static_cast<int>(rings_.size()) - 1;
+}
+void StateArena::Commit(int device, int B) {
+  B_ = B;
+  size_t total = 0;
+  offsets_.resize(rings_.size());
+  for (size_t i = 0; i < rings_.size(); ++i) {
+    offsets_[i] = total;
+    size_t n = rings_[i].StreamStride() * B;
+    n = (n + 63) / 64 * 64;  // keep every ring 256-byte aligned
+    total += n;
+  }
+  buf_.Alloc(device, total * sizeof(float), true);
+  frame_.Alloc(device, sizeof(int), true);
+  for (size_t i = 0; i < rings_.size(); ++i) rings_[i].base = buf_.as<float>() + offsets_[i];
+}
+void StateArena::Clear() {
+  rings_.clear();
+  offsets_.clear();
+  buf_.Free();
+  frame_.Free();
+  B_ = 0;
+}
+void StateArena::ZeroAll(cudaStream_t s) { B200_CHECK(cudaMemsetAsync(buf_.p, 0, buf_.bytes, s)); }
+void StateArena::ZeroStream(int b, cudaStream_t s) {
+  for (const Ring& r : rings_)
+    B200_CHECK(cudaMemsetAsync(r.base + r.StreamStride() * b, 0, r.StreamStride() * sizeof(float), s));
+}
+
+// ---------------------------------------------------------------------------------------
+// program builders
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct DescBuilder {
+  std::vector<ConvDesc> host;
+  int Add(const ConvDesc& d) {
+    host.push_back(d);
+    return static_cast<int>(host.size()) - 1;
+  }
+};
+
+ConvDesc MakeConv(const Ring& x, const ConvW& w, int dil, int stride, int T_out, const Ring& y, int in_act,
+                  int out_act) {
+  ConvDesc d;
+  std::memset(&d, 0, sizeof(d));
+  d.x[0] = x.base;
+  d.x[1] = d.x[2] = nullptr;
+  d.n_x = 1;
+  d.in_scale = 1.0f;
+  d.x_slots = x.slots;
+  d.x_T = x.T;
+  d.x_C = x.C;
+  d.in_act = in_act;
+  d.w = w.w;
+  d.bias = w.b;
+  d.k = w.k;
+  d.dil = dil;
+  d.stride = stride;
+  d.C_in = w.cin;
+  d.N = w.cout;
+  d.T = T_out;
+  d.y = y.base;
+  d.y_slots = y.slots;
+  d.y_T = y.T;
+  d.y_C = y.C;
+  d.out_act = out_act;
+  return d;
+}
+
+void SetRes(ConvDesc* d, const Ring& r) {
+  d->res = r.base;
+  d->res_slots = r.slots;
+  d->res_T = r.T;
+}
+
+double ConvFlops(const ConvDesc& d, int B) { return 2.0 * d.C_in * d.k * d.N * d.T * B; }
+double ConvBytes(const ConvDesc& d, int B) {
+  const double w = 4.0 * d.k * d.C_in * d.N;
+  const double in = 4.0 * B * d.T * d.stride * d.C_in * d.n_x;
+  const double out = 4.0 * B * d.T * d.N * (d.res ? 2 : 1);
+  return w + in + out;
+}
+
+Ring FlatRing(float* base, int T, int C) {
+  Ring r;
+  r.base = base;
+  r.slots = 1;
+  r.T = T;
+  r.C = C;
+  return r;
+}
+
+}  // namespace
+
+void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float* external_stage) {
+  B = B_;
+  device = device_;
+  model = m;
+  model_generation = m->generation;
+  program.clear();
+  arena.Clear();
+  B200_CHECK(cudaSetDevice(device));
+
+  int t_in[6], t_out[6];
+  int t = kInHop;
+  for (int i = 0; i < 6; ++i) {
+    t_in[i] = t;
+    t /= m->stride[i];
+    t_out[i] = t;
+  }
+  int ring_in[6];
+  for (int i = 0; i < 6; ++i) ring_in[i] = arena.Plan(m->front[i].k - m->stride[i], t_in[i], m->front[i].cin);
+  std::vector<int> ring_x(m->n_res + 1), ring_g(m->n_res);
+  ring_x[0] = arena.Plan(0, 1, m->width);
+  for (int r = 0; r < m->n_res; ++r) {
+    ring_g[r] = arena.Plan(2 * m->dil[r], 1, m->width);
+    ring_x[r + 1] = arena.Plan(0, 1, m->width);
+  }
+  arena.Commit(device, B);
+  if (external_stage) {
+    in_stage.Free();
+    stage_ptr = external_stage;
+  } else {
+    in_stage.Alloc(device, sizeof(float) * B * kInHop, true);
+    stage_ptr = in_stage.as<float>();
+  }
+  head_out.Alloc(device, sizeof(float) * B * m->head_out, true);
+
+  DescBuilder db;
+  std::vector<int> conv_idx;
+  for (int i = 0; i < 6; ++i) {
+    const Ring& y = (i < 5) ? arena.ring(ring_in[i + 1]) : arena.ring(ring_x[0]);
+    conv_idx.push_back(db.Add(MakeConv(arena.ring(ring_in[i]), m->front[i], 1, m->stride[i], t_out[i], y, kActNone, kActGelu)));
+  }
+  std::vector<int> res_idx;
+  for (int r = 0; r < m->n_res; ++r) {
+    ConvDesc d = MakeConv(arena.ring(ring_g[r]), m->res[r], m->dil[r], 1, 1, arena.ring(ring_x[r + 1]), kActNone, kActNone);
+    SetRes(&d, arena.ring(ring_x[r]));
+    res_idx.push_back(db.Add(d));
+  }
+  const Ring head_ring = FlatRing(head_out.as<float>(), 1, m->head_out);
+  const int head_idx = db.Add(MakeConv(arena.ring(ring_x[m->n_res]), m->head, 1, 1, 1, head_ring, kActNone, kActNone));
+
+  descs.Alloc(device, sizeof(ConvDesc) * db.host.size(), false);
+  B200_CHECK(cudaMemcpy(descs.p, db.host.data(), sizeof(ConvDesc) * db.host.size(), cudaMemcpyHostToDevice));
+  const ConvDesc* dd = descs.as<ConvDesc>();
+  const int* frame = arena.frame();
+  const int Bn = B;
+  const char* tag = m->is_pitch ? "pitch" : "phone";
+
+  {
+    const Ring in0 = arena.ring(ring_in[0]);
+    const float* stage = stage_ptr;
+    Op op;
+    op.name = std::string(tag) + ".ingest";
+    op.bytes = 8.0 * B * kInHop;
+    op.launch = [=](cudaStream_t s) { LaunchIngest(stage, in0.base, in0.slots, in0.T, in0.C, Bn, frame, s); };
+    program.push_back(op);
+  }
+  for (int i = 0; i < 6; ++i) {
+    const ConvDesc h = db.host[conv_idx[i]];
+    const ConvDesc* dp = dd + conv_idx[i];
+    Op op;
+    op.name = std::string(tag) + ".fe" + std::to_string(i);
+    op.flops = ConvFlops(h, B);
+    op.bytes = ConvBytes(h, B);
+    if (i == 0)
+      op.launch = [=](cudaStream_t s) { LaunchDirectConv(dp, h, Bn, frame, s); };
+    else
+      op.launch = [=](cudaStream_t s) { LaunchConvGemm(dp, h, 1, Bn, frame, s); };
+    program.push_back(op);
+  }
+  for (int r = 0; r < m->n_res; ++r) {
+    NormDesc nd;
+    const Ring& xr = arena.ring(ring_x[r]);
+    const Ring& gr = arena.ring(ring_g[r]);
+    nd.x = xr.base;
+    nd.x_slots = xr.slots;
+    nd.T = 1;
+    nd.C = m->width;
+    nd.gamma = m->gamma[r];
+    nd.beta = m->beta[r];
+    nd.y = gr.base;
+    nd.y_slots = gr.slots;
+    Op on;
+    on.name = std::string(tag) + ".res" + std::to_string(r) + ".norm";
+    on.bytes = 8.0 * B * m->width;
+    on.launch = [=](cudaStream_t s) { LaunchNorm(nd, Bn, frame, s); };
+    program.push_back(on);
+    const ConvDesc h = db.host[res_idx[r]];
+    const ConvDesc* dp = dd + res_idx[r];
+    Op oc;
+    oc.name = std::string(tag) + ".res" + std::to_string(r) + ".conv";
+    oc.flops = ConvFlops(h, B);
+    oc.bytes = ConvBytes(h, B);
+    oc.launch = [=](cudaStream_t s) { LaunchConvGemm(dp, h, 1, Bn, frame, s); };
+    program.push_back(oc);
+  }
+  {
+    const ConvDesc h = db.host[head_idx];
+    const ConvDesc* dp = dd + head_idx;
+    Op op;
+    op.name = std::string(tag) + ".head";
+    op.flops = ConvFlops(h, B);
+    op.bytes = ConvBytes(h, B);
+    op.launch = [=](cudaStream_t s) { LaunchConvGemm(dp, h, 1, Bn, frame, s); };
+    program.push_back(op);
+  }
+  {
+    int* f = arena.frame();
+    Op op;
+    op.name = std::string(tag) + ".advance";
+    op.launch = [=](cudaStream_t s) { LaunchAdvance(f, s); };
+    program.push_back(op);
+  }
+}
+
+void WaveState::AllocCond(const FamilyDims& dims, int B_, int device_) {
+  if (cond_ready && B == B_ && device == device_) return;
+  B = B_;
+  device = device_;
+  phone_in.Alloc(device, sizeof(float) * B * dims.phone_channels, true);
+  q_in.Alloc(device, sizeof(int) * B, true);
+  feat_in.Alloc(device, sizeof(float) * B * kPitchFeatures, true);
+  spk.Alloc(device, sizeof(float) * B * kHidden, true);
+  formant.Alloc(device, sizeof(float) * B * kHidden, true);
+  for (int s = 0; s < 4; ++s) film[s].Alloc(device, sizeof(float) * B * 2 * spec::kStageCh[s + 1], true);
+  out.Alloc(device, sizeof(float) * B * kOutHop, true);
+  cond_ready = true;
+}
+
+void WaveState::Build(const WaveModel* m, int B_, int device_) {
+  AllocCond(m->dims, B_, device_);
+  B = B_;
+  device = device_;
+  model = m;
+  model_generation = m->generation;
+  program.clear();
+  arena.Clear();
+  B200_CHECK(cudaSetDevice(device));
+  const bool rc0 = m->dims.has_setter;
+
+  ring_hidden = arena.Plan(spec::kPreK - 1, 1, kHidden);
+  ring_pre = arena.Plan(1, 1, kHidden);
+  int ring_u[4], ring_a[4][3][3], ring_y[4][3][4];
+  int t = 1;
+  for (int s = 0; s < 4; ++s) {
+    const int c = spec::kStageCh[s + 1];
+    t *= spec::kRates[s];
+    ring_u[s] = arena.Plan((spec::kMrfK[2] - 1) * spec::kMrfD[0], t, c);
+    for (int ki = 0; ki < 3; ++ki) {
+      const int k = spec::kMrfK[ki];
+      ring_y[s][ki][0] = ring_u[s];
+      for (int di = 0; di < 3; ++di) {
+        ring_a[s][ki][di] = arena.Plan(k - 1, t, c);
+        const int hist = di < 2 ? (k - 1) * spec::kMrfD[di + 1] : (s < 3 ? 1 : spec::kPostK - 1);
+        ring_y[s][ki][di + 1] = arena.Plan(hist, t, c);
+      }
+      ring_stage_out[s][ki] = ring_y[s][ki][3];
+    }
+  }
+  arena.Commit(device, B);
+
+  DescBuilder db;
+  const int pre_idx = db.Add(MakeConv(arena.ring(ring_hidden), m->pre, 1, 1, 1, arena.ring(ring_pre), kActNone, kActNone));
+  int ups_idx[4], c1_idx[4][3], c2_idx[4][3];
+  t = 1;
+  for (int s = 0; s < 4; ++s) {
+    const int c = spec::kStageCh[s + 1];
+    ConvDesc u = MakeConv(s == 0 ? arena.ring(ring_pre) : arena.ring(ring_stage_out[s - 1][0]), m->ups[s], 1, 1, t,
+                          arena.ring(ring_u[s]), kActLrelu, kActNone);
+    if (s > 0) {
+      for (int ki = 0; ki < 3; ++ki) u.x[ki] = arena.ring(ring_stage_out[s - 1][ki]).base;
+      u.n_x = 3;
+      u.in_scale = 1.0f / 3.0f;
+    }
+    if (rc0) {
+      u.film = film[s].as<float>();
+      u.film_C = c;
+    }
+    ups_idx[s] = db.Add(u);
+    t *= spec::kRates[s];
+    for (int di = 0; di < 3; ++di) {
+      for (int ki = 0; ki < 3; ++ki) {
+        ConvDesc d1 = MakeConv(arena.ring(ring_y[s][ki][di]), m->c1[s][ki][di], spec::kMrfD[di], 1, t,
+                               arena.ring(ring_a[s][ki][di]), kActLrelu, kActLrelu);
+        const int id = db.Add(d1);
+        if (ki == 0) c1_idx[s][di] = id;
+      }
+      for (int ki = 0; ki < 3; ++ki) {
+        ConvDesc d2 = MakeConv(arena.ring(ring_a[s][ki][di]), m->c2[s][ki][di], 1, 1, t,
+                               arena.ring(ring_y[s][ki][di + 1]), kActNone, kActNone);
+        SetRes(&d2, arena.ring(ring_y[s][ki][di]));
+        const int id = db.Add(d2);
+        if (ki == 0) c2_idx[s][di] = id;
+      }
+    }
+  }
+  const Ring out_ring = FlatRing(out.as<float>(), kOutHop, 1);
+  ConvDesc pd = MakeConv(arena.ring(ring_stage_out[3][0]), m->post, 1, 1, kOutHop, out_ring, kActLrelu, kActTanh);
+  for (int ki = 0; ki < 3; ++ki) pd.x[ki] = arena.ring(ring_stage_out[3][ki]).base;
+  pd.n_x = 3;
+  pd.in_scale = 1.0f / 3.0f;
+  const int post_idx = db.Add(pd);
+
+  descs.Alloc(device, sizeof(ConvDesc) * db.host.size(), false);
+  B200_CHECK(cudaMemcpy(descs.p, db.host.data(), sizeof(ConvDesc) * db.host.size(), cudaMemcpyHostToDevice));
+  const ConvDesc* dd = descs.as<ConvDesc>();
+  const int* frame = arena.frame();
+  const int Bn = B;
+
+  {
+    const Ring hr = arena.ring(ring_hidden);
+    const float* ph = phone_in.as<float>();
+    const int* q = q_in.as<int>();
+    const float* ft = feat_in.as<float>();
+    const float* sp = spk.as<float>();
+    const float* fm = rc0 ? formant.as<float>() : nullptr;
+    const WaveModel* mm = m;
+    Op op;
+    op.name = "wave.cond";
+    op.flops = 2.0 * B * (m->dims.phone_channels + kPitchFeatures) * kHidden;
+    op.bytes = 4.0 * (m->dims.phone_channels * kHidden + B * (m->dims.phone_channels + 4 * kHidden));
+    op.launch = [=](cudaStream_t s) {
+      LaunchCond(ph, mm->dims.phone_channels, q, mm->dims.pitch_bins, ft, mm->embed.w, mm->embed.b, mm->pitch_emb,
+                 mm->feat_proj, sp, fm, hr.base, hr.slots, Bn, frame, s);
+    };
+    program.push_back(op);
+  }
+  auto add_gemm = [&](const std::string& name, int idx, int nz, bool mrf) {
+    Op op;
+    op.name = name;
+    for (int z = 0; z < nz; ++z) {
+      op.flops += ConvFlops(db.host[idx + z], B);
+      op.bytes += ConvBytes(db.host[idx + z], B);
+    }
+    op.is_mrf = mrf;
+    const ConvDesc h = db.host[idx];
+    const ConvDesc* dp = dd + idx;
+    op.launch = [=](cudaStream_t s) { LaunchConvGemm(dp, h, nz, Bn, frame, s); };
+    program.push_back(op);
+  };
+  add_gemm("wave.pre", pre_idx, 1, false);
+  for (int s = 0; s < 4; ++s) {
+    add_gemm("wave.ups" + std::to_string(s), ups_idx[s], 1, false);
+    for (int di = 0; di < 3; ++di) {
+      add_gemm("wave.mrf" + std::to_string(s) + ".d" + std::to_string(spec::kMrfD[di]) + ".c1", c1_idx[s][di], 3, true);
+      add_gemm("wave.mrf" + std::to_string(s) + ".d" + std::to_string(spec::kMrfD[di]) + ".c2", c2_idx[s][di], 3, true);
+    }
+  }
+  {
+    const ConvDesc h = db.host[post_idx];
+    const ConvDesc* dp = dd + post_idx;
+    Op op;
+    op.name = "wave.post";
+    op.flops = ConvFlops(h, B);
+    op.bytes = ConvBytes(h, B);
+    op.launch = [=](cudaStream_t s) { LaunchDirectConv(dp, h, Bn, frame, s); };
+    program.push_back(op);
+  }
+  {
+    int* f = arena.frame();
+    Op op;
+    op.name = "wave.advance";
+    op.launch = [=](cudaStream_t s) { LaunchAdvance(f, s); };
+    program.push_back(op);
+  }
+}
+
+void RunProgram(const std::vector<Op>& program, cudaStream_t s) {
+  for (const Op& op : program) op.launch(s);
+}
+
+GraphRunner::~GraphRunner() { Reset(); }
+void GraphRunner::Reset() {
+  if (exec_) cudaGraphExecDestroy(exec_);
+  exec_ = nullptr;
+}
+void GraphRunner::Run(cudaStream_t s, const std::function<void(cudaStream_t)>& body, bool use_graph) {
+  if (!use_graph) {
+    body(s);
+    return;
+  }
+  if (!exec_) {
+    cudaGraph_t graph = nullptr;
+    B200_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    body(s);
+    B200_CHECK(cudaStreamEndCapture(s, &graph));
+    B200_CHECK(cudaGraphInstantiate(&exec_, graph, 0));
+    B200_CHECK(cudaGraphDestroy(graph));
+  }
+  B200_CHECK(cudaGraphLaunch(exec_, s));
+}
+
+}  // namespace b200

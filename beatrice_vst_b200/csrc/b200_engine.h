@@ -1,0 +1,219 @@
+// Host-side engine of libbeatrice_b200: parameter files -> device weights, per-stream ring
+// state, and the per-hop launch programs of the three model parts.
+#ifndef BEATRICE_B200_ENGINE_H_
+#define BEATRICE_B200_ENGINE_H_
+
+#include <atomic>
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "b200_common.h"
+#include "b200_kernels.h"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------
+// parameter files (format: beatrice_vst_b200/model_spec.py docstring)
+// ---------------------------------------------------------------------------------------
+enum FileKind : uint32_t { kKindPhone = 1, kKindPitch = 2, kKindWavegen = 3, kKindSetter = 4, kKindSpeakers = 5, kKindFormant = 6 };
+constexpr uint32_t kFileMagic = 0x42323042u;
+
+size_t PhoneParamCount(const FamilyDims& d);
+size_t PitchParamCount(const FamilyDims& d);
+size_t WaveParamCount(const FamilyDims& d);
+size_t SetterParamCount();
+size_t SpeakerPayloadFloats(const FamilyDims& d, uint32_t n_speakers);
+
+struct FileImage {
+  uint32_t family = 0, kind = 0, count = 0;
+  const float* payload = nullptr;  // points into the caller's bytes
+  size_t n_floats = 0;
+};
+// Returns a Beatrice_ErrorCode value (0 ok, 1 open, 2 too small, 3 too large, 4 invalid).
+int LoadFileBytes(const char* utf8_path, std::vector<uint8_t>* bytes);
+// expected_floats(count) < 0 -> invalid
+int ParseFileImage(const void* data, size_t size, int family, uint32_t kind_a, uint32_t kind_b,
+                   const std::function<long long(uint32_t)>& expected_floats, FileImage* out);
+
+// ---------------------------------------------------------------------------------------
+// device plumbing
+// ---------------------------------------------------------------------------------------
+int UsableDeviceCount();           // never aborts
+int DefaultDevice();               // env BEATRICE_B200_DEVICE or 0; aborts when no GPU is usable
+bool GraphsEnabled();              // env BEATRICE_B200_NO_GRAPH=1 disables CUDA graphs
+
+struct DeviceBuffer {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int device = -1;
+  DeviceBuffer() = default;
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+  ~DeviceBuffer();
+  void Alloc(int dev, size_t n_bytes, bool zero);
+  void Free();
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+struct ConvW {
+  const float* w = nullptr;
+  const float* b = nullptr;
+  int k = 0, cin = 0, cout = 0;
+};
+
+// ---------------------------------------------------------------------------------------
+// immutable model objects (weights in HBM)
+// ---------------------------------------------------------------------------------------
+struct EncoderModel {  // PhoneExtractor / PitchEstimator
+  FamilyDims dims;
+  bool is_pitch = false;
+  bool loaded = false;
+  uint64_t generation = 0;
+  int device = -1;
+  DeviceBuffer blob;
+  ConvW front[6];
+  int stride[6];
+  int n_res = 0, width = 0, head_out = 0;
+  const float* gamma[6];
+  const float* beta[6];
+  ConvW res[6];
+  int dil[6];
+  ConvW head;
+  // returns Beatrice_ErrorCode; host validation happens before any CUDA call
+  int LoadFromImage(const void* data, size_t size, int on_device = -1);
+  int LoadFromFile(const char* utf8_path, int on_device = -1);
+};
+
+struct WaveModel {
+  FamilyDims dims;
+  bool loaded = false;
+  uint64_t generation = 0;
+  int device = -1;
+  DeviceBuffer blob, ups_bias;
+  ConvW embed;
+  const float* pitch_emb = nullptr;
+  const float* feat_proj = nullptr;
+  ConvW pre;
+  ConvW ups[4];  // as 2-tap conv, cout = r*C_out, bias replicated per phase
+  ConvW c1[4][3][3], c2[4][3][3];
+  ConvW post;
+  int LoadFromImage(const void* data, size_t size, int on_device = -1);
+  int LoadFromFile(const char* utf8_path, int on_device = -1);
+};
+
+struct SetterModel {
+  FamilyDims dims;
+  bool loaded = false;
+  int device = -1;
+  DeviceBuffer blob;
+  const float *add_w = nullptr, *add_b = nullptr, *for_w = nullptr, *for_b = nullptr;
+  const float* query[4];
+  const float* film_w[4];
+  const float* film_b[4];
+  int LoadFromImage(const void* data, size_t size, int on_device = -1);
+  int LoadFromFile(const char* utf8_path, int on_device = -1);
+};
+
+// ---------------------------------------------------------------------------------------
+// per-hop launch program
+// ---------------------------------------------------------------------------------------
+struct Op {
+  std::string name;
+  std::function<void(cudaStream_t)> launch;
+  double flops = 0.0;  // algorithmic, whole batch
+  double bytes = 0.0;  // algorithmic: weights + activations read + written
+  bool is_mrf = false; // belongs to the vocoder MRF Conv1d stage (the dominant roofline)
+};
+
+struct Ring {
+  float* base = nullptr;
+  int slots = 1, T = 1, C = 1;
+  size_t StreamStride() const { return static_cast<size_t>(slots) * T * C; }
+};
+
+// Arena of rings for B streams + the device hop counter.
+class StateArena {
+ public:
+  StateArena() = default;
+  ~StateArena() = default;
+  // two-phase: Plan() rings, then Commit() allocates and patches the base pointers
+  int Plan(int history_rows, int T, int C);  // returns ring id
+  void Commit(int device, int B);
+  const Ring& ring(int id) const { return rings_[id]; }
+  int* frame() const { return frame_.as<int>(); }
+  void ZeroStream(int b, cudaStream_t s);
+  void ZeroAll(cudaStream_t s);
+  void Clear();
+  size_t bytes() const { return buf_.bytes; }
+  int B() const { return B_; }
+
+ private:
+  std::vector<Ring> rings_;
+  std::vector<size_t> offsets_;
+  DeviceBuffer buf_, frame_;
+  int B_ = 0;
+};
+
+// Encoder (front end + normalised residual backbone + head) for B streams.
+struct EncoderState {
+  int B = 0, device = -1;
+  const EncoderModel* model = nullptr;
+  uint64_t model_generation = 0;
+  StateArena arena;
+  DeviceBuffer descs;     // ConvDesc table
+  DeviceBuffer in_stage;  // [B][160]
+  DeviceBuffer head_out;  // [B][head_out]
+  std::vector<Op> program;
+  const float* stage_ptr = nullptr;  // == in_stage unless an external staging buffer is shared
+  // Builds rings + program for `m`.  `external_stage` (device, [B][160]) replaces in_stage.
+  void Build(const EncoderModel* m, int B, int device, const float* external_stage = nullptr);
+  bool Matches(const EncoderModel* m) const { return model == m && m && model_generation == m->generation; }
+};
+
+struct WaveState {
+  int B = 0, device = -1;
+  const WaveModel* model = nullptr;
+  uint64_t model_generation = 0;
+  StateArena arena;
+  DeviceBuffer descs;
+  DeviceBuffer phone_in;  // [B][P]
+  DeviceBuffer q_in;      // [B] int
+  DeviceBuffer feat_in;   // [B][4]
+  DeviceBuffer spk;       // [B][256]   rc0: projected additive embedding; a2/b1: per-call vector
+  DeviceBuffer formant;   // [B][256]   rc0 only
+  DeviceBuffer film[4];   // [B][2*C_s] rc0 only (zero = identity)
+  DeviceBuffer out;       // [B][240]
+  std::vector<Op> program;
+  int ring_hidden = -1, ring_pre = -1, ring_stage_out[4][3];
+  bool cond_ready = false;
+  // conditioning buffers depend only on the family, not on the weights: the rc0 setters
+  // (beatrice.h:323-343) may run before the first GenerateWaveform1 names the model
+  void AllocCond(const FamilyDims& dims, int B, int device);
+  void Build(const WaveModel* m, int B, int device);
+  bool Matches(const WaveModel* m) const { return model == m && m && model_generation == m->generation; }
+};
+
+// Enqueues every op; the caller accounts launches in g_kernel_launches per executed hop.
+void RunProgram(const std::vector<Op>& program, cudaStream_t s);
+
+// A program captured once into a CUDA graph and replayed per hop.
+class GraphRunner {
+ public:
+  ~GraphRunner();
+  void Reset();
+  // Runs body either directly or as a (lazily captured) graph on `s`.
+  void Run(cudaStream_t s, const std::function<void(cudaStream_t)>& body, bool use_graph);
+
+ private:
+  cudaGraphExec_t exec_ = nullptr;
+};
+
+extern std::atomic<uint64_t> g_kernel_launches;  // launches issued through Op programs
+
+}  // namespace b200
+
+#endif  // BEATRICE_B200_ENGINE_H_

@@ -1,0 +1,636 @@
+// fp32 CUDA kernels of libbeatrice_b200 (sm_100a): the parity path.
+//
+// conv_gemm_kernel is the workhorse: every Conv1d / strided Conv1d / ConvTranspose1d of the
+// content encoder, pitch estimator and HiFi-GAN-style vocoder (spec M0)
+// runs through it as an implicit GEMM over channel-last ring buffers, with the input
+// activation, bias, FiLM, residual add and output activation fused.  The bf16 tcgen05
+// variant of the same contraction lives in b200_tc.cu.
+#include <cfloat>
+#include <climits>
+
+#include "b200_common.h"
+#include "b200_kernels.h"
+
+namespace b200 {
+namespace {
+
+__device__ __forceinline__ float ActApply(float v, int act) {
+  switch (act) {
+    case kActLrelu: return v > 0.0f ? v : 0.1f * v;
+    case kActGelu: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    case kActTanh: return tanhf(v);
+    default: return v;
+  }
+}
+__device__ __forceinline__ float4 ActApply4(float4 v, int act) {
+  if (act != kActNone) {
+    v.x = ActApply(v.x, act);
+    v.y = ActApply(v.y, act);
+    v.z = ActApply(v.z, act);
+    v.w = ActApply(v.w, act);
+  }
+  return v;
+}
+__device__ __forceinline__ float4 Ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// ------------------------------------------------------------------------------------------
+// implicit-GEMM causal conv.  CTA tile BM x BN, 128 threads, 8x4 accumulators per thread,
+// K walked tap by tap in chunks of 16 input channels, register-prefetched double buffering.
+// ------------------------------------------------------------------------------------------
+template <int BM, int BN>
+__global__ void __launch_bounds__(128) conv_gemm_kernel(const ConvDesc* __restrict__ descs, int B,
+                                                        const int* __restrict__ frame_ptr) {
+  constexpr int TM = 8, TN = 4, BK = 16;
+  constexpr int TX = BN / TN;  // threads along N
+  static_assert((BM / TM) * TX == 128, "tile must map onto 128 threads");
+  constexpr int XLD = BM + 4;
+  constexpr int XV = BM / 32;                         // float4 activation loads / thread / chunk
+  constexpr int WV = (BK * BN / 4 + 127) / 128;       // float4 weight loads / thread / chunk
+  __shared__ __align__(16) float Xs[2][BK][XLD];
+  __shared__ __align__(16) float Ws[2][BK][BN];
+
+  const ConvDesc d = descs[blockIdx.z];
+  const int frame = *frame_ptr;
+  const int M = B * d.T;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
+  const int C_in = d.C_in, N = d.N;
+
+  const int x_L = d.x_slots * d.x_T;
+  const int x_cur = (frame % d.x_slots) * d.x_T;
+  const int q4 = (tid & 3) * 4;  // which 4 of the 16 chunk channels this thread stages
+
+  // rows this thread stages: row = (tid>>2) + 32*i
+  long long xbase[XV];  // element offset of stream b's ring, or -1 for rows past M
+  int xu0[XV];          // t*stride + stride-1
+#pragma unroll
+  for (int i = 0; i < XV; ++i) {
+    const int m = m0 + (tid >> 2) + 32 * i;
+    if (m < M) {
+      const int b = m / d.T, t = m - b * d.T;
+      xbase[i] = static_cast<long long>(b) * x_L * C_in;
+      xu0[i] = t * d.stride + d.stride - 1;
+    } else {
+      xbase[i] = -1;
+      xu0[i] = 0;
+    }
+  }
+
+  const int nck = C_in / BK;
+  const int nchunks = d.k * nck;
+
+  float4 xr[XV];
+  float4 wr[WV];
+
+  auto load_chunk = [&](int c) {
+    const int j = c / nck;
+    const int ci0 = (c - j * nck) * BK;
+    const int off = (d.k - 1 - j) * d.dil;
+#pragma unroll
+    for (int i = 0; i < XV; ++i) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (xbase[i] >= 0) {
+        int r = x_cur + xu0[i] - off;
+        if (r < 0) r += x_L;
+        const long long a = xbase[i] + static_cast<long long>(r) * C_in + ci0 + q4;
+        v = Ldg4(d.x[0] + a);
+        if (d.n_x > 1) {
+          const float4 v1 = Ldg4(d.x[1] + a);
+          const float4 v2 = Ldg4(d.x[2] + a);
+          v.x = ((v.x + v1.x) + v2.x) * d.in_scale;
+          v.y = ((v.y + v1.y) + v2.y) * d.in_scale;
+          v.z = ((v.z + v1.z) + v2.z) * d.in_scale;
+          v.w = ((v.w + v1.w) + v2.w) * d.in_scale;
+        }
+        v = ActApply4(v, d.in_act);
+      }
+      xr[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < WV; ++i) {
+      const int idx = tid + i * 128;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < BK * BN / 4) {
+        const int kk = idx / (BN / 4), c4 = idx % (BN / 4);
+        const int col = n0 + c4 * 4;
+        if (col < N) v = Ldg4(d.w + (static_cast<long long>(j) * C_in + ci0 + kk) * N + col);
+      }
+      wr[i] = v;
+    }
+  };
+  auto store_chunk = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < XV; ++i) {
+      const int row = (tid >> 2) + 32 * i;
+      Xs[buf][q4 + 0][row] = xr[i].x;
+      Xs[buf][q4 + 1][row] = xr[i].y;
+      Xs[buf][q4 + 2][row] = xr[i].z;
+      Xs[buf][q4 + 3][row] = xr[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < WV; ++i) {
+      const int idx = tid + i * 128;
+      if (idx < BK * BN / 4) {
+        const int kk = idx / (BN / 4), c4 = idx % (BN / 4);
+        *reinterpret_cast<float4*>(&Ws[buf][kk][c4 * 4]) = wr[i];
+      }
+    }
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  load_chunk(0);
+  store_chunk(0);
+  __syncthreads();
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c & 1;
+    if (c + 1 < nchunks) load_chunk(c + 1);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&Xs[buf][kk][ty * TM]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&Xs[buf][kk][ty * TM + 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Ws[buf][kk][tx * TN]);
+      const float a[TM] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bb[TN] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    if (c + 1 < nchunks) store_chunk(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- fused epilogue: bias -> FiLM -> residual -> activation -> ring store ----
+  const int col = n0 + tx * TN;
+  if (col >= N) return;
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (d.bias) bias4 = Ldg4(d.bias + col);
+  const int y_L = d.y_slots * d.y_T;
+  const int y_cur = (frame % d.y_slots) * d.y_T;
+  const int res_L = d.res_slots * d.res_T;
+  const int res_cur = d.res ? (frame % d.res_slots) * d.res_T : 0;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    if (m >= M) break;
+    const int b = m / d.T, t = m - b * d.T;
+    float4 v = make_float4(acc[i][0] + bias4.x, acc[i][1] + bias4.y, acc[i][2] + bias4.z, acc[i][3] + bias4.w);
+    if (d.film) {
+      const int fc = col % d.film_C;
+      const float* f = d.film + static_cast<long long>(b) * 2 * d.film_C;
+      const float4 g = Ldg4(f + fc), be = Ldg4(f + d.film_C + fc);
+      v.x = v.x * (1.0f + g.x) + be.x;
+      v.y = v.y * (1.0f + g.y) + be.y;
+      v.z = v.z * (1.0f + g.z) + be.z;
+      v.w = v.w * (1.0f + g.w) + be.w;
+    }
+    if (d.res) {
+      const float4 r = Ldg4(d.res + (static_cast<long long>(b) * res_L + res_cur + t) * N + col);
+      v.x += r.x;
+      v.y += r.y;
+      v.z += r.z;
+      v.w += r.w;
+    }
+    v = ActApply4(v, d.out_act);
+    float* out = d.y + (static_cast<long long>(b) * y_L + y_cur) * d.y_C + static_cast<long long>(t) * N + col;
+    *reinterpret_cast<float4*>(out) = v;
+  }
+}
+
+// One thread per output element; for the two layers that are not GEMM shaped
+// (front-end conv with C_in = 1, post conv with C_out = 1).
+__global__ void direct_conv_kernel(const ConvDesc* __restrict__ descs, int B, const int* __restrict__ frame_ptr) {
+  const ConvDesc d = descs[0];
+  const int frame = *frame_ptr;
+  const long long total = static_cast<long long>(B) * d.T * d.N;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int n = static_cast<int>(idx % d.N);
+  const int m = static_cast<int>(idx / d.N);
+  const int b = m / d.T, t = m - b * d.T;
+  const int x_L = d.x_slots * d.x_T;
+  const int x_cur = (frame % d.x_slots) * d.x_T;
+  const long long xb = static_cast<long long>(b) * x_L * d.C_in;
+  float acc = d.bias ? __ldg(d.bias + n) : 0.f;
+  for (int j = 0; j < d.k; ++j) {
+    int r = x_cur + t * d.stride + d.stride - 1 - (d.k - 1 - j) * d.dil;
+    if (r < 0) r += x_L;
+    const long long a = xb + static_cast<long long>(r) * d.C_in;
+    const float* wj = d.w + static_cast<long long>(j) * d.C_in * d.N + n;
+    for (int ci = 0; ci < d.C_in; ++ci) {
+      float v = __ldg(d.x[0] + a + ci);
+      if (d.n_x > 1) v = ((v + __ldg(d.x[1] + a + ci)) + __ldg(d.x[2] + a + ci)) * d.in_scale;
+      v = ActApply(v, d.in_act);
+      acc = fmaf(v, __ldg(wj + static_cast<long long>(ci) * d.N), acc);
+    }
+  }
+  if (d.res) {
+    const int res_L = d.res_slots * d.res_T;
+    const int res_cur = (frame % d.res_slots) * d.res_T;
+    acc += __ldg(d.res + (static_cast<long long>(b) * res_L + res_cur + t) * d.N + n);
+  }
+  acc = ActApply(acc, d.out_act);
+  const int y_L = d.y_slots * d.y_T;
+  const int y_cur = (frame % d.y_slots) * d.y_T;
+  d.y[(static_cast<long long>(b) * y_L + y_cur) * d.y_C + static_cast<long long>(t) * d.N + n] = acc;
+}
+
+__device__ __forceinline__ float WarpSum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// y = GELU(ChanNorm(x)*gamma+beta); one warp per (stream, row); channel statistics by
+// warp-shuffle reduction, two-pass like the oracle (mean, then centred variance).
+__global__ void channorm_gelu_kernel(NormDesc d, int B, const int* __restrict__ frame_ptr) {
+  const int frame = *frame_ptr;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * d.T) return;
+  const int b = warp / d.T, t = warp - b * d.T;
+  const float* x = d.x + (static_cast<long long>(b) * d.x_slots * d.T + (frame % d.x_slots) * d.T + t) * d.C;
+  float* y = d.y + (static_cast<long long>(b) * d.y_slots * d.T + (frame % d.y_slots) * d.T + t) * d.C;
+  constexpr int kMaxPerLane = 8;  // C <= 256
+  float v[kMaxPerLane];
+  const int per = d.C / 32;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i)
+    if (i < per) {
+      v[i] = x[lane + 32 * i];
+      s += v[i];
+    }
+  const float mean = WarpSum(s) / static_cast<float>(d.C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i)
+    if (i < per) {
+      const float dl = v[i] - mean;
+      q = fmaf(dl, dl, q);
+    }
+  const float var = WarpSum(q) / static_cast<float>(d.C);
+  const float rstd = 1.0f / sqrtf(var + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i)
+    if (i < per) {
+      const int c = lane + 32 * i;
+      y[c] = ActApply((v[i] - mean) * rstd * __ldg(d.gamma + c) + __ldg(d.beta + c), kActGelu);
+    }
+}
+
+__global__ void ingest_kernel(const float* __restrict__ staging, float* __restrict__ ring, int slots, int TC,
+                              long long total, const int* __restrict__ frame_ptr) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int frame = *frame_ptr;
+  const long long b = idx / TC;
+  const int e = static_cast<int>(idx - b * TC);
+  ring[(b * slots + (frame % slots)) * TC + e] = staging[idx];
+}
+
+__global__ void advance_kernel(int* frame) {
+  // wrap at a multiple of every slot count in use (slots <= 64 by construction: lcm-free
+  // choice 2^20 * 3*5*7*9*11*13 would overflow; slots are recomputed modulo so any wrap point
+  // that is a common multiple works -- use 720720 * 1024 (lcm(1..16) * 1024) < 2^31)
+  const int f = *frame + 1;
+  *frame = (f >= 738017280) ? 0 : f;
+}
+
+__global__ void pitch_argmax_kernel(const float* __restrict__ head, int bins, const int* __restrict__ min_q,
+                                    const int* __restrict__ max_q, int* __restrict__ q, float* __restrict__ feat,
+                                    int B) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const float* h = head + static_cast<long long>(warp) * (bins + kPitchFeatures);
+  int lo = min(max(min_q[warp], 1), bins - 1);
+  int hi = min(max(max_q[warp], 1), bins - 1);
+  if (hi < lo) hi = lo;
+  float best = -FLT_MAX;
+  int besti = INT_MAX;
+  for (int i = lo + lane; i <= hi; i += 32) {
+    const float v = h[i];
+    if (v > best) {  // strictly greater: the first maximum wins, like the oracle's scan
+      best = v;
+      besti = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ov > best || (ov == best && oi < besti)) {
+      best = ov;
+      besti = oi;
+    }
+  }
+  if (lane == 0) q[warp] = (besti == INT_MAX) ? lo : besti;
+  if (lane < kPitchFeatures) feat[warp * kPitchFeatures + lane] = h[bins + lane];
+}
+
+// reference src/common/processor_core_2.cc:190-252, evaluated in fp64 with explicit
+// round-to-nearest mul/add so that no FMA contraction changes a rounding the CPU makes.
+__global__ void pitch_transform_kernel(const int* __restrict__ q_in, const PitchParams* __restrict__ params,
+                                       int bins, int* __restrict__ q_out, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const PitchParams p = params[b];
+  constexpr double kBps = 96.0 / 12.0;  // BEATRICE_PITCH_BINS_PER_OCTAVE / 12
+  const double q = static_cast<double>(q_in[b]);
+  double tmp = __dadd_rn(__dadd_rn(p.average_source_pitch,
+                                   __dmul_rn(__dadd_rn(q, -p.average_source_pitch), p.intonation_intensity)),
+                         __dmul_rn(kBps, p.pitch_shift));
+  if (p.pitch_correction != 0.0) {
+    if (p.pitch_correction_type == 0) {
+      const double nearest = __dmul_rn(__dadd_rn(floor(tmp / kBps), 0.5), kBps);
+      const double nd = __dmul_rn(__dadd_rn(tmp, -nearest), 2.0 / kBps);
+      if (fabs(nd) < 1e-4) {
+        tmp = nearest;
+      } else {
+        tmp = __dadd_rn(nearest, __dmul_rn(__dmul_rn(nd, pow(fabs(nd), -p.pitch_correction)), kBps / 2.0));
+      }
+    } else if (p.pitch_correction_type == 1) {
+      const double nearest = __dmul_rn(round(tmp / kBps), kBps);
+      const double nd = __dmul_rn(__dadd_rn(tmp, -nearest), 2.0 / kBps);
+      if (p.pitch_correction > 1 - 1e-4) {
+        tmp = nearest;
+      } else if (nd >= 0.0) {
+        tmp = __dadd_rn(nearest, __dmul_rn(pow(nd, 1.0 / (1.0 - p.pitch_correction)), kBps / 2.0));
+      } else {
+        tmp = __dadd_rn(nearest, -__dmul_rn(pow(-nd, 1.0 / (1.0 - p.pitch_correction)), kBps / 2.0));
+      }
+    }
+  }
+  const double r = round(tmp);
+  int qi = (r < 1.0) ? 1 : ((r > static_cast<double>(bins - 1)) ? bins - 1 : static_cast<int>(r));
+  q_out[b] = qi;
+}
+
+// hidden[b][c] = be[c] + phone[b].We[:,c] + pitch_emb[q[b]][c] + feat[b].Wf[:,c] (+ spk + formant)
+__global__ void __launch_bounds__(256) cond_kernel(const float* __restrict__ phone, int P, const int* __restrict__ q,
+                                                   int bins, const float* __restrict__ feat,
+                                                   const float* __restrict__ We, const float* __restrict__ be,
+                                                   const float* __restrict__ pitch_emb, const float* __restrict__ Wf,
+                                                   const float* __restrict__ spk, const float* __restrict__ formant,
+                                                   float* __restrict__ ring, int slots,
+                                                   const int* __restrict__ frame_ptr) {
+  __shared__ float ph[256];
+  __shared__ float ft[kPitchFeatures];
+  const int b = blockIdx.x, c = threadIdx.x;
+  if (c < P) ph[c] = phone[static_cast<long long>(b) * P + c];
+  if (c < kPitchFeatures) ft[c] = feat[b * kPitchFeatures + c];
+  __syncthreads();
+  float acc = __ldg(be + c);
+  for (int i = 0; i < P; ++i) acc = fmaf(ph[i], __ldg(We + i * kHidden + c), acc);
+  const int qq = min(max(q[b], 0), bins - 1);
+  float v = acc + __ldg(pitch_emb + static_cast<long long>(qq) * kHidden + c);
+  float fp = 0.f;
+#pragma unroll
+  for (int i = 0; i < kPitchFeatures; ++i) fp = fmaf(ft[i], __ldg(Wf + i * kHidden + c), fp);
+  v += fp;
+  if (spk) v += spk[static_cast<long long>(b) * kHidden + c];
+  if (formant) v += formant[static_cast<long long>(b) * kHidden + c];
+  const int frame = *frame_ptr;
+  ring[(static_cast<long long>(b) * slots + (frame % slots)) * kHidden + c] = v;
+}
+
+// kNN-VQ against a 512 x C codebook: out = mean of the n nearest rows (squared L2, ties to
+// the lower index); n = 0 or no codebook copies the input through.
+__global__ void __launch_bounds__(kCodebookSize) vq_kernel(const float* __restrict__ phone_in,
+                                                           float* __restrict__ phone_out,
+                                                           const float* const* __restrict__ codebooks,
+                                                           const int* __restrict__ n_neighbors, int C) {
+  __shared__ float ph[256];
+  __shared__ float dist[kCodebookSize];
+  __shared__ float red_v[kCodebookSize / 32];
+  __shared__ int red_i[kCodebookSize / 32];
+  __shared__ int chosen;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* cb = codebooks ? codebooks[b] : nullptr;
+  const int n = cb ? min(max(n_neighbors[b], 0), kCodebookSize) : 0;
+  if (tid < C) ph[tid] = phone_in[static_cast<long long>(b) * C + tid];
+  __syncthreads();
+  if (n == 0) {
+    if (tid < C) phone_out[static_cast<long long>(b) * C + tid] = ph[tid];
+    return;
+  }
+  {
+    const float* e = cb + static_cast<long long>(tid) * C;
+    float nn = 0.f, dot = 0.f;
+    for (int ch = 0; ch < C; ++ch) {
+      const float ev = __ldg(e + ch);
+      nn = fmaf(ev, ev, nn);
+      dot = fmaf(ev, ph[ch], dot);
+    }
+    dist[tid] = nn - 2.0f * dot;
+  }
+  float acc = 0.f;
+  __syncthreads();
+  for (int r = 0; r < n; ++r) {
+    float v = dist[tid];
+    int vi = tid;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, vi, o);
+      if (ov < v || (ov == v && oi < vi)) {
+        v = ov;
+        vi = oi;
+      }
+    }
+    if ((tid & 31) == 0) {
+      red_v[tid >> 5] = v;
+      red_i[tid >> 5] = vi;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      v = tid < kCodebookSize / 32 ? red_v[tid] : FLT_MAX;
+      vi = tid < kCodebookSize / 32 ? red_i[tid] : INT_MAX;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, vi, o);
+        if (ov < v || (ov == v && oi < vi)) {
+          v = ov;
+          vi = oi;
+        }
+      }
+      if (tid == 0) {
+        chosen = vi;
+        dist[vi] = INFINITY;
+      }
+    }
+    __syncthreads();
+    if (tid < C) acc += __ldg(cb + static_cast<long long>(chosen) * C + tid);
+    __syncthreads();
+  }
+  if (tid < C) phone_out[static_cast<long long>(b) * C + tid] = acc * (1.0f / static_cast<float>(n));
+}
+
+__global__ void __launch_bounds__(256) project256_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                         const float* __restrict__ e, size_t e_stride,
+                                                         const int* __restrict__ e_index, float* __restrict__ out,
+                                                         const int* __restrict__ out_index) {
+  __shared__ float ev[kHidden];
+  const int item = blockIdx.x, o = threadIdx.x;
+  const size_t src = e_index ? static_cast<size_t>(e_index[item]) : static_cast<size_t>(item);
+  ev[o] = e[src * e_stride + o];
+  __syncthreads();
+  float acc = __ldg(bias + o);
+  for (int i = 0; i < kHidden; ++i) acc = fmaf(ev[i], __ldg(W + i * kHidden + o), acc);
+  const int row = out_index ? out_index[item] : item;
+  out[static_cast<long long>(row) * kHidden + o] = acc;
+}
+
+__global__ void __launch_bounds__(kKvLength) kv_film_kernel(const float* __restrict__ kv_base,
+                                                            const int* __restrict__ kv_index, size_t kv_stride,
+                                                            const float* __restrict__ query,
+                                                            const float* __restrict__ W, const float* __restrict__ bias,
+                                                            int C, float* __restrict__ film_base,
+                                                            const int* __restrict__ out_index) {
+  __shared__ float qv[kKvChannels];
+  __shared__ float p[kKvLength];
+  __shared__ float pooled[kKvChannels];
+  __shared__ float red[kKvLength / 32];
+  const int item = blockIdx.x, tid = threadIdx.x;
+  const float* kv = kv_base + (kv_index ? static_cast<size_t>(kv_index[item]) : 0) * kv_stride;
+  if (tid < kKvChannels) qv[tid] = __ldg(query + tid);
+  __syncthreads();
+  float s = 0.f;
+  {
+    const float* row = kv + static_cast<size_t>(tid) * kKvChannels;
+    for (int ch = 0; ch < kKvChannels; ++ch) s = fmaf(__ldg(row + ch), qv[ch], s);
+    s *= 1.0f / sqrtf(static_cast<float>(kKvChannels));
+  }
+  // block max
+  float m = s;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((tid & 31) == 0) red[tid >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < kKvLength / 32; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  const float ex = expf(s - m);
+  float den = WarpSum(ex);
+  if ((tid & 31) == 0) red[tid >> 5] = den;
+  __syncthreads();
+  den = 0.f;
+  for (int i = 0; i < kKvLength / 32; ++i) den += red[i];
+  p[tid] = ex / den;
+  __syncthreads();
+  if (tid < kKvChannels) {
+    float acc = 0.f;
+    for (int i = 0; i < kKvLength; ++i) acc = fmaf(p[i], __ldg(kv + static_cast<size_t>(i) * kKvChannels + tid), acc);
+    pooled[tid] = acc;
+  }
+  __syncthreads();
+  if (tid < 2 * C) {
+    float acc = __ldg(bias + tid);
+    for (int i = 0; i < kKvChannels; ++i) acc = fmaf(pooled[i], __ldg(W + i * 2 * C + tid), acc);
+    const int row = out_index ? out_index[item] : item;
+    film_base[static_cast<long long>(row) * 2 * C + tid] = acc;
+  }
+}
+
+__global__ void fill_kernel(float* p, float v, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+void LaunchConvGemm(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B, const int* d_frame,
+                    cudaStream_t s) {
+  const int M = B * h0.T, N = h0.N;
+  if (N >= 64 || (N > 32 && N % 32 != 0)) {
+    dim3 grid((M + 63) / 64, (N + 63) / 64, nz);
+    conv_gemm_kernel<64, 64><<<grid, 128, 0, s>>>(d_descs, B, d_frame);
+  } else if (N > 16) {
+    dim3 grid((M + 127) / 128, (N + 31) / 32, nz);
+    conv_gemm_kernel<128, 32><<<grid, 128, 0, s>>>(d_descs, B, d_frame);
+  } else {
+    dim3 grid((M + 255) / 256, (N + 15) / 16, nz);
+    conv_gemm_kernel<256, 16><<<grid, 128, 0, s>>>(d_descs, B, d_frame);
+  }
+  B200_CHECK(cudaGetLastError());
+}
+
+void LaunchDirectConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int* d_frame, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * h0.T * h0.N;
+  direct_conv_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, s>>>(d_desc, B, d_frame);
+  B200_CHECK(cudaGetLastError());
+}
+
+void LaunchNorm(const NormDesc& d, int B, const int* d_frame, cudaStream_t s) {
+  const int warps = B * d.T;
+  channorm_gelu_kernel<<<(warps * 32 + 127) / 128, 128, 0, s>>>(d, B, d_frame);
+  B200_CHECK(cudaGetLastError());
+}
+
+void LaunchIngest(const float* staging, float* ring, int slots, int T, int C, int B, const int* d_frame,
+                  cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * T * C;
+  ingest_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(staging, ring, slots, T * C, total, d_frame);
+  B200_CHECK(cudaGetLastError());
+}
+
+void LaunchAdvance(int* d_frame, cudaStream_t s) {
+  advance_kernel<<<1, 1, 0, s>>>(d_frame);
+  B200_CHECK(cudaGetLastError());
+}
+
+void LaunchPitchArgmax(const float* head, int bins, const int* min_q, const int* max_q, int* q, float* feat, int B,
+                       cudaStream_t s) {
+  pitch_argmax_kernel<<<(B * 32 + 127) / 128, 128, 0, s>>>(head, bins, min_q, max_q, q, feat, B);
+  B200_CHECK(cudaGetLastError());
+}
+
+void LaunchPitchTransform(const int* q_in, const PitchParams* params, int bins, int* q_out, int B, cudaStream_t s) {
+  pitch_transform_kernel<<<(B + 127) / 128, 128, 0, s>>>(q_in, params, bins, q_out, B);
+  B200_CHECK(cudaGetLastError());
+}
+
+void LaunchCond(const float* phone, int P, const int* q, int bins, const float* feat, const float* We,
+                const float* be, const float* pitch_emb, const float* Wf, const float* spk, const float* formant,
+                float* ring, int slots, int B, const int* d_frame, cudaStream_t s) {
+  cond_kernel<<<B, kHidden, 0, s>>>(phone, P, q, bins, feat, We, be, pitch_emb, Wf, spk, formant, ring, slots, d_frame);
+  B200_CHECK(cudaGetLastError());
+}
+
+void LaunchVq(const float* phone_in, float* phone_out, const float* const* codebooks, const int* n_neighbors, int C,
+              int B, cudaStream_t s) {
+  vq_kernel<<<B, kCodebookSize, 0, s>>>(phone_in, phone_out, codebooks, n_neighbors, C);
+  B200_CHECK(cudaGetLastError());
+}
+
+void LaunchProject256(const float* W, const float* b, const float* e, size_t e_stride, const int* e_index,
+                      float* out, const int* out_index, int n_items, cudaStream_t s) {
+  if (n_items <= 0) return;
+  project256_kernel<<<n_items, kHidden, 0, s>>>(W, b, e, e_stride, e_index, out, out_index);
+  B200_CHECK(cudaGetLastError());
+}
+
+void LaunchKvFilm(const float* kv_base, const int* kv_index, size_t kv_stride, const float* query, const float* W,
+                  const float* b, int C, float* film_base, const int* out_index, int n_items, cudaStream_t s) {
+  if (n_items <= 0) return;
+  kv_film_kernel<<<n_items, kKvLength, 0, s>>>(kv_base, kv_index, kv_stride, query, W, b, C, film_base, out_index);
+  B200_CHECK(cudaGetLastError());
+}
+
+void LaunchFill(float* p, float v, size_t n, cudaStream_t s) {
+  if (n == 0) return;
+  fill_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(p, v, n);
+  B200_CHECK(cudaGetLastError());
+}
+
+}  // namespace b200

@@ -1,0 +1,102 @@
+// Kernel-facing descriptors and launchers of libbeatrice_b200 (sm_100a).
+//
+// Data layout in HBM: every activation that a causal convolution
+// needs history of lives in a RING of rows, channel-last:
+//     ring[b][slot * T + t][c]      b < B streams, slot < slots, t < T rows per 10 ms hop
+// All streams of a batch advance together, so one device-resident hop counter `frame`
+// selects the slot (slot = frame % slots) for every ring of that batch; nothing about a
+// launch changes from hop to hop, which is what lets a whole hop be one CUDA graph.
+// The producer's output rows ARE the consumer's history: no shifting, no second copy.
+#ifndef BEATRICE_B200_KERNELS_H_
+#define BEATRICE_B200_KERNELS_H_
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace b200 {
+
+enum Act : int { kActNone = 0, kActLrelu = 1, kActGelu = 2, kActTanh = 3 };
+
+// One causal Conv1d (also strided, also ConvTranspose1d-as-2-tap-conv) as an implicit GEMM
+//   Y[(b,t)][n] = epilogue( sum_{j<k} sum_{ci} act_in(X[b][u(t,j)][ci]) * W[j][ci][n] )
+//   u(t,j) = t*stride + (stride-1) - (k-1-j)*dil     (negative u reaches into older slots)
+struct ConvDesc {
+  const float* x[3];  // up to three input rings of identical geometry, summed, times in_scale
+  int n_x;
+  float in_scale;
+  int x_slots, x_T, x_C;  // x_C == C_in
+  int in_act;
+  const float* w;     // [k][C_in][N]
+  const float* bias;  // [N] or nullptr
+  int k, dil, stride, C_in, N;
+  int T;              // GEMM rows (output steps) per stream per hop
+  float* y;           // output ring; row (b,t) stores N contiguous floats (y_T*y_C == T*N)
+  int y_slots, y_T, y_C;
+  const float* res;   // residual ring with N channels (current-hop rows), or nullptr
+  int res_slots, res_T;
+  const float* film;  // [B][2*film_C] = gamma | beta, applied as v*(1+gamma)+beta, or nullptr
+  int film_C;
+  int out_act;
+};
+
+struct NormDesc {  // y = GELU(ChanNorm(x) * gamma + beta), one row per warp
+  const float* x;
+  int x_slots, T, C;
+  const float* gamma;
+  const float* beta;
+  float* y;
+  int y_slots;
+};
+
+// Per-stream pitch-transform parameters == the ProcessorCore2 members of the same name
+// (reference src/common/processor_core_2.h:103-113).
+struct PitchParams {
+  double average_source_pitch;
+  double intonation_intensity;
+  double pitch_shift;
+  double pitch_correction;
+  int pitch_correction_type;
+  int pad_;
+};
+
+// ---- launchers (all asynchronous on `s`) ----
+// descs: device array of nz descriptors sharing N, T, C_in geometry class; h0 = host copy of descs[0]
+void LaunchConvGemm(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B, const int* d_frame,
+                    cudaStream_t s);
+void LaunchDirectConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int* d_frame, cudaStream_t s);
+void LaunchNorm(const NormDesc& d, int B, const int* d_frame, cudaStream_t s);
+// staging [B][T*C] -> ring slot of the current hop
+void LaunchIngest(const float* staging, float* ring, int slots, int T, int C, int B, const int* d_frame,
+                  cudaStream_t s);
+void LaunchAdvance(int* d_frame, cudaStream_t s);
+// head [B][bins+4] -> q [B] (arg-max over [min_q[b], max_q[b]]), feat [B][4]
+void LaunchPitchArgmax(const float* head, int bins, const int* min_q, const int* max_q, int* q, float* feat,
+                       int B, cudaStream_t s);
+// reference call-site transform, fp64 (processor_core_2.cc:190-252)
+void LaunchPitchTransform(const int* q_in, const PitchParams* params, int bins, int* q_out, int B,
+                          cudaStream_t s);
+// conditioning: phone 1x1 + pitch embedding gather + feature projection + speaker (+ formant)
+void LaunchCond(const float* phone, int P, const int* q, int bins, const float* feat, const float* We,
+                const float* be, const float* pitch_emb, const float* Wf, const float* spk /*[B][256]|null*/,
+                const float* formant /*[B][256]|null*/, float* ring, int slots, int B, const int* d_frame,
+                cudaStream_t s);
+// kNN-VQ: phone_in [B][C] -> phone_out [B][C]; codebooks[b] -> 512 x C device table (or null), n[b] neighbours
+void LaunchVq(const float* phone_in, float* phone_out, const float* const* codebooks, const int* n_neighbors,
+              int C, int B, cudaStream_t s);
+// y[row][256] = b + e[src] . W   (W stored [in][out]); src = e_index ? e_index[item] : item,
+// row = out_index ? out_index[item] : item
+void LaunchProject256(const float* W, const float* b, const float* e, size_t e_stride, const int* e_index,
+                      float* out, const int* out_index, int n_items, cudaStream_t s);
+// attention-pool kv (384 x 128) with `query`, then film = b + pooled . W  (W [128][2C])
+// item i reads kv_base + kv_index[i]*kv_stride (kv_index null -> 0) and writes film_base +
+// (out_index ? out_index[i] : i) * 2C
+void LaunchKvFilm(const float* kv_base, const int* kv_index, size_t kv_stride, const float* query,
+                  const float* W, const float* b, int C, float* film_base, const int* out_index, int n_items,
+                  cudaStream_t s);
+void LaunchFill(float* p, float v, size_t n, cudaStream_t s);
+
+}  // namespace b200
+
+#endif  // BEATRICE_B200_KERNELS_H_

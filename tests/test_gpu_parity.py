@@ -1,0 +1,309 @@
+"""GPU parity tests (``-m gpu``): the CUDA library through its C ABI against the CPU oracle on
+identical seeded inputs, against the committed golden vectors, and -- through the reference's
+own call site -- as a drop-in.  Tolerance: output audio <= 1e-4 RMS (fp32), the bar
+BASELINE.json's north_star states; integer outputs (pitch bins) exact.
+
+Nothing here reads /root/reference; the call site is the prebuilt oracle/_ref runner."""
+import ctypes as C
+import json
+import os
+import threading
+
+import numpy as np
+import pytest
+
+import callsite
+from beatrice_vst_b200 import batch as bbatch
+from beatrice_vst_b200 import lib as blib
+from beatrice_vst_b200 import signals
+from conftest import ROOT, rms
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+TOL_WAVE = 1e-4     # north_star: <= 1e-4 RMS (fp32)
+TOL_FEAT = 2e-5
+
+
+def _pair(product, oracle, model_dir, family=2, **kw):
+    a = blib.SingleStream(product, model_dir, family=family, **kw)
+    b = blib.SingleStream(oracle, model_dir, family=family, **kw)
+    assert a.ok and b.ok, (a.errors, b.errors)
+    return a, b
+
+
+def test_native_library_is_the_one_loaded(product):
+    assert bbatch.device_count(product) >= 1
+    assert any("libbeatrice_b200.so" in l for l in open("/proc/self/maps"))
+
+
+@pytest.mark.parametrize("family", [2, 0, 1])
+def test_single_stream_abi_matches_oracle(product, oracle, model_dirs, family):
+    x = signals.voice_like(160 * 40, 16000.0, seed=21)
+    a, b = _pair(product, oracle, model_dirs[family], family, speaker=3, formant_index=6)
+    a.set_pitch_range(1, 383)
+    b.set_pitch_range(1, 383)
+    pa, qa, fa, wa = a.run(x)
+    pb, qb, fb, wb = b.run(x)
+    a.close()
+    b.close()
+    assert np.array_equal(qa, qb)
+    assert rms(pa, pb) <= TOL_FEAT and rms(fa, fb) <= TOL_FEAT
+    assert rms(wa, wb) <= TOL_WAVE, rms(wa, wb)
+    assert np.abs(wa - wb).max() <= 1e-3
+
+
+@pytest.mark.parametrize("family", [0, 2])
+def test_single_stream_abi_matches_golden(product, model_dirs, family):
+    g = np.load(os.path.join(GOLDEN, f"m0_family{family}.npz"))
+    s = blib.SingleStream(product, model_dirs[family], family=family, speaker=1, formant_index=5)
+    s.set_pitch_range(1, 383)
+    phone, q, feat, wave = s.run(g["x"])
+    s.close()
+    assert np.array_equal(q, g["q"])
+    assert rms(phone, g["phone"]) <= TOL_FEAT and rms(wave, g["wave"]) <= TOL_WAVE
+    if family == 2:
+        s = blib.SingleStream(product, model_dirs[2], family=2, speaker=1, formant_index=5)
+        s.set_pitch_range(1, 383)
+        s.set_vq(4)
+        p2, _, _, w2 = s.run(g["x"])
+        s.close()
+        assert rms(p2, g["phone_vq4"]) <= TOL_FEAT and rms(w2, g["wave_vq4"]) <= TOL_WAVE
+
+
+def test_vocoder_stage_taps_match_oracle(product, oracle, model_dir):
+    """Per-stage activations of the vocoder (hidden, pre, 4 stage outputs)."""
+    x = signals.voice_like(160 * 6, 16000.0, seed=4)
+    a, b = _pair(product, oracle, model_dir)
+    a.run(x)
+    b.run(x)
+    product.dll.BeatriceB200_WaveformTap.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_int]
+    oracle.dll.BeatriceOracle_WaveformTap.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_int]
+    for which, n in enumerate([256, 256, 5 * 128, 20 * 64, 80 * 32, 240 * 16]):
+        ta, tb = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        fp = lambda v: v.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+        assert product.dll.BeatriceB200_WaveformTap(a.wc, which, fp(ta), n) == n
+        assert oracle.dll.BeatriceOracle_WaveformTap(b.wc, which, fp(tb), n) == n
+        scale = max(float(np.sqrt(np.mean(tb ** 2))), 1e-6)
+        assert rms(ta, tb) / scale <= 2e-5, (which, rms(ta, tb), scale)
+    a.close()
+    b.close()
+
+
+def test_vq_speaker_switch_and_formant(product, oracle, model_dir):
+    """kNN-VQ on/off, set-speaker with the key-value blocks one per hop, formant change."""
+    x = signals.voice_like(160 * 30, 16000.0, seed=8).reshape(30, 160)
+    a, b = _pair(product, oracle, model_dir)
+    outs = []
+    for s in (a, b):
+        w = []
+        for i in range(30):
+            if i == 5:
+                s.set_vq(8)
+            if i == 10:
+                s.set_speaker(6, kv_blocks_now=False)
+            if 10 <= i < 14:
+                s.set_kv_block(i - 10)
+            if i == 18:
+                s.set_formant_index(0)
+            if i == 22:
+                s.set_vq(0)
+                s.set_pitch_range(50, 200)
+            w.append(s.frame(x[i]))
+        outs.append(w)
+    for (pa, qa, fa, wa), (pb, qb, fb, wb) in zip(*outs):
+        assert qa == qb
+        assert rms(pa, pb) <= TOL_FEAT and rms(wa, wb) <= TOL_WAVE
+    a.close()
+    b.close()
+
+
+def test_context_recreation_gives_fresh_state(product, model_dir):
+    """ResetContext destroys and re-creates contexts (processor_core_2.cc:258-266)."""
+    x = signals.voice_like(160 * 8, 16000.0, seed=3)
+    s1 = blib.SingleStream(product, model_dir)
+    r1 = s1.run(x)
+    s1.close()
+    s2 = blib.SingleStream(product, model_dir)
+    r2 = s2.run(x)
+    s2.close()
+    assert np.array_equal(r1[3], r2[3]) and np.array_equal(r1[1], r2[1])
+
+
+def test_independent_instances_on_threads(product, oracle, model_dir):
+    """DAWs run many plug-in instances on different threads (SURVEY.md 8b threading)."""
+    n = 4
+    xs = [signals.voice_like(160 * 12, 16000.0, seed=30 + i) for i in range(n)]
+    res = [None] * n
+
+    def work(i):
+        s = blib.SingleStream(product, model_dir, speaker=i)
+        res[i] = s.run(xs[i])
+        s.close()
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(n):
+        o = blib.SingleStream(oracle, model_dir, speaker=i)
+        ref = o.run(xs[i])
+        o.close()
+        assert np.array_equal(res[i][1], ref[1])
+        assert rms(res[i][3], ref[3]) <= TOL_WAVE
+
+
+# ---------------------------------------------------------------------------------------
+# batched engine
+# ---------------------------------------------------------------------------------------
+def _oracle_stream(oracle, model_dir, x, speaker=0, formant_index=4, vq=0, shift_bins=0, lo=1, hi=383):
+    s = blib.SingleStream(oracle, model_dir, speaker=speaker, formant_index=formant_index)
+    s.set_pitch_range(lo, hi)
+    s.set_vq(vq)
+    out, qs = [], []
+    for i in range(len(x) // 160):
+        xi = x[i * 160:(i + 1) * 160]
+        # run the encoders once to learn q, then the vocoder with the transformed bin
+        f = s.f
+        fp = lambda v: v.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+        xi = np.ascontiguousarray(xi, np.float32)
+        ph, ft, w = np.empty(128, np.float32), np.empty(4, np.float32), np.empty(240, np.float32)
+        q = C.c_int(0)
+        f("ExtractPhone1")(s.pe, fp(xi), fp(ph), s.pc)
+        f("EstimatePitch1")(s.pi, fp(xi), C.byref(q), fp(ft), s.pic)
+        qq = C.c_int(min(max(q.value + shift_bins, 1), 447))
+        f("GenerateWaveform1")(s.wg, fp(ph), C.byref(qq), fp(ft), fp(w), s.wc)
+        out.append(w)
+        qs.append((q.value, qq.value))
+    s.close()
+    return np.stack(out), qs
+
+
+def test_batched_frames_match_oracle_per_stream(product, oracle, model_dir):
+    n, hops = 6, 12
+    xs = signals.batch_16k(n, hops, seed0=100)
+    eng = bbatch.Engine(product, n)
+    assert eng.load(model_dir) == 0 and eng.n_speakers == 8
+    spk = [0, 3, 7, 1, 2, 5]
+    shift = [0.0, 12.0, -12.0, 3.0, 0.0, 24.0]
+    fidx = [4, 0, 8, 4, 6, 2]
+    vq = [0, 0, 4, 0, 8, 0]
+    for s in range(n):
+        assert eng.set("TargetSpeaker", spk[s], s) == 0
+        assert eng.set("PitchShift", shift[s], s) == 0
+        assert eng.set("FormantShift", (fidx[s] - 4) / 2.0, s) == 0
+        assert eng.set("VQNumNeighbors", vq[s], s) == 0
+    eng.reset_stream(-1)   # applies all four key-value blocks at once, like ResetContext
+    got = np.stack([eng.process_frames(xs[h]).copy() for h in range(hops)], axis=1)   # [n][hops][240]
+    _, q_raw, q_used, _ = eng.last_intermediates()
+    for s in range(n):
+        ref, qs = _oracle_stream(oracle, model_dir, xs[:, s, :].reshape(-1), spk[s], fidx[s], vq[s],
+                                 int(round(shift[s] * 8)))
+        assert (q_raw[s], q_used[s]) == qs[-1]
+        assert rms(got[s], ref) <= TOL_WAVE, (s, rms(got[s], ref))
+    assert eng.kernel_launches() > 0
+    eng.close()
+
+
+def test_batched_rejects_bad_arguments(product, model_dir):
+    eng = bbatch.Engine(product, 2)
+    assert eng.set("PitchShift", 1.0, 0) == 9            # kModelNotLoaded before LoadModel
+    assert eng.load(model_dir) == 0
+    assert eng.set("TargetSpeaker", 8, 0) == 7           # morph slot / out of range -> kSpeakerIDOutOfRange
+    assert eng.set("TargetSpeaker", -1, 0) == 7
+    assert eng.set("PitchCorrectionType", 2, 0) == 8     # kInvalidPitchCorrectionType
+    assert eng.set("PitchShift", 1.0, 5) == -1           # no such stream
+    assert eng.load(os.path.join(model_dir, "nope")) == 1
+    eng.close()
+
+
+@pytest.mark.skipif(not callsite.available("oracle"), reason="oracle/_ref not built")
+def test_batched_48k_matches_reference_callsite(product, model_dir):
+    """Process48k == ProcessorCore2::Process at 48 kHz / 480-sample blocks, per stream, incl.
+    gain slews, pitch shift, correction and a speaker change (4-hop key-value schedule)."""
+    n, hops = 3, 24
+    x = signals.batch_48k(n, hops, seed0=40)
+    plans = [
+        [(-1, "input_gain", -6.0), (-1, "pitch_shift", 7.0), (5, "output_gain", 3.0), (9, "voice", 4)],
+        [(-1, "pitch_correction", 0.5), (3, "formant_shift", -1.5), (12, "vq_num_neighbors", 4)],
+        [(-1, "pitch_correction_type", 1), (-1, "pitch_correction", 0.3), (7, "intonation_intensity", 0.5),
+         (10, "min_source_pitch", 45.0), (10, "max_source_pitch", 70.0), (15, "voice", 2)],
+    ]
+    setter = dict(input_gain="InputGain", output_gain="OutputGain", pitch_shift="PitchShift", voice="TargetSpeaker",
+                  pitch_correction="PitchCorrection", formant_shift="FormantShift", vq_num_neighbors="VQNumNeighbors",
+                  pitch_correction_type="PitchCorrectionType", intonation_intensity="IntonationIntensity",
+                  min_source_pitch="MinSourcePitch", max_source_pitch="MaxSourcePitch")
+    eng = bbatch.Engine(product, n)
+    assert eng.load(model_dir) == 0
+    out = np.empty((n, hops, 480), np.float32)
+    for h in range(hops):
+        for s in range(n):
+            for (b, name, v) in plans[s]:
+                if b == h or (b == -1 and h == 0):
+                    val = int(v) if name in ("voice", "vq_num_neighbors", "pitch_correction_type") else float(v)
+                    assert eng.set(setter[name], val, s) == 0
+        out[:, h, :] = eng.process_48k(x[h])
+    eng.close()
+    for s in range(n):
+        y, info = callsite.run("oracle", os.path.join(model_dir, "model.toml"), x[:, s, :].reshape(-1),
+                               events=plans[s])
+        assert info["load"] == 0 and info["last"] == 0
+        e = rms(out[s].reshape(-1), y)
+        assert e <= TOL_WAVE, (s, e)
+
+
+def test_batched_48k_matches_committed_callsite_golden(product, model_dir):
+    g = np.load(os.path.join(GOLDEN, "callsite_48k.npz"))
+    events = [tuple(e) for e in json.loads(str(g["events"]))]
+    setter = dict(input_gain="InputGain", output_gain="OutputGain", pitch_shift="PitchShift", voice="TargetSpeaker",
+                  pitch_correction="PitchCorrection", formant_shift="FormantShift")
+    x = g["x"].reshape(-1, 480)
+    eng = bbatch.Engine(product, 1)
+    assert eng.load(model_dir) == 0
+    out = []
+    for h in range(len(x)):
+        for (b, name, v) in events:
+            if b == h or (b == -1 and h == 0):
+                assert eng.set(setter[name], int(v) if name == "voice" else float(v), 0) == 0
+        out.append(eng.process_48k(x[h][None, :])[0].copy())
+    eng.close()
+    assert rms(np.concatenate(out), g["y"]) <= TOL_WAVE
+
+
+@pytest.mark.skipif(not (callsite.available("oracle") and callsite.available("b200")), reason="oracle/_ref not built")
+def test_dropin_through_reference_callsite(model_dir):
+    """The reference's unmodified ProcessorProxy/ProcessorCore2 linked against the CUDA library
+    produces the same audio as the same call site linked against the CPU oracle."""
+    x = signals.voice_like(480 * 40, 48000.0, seed=77)
+    events = [(-1, "pitch_shift", -5.0), (6, "voice", 2), (11, "vq_num_neighbors", 4), (20, "reset", 1),
+              (25, "formant_shift", 2.0)]
+    toml = os.path.join(model_dir, "model.toml")
+    ya, ia = callsite.run("b200", toml, x, events=events, block=333)
+    yb, ib = callsite.run("oracle", toml, x, events=events, block=333)
+    assert ia == ib == {"load": 0, "last": 0, "version": 2}
+    assert rms(ya, yb) <= TOL_WAVE, rms(ya, yb)
+
+
+def test_full_size_batch_properties(product, model_dir):
+    """256 streams (BASELINE.json configs[1]): determinism, stream independence (a stream's
+    output does not depend on what the other 255 carry) and equality with the batch-of-1 path."""
+    n, hops = 256, 4
+    xs = signals.batch_16k(8, hops, seed0=500)
+    xs = np.tile(xs, (1, n // 8, 1))                      # stream s carries signal s % 8
+    eng = bbatch.Engine(product, n)
+    assert eng.load(model_dir) == 0
+    got = np.stack([eng.process_frames(xs[h]).copy() for h in range(hops)], axis=1)
+    eng.close()
+    assert np.isfinite(got).all() and got.std() > 0.05
+    for s in range(8, n):
+        assert np.array_equal(got[s], got[s % 8]), s      # same input -> bitwise same output
+    eng = bbatch.Engine(product, n)
+    eng.load(model_dir)
+    xs2 = xs.copy()
+    xs2[:, 8:, :] = signals.batch_16k(n - 8, hops, seed0=900)
+    got2 = np.stack([eng.process_frames(xs2[h]).copy() for h in range(hops)], axis=1)
+    eng.close()
+    assert np.array_equal(got2[:8], got[:8])              # independence
+    one = blib.SingleStream(product, model_dir)
+    one.set_pitch_range(1, 383)
+    _, _, _, w = one.run(xs[:, 3, :].reshape(-1))
+    one.close()
+    assert rms(w, got[3]) <= 1e-6
