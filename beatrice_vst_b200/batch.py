@@ -50,6 +50,7 @@ BATCH_SYMBOLS = {
     "BeatriceB200_CopyToHost": (None, [_vp, _vp, _vp, C.c_size_t]),
     "BeatriceB200_Stream": (_vp, [_vp]),
     "BeatriceB200_GetLastIntermediates": (C.c_int, [_vp, _f32p, _i32p, _i32p, _f32p]),
+    "BeatriceB200_ResidentBytes": (C.c_size_t, [_vp]),
     "BeatriceB200_KernelLaunchCount": (C.c_uint64, [_vp]),
     "BeatriceB200_ProfileHop": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
     "BeatriceB200_WaveformTap": (C.c_int, [_vp, C.c_int, _f32p, C.c_int]),
@@ -180,6 +181,9 @@ class Engine:
             self.h, phone.ctypes.data_as(_f32p), q_raw.ctypes.data_as(_i32p), q_used.ctypes.data_as(_i32p),
             feat.ctypes.data_as(_f32p))
         return phone, q_raw, q_used, feat
+
+    def resident_bytes(self) -> int:
+        return int(self.dll.BeatriceB200_ResidentBytes(self.h))
 
     def kernel_launches(self) -> int:
         return int(self.dll.BeatriceB200_KernelLaunchCount(self.h))

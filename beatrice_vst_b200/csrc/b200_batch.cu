@@ -615,6 +615,13 @@ int BeatriceB200_GetLastIntermediates(BeatriceB200_Engine* e, float* phone, int*
   return 0;
 }
 
+size_t BeatriceB200_ResidentBytes(const BeatriceB200_Engine* e) {
+  if (!e || !e->loaded) return 0;
+  return e->phone_st.arena.bytes() + e->pitch_st.arena.bytes() + e->wave_st.arena.bytes() + e->phone_m.blob.bytes +
+         e->pitch_m.blob.bytes + e->wave_m.blob.bytes + e->setter_m.blob.bytes + e->codebooks.bytes +
+         e->additive.bytes + e->kv.bytes;
+}
+
 uint64_t BeatriceB200_KernelLaunchCount(const BeatriceB200_Engine* e) { return e ? e->launches : 0; }
 
 int BeatriceB200_ProfileHop(BeatriceB200_Engine* e, const float* in_dev, float* out_dev,

@@ -48,7 +48,7 @@ const Param kParams[] = {{"voice", 2, true},
                          {"pitch_correction_type", 11, true},
                          {"min_source_pitch", 12, false},
                          {"max_source_pitch", 13, false},
-                         {"vq_num_neighbors", 14, true}};
+                         {"vq_num_neighbors", 14, false}};
 
 struct Event {
   long block;

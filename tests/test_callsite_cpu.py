@@ -115,7 +115,7 @@ def test_parameters_events_match_emulation_bit_exact(oracle, model_dir):
     x = signals.voice_like(480 * 30, 48000.0, 5)
     events = [(-1, "input_gain", -6.0), (-1, "pitch_shift", 12.0), (4, "output_gain", 3.0),
               (8, "voice", 5), (15, "formant_shift", 1.0), (20, "pitch_correction", 0.4),
-              (22, "intonation_intensity", 1.5), (24, "average_source_pitch", 60.0)]
+              (22, "intonation_intensity", 1.5), (24, "average_source_pitch", 60.0), (26, "vq_num_neighbors", 3)]
     y, info = callsite.run("oracle", _toml(model_dir), x, events=events)
     assert info["load"] == 0 and info["last"] == 0
     emu = Core2Emu(oracle, model_dir)
@@ -136,6 +136,8 @@ def test_parameters_events_match_emulation_bit_exact(oracle, model_dir):
             emu.inton = 1.5
         if i == 24:
             emu.avg = 60.0
+        if i == 26:
+            emu.s.set_vq(3)
         out.append(hr.process(x[i * 480:(i + 1) * 480]))
     assert np.array_equal(y, np.concatenate(out))
     raw, used = zip(*emu.q_log[:20])
