@@ -290,10 +290,11 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
 
   const int B = e->B;
   e->in16.Alloc(e->device, sizeof(float) * B * kInHop, true);
-  e->phone_st.Build(&e->phone_m, B, e->device, e->in16.as<float>());
-  e->pitch_st.Build(&e->pitch_m, B, e->device, e->in16.as<float>());
+  const TcMode tc = static_cast<TcMode>(e->precision);
+  e->phone_st.Build(&e->phone_m, B, e->device, e->in16.as<float>(), tc);
+  e->pitch_st.Build(&e->pitch_m, B, e->device, e->in16.as<float>(), tc);
   e->wave_st.cond_ready = false;
-  e->wave_st.Build(&e->wave_m, B, e->device);
+  e->wave_st.Build(&e->wave_m, B, e->device, tc);
   e->q_raw.Alloc(e->device, sizeof(int) * B, true);
   e->min_q.Alloc(e->device, sizeof(int) * B, true);
   e->max_q.Alloc(e->device, sizeof(int) * B, true);
@@ -360,7 +361,7 @@ const char* BeatriceB200_Version(void) { return "beatrice-b200 0.1 (spec M0, sm_
 
 BeatriceB200_Engine* BeatriceB200_CreateEngine(int device, int n_streams, int precision) {
   if (n_streams <= 0 || device < 0 || device >= UsableDeviceCount()) return nullptr;
-  if (precision != BEATRICE_B200_PRECISION_F32) return nullptr;  // no silent fallback for other modes
+  if (precision < BEATRICE_B200_PRECISION_F32 || precision > BEATRICE_B200_PRECISION_BF16X3) return nullptr;
   auto* e = new Engine();
   e->device = device;
   e->B = n_streams;

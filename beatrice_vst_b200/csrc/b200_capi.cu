@@ -147,7 +147,7 @@ void ExtractPhone(const PhoneExtractorObj* pe, const float* in, float* out, Phon
   if (!c->st.Matches(&pe->m)) {
     B200_CHECK(cudaStreamSynchronize(s));
     c->graph.Reset();
-    c->st.Build(&pe->m, 1, dev);
+    c->st.Build(&pe->m, 1, dev, nullptr, DefaultTcMode());
     c->in.Alloc(sizeof(float) * kInHop);
     c->out.Alloc(sizeof(float) * P);
     c->phone_out.Alloc(dev, sizeof(float) * P, true);
@@ -209,7 +209,7 @@ void EstimatePitch(const PitchEstimatorObj* pi, const float* in, int* q, float* 
   if (!c->st.Matches(&pi->m)) {
     B200_CHECK(cudaStreamSynchronize(s));
     c->graph.Reset();
-    c->st.Build(&pi->m, 1, dev);
+    c->st.Build(&pi->m, 1, dev, nullptr, DefaultTcMode());
     c->in.Alloc(sizeof(float) * kInHop);
     c->out.Alloc(sizeof(float) * 8);
     c->range.Alloc(dev, sizeof(int) * 2, true);
@@ -255,7 +255,7 @@ void GenerateWaveform(const WaveformGeneratorObj* wg, const float* phone, const 
   if (!c->st.Matches(&wg->m)) {
     B200_CHECK(cudaStreamSynchronize(s));
     c->graph.Reset();
-    c->st.Build(&wg->m, 1, dev);
+    c->st.Build(&wg->m, 1, dev, DefaultTcMode());
     c->in.Alloc(sizeof(float) * (P + 8 + kHidden));
     c->out.Alloc(sizeof(float) * kOutHop);
   }

@@ -132,6 +132,48 @@ int DefaultDevice() {
   return dev;
 }
 
+TcMode DefaultTcMode() {
+  static TcMode mode = [] {
+    const char* e = std::getenv("BEATRICE_B200_PRECISION");
+    if (!e) return kTcOff;
+    const std::string v(e);
+    if (v == "bf16") return kTcBf16;
+    if (v == "bf16x3") return kTcSplit;
+    if (v == "f32" || v.empty()) return kTcOff;
+    std::fprintf(stderr, "[libbeatrice_b200] FATAL: BEATRICE_B200_PRECISION=%s (expected f32|bf16|bf16x3)\n", e);
+    std::abort();
+  }();
+  return mode;
+}
+
+void TcWeights::Pack(int device, const float* host_blob, const float* dev_blob, const std::vector<ConvW*>& convs) {
+  std::vector<uint16_t> all;
+  struct Slot {
+    ConvW* c;
+    size_t off_hi, off_lo;
+  };
+  std::vector<Slot> slots;
+  for (ConvW* c : convs) {
+    const bool ok = (c->cin == 16 || c->cin == 32 || c->cin == 64 || c->cin == 128 || c->cin == 256) && c->cout % 4 == 0;
+    if (!ok) continue;
+    int bn = 0, kc = 0;
+    const size_t bytes = PackWeightsTc(nullptr, c->k, c->cin, c->cout, &bn, &kc, nullptr, nullptr);
+    const size_t n = bytes / sizeof(uint16_t);
+    const size_t off = all.size();
+    all.resize(off + 2 * n);
+    PackWeightsTc(host_blob + (c->w - dev_blob), c->k, c->cin, c->cout, &bn, &kc, all.data() + off, all.data() + off + n);
+    c->tc_bn = bn;
+    c->tc_kc = kc;
+    slots.push_back({c, off, off + n});
+  }
+  buf.Alloc(device, all.size() * sizeof(uint16_t), false);
+  B200_CHECK(cudaMemcpy(buf.p, all.data(), all.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  for (const Slot& sl : slots) {
+    sl.c->tc_hi = buf.as<uint16_t>() + sl.off_hi;
+    sl.c->tc_lo = buf.as<uint16_t>() + sl.off_lo;
+  }
+}
+
 bool GraphsEnabled() {
   static bool on = [] {
     const char* e = std::getenv("BEATRICE_B200_NO_GRAPH");
@@ -218,6 +260,13 @@ int EncoderModel::LoadFromImage(const void* data, size_t size, int on_device) {
     dil[i] = dl[i];
   }
   head = TakeConv(&c, 1, width, head_out);
+  {
+    std::vector<ConvW*> convs;
+    for (int i = 1; i < 6; ++i) convs.push_back(&front[i]);
+    for (int i = 0; i < n_res; ++i) convs.push_back(&res[i]);
+    convs.push_back(&head);
+    tc.Pack(device, img.payload, blob.as<float>(), convs);
+  }
   ++generation;
   loaded = true;
   return 0;
@@ -265,6 +314,19 @@ int WaveModel::LoadFromImage(const void* data, size_t size, int on_device) {
   }
   post = TakeConv(&c, spec::kPostK, 16, 1);
   Upload(&ups_bias, device, rep.data(), rep.size());
+  {
+    std::vector<ConvW*> convs;
+    convs.push_back(&pre);
+    for (int s = 0; s < 4; ++s) {
+      convs.push_back(&ups[s]);
+      for (int ki = 0; ki < 3; ++ki)
+        for (int di = 0; di < 3; ++di) {
+          convs.push_back(&c1[s][ki][di]);
+          convs.push_back(&c2[s][ki][di]);
+        }
+    }
+    tc.Pack(device, img.payload, blob.as<float>(), convs);
+  }
   for (int s = 0; s < 4; ++s) ups[s].b = ups_bias.as<float>() + rep_off[s];
   ++generation;
   loaded = true;
@@ -385,6 +447,10 @@ ConvDesc MakeConv(const Ring& x, const ConvW& w, int dil, int stride, int T_out,
   d.y_T = y.T;
   d.y_C = y.C;
   d.out_act = out_act;
+  d.w_tc = w.tc_hi;
+  d.w_tc_lo = w.tc_lo;
+  d.tc_bn = w.tc_bn;
+  d.tc_kc = w.tc_kc;
   return d;
 }
 
@@ -402,6 +468,16 @@ double ConvBytes(const ConvDesc& d, int B) {
   return w + in + out;
 }
 
+// CUDA-core or tensor-core launcher for one (possibly z-batched) conv GEMM.
+std::function<void(cudaStream_t)> GemmLauncher(const ConvDesc* dp, const ConvDesc& h, int nz, int B, const int* frame,
+                                               TcMode tc, bool tc_allowed) {
+  if (tc != kTcOff && tc_allowed && h.w_tc != nullptr) {
+    const bool split = tc == kTcSplit;
+    return [=](cudaStream_t s) { LaunchConvGemmTc(dp, h, nz, B, frame, split, s); };
+  }
+  return [=](cudaStream_t s) { LaunchConvGemm(dp, h, nz, B, frame, s); };
+}
+
 Ring FlatRing(float* base, int T, int C) {
   Ring r;
   r.base = base;
@@ -413,7 +489,7 @@ Ring FlatRing(float* base, int T, int C) {
 
 }  // namespace
 
-void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float* external_stage) {
+void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float* external_stage, TcMode tc) {
   B = B_;
   device = device_;
   model = m;
@@ -488,7 +564,7 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     if (i == 0)
       op.launch = [=](cudaStream_t s) { LaunchDirectConv(dp, h, Bn, frame, s); };
     else
-      op.launch = [=](cudaStream_t s) { LaunchConvGemm(dp, h, 1, Bn, frame, s); };
+      op.launch = GemmLauncher(dp, h, 1, Bn, frame, tc, tc == kTcSplit);
     program.push_back(op);
   }
   for (int r = 0; r < m->n_res; ++r) {
@@ -514,7 +590,7 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     oc.name = std::string(tag) + ".res" + std::to_string(r) + ".conv";
     oc.flops = ConvFlops(h, B);
     oc.bytes = ConvBytes(h, B);
-    oc.launch = [=](cudaStream_t s) { LaunchConvGemm(dp, h, 1, Bn, frame, s); };
+    oc.launch = GemmLauncher(dp, h, 1, Bn, frame, tc, tc == kTcSplit);
     program.push_back(oc);
   }
   {
@@ -524,7 +600,7 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     op.name = std::string(tag) + ".head";
     op.flops = ConvFlops(h, B);
     op.bytes = ConvBytes(h, B);
-    op.launch = [=](cudaStream_t s) { LaunchConvGemm(dp, h, 1, Bn, frame, s); };
+    op.launch = GemmLauncher(dp, h, 1, Bn, frame, tc, tc == kTcSplit);
     program.push_back(op);
   }
   {
@@ -550,7 +626,7 @@ void WaveState::AllocCond(const FamilyDims& dims, int B_, int device_) {
   cond_ready = true;
 }
 
-void WaveState::Build(const WaveModel* m, int B_, int device_) {
+void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
   AllocCond(m->dims, B_, device_);
   B = B_;
   device = device_;
@@ -658,7 +734,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_) {
     op.is_mrf = mrf;
     const ConvDesc h = db.host[idx];
     const ConvDesc* dp = dd + idx;
-    op.launch = [=](cudaStream_t s) { LaunchConvGemm(dp, h, nz, Bn, frame, s); };
+    op.launch = GemmLauncher(dp, h, nz, Bn, frame, tc, true);
     program.push_back(op);
   };
   add_gemm("wave.pre", pre_idx, 1, false);

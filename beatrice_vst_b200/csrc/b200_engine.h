@@ -63,6 +63,23 @@ struct ConvW {
   const float* w = nullptr;
   const float* b = nullptr;
   int k = 0, cin = 0, cout = 0;
+  // tensor-core operand images (b200_tc.cu), filled by TcWeights::Pack
+  const void* tc_hi = nullptr;
+  const void* tc_lo = nullptr;
+  int tc_bn = 0, tc_kc = 0;
+};
+
+// Precision of the conv GEMMs: fp32 CUDA cores (parity path), bf16 tcgen05, or split-bf16
+// tcgen05 (hi/lo decomposition, three MMAs, near-fp32 accuracy).
+enum TcMode : int { kTcOff = 0, kTcBf16 = 1, kTcSplit = 2 };
+TcMode DefaultTcMode();  // env BEATRICE_B200_PRECISION = f32 | bf16 | bf16x3 (default f32)
+
+// bf16 re-packing of a set of conv weights, resident in HBM next to the fp32 blob.
+struct TcWeights {
+  DeviceBuffer buf;
+  // packs every conv in `convs` whose shape the tensor-core kernel supports; host_blob/dev_blob
+  // give the fp32 payload the ConvW pointers refer to
+  void Pack(int device, const float* host_blob, const float* dev_blob, const std::vector<ConvW*>& convs);
 };
 
 // ---------------------------------------------------------------------------------------
@@ -83,6 +100,7 @@ struct EncoderModel {  // PhoneExtractor / PitchEstimator
   ConvW res[6];
   int dil[6];
   ConvW head;
+  TcWeights tc;
   // returns Beatrice_ErrorCode; host validation happens before any CUDA call
   int LoadFromImage(const void* data, size_t size, int on_device = -1);
   int LoadFromFile(const char* utf8_path, int on_device = -1);
@@ -101,6 +119,7 @@ struct WaveModel {
   ConvW ups[4];  // as 2-tap conv, cout = r*C_out, bias replicated per phase
   ConvW c1[4][3][3], c2[4][3][3];
   ConvW post;
+  TcWeights tc;
   int LoadFromImage(const void* data, size_t size, int on_device = -1);
   int LoadFromFile(const char* utf8_path, int on_device = -1);
 };
@@ -170,7 +189,8 @@ struct EncoderState {
   std::vector<Op> program;
   const float* stage_ptr = nullptr;  // == in_stage unless an external staging buffer is shared
   // Builds rings + program for `m`.  `external_stage` (device, [B][160]) replaces in_stage.
-  void Build(const EncoderModel* m, int B, int device, const float* external_stage = nullptr);
+  void Build(const EncoderModel* m, int B, int device, const float* external_stage = nullptr,
+             TcMode tc = kTcOff);
   bool Matches(const EncoderModel* m) const { return model == m && m && model_generation == m->generation; }
 };
 
@@ -193,7 +213,7 @@ struct WaveState {
   // conditioning buffers depend only on the family, not on the weights: the rc0 setters
   // (beatrice.h:323-343) may run before the first GenerateWaveform1 names the model
   void AllocCond(const FamilyDims& dims, int B, int device);
-  void Build(const WaveModel* m, int B, int device);
+  void Build(const WaveModel* m, int B, int device, TcMode tc = kTcOff);
   bool Matches(const WaveModel* m) const { return model == m && m && model_generation == m->generation; }
 };
 

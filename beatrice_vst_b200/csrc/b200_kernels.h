@@ -39,6 +39,11 @@ struct ConvDesc {
   const float* film;  // [B][2*film_C] = gamma | beta, applied as v*(1+gamma)+beta, or nullptr
   int film_C;
   int out_act;
+  // tcgen05 path (b200_tc.cu): weights re-packed as bf16 UMMA operand tiles, see PackWeightsTc
+  const void* w_tc;   // nullptr -> this conv has no tensor-core form
+  const void* w_tc_lo;  // low-order bf16 residual of the weights (split-bf16 mode) or nullptr
+  int tc_bn;          // N tile width (multiple of 16, <= 256)
+  int tc_kc;          // K elements per chunk (taps_per_chunk * C_in or 64)
 };
 
 struct NormDesc {  // y = GELU(ChanNorm(x) * gamma + beta), one row per warp
@@ -65,6 +70,14 @@ struct PitchParams {
 // descs: device array of nz descriptors sharing N, T, C_in geometry class; h0 = host copy of descs[0]
 void LaunchConvGemm(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B, const int* d_frame,
                     cudaStream_t s);
+// Same contraction on the 5th-gen tensor cores: bf16 operands staged in shared memory (weights
+// by TMA bulk copy), fp32 accumulators in TMEM, same fused epilogue.  split = true adds the two
+// cross terms of a hi/lo bf16 decomposition of both operands (near-fp32 accuracy, 3 MMAs).
+void LaunchConvGemmTc(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B, const int* d_frame, bool split,
+                      cudaStream_t s);
+// Host-side packing of one conv's weights w[k][C_in][N] (fp32) into the tile order the kernel
+// consumes; returns bytes written per array.  hi/lo may be nullptr to query the size.
+size_t PackWeightsTc(const float* w, int k, int C_in, int N, int* bn_out, int* kc_out, uint16_t* hi, uint16_t* lo);
 void LaunchDirectConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int* d_frame, cudaStream_t s);
 void LaunchNorm(const NormDesc& d, int B, const int* d_frame, cudaStream_t s);
 // staging [B][T*C] -> ring slot of the current hop

@@ -1,0 +1,441 @@
+// tcgen05 (5th-generation tensor core) form of the causal-conv implicit GEMM, sm_100a only.
+//
+//   D[128 rows x BN cols] (fp32, in TMEM)  +=  A[128 x 64] (bf16, smem)  *  W[64 x BN] (bf16, smem)
+//
+// One CTA = one 128-row tile of the (stream, time) axis x one BN-wide tile of output channels.
+// K is walked in chunks of 64 (one tap x 64 input channels, or several taps when C_in < 64).
+// Per chunk and pipeline stage:
+//   * the weight tile arrives by ONE TMA bulk copy (cp.async.bulk, mbarrier complete_tx) from a
+//     host-prepacked image that already has the UMMA canonical K-major / no-swizzle layout
+//       [K/8 panels][rows][8 elements]   (core matrix = 8 rows x 16 B contiguous)
+//   * the 128 threads gather their own activation row for that tap from the fp32 ring buffers
+//     (sum of up to three branches, scale, LeakyReLU), convert to bf16 and write one 16-byte
+//     vector per panel -- conflict free because consecutive threads own consecutive rows;
+//   * one elected thread issues 4 tcgen05.mma (K = 16 each) and tcgen05.commit's the stage's
+//     "empty" mbarrier, so the gather of the next chunk overlaps the MMAs of this one.
+// Epilogue: tcgen05.ld (32 lanes x 32-bit x 16 columns per warp) -> bias / FiLM / residual /
+// activation -> fp32 ring store, identical to the CUDA-core kernel's epilogue.
+//
+// kSplit adds the hi/lo bf16 decomposition of both operands (x = hi + lo): three MMAs
+// hi*hi + hi*lo + lo*hi per K step recover ~16 mantissa bits with fp32 accumulation.
+#include <cuda_bf16.h>
+
+#include <cstring>
+#include <vector>
+
+#include "b200_common.h"
+#include "b200_kernels.h"
+
+namespace b200 {
+namespace {
+
+constexpr int kTcM = 128;   // rows per CTA == TMEM lanes
+constexpr int kTcKC = 64;   // K elements per chunk
+constexpr int kPanelA = kTcM * 16;  // bytes of one 8-element K panel of the activation tile
+
+__device__ __forceinline__ uint32_t SmemAddr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void MbarInit(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void MbarExpectTx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void MbarWait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void TmaBulkLoad(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void FenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void TcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void TcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave"):
+// bits [0,14) start>>4, [16,30) LBO>>4 (next K panel), [32,46) SBO>>4 (next 8-row group),
+// [46,48) version = 1 on sm_100, [61,64) layout type = 0.
+__device__ __forceinline__ uint64_t MakeDesc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+// Instruction descriptor, kind::f16: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1),
+// both K-major (bits 15, 16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
+__device__ __forceinline__ uint32_t MakeIdesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(kTcM >> 4) << 24);
+}
+__device__ __forceinline__ void Mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void MmaCommit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void TmemLd16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float ActTc(float v, int act) {
+  switch (act) {
+    case kActLrelu: return v > 0.0f ? v : 0.1f * v;
+    case kActGelu: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    case kActTanh: return tanhf(v);
+    default: return v;
+  }
+}
+
+// 8 fp32 -> 8 bf16 (round to nearest even) packed in a uint4; optionally the bf16 of the residual.
+template <bool kSplit>
+__device__ __forceinline__ void Pack8(const float* v, uint4* hi, uint4* lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 a = __float2bfloat16_rn(v[2 * i]), b = __float2bfloat16_rn(v[2 * i + 1]);
+    h[i] = static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+    if (kSplit) {
+      const __nv_bfloat16 ra = __float2bfloat16_rn(v[2 * i] - __bfloat162float(a));
+      const __nv_bfloat16 rb = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(b));
+      l[i] = static_cast<uint32_t>(__bfloat16_as_ushort(ra)) | (static_cast<uint32_t>(__bfloat16_as_ushort(rb)) << 16);
+    }
+  }
+  *hi = make_uint4(h[0], h[1], h[2], h[3]);
+  if (kSplit) *lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <bool kSplit>
+__global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __restrict__ descs, int B,
+                                                           const int* __restrict__ frame_ptr) {
+  constexpr int kStages = kSplit ? 2 : 3;
+  constexpr int kOperands = kSplit ? 2 : 1;
+  extern __shared__ __align__(1024) uint8_t smem[];
+
+  const ConvDesc d = descs[blockIdx.z];
+  const int BN = d.tc_bn;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int frame = *frame_ptr;
+  const int M = B * d.T;
+  const int m0 = blockIdx.x * kTcM, n0 = blockIdx.y * BN;
+  const int C_in = d.C_in, N = d.N;
+
+  const uint32_t a_bytes = kTcM * kTcKC * 2;          // 16 KiB
+  const uint32_t w_bytes = static_cast<uint32_t>(BN) * kTcKC * 2;
+  const uint32_t stage_bytes = (a_bytes + w_bytes) * kOperands;
+  uint8_t* tail = smem + kStages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);  // full[kStages], empty[kStages], done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  const uint32_t bar_full = SmemAddr(bars), bar_empty = SmemAddr(bars + kStages), bar_done = SmemAddr(bars + 2 * kStages);
+  const uint32_t smem_base = SmemAddr(smem);
+
+  // TMEM columns: power of two >= 32 covering BN fp32 accumulator columns
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(BN)) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      MbarInit(bar_full + 8 * i, 1);
+      MbarInit(bar_empty + 8 * i, 1);
+    }
+    MbarInit(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemAddr(tmem_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  TcFenceBefore();
+  __syncthreads();
+  TcFenceAfter();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- this thread's activation row ----
+  const int x_L = d.x_slots * d.x_T;
+  const int x_cur = (frame % d.x_slots) * d.x_T;
+  const int m = m0 + tid;
+  const bool row_ok = m < M;
+  long long xbase = 0;
+  int xu0 = 0;
+  if (row_ok) {
+    const int b = m / d.T, t = m - b * d.T;
+    xbase = static_cast<long long>(b) * x_L * C_in;
+    xu0 = t * d.stride + d.stride - 1;
+  }
+
+  // ---- chunk enumeration (must match PackWeightsTc) ----
+  const int n_sub = C_in >= kTcKC ? C_in / kTcKC : 1;
+  const int tpc = C_in >= kTcKC ? 1 : kTcKC / C_in;       // taps per chunk
+  const int cw = C_in >= kTcKC ? kTcKC : C_in;            // channels gathered per tap
+  const int n_chunks = C_in >= kTcKC ? d.k * n_sub : (d.k + tpc - 1) / tpc;
+  const uint32_t idesc = MakeIdesc(BN);
+  const uint8_t* w_hi = static_cast<const uint8_t*>(d.w_tc) +
+                        static_cast<size_t>(blockIdx.y) * n_chunks * w_bytes;
+  const uint8_t* w_lo = kSplit ? static_cast<const uint8_t*>(d.w_tc_lo) + static_cast<size_t>(blockIdx.y) * n_chunks * w_bytes
+                               : nullptr;
+
+  for (int c = 0; c < n_chunks; ++c) {
+    const int s = c % kStages;
+    const int round = c / kStages;
+    const int j0 = C_in >= kTcKC ? c / n_sub : c * tpc;
+    const int ci0 = C_in >= kTcKC ? (c - j0 * n_sub) * kTcKC : 0;
+    const int taps = C_in >= kTcKC ? 1 : min(tpc, d.k - j0);
+    const uint32_t st_base = smem_base + s * stage_bytes;
+    const uint32_t a_hi = st_base, w_hi_s = st_base + a_bytes * kOperands;
+    const uint32_t a_lo = st_base + a_bytes, w_lo_s = w_hi_s + w_bytes;
+
+    // stage s is free once the MMAs of its previous use have completed
+    if (round > 0) MbarWait(bar_empty + 8 * s, (round - 1) & 1);
+
+    if (tid == 0) {
+      MbarExpectTx(bar_full + 8 * s, w_bytes * kOperands);
+      TmaBulkLoad(w_hi_s, w_hi + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * s);
+      if (kSplit) TmaBulkLoad(w_lo_s, w_lo + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * s);
+    }
+
+    // gather this thread's row: taps x cw channels -> bf16 panels
+    uint8_t* a_hi_p = smem + s * stage_bytes + tid * 16;
+    uint8_t* a_lo_p = a_hi_p + a_bytes;
+    for (int tl = 0; tl < taps; ++tl) {
+      const int j = j0 + tl;
+      int r = x_cur + xu0 - (d.k - 1 - j) * d.dil;
+      if (r < 0) r += x_L;
+      const long long a0 = xbase + static_cast<long long>(r) * C_in + ci0;
+      const int panel0 = tl * (cw >> 3);
+      for (int v8 = 0; v8 < (cw >> 3); ++v8) {
+        float v[8];
+        if (row_ok) {
+          const float4 p0 = __ldg(reinterpret_cast<const float4*>(d.x[0] + a0 + v8 * 8));
+          const float4 p1 = __ldg(reinterpret_cast<const float4*>(d.x[0] + a0 + v8 * 8 + 4));
+          v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w;
+          v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+          if (d.n_x > 1) {
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(d.x[1] + a0 + v8 * 8));
+            const float4 q1 = __ldg(reinterpret_cast<const float4*>(d.x[1] + a0 + v8 * 8 + 4));
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(d.x[2] + a0 + v8 * 8));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(d.x[2] + a0 + v8 * 8 + 4));
+            const float qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = ((v[e] + qq[e]) + ss[e]) * d.in_scale;
+          }
+          if (d.in_act != kActNone) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = ActTc(v[e], d.in_act);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        }
+        uint4 hi, lo;
+        Pack8<kSplit>(v, &hi, &lo);
+        *reinterpret_cast<uint4*>(a_hi_p + (panel0 + v8) * kPanelA) = hi;
+        if (kSplit) *reinterpret_cast<uint4*>(a_lo_p + (panel0 + v8) * kPanelA) = lo;
+      }
+    }
+    FenceProxyAsync();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+
+    if (tid == 0) {
+      MbarWait(bar_full + 8 * s, round & 1);   // weight tile landed
+      TcFenceAfter();
+      const int ksteps = (taps * cw) >> 4;
+      for (int kk = 0; kk < ksteps; ++kk) {
+        const uint64_t ah = MakeDesc(a_hi + 2 * kk * kPanelA, kPanelA, 128);
+        const uint64_t wh = MakeDesc(w_hi_s + 2 * kk * BN * 16, BN * 16, 128);
+        const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
+        Mma(tmem_base, ah, wh, idesc, acc);
+        if (kSplit) {
+          const uint64_t al = MakeDesc(a_lo + 2 * kk * kPanelA, kPanelA, 128);
+          const uint64_t wl = MakeDesc(w_lo_s + 2 * kk * BN * 16, BN * 16, 128);
+          Mma(tmem_base, ah, wl, idesc, 1u);
+          Mma(tmem_base, al, wh, idesc, 1u);
+        }
+      }
+      MmaCommit(bar_empty + 8 * s);            // frees the stage when these MMAs retire
+      if (c == n_chunks - 1) MmaCommit(bar_done);
+    }
+  }
+
+  // ---- epilogue: TMEM -> registers -> bias / FiLM / residual / activation -> ring ----
+  MbarWait(bar_done, 0);
+  TcFenceAfter();
+  const int row = warp * 32 + lane;
+  const int mm = m0 + row;
+  const bool out_ok = mm < M;
+  int ob = 0, ot = 0;
+  if (out_ok) {
+    ob = mm / d.T;
+    ot = mm - ob * d.T;
+  }
+  const int y_L = d.y_slots * d.y_T;
+  const int y_cur = (frame % d.y_slots) * d.y_T;
+  const int res_L = d.res_slots * d.res_T;
+  const int res_cur = d.res ? (frame % d.res_slots) * d.res_T : 0;
+  float* out_row = d.y + (static_cast<long long>(ob) * y_L + y_cur) * d.y_C + static_cast<long long>(ot) * N;
+  const float* res_row = d.res ? d.res + (static_cast<long long>(ob) * res_L + res_cur + ot) * N : nullptr;
+  const float* film_row = d.film ? d.film + static_cast<long long>(ob) * 2 * d.film_C : nullptr;
+  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  for (int c0 = 0; c0 < BN; c0 += 16) {
+    uint32_t rr[16];
+    TmemLd16(t_lane + c0, rr);   // whole warp, even when some rows are past M
+    if (!out_ok) continue;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = n0 + c0 + 4 * g;
+      if (col >= N) break;
+      float4 v = make_float4(__uint_as_float(rr[4 * g]), __uint_as_float(rr[4 * g + 1]), __uint_as_float(rr[4 * g + 2]),
+                             __uint_as_float(rr[4 * g + 3]));
+      if (d.bias) {
+        const float4 bz = __ldg(reinterpret_cast<const float4*>(d.bias + col));
+        v.x += bz.x; v.y += bz.y; v.z += bz.z; v.w += bz.w;
+      }
+      if (film_row) {
+        const int fc = col % d.film_C;
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(film_row + fc));
+        const float4 be = __ldg(reinterpret_cast<const float4*>(film_row + d.film_C + fc));
+        v.x = v.x * (1.0f + ga.x) + be.x;
+        v.y = v.y * (1.0f + ga.y) + be.y;
+        v.z = v.z * (1.0f + ga.z) + be.z;
+        v.w = v.w * (1.0f + ga.w) + be.w;
+      }
+      if (res_row) {
+        const float4 rz = __ldg(reinterpret_cast<const float4*>(res_row + col));
+        v.x += rz.x; v.y += rz.y; v.z += rz.z; v.w += rz.w;
+      }
+      if (d.out_act != kActNone) {
+        v.x = ActTc(v.x, d.out_act);
+        v.y = ActTc(v.y, d.out_act);
+        v.z = ActTc(v.z, d.out_act);
+        v.w = ActTc(v.w, d.out_act);
+      }
+      *reinterpret_cast<float4*>(out_row + col) = v;
+    }
+  }
+  TcFenceBefore();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+uint16_t Bf16Rn(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);  // NaN
+  const uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;
+  return static_cast<uint16_t>(u >> 16);
+}
+float Bf16ToF(uint16_t h) {
+  const uint32_t u = static_cast<uint32_t>(h) << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+
+size_t TcSmemBytes(bool split, int bn) {
+  const int stages = split ? 2 : 3;
+  const size_t stage = (static_cast<size_t>(kTcM) * kTcKC * 2 + static_cast<size_t>(bn) * kTcKC * 2) * (split ? 2 : 1);
+  return stages * stage + 128;
+}
+
+}  // namespace
+
+size_t PackWeightsTc(const float* w, int k, int C_in, int N, int* bn_out, int* kc_out, uint16_t* hi, uint16_t* lo) {
+  const int n16 = (N + 15) / 16 * 16;
+  int bn, n_tiles;
+  if (n16 <= 256) {
+    bn = n16;
+    n_tiles = 1;
+  } else {
+    bn = 128;
+    n_tiles = (N + 127) / 128;
+  }
+  const int n_sub = C_in >= kTcKC ? C_in / kTcKC : 1;
+  const int tpc = C_in >= kTcKC ? 1 : kTcKC / C_in;
+  const int n_chunks = C_in >= kTcKC ? k * n_sub : (k + tpc - 1) / tpc;
+  if (bn_out) *bn_out = bn;
+  if (kc_out) *kc_out = kTcKC;
+  const size_t block = static_cast<size_t>(kTcKC) * bn;
+  const size_t total = static_cast<size_t>(n_tiles) * n_chunks * block;
+  if (!hi) return total * sizeof(uint16_t);
+  for (int nt = 0; nt < n_tiles; ++nt)
+    for (int c = 0; c < n_chunks; ++c) {
+      const size_t base = (static_cast<size_t>(nt) * n_chunks + c) * block;
+      for (int p = 0; p < kTcKC / 8; ++p)
+        for (int n = 0; n < bn; ++n)
+          for (int e = 0; e < 8; ++e) {
+            const int kidx = p * 8 + e;
+            int j, ci;
+            if (C_in >= kTcKC) {
+              j = c / n_sub;
+              ci = (c - j * n_sub) * kTcKC + kidx;
+            } else {
+              j = c * tpc + kidx / C_in;
+              ci = kidx % C_in;
+            }
+            const int col = nt * bn + n;
+            float val = 0.f;
+            if (j < k && col < N) val = w[(static_cast<size_t>(j) * C_in + ci) * N + col];
+            const uint16_t h = Bf16Rn(val);
+            const size_t o = base + (static_cast<size_t>(p) * bn + n) * 8 + e;
+            hi[o] = h;
+            if (lo) lo[o] = Bf16Rn(val - Bf16ToF(h));
+          }
+    }
+  return total * sizeof(uint16_t);
+}
+
+void LaunchConvGemmTc(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B, const int* d_frame, bool split,
+                      cudaStream_t s) {
+  const int M = B * h0.T;
+  const int bn = h0.tc_bn;
+  const int n_tiles = ((h0.N + 15) / 16 * 16 <= 256) ? 1 : (h0.N + 127) / 128;
+  const size_t smem = TcSmemBytes(split, bn);
+  static bool attr_set[2][64] = {};
+  int dev = 0;
+  B200_CHECK(cudaGetDevice(&dev));
+  if (!attr_set[split ? 1 : 0][dev & 63]) {
+    if (split)
+      B200_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    else
+      B200_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[split ? 1 : 0][dev & 63] = true;
+  }
+  dim3 grid((M + kTcM - 1) / kTcM, n_tiles, nz);
+  if (split)
+    conv_gemm_tc_kernel<true><<<grid, 128, smem, s>>>(d_descs, B, d_frame);
+  else
+    conv_gemm_tc_kernel<false><<<grid, 128, smem, s>>>(d_descs, B, d_frame);
+  B200_CHECK(cudaGetLastError());
+}
+
+}  // namespace b200

@@ -46,8 +46,10 @@ def main():
         for i in range(50):
             a.frame(x[:160])
         print("single-stream ABI: %.1f us/hop" % ((time.time() - t) / 50 * 1e6))
-        for n in (4, 256):
-            eng = bbatch.Engine(product, n)
+        import itertools
+        for n, prec in itertools.product((4, 256), (0, 1, 2)):
+            print(f"---- batch {n} precision {prec} (0 f32, 1 bf16 tcgen05, 2 split-bf16 tcgen05) ----", flush=True)
+            eng = bbatch.Engine(product, n, precision=prec)
             print("batch load", eng.load(d))
             xs = signals.batch_16k(min(n, 8), 3, seed0=5)
             xs = np.tile(xs, (1, n // min(n, 8), 1))
@@ -56,7 +58,7 @@ def main():
             o = blib.SingleStream(oracle, d)
             o.set_pitch_range(1, 383)
             _, _, _, w = o.run(xs[:, 1, :].reshape(-1))
-            print(f"batch {n}: stream1 last-hop rms vs oracle {rms(out[1], w[-1]):.2e}")
+            print(f"batch {n}: stream1 last-hop rms vs oracle {rms(out[1], w[-1]):.2e}  (signal rms {float(np.sqrt(np.mean(w[-1] ** 2))):.3f})", flush=True)
             t = time.time()
             for i in range(20):
                 eng.process_frames(xs[0])
