@@ -14,20 +14,34 @@
 namespace b200 {
 namespace {
 
+// The transcendental activations are kept out of line: inlining erff/tanhf at every use made
+// the conv kernels > 100 KB of SASS and instruction-fetch bound (ncu: stall "no_instructions").
+__device__ __noinline__ float SlowAct(float v, int act) {
+  if (act == kActGelu) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+  return tanhf(v);
+}
 __device__ __forceinline__ float ActApply(float v, int act) {
-  switch (act) {
-    case kActLrelu: return v > 0.0f ? v : 0.1f * v;
-    case kActGelu: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
-    case kActTanh: return tanhf(v);
-    default: return v;
+  if (act == kActNone) return v;
+  if (act == kActLrelu) return v > 0.0f ? v : 0.1f * v;
+  return SlowAct(v, act);
+}
+// input side: only "none" and LeakyReLU occur (spec M0 applies GELU/tanh on the output side)
+__device__ __forceinline__ float4 InAct4(float4 v, int act) {
+  if (act == kActLrelu) {
+    v.x = v.x > 0.0f ? v.x : 0.1f * v.x;
+    v.y = v.y > 0.0f ? v.y : 0.1f * v.y;
+    v.z = v.z > 0.0f ? v.z : 0.1f * v.z;
+    v.w = v.w > 0.0f ? v.w : 0.1f * v.w;
   }
+  return v;
 }
 __device__ __forceinline__ float4 ActApply4(float4 v, int act) {
+  if (act == kActLrelu) return InAct4(v, act);
   if (act != kActNone) {
-    v.x = ActApply(v.x, act);
-    v.y = ActApply(v.y, act);
-    v.z = ActApply(v.z, act);
-    v.w = ActApply(v.w, act);
+    v.x = SlowAct(v.x, act);
+    v.y = SlowAct(v.y, act);
+    v.z = SlowAct(v.z, act);
+    v.w = SlowAct(v.w, act);
   }
   return v;
 }
@@ -102,7 +116,7 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const ConvDesc* __restri
           v.z = ((v.z + v1.z) + v2.z) * d.in_scale;
           v.w = ((v.w + v1.w) + v2.w) * d.in_scale;
         }
-        v = ActApply4(v, d.in_act);
+        v = InAct4(v, d.in_act);
       }
       xr[i] = v;
     }

@@ -103,13 +103,14 @@ __device__ __forceinline__ void TmemLd16(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// transcendental activations out of line (code size; see b200_kernels.cu)
+__device__ __noinline__ float SlowActTc(float v, int act) {
+  if (act == kActGelu) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+  return tanhf(v);
+}
 __device__ __forceinline__ float ActTc(float v, int act) {
-  switch (act) {
-    case kActLrelu: return v > 0.0f ? v : 0.1f * v;
-    case kActGelu: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
-    case kActTanh: return tanhf(v);
-    default: return v;
-  }
+  if (act == kActLrelu) return v > 0.0f ? v : 0.1f * v;
+  return SlowActTc(v, act);
 }
 
 // 8 fp32 -> 8 bf16 (round to nearest even) packed in a uint4; optionally the bf16 of the residual.
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __res
   const int tpc = C_in >= kTcKC ? 1 : kTcKC / C_in;       // taps per chunk
   const int cw = C_in >= kTcKC ? kTcKC : C_in;            // channels gathered per tap
   const int n_chunks = C_in >= kTcKC ? d.k * n_sub : (d.k + tpc - 1) / tpc;
+  const int lcw = 31 - __clz(cw);                         // cw is 16, 32 or 64
   const uint32_t idesc = MakeIdesc(BN);
   const uint8_t* w_hi = static_cast<const uint8_t*>(d.w_tc) +
                         static_cast<size_t>(blockIdx.y) * n_chunks * w_bytes;
@@ -220,44 +222,58 @@ __global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __res
       if (kSplit) TmaBulkLoad(w_lo_s, w_lo + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * s);
     }
 
-    // gather this thread's row: taps x cw channels -> bf16 panels
+    // gather this thread's row: 64 K-elements (taps x cw channels) -> eight bf16 panels.
+    // All global loads of a half-chunk are issued before the first use so their latency overlaps.
     uint8_t* a_hi_p = smem + s * stage_bytes + tid * 16;
     uint8_t* a_lo_p = a_hi_p + a_bytes;
-    for (int tl = 0; tl < taps; ++tl) {
-      const int j = j0 + tl;
+    long long ro[4];
+#pragma unroll
+    for (int tl = 0; tl < 4; ++tl) {
+      const int j = min(j0 + tl, d.k - 1);
       int r = x_cur + xu0 - (d.k - 1 - j) * d.dil;
       if (r < 0) r += x_L;
-      const long long a0 = xbase + static_cast<long long>(r) * C_in + ci0;
-      const int panel0 = tl * (cw >> 3);
-      for (int v8 = 0; v8 < (cw >> 3); ++v8) {
-        float v[8];
-        if (row_ok) {
-          const float4 p0 = __ldg(reinterpret_cast<const float4*>(d.x[0] + a0 + v8 * 8));
-          const float4 p1 = __ldg(reinterpret_cast<const float4*>(d.x[0] + a0 + v8 * 8 + 4));
-          v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w;
-          v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+      ro[tl] = xbase + static_cast<long long>(r) * C_in + ci0;
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float4 x0[8], x1[8], x2[8];
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ch = half * 32 + i * 4;          // K index inside the chunk
+          const int tl = ch >> lcw, cc = ch & (cw - 1);
+          const long long a = (tl == 0 ? ro[0] : tl == 1 ? ro[1] : tl == 2 ? ro[2] : ro[3]) + cc;
+          x0[i] = __ldg(reinterpret_cast<const float4*>(d.x[0] + a));
           if (d.n_x > 1) {
-            const float4 q0 = __ldg(reinterpret_cast<const float4*>(d.x[1] + a0 + v8 * 8));
-            const float4 q1 = __ldg(reinterpret_cast<const float4*>(d.x[1] + a0 + v8 * 8 + 4));
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(d.x[2] + a0 + v8 * 8));
-            const float4 s1 = __ldg(reinterpret_cast<const float4*>(d.x[2] + a0 + v8 * 8 + 4));
-            const float qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-            const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = ((v[e] + qq[e]) + ss[e]) * d.in_scale;
+            x1[i] = __ldg(reinterpret_cast<const float4*>(d.x[1] + a));
+            x2[i] = __ldg(reinterpret_cast<const float4*>(d.x[2] + a));
           }
-          if (d.in_act != kActNone) {
+        }
+        if (d.n_x > 1) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = ActTc(v[e], d.in_act);
+          for (int i = 0; i < 8; ++i) {
+            x0[i].x = ((x0[i].x + x1[i].x) + x2[i].x) * d.in_scale;
+            x0[i].y = ((x0[i].y + x1[i].y) + x2[i].y) * d.in_scale;
+            x0[i].z = ((x0[i].z + x1[i].z) + x2[i].z) * d.in_scale;
+            x0[i].w = ((x0[i].w + x1[i].w) + x2[i].w) * d.in_scale;
           }
-        } else {
+        }
+      } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        for (int i = 0; i < 8; ++i) x0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float v[8] = {x0[2 * p].x, x0[2 * p].y, x0[2 * p].z, x0[2 * p].w,
+                      x0[2 * p + 1].x, x0[2 * p + 1].y, x0[2 * p + 1].z, x0[2 * p + 1].w};
+        if (d.in_act == kActLrelu) {   // the only input activation of spec M0
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.0f ? v[e] : 0.1f * v[e];
         }
         uint4 hi, lo;
         Pack8<kSplit>(v, &hi, &lo);
-        *reinterpret_cast<uint4*>(a_hi_p + (panel0 + v8) * kPanelA) = hi;
-        if (kSplit) *reinterpret_cast<uint4*>(a_lo_p + (panel0 + v8) * kPanelA) = lo;
+        *reinterpret_cast<uint4*>(a_hi_p + (half * 4 + p) * kPanelA) = hi;
+        if (kSplit) *reinterpret_cast<uint4*>(a_lo_p + (half * 4 + p) * kPanelA) = lo;
       }
     }
     FenceProxyAsync();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
