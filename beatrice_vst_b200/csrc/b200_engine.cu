@@ -157,11 +157,12 @@ void TcWeights::Pack(int device, const float* host_blob, const float* dev_blob, 
     const bool ok = (c->cin == 16 || c->cin == 32 || c->cin == 64 || c->cin == 128 || c->cin == 256) && c->cout % 4 == 0;
     if (!ok) continue;
     int bn = 0, kc = 0;
-    const size_t bytes = PackWeightsTc(nullptr, c->k, c->cin, c->cout, &bn, &kc, nullptr, nullptr);
+    const size_t bytes = PackWeightsTc(nullptr, c->k, c->cin, c->cout, c->tc_bn_cap, &bn, &kc, nullptr, nullptr);
     const size_t n = bytes / sizeof(uint16_t);
     const size_t off = all.size();
     all.resize(off + 2 * n);
-    PackWeightsTc(host_blob + (c->w - dev_blob), c->k, c->cin, c->cout, &bn, &kc, all.data() + off, all.data() + off + n);
+    PackWeightsTc(host_blob + (c->w - dev_blob), c->k, c->cin, c->cout, c->tc_bn_cap, &bn, &kc, all.data() + off,
+                  all.data() + off + n);
     c->tc_bn = bn;
     c->tc_kc = kc;
     slots.push_back({c, off, off + n});
@@ -265,6 +266,7 @@ int EncoderModel::LoadFromImage(const void* data, size_t size, int on_device) {
     for (int i = 1; i < 6; ++i) convs.push_back(&front[i]);
     for (int i = 0; i < n_res; ++i) convs.push_back(&res[i]);
     convs.push_back(&head);
+    for (ConvW* cv : convs) cv->tc_bn_cap = 64;   // few rows per hop (T <= 16): favour CTA count
     tc.Pack(device, img.payload, blob.as<float>(), convs);
   }
   ++generation;
@@ -316,6 +318,8 @@ int WaveModel::LoadFromImage(const void* data, size_t size, int on_device) {
   Upload(&ups_bias, device, rep.data(), rep.size());
   {
     std::vector<ConvW*> convs;
+    pre.tc_bn_cap = 64;
+    ups[0].tc_bn_cap = 128;
     convs.push_back(&pre);
     for (int s = 0; s < 4; ++s) {
       convs.push_back(&ups[s]);
@@ -370,15 +374,29 @@ int SetterModel::LoadFromFile(const char* path, int on_device) {
 // ---------------------------------------------------------------------------------------
 // state arena
 // ---------------------------------------------------------------------------------------
+static int SlotsFor(int history_rows, int T) {
+  const int slots = history_rows > 0 ? (history_rows + T - 1) / T + 1 : 1;
+  if (slots > 16) {
+    std::fprintf(stderr, "[libbeatrice_b200] FATAL: ring needs %d slots (> 16)\n", slots);
+    std::abort();
+  }
+  return slots;
+}
 int StateArena::Plan(int history_rows, int T, int C) {
   Ring r;
   r.T = T;
   r.C = C;
-  r.slots = history_rows > 0 ? (history_rows + T - 1) / T + 1 : 1;
-  if (r.slots > 16) {
-    std::fprintf(stderr, "[libbeatrice_b200] FATAL: ring needs %d slots (> 16)\n", r.slots);
-    std::abort();
-  }
+  r.slots = SlotsFor(history_rows, T);
+  rings_.push_back(r);
+  return static_cast<int>(rings_.size()) - 1;
+}
+int StateArena::PlanH(int history_rows, int T, int C, bool with_lo) {
+  Ring r;
+  r.T = T;
+  r.C = C;
+  r.slots = SlotsFor(history_rows, T);
+  r.is_bf16 = true;
+  r.has_lo = with_lo;
   rings_.push_back(r);
   return static_cast<int>(rings_.size()) - 1;
 }
@@ -388,13 +406,23 @@ void StateArena::Commit(int device, int B) {
   offsets_.resize(rings_.size());
   for (size_t i = 0; i < rings_.size(); ++i) {
     offsets_[i] = total;
-    size_t n = rings_[i].StreamStride() * B;
-    n = (n + 63) / 64 * 64;  // keep every ring 256-byte aligned
-    total += n;
+    const size_t elems = rings_[i].StreamStride() * B;
+    size_t bytes = rings_[i].is_bf16 ? elems * 2 * (rings_[i].has_lo ? 2 : 1) : elems * 4;
+    bytes = (bytes + 255) / 256 * 256;  // keep every ring 256-byte aligned
+    total += bytes;
   }
-  buf_.Alloc(device, total * sizeof(float), true);
+  buf_.Alloc(device, total, true);
   frame_.Alloc(device, sizeof(int), true);
-  for (size_t i = 0; i < rings_.size(); ++i) rings_[i].base = buf_.as<float>() + offsets_[i];
+  for (size_t i = 0; i < rings_.size(); ++i) {
+    uint8_t* p = buf_.as<uint8_t>() + offsets_[i];
+    Ring& r = rings_[i];
+    if (r.is_bf16) {
+      r.hi = reinterpret_cast<uint16_t*>(p);
+      if (r.has_lo) r.lo = r.hi + r.StreamStride() * B;
+    } else {
+      r.base = reinterpret_cast<float*>(p);
+    }
+  }
 }
 void StateArena::Clear() {
   rings_.clear();
@@ -405,8 +433,15 @@ void StateArena::Clear() {
 }
 void StateArena::ZeroAll(cudaStream_t s) { B200_CHECK(cudaMemsetAsync(buf_.p, 0, buf_.bytes, s)); }
 void StateArena::ZeroStream(int b, cudaStream_t s) {
-  for (const Ring& r : rings_)
-    B200_CHECK(cudaMemsetAsync(r.base + r.StreamStride() * b, 0, r.StreamStride() * sizeof(float), s));
+  for (const Ring& r : rings_) {
+    const size_t n = r.StreamStride();
+    if (r.is_bf16) {
+      B200_CHECK(cudaMemsetAsync(r.hi + n * b, 0, n * 2, s));
+      if (r.lo) B200_CHECK(cudaMemsetAsync(r.lo + n * b, 0, n * 2, s));
+    } else {
+      B200_CHECK(cudaMemsetAsync(r.base + n * b, 0, n * 4, s));
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -454,6 +489,22 @@ ConvDesc MakeConv(const Ring& x, const ConvW& w, int dil, int stride, int T_out,
   return d;
 }
 
+// input taken from a bf16 ring by cp.async (tensor-core path only)
+void SetInH(ConvDesc* d, const Ring& h) {
+  d->xh = h.hi;
+  d->xl = h.lo;
+  d->x_slots = h.slots;
+  d->x_T = h.T;
+  d->x_C = h.C;
+}
+// the epilogue additionally stores bf16(act(v)) for the tensor-core consumer
+void SetOutH(ConvDesc* d, const Ring& h, int act) {
+  d->yh = h.hi;
+  d->yl = h.lo;
+  d->yh_slots = h.slots;
+  d->yh_act = act;
+}
+
 void SetRes(ConvDesc* d, const Ring& r) {
   d->res = r.base;
   d->res_slots = r.slots;
@@ -497,6 +548,10 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
   program.clear();
   arena.Clear();
   B200_CHECK(cudaSetDevice(device));
+  // the encoders feed the discrete pitch arg-max: whenever tensor cores are on they run the
+  // near-fp32 split-bf16 form, also in "bf16" mode (plain bf16 is for the vocoder only)
+  const bool tcm = tc != kTcOff;
+  if (tcm) tc = kTcSplit;
 
   int t_in[6], t_out[6];
   int t = kInHop;
@@ -505,12 +560,17 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     t /= m->stride[i];
     t_out[i] = t;
   }
+  // ring_in[i] = input of front-end layer i.  Tensor-core mode: layers 2..5 read bf16 rings.
   int ring_in[6];
-  for (int i = 0; i < 6; ++i) ring_in[i] = arena.Plan(m->front[i].k - m->stride[i], t_in[i], m->front[i].cin);
+  for (int i = 0; i < 6; ++i) {
+    const int hist = m->front[i].k - m->stride[i];
+    ring_in[i] = (tcm && i >= 2) ? arena.PlanH(hist, t_in[i], m->front[i].cin, true)
+                                 : arena.Plan(hist, t_in[i], m->front[i].cin);
+  }
   std::vector<int> ring_x(m->n_res + 1), ring_g(m->n_res);
   ring_x[0] = arena.Plan(0, 1, m->width);
   for (int r = 0; r < m->n_res; ++r) {
-    ring_g[r] = arena.Plan(2 * m->dil[r], 1, m->width);
+    ring_g[r] = tcm ? arena.PlanH(2 * m->dil[r], 1, m->width, true) : arena.Plan(2 * m->dil[r], 1, m->width);
     ring_x[r + 1] = arena.Plan(0, 1, m->width);
   }
   arena.Commit(device, B);
@@ -526,12 +586,18 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
   DescBuilder db;
   std::vector<int> conv_idx;
   for (int i = 0; i < 6; ++i) {
+    const Ring& x = arena.ring(ring_in[i]);
     const Ring& y = (i < 5) ? arena.ring(ring_in[i + 1]) : arena.ring(ring_x[0]);
-    conv_idx.push_back(db.Add(MakeConv(arena.ring(ring_in[i]), m->front[i], 1, m->stride[i], t_out[i], y, kActNone, kActGelu)));
+    ConvDesc d = MakeConv(x, m->front[i], 1, m->stride[i], t_out[i], y, kActNone, kActGelu);
+    if (x.is_bf16) SetInH(&d, x);
+    if (y.is_bf16) SetOutH(&d, y, kActNone);   // v is already GELU'd by out_act
+    conv_idx.push_back(db.Add(d));
   }
   std::vector<int> res_idx;
   for (int r = 0; r < m->n_res; ++r) {
-    ConvDesc d = MakeConv(arena.ring(ring_g[r]), m->res[r], m->dil[r], 1, 1, arena.ring(ring_x[r + 1]), kActNone, kActNone);
+    const Ring& g = arena.ring(ring_g[r]);
+    ConvDesc d = MakeConv(g, m->res[r], m->dil[r], 1, 1, arena.ring(ring_x[r + 1]), kActNone, kActNone);
+    if (g.is_bf16) SetInH(&d, g);
     SetRes(&d, arena.ring(ring_x[r]));
     res_idx.push_back(db.Add(d));
   }
@@ -564,11 +630,12 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     if (i == 0)
       op.launch = [=](cudaStream_t s) { LaunchDirectConv(dp, h, Bn, frame, s); };
     else
-      op.launch = GemmLauncher(dp, h, 1, Bn, frame, tc, tc == kTcSplit);
+      op.launch = GemmLauncher(dp, h, 1, Bn, frame, tc, tcm);
     program.push_back(op);
   }
   for (int r = 0; r < m->n_res; ++r) {
     NormDesc nd;
+    std::memset(&nd, 0, sizeof(nd));
     const Ring& xr = arena.ring(ring_x[r]);
     const Ring& gr = arena.ring(ring_g[r]);
     nd.x = xr.base;
@@ -577,8 +644,11 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     nd.C = m->width;
     nd.gamma = m->gamma[r];
     nd.beta = m->beta[r];
-    nd.y = gr.base;
+    nd.y = gr.base;      // nullptr in tensor-core mode: only the bf16 planes are kept
     nd.y_slots = gr.slots;
+    nd.yh = gr.hi;
+    nd.yl = gr.lo;
+    nd.yh_slots = gr.slots;
     Op on;
     on.name = std::string(tag) + ".res" + std::to_string(r) + ".norm";
     on.bytes = 8.0 * B * m->width;
@@ -590,7 +660,7 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     oc.name = std::string(tag) + ".res" + std::to_string(r) + ".conv";
     oc.flops = ConvFlops(h, B);
     oc.bytes = ConvBytes(h, B);
-    oc.launch = GemmLauncher(dp, h, 1, Bn, frame, tc, tc == kTcSplit);
+    oc.launch = GemmLauncher(dp, h, 1, Bn, frame, tc, tcm);
     program.push_back(oc);
   }
   {
@@ -600,7 +670,7 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     op.name = std::string(tag) + ".head";
     op.flops = ConvFlops(h, B);
     op.bytes = ConvBytes(h, B);
-    op.launch = GemmLauncher(dp, h, 1, Bn, frame, tc, tc == kTcSplit);
+    op.launch = GemmLauncher(dp, h, 1, Bn, frame, tc, tcm);
     program.push_back(op);
   }
   {
@@ -636,22 +706,32 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
   arena.Clear();
   B200_CHECK(cudaSetDevice(device));
   const bool rc0 = m->dims.has_setter;
+  const bool tcm = tc != kTcOff;
+  const bool with_lo = tc == kTcSplit;
 
   ring_hidden = arena.Plan(spec::kPreK - 1, 1, kHidden);
   ring_pre = arena.Plan(1, 1, kHidden);
-  int ring_u[4], ring_a[4][3][3], ring_y[4][3][4];
+  // fp32 rings: u (upsampler output), y (residual stream of each MRF branch), a (CUDA-core
+  // path only).  Tensor-core mode keeps fp32 only where a residual / the branch sum needs it
+  // (current rows) and adds bf16 rings -- already LeakyReLU'd -- that carry the conv history.
+  int ring_u[4], ring_uh[4], ring_a[4][3][3], ring_y[4][3][4], ring_yh[4][3][4];
   int t = 1;
   for (int s = 0; s < 4; ++s) {
     const int c = spec::kStageCh[s + 1];
     t *= spec::kRates[s];
-    ring_u[s] = arena.Plan((spec::kMrfK[2] - 1) * spec::kMrfD[0], t, c);
+    const int u_hist = (spec::kMrfK[2] - 1) * spec::kMrfD[0];
+    ring_u[s] = arena.Plan(tcm ? 0 : u_hist, t, c);
+    ring_uh[s] = tcm ? arena.PlanH(u_hist, t, c, with_lo) : -1;
     for (int ki = 0; ki < 3; ++ki) {
       const int k = spec::kMrfK[ki];
       ring_y[s][ki][0] = ring_u[s];
+      ring_yh[s][ki][0] = ring_uh[s];
       for (int di = 0; di < 3; ++di) {
-        ring_a[s][ki][di] = arena.Plan(k - 1, t, c);
-        const int hist = di < 2 ? (k - 1) * spec::kMrfD[di + 1] : (s < 3 ? 1 : spec::kPostK - 1);
-        ring_y[s][ki][di + 1] = arena.Plan(hist, t, c);
+        ring_a[s][ki][di] = tcm ? arena.PlanH(k - 1, t, c, with_lo) : arena.Plan(k - 1, t, c);
+        const bool last = di == 2;
+        const int hist = last ? (s < 3 ? 1 : spec::kPostK - 1) : (k - 1) * spec::kMrfD[di + 1];
+        ring_y[s][ki][di + 1] = arena.Plan((tcm && !last) ? 0 : hist, t, c);
+        ring_yh[s][ki][di + 1] = (tcm && !last) ? arena.PlanH(hist, t, c, with_lo) : -1;
       }
       ring_stage_out[s][ki] = ring_y[s][ki][3];
     }
@@ -675,19 +755,29 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
       u.film = film[s].as<float>();
       u.film_C = c;
     }
+    if (tcm) SetOutH(&u, arena.ring(ring_uh[s]), kActLrelu);
     ups_idx[s] = db.Add(u);
     t *= spec::kRates[s];
     for (int di = 0; di < 3; ++di) {
       for (int ki = 0; ki < 3; ++ki) {
-        ConvDesc d1 = MakeConv(arena.ring(ring_y[s][ki][di]), m->c1[s][ki][di], spec::kMrfD[di], 1, t,
-                               arena.ring(ring_a[s][ki][di]), kActLrelu, kActLrelu);
+        const Ring& a = arena.ring(ring_a[s][ki][di]);
+        ConvDesc d1 = MakeConv(arena.ring(ring_y[s][ki][di]), m->c1[s][ki][di], spec::kMrfD[di], 1, t, a, kActLrelu,
+                               kActLrelu);
+        if (tcm) {
+          SetInH(&d1, arena.ring(ring_yh[s][ki][di]));   // lrelu(y) with history, bf16
+          SetOutH(&d1, a, kActNone);                      // v = lrelu(a) already
+        }
         const int id = db.Add(d1);
         if (ki == 0) c1_idx[s][di] = id;
       }
       for (int ki = 0; ki < 3; ++ki) {
-        ConvDesc d2 = MakeConv(arena.ring(ring_a[s][ki][di]), m->c2[s][ki][di], 1, 1, t,
-                               arena.ring(ring_y[s][ki][di + 1]), kActNone, kActNone);
+        const Ring& a = arena.ring(ring_a[s][ki][di]);
+        ConvDesc d2 = MakeConv(a, m->c2[s][ki][di], 1, 1, t, arena.ring(ring_y[s][ki][di + 1]), kActNone, kActNone);
         SetRes(&d2, arena.ring(ring_y[s][ki][di]));
+        if (tcm) {
+          SetInH(&d2, a);
+          if (ring_yh[s][ki][di + 1] >= 0) SetOutH(&d2, arena.ring(ring_yh[s][ki][di + 1]), kActLrelu);
+        }
         const int id = db.Add(d2);
         if (ki == 0) c2_idx[s][di] = id;
       }
@@ -752,7 +842,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
     op.name = "wave.post";
     op.flops = ConvFlops(h, B);
     op.bytes = ConvBytes(h, B);
-    op.launch = [=](cudaStream_t s) { LaunchDirectConv(dp, h, Bn, frame, s); };
+    op.launch = [=](cudaStream_t s) { LaunchPostConv(dp, h, Bn, frame, s); };
     program.push_back(op);
   }
   {

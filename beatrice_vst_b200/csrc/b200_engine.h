@@ -67,6 +67,7 @@ struct ConvW {
   const void* tc_hi = nullptr;
   const void* tc_lo = nullptr;
   int tc_bn = 0, tc_kc = 0;
+  int tc_bn_cap = 128;  // requested N-tile cap (smaller = more CTAs for layers with few rows)
 };
 
 // Precision of the conv GEMMs: fp32 CUDA cores (parity path), bf16 tcgen05, or split-bf16
@@ -149,8 +150,11 @@ struct Op {
 };
 
 struct Ring {
-  float* base = nullptr;
+  float* base = nullptr;    // fp32 ring, or nullptr for a bf16-only ring
+  uint16_t* hi = nullptr;   // bf16 ring: rounded value
+  uint16_t* lo = nullptr;   // bf16 of the rounding residual (split-bf16 mode only)
   int slots = 1, T = 1, C = 1;
+  bool is_bf16 = false, has_lo = false;
   size_t StreamStride() const { return static_cast<size_t>(slots) * T * C; }
 };
 
@@ -160,7 +164,8 @@ class StateArena {
   StateArena() = default;
   ~StateArena() = default;
   // two-phase: Plan() rings, then Commit() allocates and patches the base pointers
-  int Plan(int history_rows, int T, int C);  // returns ring id
+  int Plan(int history_rows, int T, int C);  // fp32 ring; returns ring id
+  int PlanH(int history_rows, int T, int C, bool with_lo);  // bf16 ring (hi [+ lo] planes)
   void Commit(int device, int B);
   const Ring& ring(int id) const { return rings_[id]; }
   int* frame() const { return frame_.as<int>(); }
@@ -172,7 +177,7 @@ class StateArena {
 
  private:
   std::vector<Ring> rings_;
-  std::vector<size_t> offsets_;
+  std::vector<size_t> offsets_;  // byte offsets
   DeviceBuffer buf_, frame_;
   int B_ = 0;
 };

@@ -5,6 +5,8 @@
 // runs through it as an implicit GEMM over channel-last ring buffers, with the input
 // activation, bias, FiLM, residual add and output activation fused.  The bf16 tcgen05
 // variant of the same contraction lives in b200_tc.cu.
+#include <cuda_bf16.h>
+
 #include <cfloat>
 #include <climits>
 
@@ -254,6 +256,52 @@ __global__ void direct_conv_kernel(const ConvDesc* __restrict__ descs, int B, co
   d.y[(static_cast<long long>(b) * y_L + y_cur) * d.y_C + static_cast<long long>(t) * d.N + n] = acc;
 }
 
+// Vocoder post conv: out[b][t] = tanh(b0 + sum_{j<7} sum_{ci<16} lrelu(x[b][t-(6-j)][ci]) * w[j][ci]) with
+// x = (x0 + x1 + x2) * in_scale (the three MRF branches).  One thread per output sample; rows
+// are 64 bytes so every load is a float4; neighbouring threads share 6 of their 7 rows (L1).
+__global__ void __launch_bounds__(128) post_conv_kernel(const ConvDesc* __restrict__ descs, int B,
+                                                         const int* __restrict__ frame_ptr) {
+  __shared__ float ws[7 * 16];
+  const ConvDesc d = descs[0];
+  if (threadIdx.x < 7 * 16) ws[threadIdx.x] = __ldg(d.w + threadIdx.x);
+  __syncthreads();
+  const int frame = *frame_ptr;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= B * d.T) return;
+  const int b = m / d.T, t = m - b * d.T;
+  const int x_L = d.x_slots * d.x_T;
+  const int x_cur = (frame % d.x_slots) * d.x_T;
+  const long long xb = static_cast<long long>(b) * x_L * 16;
+  float acc = d.bias ? __ldg(d.bias) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    int r = x_cur + t - (6 - j);
+    if (r < 0) r += x_L;
+    const long long a = xb + static_cast<long long>(r) * 16;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 v = Ldg4(d.x[0] + a + 4 * q);
+      if (d.n_x > 1) {
+        const float4 v1 = Ldg4(d.x[1] + a + 4 * q), v2 = Ldg4(d.x[2] + a + 4 * q);
+        v.x = ((v.x + v1.x) + v2.x) * d.in_scale;
+        v.y = ((v.y + v1.y) + v2.y) * d.in_scale;
+        v.z = ((v.z + v1.z) + v2.z) * d.in_scale;
+        v.w = ((v.w + v1.w) + v2.w) * d.in_scale;
+      }
+      v = InAct4(v, d.in_act);
+      const float* wq = ws + j * 16 + 4 * q;
+      acc = fmaf(v.x, wq[0], acc);
+      acc = fmaf(v.y, wq[1], acc);
+      acc = fmaf(v.z, wq[2], acc);
+      acc = fmaf(v.w, wq[3], acc);
+    }
+  }
+  acc = ActApply(acc, d.out_act);
+  const int y_L = d.y_slots * d.y_T;
+  const int y_cur = (frame % d.y_slots) * d.y_T;
+  d.y[(static_cast<long long>(b) * y_L + y_cur) * d.y_C + t] = acc;
+}
+
 __device__ __forceinline__ float WarpSum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -294,7 +342,14 @@ __global__ void channorm_gelu_kernel(NormDesc d, int B, const int* __restrict__ 
   for (int i = 0; i < kMaxPerLane; ++i)
     if (i < per) {
       const int c = lane + 32 * i;
-      y[c] = ActApply((v[i] - mean) * rstd * __ldg(d.gamma + c) + __ldg(d.beta + c), kActGelu);
+      const float o = ActApply((v[i] - mean) * rstd * __ldg(d.gamma + c) + __ldg(d.beta + c), kActGelu);
+      if (d.y) y[c] = o;
+      if (d.yh) {
+        const long long off = (static_cast<long long>(b) * d.yh_slots * d.T + (frame % d.yh_slots) * d.T + t) * d.C + c;
+        const __nv_bfloat16 h = __float2bfloat16_rn(o);
+        d.yh[off] = __bfloat16_as_ushort(h);
+        if (d.yl) d.yl[off] = __bfloat16_as_ushort(__float2bfloat16_rn(o - __bfloat162float(h)));
+      }
     }
 }
 
@@ -582,6 +637,16 @@ void LaunchConvGemm(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B, 
 void LaunchDirectConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int* d_frame, cudaStream_t s) {
   const long long total = static_cast<long long>(B) * h0.T * h0.N;
   direct_conv_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, s>>>(d_desc, B, d_frame);
+  B200_CHECK(cudaGetLastError());
+}
+
+void LaunchPostConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int* d_frame, cudaStream_t s) {
+  if (h0.k != 7 || h0.C_in != 16 || h0.N != 1 || h0.stride != 1 || h0.dil != 1) {
+    LaunchDirectConv(d_desc, h0, B, d_frame, s);
+    return;
+  }
+  const int total = B * h0.T;
+  post_conv_kernel<<<(total + 127) / 128, 128, 0, s>>>(d_desc, B, d_frame);
   B200_CHECK(cudaGetLastError());
 }
 

@@ -44,6 +44,16 @@ struct ConvDesc {
   const void* w_tc_lo;  // low-order bf16 residual of the weights (split-bf16 mode) or nullptr
   int tc_bn;          // N tile width (multiple of 16, <= 256)
   int tc_kc;          // K elements per chunk (taps_per_chunk * C_in or 64)
+  // bf16 activation rings of the tensor-core path.  xh/xl: the input already activated and
+  // rounded to bf16 (hi) plus the bf16 of the rounding residual (lo, split mode), same ring
+  // geometry as x[]; when set, activation rows are moved global -> shared with cp.async and
+  // never touch registers.  yh/yl: where the epilogue stores bf16(yh_act(v)) for the consumer.
+  const uint16_t* xh;
+  const uint16_t* xl;
+  uint16_t* yh;
+  uint16_t* yl;
+  int yh_slots;
+  int yh_act;
 };
 
 struct NormDesc {  // y = GELU(ChanNorm(x) * gamma + beta), one row per warp
@@ -53,6 +63,9 @@ struct NormDesc {  // y = GELU(ChanNorm(x) * gamma + beta), one row per warp
   const float* beta;
   float* y;
   int y_slots;
+  uint16_t* yh;  // optional bf16 copy (hi / lo planes) for the tensor-core consumer
+  uint16_t* yl;
+  int yh_slots;
 };
 
 // Per-stream pitch-transform parameters == the ProcessorCore2 members of the same name
@@ -77,7 +90,10 @@ void LaunchConvGemmTc(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B
                       cudaStream_t s);
 // Host-side packing of one conv's weights w[k][C_in][N] (fp32) into the tile order the kernel
 // consumes; returns bytes written per array.  hi/lo may be nullptr to query the size.
-size_t PackWeightsTc(const float* w, int k, int C_in, int N, int* bn_out, int* kc_out, uint16_t* hi, uint16_t* lo);
+size_t PackWeightsTc(const float* w, int k, int C_in, int N, int bn_cap, int* bn_out, int* kc_out, uint16_t* hi,
+                     uint16_t* lo);
+// post conv of the vocoder (16 -> 1 channels, k = 7, tanh): one thread per output sample
+void LaunchPostConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int* d_frame, cudaStream_t s);
 void LaunchDirectConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int* d_frame, cudaStream_t s);
 void LaunchNorm(const NormDesc& d, int B, const int* d_frame, cudaStream_t s);
 // staging [B][T*C] -> ring slot of the current hop

@@ -131,10 +131,19 @@ __device__ __forceinline__ void Pack8(const float* v, uint4* hi, uint4* lo) {
   if (kSplit) *lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-template <bool kSplit>
+__device__ __forceinline__ void CpAsync16(uint32_t dst_smem, const void* src, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;   // src-size 0 -> the 16 destination bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void CpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void CpAsyncWait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
+template <bool kSplit, int kStages>
 __global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __restrict__ descs, int B,
                                                            const int* __restrict__ frame_ptr) {
-  constexpr int kStages = kSplit ? 2 : 3;
   constexpr int kOperands = kSplit ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];
 
@@ -152,6 +161,7 @@ __global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __res
   uint8_t* tail = smem + kStages * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);  // full[kStages], empty[kStages], done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  float* bias_s = reinterpret_cast<float*>(tail + 128);   // BN floats
   const uint32_t bar_full = SmemAddr(bars), bar_empty = SmemAddr(bars + kStages), bar_done = SmemAddr(bars + 2 * kStages);
   const uint32_t smem_base = SmemAddr(smem);
 
@@ -159,6 +169,10 @@ __global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __res
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(BN)) tmem_cols <<= 1;
 
+  for (int i = tid; i < BN; i += 128) {
+    const int col = blockIdx.y * BN + i;
+    bias_s[i] = (d.bias && col < d.N) ? __ldg(d.bias + col) : 0.0f;
+  }
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
       MbarInit(bar_full + 8 * i, 1);
@@ -202,31 +216,12 @@ __global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __res
                         static_cast<size_t>(blockIdx.y) * n_chunks * w_bytes;
   const uint8_t* w_lo = kSplit ? static_cast<const uint8_t*>(d.w_tc_lo) + static_cast<size_t>(blockIdx.y) * n_chunks * w_bytes
                                : nullptr;
+  const bool async_a = d.xh != nullptr;   // activations pre-rounded to bf16 by their producer
 
-  for (int c = 0; c < n_chunks; ++c) {
-    const int s = c % kStages;
-    const int round = c / kStages;
+  // element offsets of the (up to four) taps of chunk c for this thread's row
+  auto tap_offsets = [&](int c, long long* ro) {
     const int j0 = C_in >= kTcKC ? c / n_sub : c * tpc;
     const int ci0 = C_in >= kTcKC ? (c - j0 * n_sub) * kTcKC : 0;
-    const int taps = C_in >= kTcKC ? 1 : min(tpc, d.k - j0);
-    const uint32_t st_base = smem_base + s * stage_bytes;
-    const uint32_t a_hi = st_base, w_hi_s = st_base + a_bytes * kOperands;
-    const uint32_t a_lo = st_base + a_bytes, w_lo_s = w_hi_s + w_bytes;
-
-    // stage s is free once the MMAs of its previous use have completed
-    if (round > 0) MbarWait(bar_empty + 8 * s, (round - 1) & 1);
-
-    if (tid == 0) {
-      MbarExpectTx(bar_full + 8 * s, w_bytes * kOperands);
-      TmaBulkLoad(w_hi_s, w_hi + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * s);
-      if (kSplit) TmaBulkLoad(w_lo_s, w_lo + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * s);
-    }
-
-    // gather this thread's row: 64 K-elements (taps x cw channels) -> eight bf16 panels.
-    // All global loads of a half-chunk are issued before the first use so their latency overlaps.
-    uint8_t* a_hi_p = smem + s * stage_bytes + tid * 16;
-    uint8_t* a_lo_p = a_hi_p + a_bytes;
-    long long ro[4];
 #pragma unroll
     for (int tl = 0; tl < 4; ++tl) {
       const int j = min(j0 + tl, d.k - 1);
@@ -234,46 +229,107 @@ __global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __res
       if (r < 0) r += x_L;
       ro[tl] = xbase + static_cast<long long>(r) * C_in + ci0;
     }
+  };
+  // stage c % kStages: wait until its previous MMAs retired, then start the weight TMA and
+  // (async mode) the 16-byte cp.async's that drop this thread's row straight into the panels
+  auto issue = [&](int c) {
+    const int s = c % kStages, round = c / kStages;
+    if (round > 0) MbarWait(bar_empty + 8 * s, (round - 1) & 1);
+    const uint32_t st_base = smem_base + s * stage_bytes;
+    const uint32_t w_hi_s = st_base + a_bytes * kOperands;
+    if (tid == 0) {
+      MbarExpectTx(bar_full + 8 * s, w_bytes * kOperands);
+      TmaBulkLoad(w_hi_s, w_hi + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * s);
+      if (kSplit) TmaBulkLoad(w_hi_s + w_bytes, w_lo + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * s);
+    }
+    if (async_a) {
+      long long ro[4];
+      tap_offsets(c, ro);
+      const uint32_t dst = st_base + tid * 16;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float4 x0[8], x1[8], x2[8];
-      if (row_ok) {
+      for (int p = 0; p < 8; ++p) {
+        const int ch = p * 8;
+        const int tl = ch >> lcw, cc = ch & (cw - 1);
+        const long long a = (tl == 0 ? ro[0] : tl == 1 ? ro[1] : tl == 2 ? ro[2] : ro[3]) + cc;
+        CpAsync16(dst + p * kPanelA, d.xh + a, row_ok);
+        if (kSplit) CpAsync16(dst + a_bytes + p * kPanelA, d.xl + a, row_ok);
+      }
+    }
+  };
+
+  // Look-ahead is kStages-2 chunks, not kStages-1: the stage refilled in iteration c is the one
+  // read by the MMAs of chunk c-2, which have had a whole iteration to retire, so the threads
+  // never stall on the tensor pipe they have just fed.
+  if (async_a) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int ch = half * 32 + i * 4;          // K index inside the chunk
-          const int tl = ch >> lcw, cc = ch & (cw - 1);
-          const long long a = (tl == 0 ? ro[0] : tl == 1 ? ro[1] : tl == 2 ? ro[2] : ro[3]) + cc;
-          x0[i] = __ldg(reinterpret_cast<const float4*>(d.x[0] + a));
-          if (d.n_x > 1) {
-            x1[i] = __ldg(reinterpret_cast<const float4*>(d.x[1] + a));
-            x2[i] = __ldg(reinterpret_cast<const float4*>(d.x[2] + a));
-          }
-        }
-        if (d.n_x > 1) {
+    for (int c = 0; c < kStages - 2; ++c) {
+      if (c < n_chunks) issue(c);
+      CpAsyncCommit();
+    }
+  }
+
+  for (int c = 0; c < n_chunks; ++c) {
+    const int s = c % kStages;
+    const int round = c / kStages;
+    const int j0 = C_in >= kTcKC ? c / n_sub : c * tpc;
+    const int taps = C_in >= kTcKC ? 1 : min(tpc, d.k - j0);
+    const uint32_t st_base = smem_base + s * stage_bytes;
+    const uint32_t a_hi = st_base, w_hi_s = st_base + a_bytes * kOperands;
+    const uint32_t a_lo = st_base + a_bytes, w_lo_s = w_hi_s + w_bytes;
+
+    if (async_a) {
+      if (c + kStages - 2 < n_chunks) issue(c + kStages - 2);
+      CpAsyncCommit();
+      CpAsyncWait<kStages - 2>();   // this thread's part of chunk c has landed
+    } else {
+      issue(c);
+      // register path: gather this thread's row from the fp32 ring(s): 64 K-elements -> eight
+      // bf16 panels.  All loads of a half-chunk are issued before the first use.
+      uint8_t* a_hi_p = smem + s * stage_bytes + tid * 16;
+      uint8_t* a_lo_p = a_hi_p + a_bytes;
+      long long ro[4];
+      tap_offsets(c, ro);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float4 x0[8], x1[8], x2[8];
+        if (row_ok) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            x0[i].x = ((x0[i].x + x1[i].x) + x2[i].x) * d.in_scale;
-            x0[i].y = ((x0[i].y + x1[i].y) + x2[i].y) * d.in_scale;
-            x0[i].z = ((x0[i].z + x1[i].z) + x2[i].z) * d.in_scale;
-            x0[i].w = ((x0[i].w + x1[i].w) + x2[i].w) * d.in_scale;
+            const int ch = half * 32 + i * 4;          // K index inside the chunk
+            const int tl = ch >> lcw, cc = ch & (cw - 1);
+            const long long a = (tl == 0 ? ro[0] : tl == 1 ? ro[1] : tl == 2 ? ro[2] : ro[3]) + cc;
+            x0[i] = __ldg(reinterpret_cast<const float4*>(d.x[0] + a));
+            if (d.n_x > 1) {
+              x1[i] = __ldg(reinterpret_cast<const float4*>(d.x[1] + a));
+              x2[i] = __ldg(reinterpret_cast<const float4*>(d.x[2] + a));
+            }
           }
+          if (d.n_x > 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              x0[i].x = ((x0[i].x + x1[i].x) + x2[i].x) * d.in_scale;
+              x0[i].y = ((x0[i].y + x1[i].y) + x2[i].y) * d.in_scale;
+              x0[i].z = ((x0[i].z + x1[i].z) + x2[i].z) * d.in_scale;
+              x0[i].w = ((x0[i].w + x1[i].w) + x2[i].w) * d.in_scale;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+        for (int p = 0; p < 4; ++p) {
+          float v[8] = {x0[2 * p].x, x0[2 * p].y, x0[2 * p].z, x0[2 * p].w,
+                        x0[2 * p + 1].x, x0[2 * p + 1].y, x0[2 * p + 1].z, x0[2 * p + 1].w};
+          if (d.in_act == kActLrelu) {   // the only input activation of spec M0
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        float v[8] = {x0[2 * p].x, x0[2 * p].y, x0[2 * p].z, x0[2 * p].w,
-                      x0[2 * p + 1].x, x0[2 * p + 1].y, x0[2 * p + 1].z, x0[2 * p + 1].w};
-        if (d.in_act == kActLrelu) {   // the only input activation of spec M0
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.0f ? v[e] : 0.1f * v[e];
+            for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.0f ? v[e] : 0.1f * v[e];
+          }
+          uint4 hi, lo;
+          Pack8<kSplit>(v, &hi, &lo);
+          *reinterpret_cast<uint4*>(a_hi_p + (half * 4 + p) * kPanelA) = hi;
+          if (kSplit) *reinterpret_cast<uint4*>(a_lo_p + (half * 4 + p) * kPanelA) = lo;
         }
-        uint4 hi, lo;
-        Pack8<kSplit>(v, &hi, &lo);
-        *reinterpret_cast<uint4*>(a_hi_p + (half * 4 + p) * kPanelA) = hi;
-        if (kSplit) *reinterpret_cast<uint4*>(a_lo_p + (half * 4 + p) * kPanelA) = lo;
       }
     }
     FenceProxyAsync();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -300,10 +356,11 @@ __global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __res
     }
   }
 
-  // ---- epilogue: TMEM -> registers -> bias / FiLM / residual / activation -> ring ----
-  MbarWait(bar_done, 0);
-  TcFenceAfter();
-  const int row = warp * 32 + lane;
+  // ---- epilogue: TMEM -> registers -> bias / FiLM / residual / activation -> rings ----
+  // Every row of the tile is owned by one thread (TMEM lane == thread).  Bias sits in shared
+  // memory since kernel start; the residual tile is pulled into the (now idle) pipeline
+  // buffers with one batch of cp.async so its DRAM latency is paid once, not per 16 columns.
+  const int row = tid;
   const int mm = m0 + row;
   const bool out_ok = mm < M;
   int ob = 0, ot = 0;
@@ -313,46 +370,80 @@ __global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __res
   }
   const int y_L = d.y_slots * d.y_T;
   const int y_cur = (frame % d.y_slots) * d.y_T;
+  const int yh_L = d.yh_slots * d.y_T;
+  const int yh_cur = d.yh ? (frame % d.yh_slots) * d.y_T : 0;
   const int res_L = d.res_slots * d.res_T;
   const int res_cur = d.res ? (frame % d.res_slots) * d.res_T : 0;
-  float* out_row = d.y + (static_cast<long long>(ob) * y_L + y_cur) * d.y_C + static_cast<long long>(ot) * N;
+  float* out_row = d.y ? d.y + (static_cast<long long>(ob) * y_L + y_cur) * d.y_C + static_cast<long long>(ot) * N : nullptr;
+  const long long oh = (static_cast<long long>(ob) * yh_L + yh_cur) * d.y_C + static_cast<long long>(ot) * N;
   const float* res_row = d.res ? d.res + (static_cast<long long>(ob) * res_L + res_cur + ot) * N : nullptr;
   const float* film_row = d.film ? d.film + static_cast<long long>(ob) * 2 * d.film_C : nullptr;
+  const int res_ld = BN + 4;   // floats; +4 keeps the per-thread 16-byte reads conflict free
+  const bool res_in_smem = d.res != nullptr && static_cast<uint32_t>(kTcM * res_ld * 4) <= kStages * stage_bytes;
+
+  MbarWait(bar_done, 0);
+  TcFenceAfter();
+  float* res_s = reinterpret_cast<float*>(smem) + row * res_ld;
+  if (res_in_smem) {
+    const uint32_t dst = smem_base + row * res_ld * 4;
+    for (int cc = 0; cc < BN; cc += 4) CpAsync16(dst + cc * 4, res_row + n0 + cc, out_ok && (n0 + cc) < N);
+    CpAsyncCommit();
+    CpAsyncWait<0>();   // own row only: no block-level barrier needed
+  }
   const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
   for (int c0 = 0; c0 < BN; c0 += 16) {
     uint32_t rr[16];
     TmemLd16(t_lane + c0, rr);   // whole warp, even when some rows are past M
-    if (!out_ok) continue;
+    if (!out_ok || n0 + c0 >= N) continue;
+    float hv[16];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const int col = n0 + c0 + 4 * g;
-      if (col >= N) break;
       float4 v = make_float4(__uint_as_float(rr[4 * g]), __uint_as_float(rr[4 * g + 1]), __uint_as_float(rr[4 * g + 2]),
                              __uint_as_float(rr[4 * g + 3]));
-      if (d.bias) {
-        const float4 bz = __ldg(reinterpret_cast<const float4*>(d.bias + col));
+      if (col < N) {
+        const float4 bz = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * g);
         v.x += bz.x; v.y += bz.y; v.z += bz.z; v.w += bz.w;
+        if (film_row) {
+          const int fc = col % d.film_C;
+          const float4 ga = __ldg(reinterpret_cast<const float4*>(film_row + fc));
+          const float4 be = __ldg(reinterpret_cast<const float4*>(film_row + d.film_C + fc));
+          v.x = v.x * (1.0f + ga.x) + be.x;
+          v.y = v.y * (1.0f + ga.y) + be.y;
+          v.z = v.z * (1.0f + ga.z) + be.z;
+          v.w = v.w * (1.0f + ga.w) + be.w;
+        }
+        if (res_row) {
+          const float4 rz = res_in_smem ? *reinterpret_cast<const float4*>(res_s + c0 + 4 * g)
+                                        : __ldg(reinterpret_cast<const float4*>(res_row + col));
+          v.x += rz.x; v.y += rz.y; v.z += rz.z; v.w += rz.w;
+        }
+        if (d.out_act != kActNone) {
+          v.x = ActTc(v.x, d.out_act);
+          v.y = ActTc(v.y, d.out_act);
+          v.z = ActTc(v.z, d.out_act);
+          v.w = ActTc(v.w, d.out_act);
+        }
+        if (out_row) *reinterpret_cast<float4*>(out_row + col) = v;
       }
-      if (film_row) {
-        const int fc = col % d.film_C;
-        const float4 ga = __ldg(reinterpret_cast<const float4*>(film_row + fc));
-        const float4 be = __ldg(reinterpret_cast<const float4*>(film_row + d.film_C + fc));
-        v.x = v.x * (1.0f + ga.x) + be.x;
-        v.y = v.y * (1.0f + ga.y) + be.y;
-        v.z = v.z * (1.0f + ga.z) + be.z;
-        v.w = v.w * (1.0f + ga.w) + be.w;
+      hv[4 * g] = v.x; hv[4 * g + 1] = v.y; hv[4 * g + 2] = v.z; hv[4 * g + 3] = v.w;
+    }
+    if (d.yh && n0 + c0 + 16 <= N) {   // bf16 consumer copy (N is a multiple of 16 wherever one exists)
+      if (d.yh_act == kActLrelu) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) hv[e] = hv[e] > 0.0f ? hv[e] : 0.1f * hv[e];
       }
-      if (res_row) {
-        const float4 rz = __ldg(reinterpret_cast<const float4*>(res_row + col));
-        v.x += rz.x; v.y += rz.y; v.z += rz.z; v.w += rz.w;
+      uint4 h0, l0, h1, l1;
+      Pack8<true>(hv, &h0, &l0);
+      Pack8<true>(hv + 8, &h1, &l1);
+      uint4* ph = reinterpret_cast<uint4*>(d.yh + oh + n0 + c0);
+      ph[0] = h0;
+      ph[1] = h1;
+      if (d.yl) {
+        uint4* pl = reinterpret_cast<uint4*>(d.yl + oh + n0 + c0);
+        pl[0] = l0;
+        pl[1] = l1;
       }
-      if (d.out_act != kActNone) {
-        v.x = ActTc(v.x, d.out_act);
-        v.y = ActTc(v.y, d.out_act);
-        v.z = ActTc(v.z, d.out_act);
-        v.w = ActTc(v.w, d.out_act);
-      }
-      *reinterpret_cast<float4*>(out_row + col) = v;
     }
   }
   TcFenceBefore();
@@ -377,24 +468,44 @@ float Bf16ToF(uint16_t h) {
   return f;
 }
 
-size_t TcSmemBytes(bool split, int bn) {
-  const int stages = split ? 2 : 3;
-  const size_t stage = (static_cast<size_t>(kTcM) * kTcKC * 2 + static_cast<size_t>(bn) * kTcKC * 2) * (split ? 2 : 1);
-  return stages * stage + 128;
+size_t TcStageBytes(bool split, int bn) {
+  return (static_cast<size_t>(kTcM) * kTcKC * 2 + static_cast<size_t>(bn) * kTcKC * 2) * (split ? 2 : 1);
+}
+// Pipeline depth: as deep as the K loop is long (<= 4), within ~100 KB of shared memory so that
+// two CTAs fit on an SM when the tiles are small (latency hiding across CTAs).
+int TcStages(bool split, int bn, int n_chunks) {
+  const size_t stage = TcStageBytes(split, bn);
+  int s = static_cast<int>((100 * 1024) / stage);
+  if (s < 3) s = static_cast<int>((200 * 1024) / stage) >= 3 ? 3 : 2;
+  if (s > 4) s = 4;
+  if (s > n_chunks + 1) s = n_chunks + 1 < 3 ? 3 : n_chunks + 1;
+  if (static_cast<size_t>(s) * stage > 200 * 1024) s = 2;
+  return s;
+}
+
+template <bool kSplit, int kStages>
+void LaunchTcT(const ConvDesc* d_descs, dim3 grid, size_t smem, int B, const int* d_frame, cudaStream_t s) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  B200_CHECK(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    B200_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel<kSplit, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024));
+    attr_set[dev & 63] = true;
+  }
+  conv_gemm_tc_kernel<kSplit, kStages><<<grid, 128, smem, s>>>(d_descs, B, d_frame);
 }
 
 }  // namespace
 
-size_t PackWeightsTc(const float* w, int k, int C_in, int N, int* bn_out, int* kc_out, uint16_t* hi, uint16_t* lo) {
+size_t PackWeightsTc(const float* w, int k, int C_in, int N, int bn_cap, int* bn_out, int* kc_out, uint16_t* hi,
+                     uint16_t* lo) {
+  // N tile: the whole (16-padded) N when it fits under the cap, else tiles of `bn_cap` columns.
+  // Small caps trade activation re-reads for more CTAs on the layers that have few rows.
   const int n16 = (N + 15) / 16 * 16;
-  int bn, n_tiles;
-  if (n16 <= 256) {
-    bn = n16;
-    n_tiles = 1;
-  } else {
-    bn = 128;
-    n_tiles = (N + 127) / 128;
-  }
+  if (bn_cap > 256) bn_cap = 256;
+  const int bn = n16 <= bn_cap ? n16 : bn_cap;
+  const int n_tiles = (N + bn - 1) / bn;
   const int n_sub = C_in >= kTcKC ? C_in / kTcKC : 1;
   const int tpc = C_in >= kTcKC ? 1 : kTcKC / C_in;
   const int n_chunks = C_in >= kTcKC ? k * n_sub : (k + tpc - 1) / tpc;
@@ -434,23 +545,21 @@ void LaunchConvGemmTc(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B
                       cudaStream_t s) {
   const int M = B * h0.T;
   const int bn = h0.tc_bn;
-  const int n_tiles = ((h0.N + 15) / 16 * 16 <= 256) ? 1 : (h0.N + 127) / 128;
-  const size_t smem = TcSmemBytes(split, bn);
-  static bool attr_set[2][64] = {};
-  int dev = 0;
-  B200_CHECK(cudaGetDevice(&dev));
-  if (!attr_set[split ? 1 : 0][dev & 63]) {
-    if (split)
-      B200_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    else
-      B200_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set[split ? 1 : 0][dev & 63] = true;
-  }
+  const int n_tiles = (h0.N + bn - 1) / bn;
+  const int kmax = nz > 1 ? 11 : h0.k;   // z-batched launches are the MRF branches k = 3, 7, 11
+  const int n_chunks = h0.C_in >= kTcKC ? kmax * (h0.C_in / kTcKC) : (kmax + kTcKC / h0.C_in - 1) / (kTcKC / h0.C_in);
+  const int stages = TcStages(split, bn, n_chunks);
+  const size_t smem = stages * TcStageBytes(split, bn) + 128 + static_cast<size_t>(bn) * 4;
   dim3 grid((M + kTcM - 1) / kTcM, n_tiles, nz);
-  if (split)
-    conv_gemm_tc_kernel<true><<<grid, 128, smem, s>>>(d_descs, B, d_frame);
-  else
-    conv_gemm_tc_kernel<false><<<grid, 128, smem, s>>>(d_descs, B, d_frame);
+  if (split) {
+    if (stages == 4) LaunchTcT<true, 4>(d_descs, grid, smem, B, d_frame, s);
+    else if (stages == 3) LaunchTcT<true, 3>(d_descs, grid, smem, B, d_frame, s);
+    else LaunchTcT<true, 2>(d_descs, grid, smem, B, d_frame, s);
+  } else {
+    if (stages == 4) LaunchTcT<false, 4>(d_descs, grid, smem, B, d_frame, s);
+    else if (stages == 3) LaunchTcT<false, 3>(d_descs, grid, smem, B, d_frame, s);
+    else LaunchTcT<false, 2>(d_descs, grid, smem, B, d_frame, s);
+  }
   B200_CHECK(cudaGetLastError());
 }
 

@@ -117,6 +117,28 @@ def cpu_reference_run(model_toml: str, threads: int, frames_per_thread: int, war
     return frames_per_thread / (time.time() - t0), "CPU oracle of spec M0 through the beatrice.h ABI, 1 thread"
 
 
+def parity_sample(product, model_dir, prec):
+    """RMS of the engine's 24 kHz output against the CPU oracle (checker) on 2 streams x 20 hops."""
+    from beatrice_vst_b200 import batch as bbatch
+    from beatrice_vst_b200 import lib as blib
+    from beatrice_vst_b200 import signals
+    oracle = blib.load_oracle()
+    n, hops = 2, 20
+    xs = signals.batch_16k(n, hops, seed0=77)
+    eng = bbatch.Engine(product, n, precision=prec)
+    eng.load(model_dir)
+    got = np.stack([eng.process_frames(xs[h]).copy() for h in range(hops)], axis=1)
+    eng.close()
+    err = 0.0
+    for s in range(n):
+        o = blib.SingleStream(oracle, model_dir)
+        o.set_pitch_range(1, 383)
+        _, _, _, w = o.run(xs[:, s, :].reshape(-1))
+        o.close()
+        err = max(err, float(np.sqrt(np.mean((got[s] - w) ** 2))))
+    return err
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -152,6 +174,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU (default = the named config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16x3", choices=["f32", "bf16", "bf16x3"],
+                    help="conv GEMM arithmetic: f32 CUDA cores | bf16 tcgen05 (vocoder) | split-bf16 tcgen05 "
+                         "(hi/lo operands, fp32 accumulate; meets the 1e-4 RMS bar) [default]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -187,7 +212,8 @@ def main():
         images = bdist.read_model_images(tmp.name)
     if world > 1:
         images = bdist.broadcast_model_images(images, src=0, device=torch.device("cuda", local_rank))
-    eng = bbatch.Engine(product, B, device=local_rank)
+    prec = {"f32": 0, "bf16": 1, "bf16x3": 2}[args.precision]
+    eng = bbatch.Engine(product, B, device=local_rank, precision=prec)
     rc = eng.load_from_memory(images)
     if rc != 0:
         raise SystemExit(f"LoadModelFromMemory -> {rc}")
@@ -285,7 +311,8 @@ def main():
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tflops"], "traffic": None,
-        "kernel": "conv_gemm (vocoder MRF dilated Conv1d stage)", "launches_per_step": len(mrf),
+        "kernel": ("conv_gemm_kernel (CUDA cores)" if args.precision == "f32" else "conv_gemm_tc_kernel (tcgen05)")
+                  + ", vocoder MRF dilated Conv1d stage", "launches_per_step": len(mrf),
         "algorithmic_flops_per_step": mrf_flops, "avg_launch_us": 1e3 * mrf_ms / max(len(mrf), 1),
         "share_of_step": mrf_ms / tot_ms if tot_ms > 0 else None, "peak_source": peaks["source"] + " bf16 sustained",
     }
@@ -293,7 +320,9 @@ def main():
     eng.close()
 
     cpu = None
+    rms_check = None
     if not args.no_cpu_baseline:
+        rms_check = parity_sample(product, tmp.name, prec)
         cores = os.cpu_count() or 1
         frames = 300
         t0 = time.time()
@@ -304,8 +333,10 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "streams_per_gpu": B, "model": "spec M0 (seeded synthetic weights, 8 speakers)",
+        "dtype": {"f32": "f32", "bf16": "bf16 (tcgen05, fp32 accumulate; encoders split-bf16)",
+                  "bf16x3": "bf16x3 (split-bf16 tcgen05 operands, fp32 accumulate)"}[args.precision],
+        "data": "synthetic", "rms_vs_cpu_oracle": rms_check,
+        "config": {"workload": WORKLOAD, "streams_per_gpu": B, "precision": args.precision, "model": "spec M0 (seeded synthetic weights, 8 speakers)",
                    "parallelism": f"{world} x independent stream shards, no per-hop collective; weights broadcast once over NCCL",
                    "l2": f"inputs cycle through {bank_hops} distinct device-resident hops "
                          f"({bank_hops * hop_floats * 4 / 1e6:.0f} MB > 126 MB L2); weights + stream state "

@@ -69,6 +69,10 @@ def main():
             recs = eng.profile_hop(din, dout)
             tot = sum(r["ms"] for r in recs)
             print(f"profile: {len(recs)} kernels, {tot * 1e3:.0f} us total")
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", f"diag_b{n}_p{prec}.txt"), "w") as fh:
+                for r in recs:
+                    fh.write(f"{r['name']:28s} {r['ms'] * 1e3:8.1f} us {r['flops'] / 1e6:10.1f} MFLOP\n")
             for r in sorted(recs, key=lambda r: -r["ms"])[:12]:
                 print(f"   {r['name']:28s} {r['ms'] * 1e3:8.1f} us  {r['flops'] / max(r['ms'], 1e-9) / 1e9:8.2f} TFLOP/s")
             eng.close()
