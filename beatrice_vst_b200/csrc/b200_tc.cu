@@ -42,6 +42,9 @@ __device__ __forceinline__ void MbarInit(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void MbarExpectTx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void MbarArrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void MbarWait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -141,8 +144,10 @@ __device__ __forceinline__ void CpAsyncWait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
 }
 
-template <bool kSplit, int kStages>
-__global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __restrict__ descs, int B,
+// kGather = false compiles the cp.async-only producer (no fp32 gather code): ~half the registers,
+// so three to four CTAs fit on an SM for the small-tile layers.
+template <bool kSplit, int kStages, bool kGather>
+__global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(const ConvDesc* __restrict__ descs, int B,
                                                            const int* __restrict__ frame_ptr) {
   constexpr int kOperands = kSplit ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -169,13 +174,13 @@ __global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __res
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(BN)) tmem_cols <<= 1;
 
-  for (int i = tid; i < BN; i += 128) {
+  for (int i = tid; i < BN; i += 160) {
     const int col = blockIdx.y * BN + i;
     bias_s[i] = (d.bias && col < d.N) ? __ldg(d.bias + col) : 0.0f;
   }
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
-      MbarInit(bar_full + 8 * i, 1);
+      MbarInit(bar_full + 8 * i, kTcM + 1);   // 128 producer rows + the weight TMA's expect_tx arrive
       MbarInit(bar_empty + 8 * i, 1);
     }
     MbarInit(bar_done, 1);
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __res
                         static_cast<size_t>(blockIdx.y) * n_chunks * w_bytes;
   const uint8_t* w_lo = kSplit ? static_cast<const uint8_t*>(d.w_tc_lo) + static_cast<size_t>(blockIdx.y) * n_chunks * w_bytes
                                : nullptr;
-  const bool async_a = d.xh != nullptr;   // activations pre-rounded to bf16 by their producer
+  const bool async_a = !kGather;          // activations pre-rounded to bf16 by their producer (d.xh)
 
   // element offsets of the (up to four) taps of chunk c for this thread's row
   auto tap_offsets = [&](int c, long long* ro) {
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __res
       TmaBulkLoad(w_hi_s, w_hi + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * s);
       if (kSplit) TmaBulkLoad(w_hi_s + w_bytes, w_lo + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * s);
     }
-    if (async_a) {
+    if constexpr (!kGather) {
       long long ro[4];
       tap_offsets(c, ro);
       const uint32_t dst = st_base + tid * 16;
@@ -257,86 +262,92 @@ __global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __res
     }
   };
 
-  // Look-ahead is kStages-2 chunks, not kStages-1: the stage refilled in iteration c is the one
-  // read by the MMAs of chunk c-2, which have had a whole iteration to retire, so the threads
-  // never stall on the tensor pipe they have just fed.
-  if (async_a) {
-#pragma unroll
-    for (int c = 0; c < kStages - 2; ++c) {
-      if (c < n_chunks) issue(c);
-      CpAsyncCommit();
-    }
-  }
-
-  for (int c = 0; c < n_chunks; ++c) {
-    const int s = c % kStages;
-    const int round = c / kStages;
-    const int j0 = C_in >= kTcKC ? c / n_sub : c * tpc;
-    const int taps = C_in >= kTcKC ? 1 : min(tpc, d.k - j0);
-    const uint32_t st_base = smem_base + s * stage_bytes;
-    const uint32_t a_hi = st_base, w_hi_s = st_base + a_bytes * kOperands;
-    const uint32_t a_lo = st_base + a_bytes, w_lo_s = w_hi_s + w_bytes;
-
-    if (async_a) {
-      if (c + kStages - 2 < n_chunks) issue(c + kStages - 2);
-      CpAsyncCommit();
-      CpAsyncWait<kStages - 2>();   // this thread's part of chunk c has landed
-    } else {
+  // ---- warp-specialised main loop ----
+  // warps 0-3 (128 threads, one activation row each) are PRODUCERS: they fill pipeline stages and
+  // arrive on the stage's "full" mbarrier when their own bytes have landed -- no block barrier.
+  // warp 4 is the MMA ISSUER: one elected lane waits on "full", issues the tcgen05.mma's of the
+  // chunk and commits the stage's "empty" mbarrier.  The roles only meet through mbarriers, so
+  // the tensor pipe is fed back-to-back while the producers run up to kStages chunks ahead.
+  constexpr int kRetire = kStages >= 3 ? kStages - 2 : 0;   // cp.async groups left in flight
+  if (warp < 4) {
+    for (int c = 0; c < n_chunks; ++c) {
+      const int s = c % kStages;
       issue(c);
-      // register path: gather this thread's row from the fp32 ring(s): 64 K-elements -> eight
-      // bf16 panels.  All loads of a half-chunk are issued before the first use.
-      uint8_t* a_hi_p = smem + s * stage_bytes + tid * 16;
-      uint8_t* a_lo_p = a_hi_p + a_bytes;
-      long long ro[4];
-      tap_offsets(c, ro);
+      if constexpr (!kGather) {
+        CpAsyncCommit();
+        if (c >= kRetire) {
+          CpAsyncWait<kRetire>();   // this thread's part of chunk c-kRetire has landed
+          FenceProxyAsync();        // ... and is visible to the tensor core (async proxy)
+          MbarArrive(bar_full + 8 * ((c - kRetire) % kStages));
+        }
+      } else {
+        // register path: gather this thread's row from the fp32 ring(s): 64 K-elements -> eight
+        // bf16 panels.  All loads of a half-chunk are issued before the first use.
+        uint8_t* a_hi_p = smem + s * stage_bytes + tid * 16;
+        uint8_t* a_lo_p = a_hi_p + a_bytes;
+        long long ro[4];
+        tap_offsets(c, ro);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float4 x0[8], x1[8], x2[8];
-        if (row_ok) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int ch = half * 32 + i * 4;          // K index inside the chunk
-            const int tl = ch >> lcw, cc = ch & (cw - 1);
-            const long long a = (tl == 0 ? ro[0] : tl == 1 ? ro[1] : tl == 2 ? ro[2] : ro[3]) + cc;
-            x0[i] = __ldg(reinterpret_cast<const float4*>(d.x[0] + a));
-            if (d.n_x > 1) {
-              x1[i] = __ldg(reinterpret_cast<const float4*>(d.x[1] + a));
-              x2[i] = __ldg(reinterpret_cast<const float4*>(d.x[2] + a));
-            }
-          }
-          if (d.n_x > 1) {
+        for (int half = 0; half < 2; ++half) {
+          float4 x0[8], x1[8], x2[8];
+          if (row_ok) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              x0[i].x = ((x0[i].x + x1[i].x) + x2[i].x) * d.in_scale;
-              x0[i].y = ((x0[i].y + x1[i].y) + x2[i].y) * d.in_scale;
-              x0[i].z = ((x0[i].z + x1[i].z) + x2[i].z) * d.in_scale;
-              x0[i].w = ((x0[i].w + x1[i].w) + x2[i].w) * d.in_scale;
+              const int ch = half * 32 + i * 4;          // K index inside the chunk
+              const int tl = ch >> lcw, cc = ch & (cw - 1);
+              const long long a = (tl == 0 ? ro[0] : tl == 1 ? ro[1] : tl == 2 ? ro[2] : ro[3]) + cc;
+              x0[i] = __ldg(reinterpret_cast<const float4*>(d.x[0] + a));
+              if (d.n_x > 1) {
+                x1[i] = __ldg(reinterpret_cast<const float4*>(d.x[1] + a));
+                x2[i] = __ldg(reinterpret_cast<const float4*>(d.x[2] + a));
+              }
             }
+            if (d.n_x > 1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                x0[i].x = ((x0[i].x + x1[i].x) + x2[i].x) * d.in_scale;
+                x0[i].y = ((x0[i].y + x1[i].y) + x2[i].y) * d.in_scale;
+                x0[i].z = ((x0[i].z + x1[i].z) + x2[i].z) * d.in_scale;
+                x0[i].w = ((x0[i].w + x1[i].w) + x2[i].w) * d.in_scale;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-        } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+          for (int p = 0; p < 4; ++p) {
+            float v[8] = {x0[2 * p].x, x0[2 * p].y, x0[2 * p].z, x0[2 * p].w,
+                          x0[2 * p + 1].x, x0[2 * p + 1].y, x0[2 * p + 1].z, x0[2 * p + 1].w};
+            if (d.in_act == kActLrelu) {   // the only input activation of spec M0
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          float v[8] = {x0[2 * p].x, x0[2 * p].y, x0[2 * p].z, x0[2 * p].w,
-                        x0[2 * p + 1].x, x0[2 * p + 1].y, x0[2 * p + 1].z, x0[2 * p + 1].w};
-          if (d.in_act == kActLrelu) {   // the only input activation of spec M0
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.0f ? v[e] : 0.1f * v[e];
+              for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.0f ? v[e] : 0.1f * v[e];
+            }
+            uint4 hi, lo;
+            Pack8<kSplit>(v, &hi, &lo);
+            *reinterpret_cast<uint4*>(a_hi_p + (half * 4 + p) * kPanelA) = hi;
+            if (kSplit) *reinterpret_cast<uint4*>(a_lo_p + (half * 4 + p) * kPanelA) = lo;
           }
-          uint4 hi, lo;
-          Pack8<kSplit>(v, &hi, &lo);
-          *reinterpret_cast<uint4*>(a_hi_p + (half * 4 + p) * kPanelA) = hi;
-          if (kSplit) *reinterpret_cast<uint4*>(a_lo_p + (half * 4 + p) * kPanelA) = lo;
         }
+        FenceProxyAsync();
+        MbarArrive(bar_full + 8 * s);
       }
     }
-    FenceProxyAsync();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    __syncthreads();
-
-    if (tid == 0) {
-      MbarWait(bar_full + 8 * s, round & 1);   // weight tile landed
+    if (!kGather && kRetire > 0) {   // drain: the last kRetire chunks
+      CpAsyncWait<0>();
+      FenceProxyAsync();
+      for (int c = (n_chunks > kRetire ? n_chunks - kRetire : 0); c < n_chunks; ++c)
+        MbarArrive(bar_full + 8 * (c % kStages));
+    }
+  } else if (lane == 0) {
+    for (int c = 0; c < n_chunks; ++c) {
+      const int s = c % kStages, round = c / kStages;
+      const int j0 = C_in >= kTcKC ? c / n_sub : c * tpc;
+      const int taps = C_in >= kTcKC ? 1 : min(tpc, d.k - j0);
+      const uint32_t st_base = smem_base + s * stage_bytes;
+      const uint32_t a_hi = st_base, w_hi_s = st_base + a_bytes * kOperands;
+      const uint32_t a_lo = st_base + a_bytes, w_lo_s = w_hi_s + w_bytes;
+      MbarWait(bar_full + 8 * s, round & 1);   // 128 row arrivals + the weight TMA's bytes
       TcFenceAfter();
       const int ksteps = (taps * cw) >> 4;
       for (int kk = 0; kk < ksteps; ++kk) {
@@ -355,11 +366,13 @@ __global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __res
       if (c == n_chunks - 1) MmaCommit(bar_done);
     }
   }
+  __syncwarp();   // re-converge the MMA warp (its other 31 lanes skipped the loop)
 
   // ---- epilogue: TMEM -> registers -> bias / FiLM / residual / activation -> rings ----
   // Every row of the tile is owned by one thread (TMEM lane == thread).  Bias sits in shared
   // memory since kernel start; the residual tile is pulled into the (now idle) pipeline
   // buffers with one batch of cp.async so its DRAM latency is paid once, not per 16 columns.
+  if (warp < 4) {   // the four producer warps own TMEM lanes 0-127 == the tile's rows
   const int row = tid;
   const int mm = m0 + row;
   const bool out_ok = mm < M;
@@ -446,6 +459,7 @@ __global__ void __launch_bounds__(128) conv_gemm_tc_kernel(const ConvDesc* __res
       }
     }
   }
+  }
   TcFenceBefore();
   __syncthreads();
   if (warp == 0) {
@@ -475,25 +489,26 @@ size_t TcStageBytes(bool split, int bn) {
 // two CTAs fit on an SM when the tiles are small (latency hiding across CTAs).
 int TcStages(bool split, int bn, int n_chunks) {
   const size_t stage = TcStageBytes(split, bn);
-  int s = static_cast<int>((100 * 1024) / stage);
+  // short K loops (the C = 16 / 32 stages: 3-6 chunks, hundreds of CTAs): occupancy beats depth,
+  // keep the CTA under ~74 KB so three fit on an SM
+  if (n_chunks <= 6) return (3 * stage <= 74 * 1024) ? 3 : 2;
+  int s = static_cast<int>((110 * 1024) / stage);
   if (s < 3) s = static_cast<int>((200 * 1024) / stage) >= 3 ? 3 : 2;
   if (s > 4) s = 4;
-  if (s > n_chunks + 1) s = n_chunks + 1 < 3 ? 3 : n_chunks + 1;
-  if (static_cast<size_t>(s) * stage > 200 * 1024) s = 2;
   return s;
 }
 
-template <bool kSplit, int kStages>
+template <bool kSplit, int kStages, bool kGather>
 void LaunchTcT(const ConvDesc* d_descs, dim3 grid, size_t smem, int B, const int* d_frame, cudaStream_t s) {
   static bool attr_set[64] = {};
   int dev = 0;
   B200_CHECK(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    B200_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel<kSplit, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel<kSplit, kStages, kGather>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     227 * 1024));
     attr_set[dev & 63] = true;
   }
-  conv_gemm_tc_kernel<kSplit, kStages><<<grid, 128, smem, s>>>(d_descs, B, d_frame);
+  conv_gemm_tc_kernel<kSplit, kStages, kGather><<<grid, 160, smem, s>>>(d_descs, B, d_frame);
 }
 
 }  // namespace
@@ -551,15 +566,21 @@ void LaunchConvGemmTc(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B
   const int stages = TcStages(split, bn, n_chunks);
   const size_t smem = stages * TcStageBytes(split, bn) + 128 + static_cast<size_t>(bn) * 4;
   dim3 grid((M + kTcM - 1) / kTcM, n_tiles, nz);
+  const bool gather = h0.xh == nullptr;
+#define B200_TC_DISPATCH(SPLIT, GATHER)                                                    \
+  do {                                                                                     \
+    if (stages == 4) LaunchTcT<SPLIT, 4, GATHER>(d_descs, grid, smem, B, d_frame, s);      \
+    else if (stages == 3) LaunchTcT<SPLIT, 3, GATHER>(d_descs, grid, smem, B, d_frame, s); \
+    else LaunchTcT<SPLIT, 2, GATHER>(d_descs, grid, smem, B, d_frame, s);                  \
+  } while (0)
   if (split) {
-    if (stages == 4) LaunchTcT<true, 4>(d_descs, grid, smem, B, d_frame, s);
-    else if (stages == 3) LaunchTcT<true, 3>(d_descs, grid, smem, B, d_frame, s);
-    else LaunchTcT<true, 2>(d_descs, grid, smem, B, d_frame, s);
+    if (gather) B200_TC_DISPATCH(true, true);
+    else B200_TC_DISPATCH(true, false);
   } else {
-    if (stages == 4) LaunchTcT<false, 4>(d_descs, grid, smem, B, d_frame, s);
-    else if (stages == 3) LaunchTcT<false, 3>(d_descs, grid, smem, B, d_frame, s);
-    else LaunchTcT<false, 2>(d_descs, grid, smem, B, d_frame, s);
+    if (gather) B200_TC_DISPATCH(false, true);
+    else B200_TC_DISPATCH(false, false);
   }
+#undef B200_TC_DISPATCH
   B200_CHECK(cudaGetLastError());
 }
 
