@@ -507,7 +507,7 @@ int BeatriceB200_ResetStream(BeatriceB200_Engine* e, int stream) {
   ForStreams(e, stream, [&](int b) {
     e->phone_st.arena.ZeroStream(b, e->stream);
     e->pitch_st.arena.ZeroStream(b, e->stream);
-    e->wave_st.arena.ZeroStream(b, e->stream);
+    e->wave_st.ZeroStream(b, e->stream);
     e->sp[b].kv_set_count = 0;
     e->pending_speaker.push_back(b);
     e->pending_formant.push_back(b);

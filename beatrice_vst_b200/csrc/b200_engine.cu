@@ -183,6 +183,14 @@ bool GraphsEnabled() {
   return on;
 }
 
+bool FusedMrfEnabled() {
+  static bool on = [] {
+    const char* e = std::getenv("BEATRICE_B200_NO_FUSED_MRF");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
 DeviceBuffer::~DeviceBuffer() { Free(); }
 void DeviceBuffer::Free() {
   if (p) {
@@ -332,6 +340,49 @@ int WaveModel::LoadFromImage(const void* data, size_t size, int on_device) {
     tc.Pack(device, img.payload, blob.as<float>(), convs);
   }
   for (int s = 0; s < 4; ++s) ups[s].b = ups_bias.as<float>() + rep_off[s];
+  {
+    // fused MRF kernel images: for every stage the kernel has a form for, both precisions
+    std::vector<float> bias_all;
+    size_t bias_off[4][3] = {};
+    std::vector<uint16_t> packed[2];
+    size_t w_off[2][4][3] = {};
+    bool have[4] = {};
+    for (int s = 0; s < 4; ++s) {
+      const int co = spec::kStageCh[s + 1];
+      if (co != 16 && co != 32 && co != 64) continue;
+      have[s] = true;
+      for (int ki = 0; ki < 3; ++ki) {
+        const float* wsrc[6];
+        bias_off[s][ki] = bias_all.size();
+        for (int di = 0; di < 3; ++di) {
+          wsrc[2 * di] = c.HostAt(c1[s][ki][di].w);
+          wsrc[2 * di + 1] = c.HostAt(c2[s][ki][di].w);
+          const float* b1 = c.HostAt(c1[s][ki][di].b);
+          const float* b2 = c.HostAt(c2[s][ki][di].b);
+          bias_all.insert(bias_all.end(), b1, b1 + co);
+          bias_all.insert(bias_all.end(), b2, b2 + co);
+        }
+        for (int sp = 0; sp < 2; ++sp) {
+          const size_t n = PackMrfWeights(wsrc, spec::kMrfK[ki], co, sp == 1, nullptr);
+          size_t off = (packed[sp].size() + 127) / 128 * 128;   // 256-byte aligned images
+          packed[sp].resize(off + n);
+          PackMrfWeights(wsrc, spec::kMrfK[ki], co, sp == 1, packed[sp].data() + off);
+          w_off[sp][s][ki] = off;
+        }
+      }
+    }
+    Upload(&mrf_bias, device, bias_all.data(), bias_all.size());
+    for (int sp = 0; sp < 2; ++sp) {
+      mrf_w[sp].Alloc(device, packed[sp].size() * sizeof(uint16_t), false);
+      if (!packed[sp].empty())
+        B200_CHECK(cudaMemcpy(mrf_w[sp].p, packed[sp].data(), packed[sp].size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
+    for (int s = 0; s < 4; ++s)
+      for (int ki = 0; ki < 3; ++ki) {
+        mrf_bias_ptr[s][ki] = have[s] ? mrf_bias.as<float>() + bias_off[s][ki] : nullptr;
+        for (int sp = 0; sp < 2; ++sp) mrf_w_ptr[sp][s][ki] = have[s] ? mrf_w[sp].as<uint16_t>() + w_off[sp][s][ki] : nullptr;
+      }
+  }
   ++generation;
   loaded = true;
   return 0;
@@ -715,10 +766,37 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
   // path only).  Tensor-core mode keeps fp32 only where a residual / the branch sum needs it
   // (current rows) and adds bf16 rings -- already LeakyReLU'd -- that carry the conv history.
   int ring_u[4], ring_uh[4], ring_a[4][3][3], ring_y[4][3][4], ring_yh[4][3][4];
+  // stages the fused MRF kernel covers (b200_mrf.cu): S streams per CTA, histories in mrf_hist
+  bool fused[4] = {};
+  int fused_S[4] = {}, fused_groups[4] = {};
   int t = 1;
   for (int s = 0; s < 4; ++s) {
     const int c = spec::kStageCh[s + 1];
     t *= spec::kRates[s];
+    {
+      int S = c >= 64 ? 6 : (c == 32 ? 3 : 1);
+      // developer overrides: BEATRICE_B200_MRF_S="s1,s2,s3" (streams per CTA of stages 1..3),
+      // BEATRICE_B200_MRF_STAGES=bitmask of stages allowed to use the fused kernel
+      int mask = 0xF;
+      if (const char* ev = std::getenv("BEATRICE_B200_MRF_STAGES")) mask = std::atoi(ev);
+      if (const char* ev = std::getenv("BEATRICE_B200_MRF_S")) {
+        int v[3] = {0, 0, 0};
+        if (std::sscanf(ev, "%d,%d,%d", &v[0], &v[1], &v[2]) == 3 && s >= 1 && v[s - 1] > 0) S = v[s - 1];
+      }
+      fused[s] = tcm && FusedMrfEnabled() && ((mask >> s) & 1) && m->mrf_w_ptr[with_lo ? 1 : 0][s][0] != nullptr &&
+                 MrfFusedSupported(c, t, S, with_lo);
+      fused_S[s] = S;
+      fused_groups[s] = (B + S - 1) / S;
+    }
+    if (fused[s]) {
+      ring_u[s] = arena.Plan(0, t, c);
+      ring_uh[s] = -1;
+      for (int ki = 0; ki < 3; ++ki) {
+        ring_y[s][ki][3] = arena.Plan(s < 3 ? 1 : spec::kPostK - 1, t, c);
+        ring_stage_out[s][ki] = ring_y[s][ki][3];
+      }
+      continue;
+    }
     const int u_hist = (spec::kMrfK[2] - 1) * spec::kMrfD[0];
     ring_u[s] = arena.Plan(tcm ? 0 : u_hist, t, c);
     ring_uh[s] = tcm ? arena.PlanH(u_hist, t, c, with_lo) : -1;
@@ -738,6 +816,43 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
   }
   arena.Commit(device, B);
 
+  // fused-stage histories: one block per (stage, branch, conv), zero = silence
+  size_t hist_off[4][3] = {};
+  {
+    size_t total = 0;
+    std::vector<MrfHistBlock> blocks;
+    for (int s = 0; s < 4; ++s) {
+      if (!fused[s]) continue;
+      for (int ki = 0; ki < 3; ++ki) {
+        hist_off[s][ki] = total;
+        total += (MrfHistElems(spec::kStageCh[s + 1], spec::kMrfK[ki], fused_S[s], fused_groups[s], with_lo) + 127) / 128 * 128;
+      }
+    }
+    mrf_hist.Alloc(device, total * sizeof(uint16_t), true);
+    static const int kDilPrefix[6] = {0, 1, 2, 5, 6, 11}, kDil[6] = {1, 1, 3, 1, 5, 1};
+    for (int s = 0; s < 4; ++s) {
+      if (!fused[s]) continue;
+      const int c = spec::kStageCh[s + 1], P = with_lo ? 2 : 1;
+      for (int ki = 0; ki < 3; ++ki) {
+        const int k = spec::kMrfK[ki];
+        const size_t unit = static_cast<size_t>(fused_groups[s]) * P * (c / 8) * fused_S[s] * 8 * (k - 1);
+        for (int i = 0; i < 6; ++i) {
+          MrfHistBlock hb;
+          hb.base = mrf_hist.as<uint16_t>() + hist_off[s][ki] + unit * kDilPrefix[i];
+          hb.planes_panels = P * (c / 8);
+          hb.H = (k - 1) * kDil[i];
+          hb.S = fused_S[s];
+          hb.pad_ = 0;
+          blocks.push_back(hb);
+        }
+      }
+    }
+    n_mrf_blocks = static_cast<int>(blocks.size());
+    mrf_blocks.Alloc(device, sizeof(MrfHistBlock) * std::max<size_t>(blocks.size(), 1), true);
+    if (!blocks.empty())
+      B200_CHECK(cudaMemcpy(mrf_blocks.p, blocks.data(), sizeof(MrfHistBlock) * blocks.size(), cudaMemcpyHostToDevice));
+  }
+
   DescBuilder db;
   const int pre_idx = db.Add(MakeConv(arena.ring(ring_hidden), m->pre, 1, 1, 1, arena.ring(ring_pre), kActNone, kActNone));
   int ups_idx[4], c1_idx[4][3], c2_idx[4][3];
@@ -755,10 +870,10 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
       u.film = film[s].as<float>();
       u.film_C = c;
     }
-    if (tcm) SetOutH(&u, arena.ring(ring_uh[s]), kActLrelu);
+    if (tcm && !fused[s]) SetOutH(&u, arena.ring(ring_uh[s]), kActLrelu);
     ups_idx[s] = db.Add(u);
     t *= spec::kRates[s];
-    for (int di = 0; di < 3; ++di) {
+    for (int di = 0; di < 3 && !fused[s]; ++di) {
       for (int ki = 0; ki < 3; ++ki) {
         const Ring& a = arena.ring(ring_a[s][ki][di]);
         ConvDesc d1 = MakeConv(arena.ring(ring_y[s][ki][di]), m->c1[s][ki][di], spec::kMrfD[di], 1, t, a, kActLrelu,
@@ -828,8 +943,41 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
     program.push_back(op);
   };
   add_gemm("wave.pre", pre_idx, 1, false);
+  int t_stage = 1;
   for (int s = 0; s < 4; ++s) {
     add_gemm("wave.ups" + std::to_string(s), ups_idx[s], 1, false);
+    t_stage *= spec::kRates[s];
+    if (fused[s]) {
+      const int c = spec::kStageCh[s + 1];
+      MrfStageParams mp;
+      std::memset(&mp, 0, sizeof(mp));
+      for (int ki = 0; ki < 3; ++ki) {
+        const Ring& o = arena.ring(ring_stage_out[s][ki]);
+        mp.br[ki].w = m->mrf_w_ptr[with_lo ? 1 : 0][s][ki];
+        mp.br[ki].bias = m->mrf_bias_ptr[s][ki];
+        mp.br[ki].hist = mrf_hist.as<uint16_t>() + hist_off[s][ki];
+        mp.br[ki].out = o.base;
+        mp.br[ki].out_slots = o.slots;
+        mp.br[ki].k = spec::kMrfK[ki];
+      }
+      const Ring& ur = arena.ring(ring_u[s]);
+      mp.u = ur.base;
+      mp.u_slots = ur.slots;
+      mp.T = t_stage;
+      mp.S = fused_S[s];
+      mp.MT = (fused_S[s] * t_stage + 127) / 128;
+      mp.B = B;
+      mp.n_groups = fused_groups[s];
+      mp.frame = frame;
+      Op op;
+      op.name = "wave.mrf" + std::to_string(s) + ".fused";
+      op.flops = 2.0 * c * c * t_stage * B * 6.0 * (3 + 7 + 11);
+      op.bytes = 2.0 * 6 * 21 * c * c + 4.0 * B * t_stage * c * 4;
+      op.is_mrf = true;
+      op.launch = [=](cudaStream_t st) { LaunchMrfStage(mp, c, with_lo, st); };
+      program.push_back(op);
+      continue;
+    }
     for (int di = 0; di < 3; ++di) {
       add_gemm("wave.mrf" + std::to_string(s) + ".d" + std::to_string(spec::kMrfD[di]) + ".c1", c1_idx[s][di], 3, true);
       add_gemm("wave.mrf" + std::to_string(s) + ".d" + std::to_string(spec::kMrfD[di]) + ".c2", c2_idx[s][di], 3, true);
@@ -852,6 +1000,11 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
     op.launch = [=](cudaStream_t s) { LaunchAdvance(f, s); };
     program.push_back(op);
   }
+}
+
+void WaveState::ZeroStream(int b, cudaStream_t s) {
+  arena.ZeroStream(b, s);
+  LaunchMrfZeroStream(mrf_blocks.as<MrfHistBlock>(), n_mrf_blocks, b, s);
 }
 
 void RunProgram(const std::vector<Op>& program, cudaStream_t s) {

@@ -12,6 +12,7 @@
 
 #include "b200_common.h"
 #include "b200_kernels.h"
+#include "b200_mrf.h"
 
 namespace b200 {
 
@@ -44,6 +45,7 @@ int ParseFileImage(const void* data, size_t size, int family, uint32_t kind_a, u
 int UsableDeviceCount();           // never aborts
 int DefaultDevice();               // env BEATRICE_B200_DEVICE or 0; aborts when no GPU is usable
 bool GraphsEnabled();              // env BEATRICE_B200_NO_GRAPH=1 disables CUDA graphs
+bool FusedMrfEnabled();            // env BEATRICE_B200_NO_FUSED_MRF=1 keeps the per-conv kernels
 
 struct DeviceBuffer {
   void* p = nullptr;
@@ -121,6 +123,11 @@ struct WaveModel {
   ConvW c1[4][3][3], c2[4][3][3];
   ConvW post;
   TcWeights tc;
+  // fused MRF kernel (b200_mrf.cu): weight images per precision [0] bf16, [1] split bf16, and
+  // the six biases of a branch made contiguous
+  DeviceBuffer mrf_w[2], mrf_bias;
+  const uint16_t* mrf_w_ptr[2][4][3] = {};
+  const float* mrf_bias_ptr[4][3] = {};
   int LoadFromImage(const void* data, size_t size, int on_device = -1);
   int LoadFromFile(const char* utf8_path, int on_device = -1);
 };
@@ -215,6 +222,10 @@ struct WaveState {
   std::vector<Op> program;
   int ring_hidden = -1, ring_pre = -1, ring_stage_out[4][3];
   bool cond_ready = false;
+  // fused MRF stages: conv-input histories (bf16, stream-group layout) + reset table
+  DeviceBuffer mrf_hist, mrf_blocks;
+  int n_mrf_blocks = 0;
+  void ZeroStream(int b, cudaStream_t s);   // arena + fused-kernel histories of stream b
   // conditioning buffers depend only on the family, not on the weights: the rc0 setters
   // (beatrice.h:323-343) may run before the first GenerateWaveform1 names the model
   void AllocCond(const FamilyDims& dims, int B, int device);

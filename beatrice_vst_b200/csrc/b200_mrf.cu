@@ -1,0 +1,493 @@
+// Fused MRF branch kernel (vocoder stages with C <= 64), tcgen05 / TMEM / TMA, sm_100a only.
+//
+// One CTA runs ONE branch (kernel size k in {3,7,11}) of one vocoder stage for a group of S
+// streams, all six convolutions of the branch back to back:
+//     x0 = u;  for d in {1,3,5}:  a = c1_d(lrelu(x)) ; x = x + c2_d(lrelu(a))        (oracle: Generate(), MRF loop)
+// Nothing but the stage input u, the branch output and the conv histories touches HBM.
+//
+//  * Rows are TIME-MAJOR inside the group:  row = t * S + s.  The input of every conv sits in shared
+//    memory as bf16 K-panels [C/8][rows][8] (UMMA canonical K-major, no swizzle, 16 B per row per
+//    panel) with the causal history in front of the hop's new rows, so tap j of a dilated conv is
+//    the SAME buffer at a row offset of (k-1-j)*dil*S rows: an implicit GEMM with no im2col and no
+//    per-tap data movement -- the tap is a shift of the descriptor's start address.
+//  * Accumulators live in TMEM.  The residual stream x stays in TMEM as fp32 for the whole chain:
+//    c2's MMAs accumulate straight onto it.  The epilogue warps read 16 columns at a time
+//    (tcgen05.ld), add the bias, write x back (tcgen05.st), and store lrelu(.) as bf16 (hi [+ lo])
+//    panels for the next conv; each 16-channel group is handed to the MMA warp through its own
+//    mbarrier, so the next conv starts on channel group 0 while the epilogue is still on group 1.
+//  * Weights stream through a 4-stage ring of TMA bulk copies (one warp), K ordered
+//    [channel group][tap] to match that hand-off.  A third control warp moves the conv histories:
+//    TMA bulk loads global -> shared before a conv, bulk stores of the new tail shared -> global
+//    after its input is complete.
+//  * Precision: plain bf16 (1 MMA per K step) or split bf16 (x = hi + lo for both operands,
+//    hi*hi + hi*lo + lo*hi, fp32 accumulate): same scheme as b200_tc.cu.
+#include <cstring>
+#include <vector>
+
+#include "b200_common.h"
+#include "b200_mrf.h"
+#include "b200_tc_common.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int kNst = 4;          // weight ring stages
+constexpr int kEpiWarps = 4;     // warps 0-3: epilogue (TMEM lane quarter == warp)
+constexpr int kWarpMma = 4, kWarpW = 5, kWarpH = 6;
+constexpr int kThreads = 7 * 32;
+
+__device__ __forceinline__ void TmemSt16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void TmemStWait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void TmaBulkStore(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void BulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void BulkWaitRead0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void BulkWait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void SpinUntil(volatile uint32_t* cnt, uint32_t target) {
+  uint32_t spins = 0;
+  while (*cnt < target) {
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ int ConvDil(int i) { return (i & 1) ? 1 : (i == 0 ? 1 : (i == 2 ? 3 : 5)); }
+// sum of the dilations of convs 0..i-1 (1,1,3,1,5,1)
+__device__ __forceinline__ int DilPrefix(int i) {
+  const int pre[7] = {0, 1, 2, 5, 6, 11, 12};
+  return pre[i];
+}
+
+template <int C>
+struct MrfCfg {
+  static constexpr int kG = C / 16;                       // 16-channel groups == K steps per tap
+  static constexpr int kPan = C / 8;                      // 8-channel K panels
+  static constexpr int kNk = C <= 16 ? 4 : (C <= 64 ? 2 : 1);   // K steps per weight chunk
+};
+
+template <int C, bool kSplit>
+__global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf_branch_kernel(const __grid_constant__ MrfStageParams p) {
+  using Cfg = MrfCfg<C>;
+  constexpr int G = Cfg::kG, PAN = Cfg::kPan, NK = Cfg::kNk;
+  constexpr int P = kSplit ? 2 : 1;
+  constexpr uint32_t kKstepBytes = P * C * 32;
+  constexpr uint32_t kChunkBytes = NK * kKstepBytes;
+  extern __shared__ __align__(1024) uint8_t smem[];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const MrfBranchDesc& br = p.br[2 - blockIdx.y];   // longest branch (k = 11) is scheduled first
+  const int k = br.k, T = p.T, S = p.S, MT = p.MT;
+  const int group = blockIdx.x;
+  const int HX = (k - 1) * 5, HY = k - 1;            // history rows (time steps) in front of X / Y
+  const int RX = HX * S + MT * 128, RY = HY * S + MT * 128;
+  const int frame = *p.frame;
+
+  // ---- shared memory carve-up ----
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  // [0,NST) w_full  [NST,2NST) w_empty  [2NST,+2) hist_full  [+2,+4) buf_free  then in_ready[MT*G], acc_ready[MT]
+  const uint32_t bar0 = SmemAddr(bars);
+  const uint32_t bar_w_full = bar0, bar_w_empty = bar0 + 8 * kNst, bar_hist = bar0 + 16 * kNst,
+                 bar_free = bar_hist + 16, bar_in = bar_free + 16, bar_acc = bar_in + 8 * MT * G;
+  const int n_bars = 2 * kNst + 4 + MT * G + MT;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * 40);
+  // hand-off counters for the history mover (monotonic, so a late reader can never alias a phase)
+  volatile uint32_t* in_cnt = reinterpret_cast<volatile uint32_t*>(smem + 8 * 40 + 4);   // += 1 per epilogue warp per conv input
+  volatile uint32_t* acc_cnt = reinterpret_cast<volatile uint32_t*>(smem + 8 * 40 + 8);  // += 1 per conv whose MMAs retired
+  float* bias_s = reinterpret_cast<float*>(smem + 8 * 40 + 16);          // [6][C]
+  const uint32_t x_off = (8 * 40 + 16 + 6 * C * 4 + 127) / 128 * 128;
+  const uint32_t x_pstride = static_cast<uint32_t>(RX) * 16, y_pstride = static_cast<uint32_t>(RY) * 16;
+  const uint32_t x_plane = PAN * x_pstride, y_plane = PAN * y_pstride;
+  const uint32_t y_off = x_off + P * x_plane;
+  const uint32_t w_off = (y_off + P * y_plane + 127) / 128 * 128;
+  const uint32_t smem_base = SmemAddr(smem);
+  const uint32_t x_base = smem_base + x_off, y_base = smem_base + y_off, w_base = smem_base + w_off;
+
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(2 * MT * C)) tmem_cols <<= 1;
+
+  for (int i = tid; i < 6 * C; i += kThreads) bias_s[i] = __ldg(br.bias + i);
+  if (tid == 0) {
+    *in_cnt = 0;
+    *acc_cnt = 0;
+    for (int i = 0; i < n_bars; ++i) {
+      const uint32_t b = bar0 + 8 * i;
+      const bool is_in = b >= bar_in && b < bar_acc;
+      MbarInit(b, is_in ? kEpiWarps : 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kWarpMma) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemAddr(tmem_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  TcFenceBefore();
+  __syncthreads();
+  TcFenceAfter();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int rows_valid = S * T;
+  const size_t hist_unit = static_cast<size_t>(p.n_groups) * P * PAN * S * 8 * (k - 1);   // elements per unit dilation
+
+  if (warp < kEpiWarps) {
+    // =========================== epilogue warps ===========================
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    // ---- prologue: u -> TMEM (fp32 residual stream) and lrelu(u) -> X new rows ----
+    for (int m = 0; m < MT; ++m) {
+      const int r = m * 128 + tid;
+      const int t = r / S, s = r - t * S;
+      const int b = group * S + s;
+      const bool valid = r < rows_valid && b < p.B;
+      const float* urow = p.u + (static_cast<size_t>(b) * p.u_slots * T + (frame % p.u_slots) * T + t) * C;
+      const uint32_t srow = x_base + static_cast<uint32_t>(HX * S + r) * 16;
+#pragma unroll 1
+      for (int g = 0; g < G; ++g) {
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) f = __ldg(reinterpret_cast<const float4*>(urow + 16 * g + 4 * q));
+          v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+        }
+        uint32_t raw[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) raw[e] = __float_as_uint(v[e]);
+        TmemSt16(t_lane + m * C + 16 * g, raw);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.0f ? v[e] : 0.1f * v[e];
+        uint4 h0, l0, h1, l1;
+        Pack8<kSplit>(v, &h0, &l0);
+        Pack8<kSplit>(v + 8, &h1, &l1);
+        const uint32_t a0 = srow + (2 * g) * x_pstride;
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(h0.x), "r"(h0.y), "r"(h0.z), "r"(h0.w) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + x_pstride), "r"(h1.x), "r"(h1.y), "r"(h1.z), "r"(h1.w) : "memory");
+        if (kSplit) {
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + x_plane), "r"(l0.x), "r"(l0.y), "r"(l0.z), "r"(l0.w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + x_plane + x_pstride), "r"(l1.x), "r"(l1.y), "r"(l1.z), "r"(l1.w) : "memory");
+        }
+        TmemStWait();
+        FenceProxyAsync();
+        TcFenceBefore();
+        __syncwarp();
+        if (lane == 0) MbarArrive(bar_in + 8 * (m * G + g));
+      }
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicAdd(const_cast<uint32_t*>(in_cnt), 1u);
+    // ---- the six convs ----
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i) {
+      const bool is_c1 = (i & 1) == 0;
+      const bool last = i == 5;
+      // destination of lrelu(.): the OTHER buffer (c1 -> Y, c2 -> X)
+      const uint32_t d_base = is_c1 ? y_base : x_base;
+      const uint32_t d_pstride = is_c1 ? y_pstride : x_pstride, d_plane = is_c1 ? y_plane : x_plane;
+      const int d_hmax = is_c1 ? HY : HX;
+      const float* bias = bias_s + i * C;
+      if (i >= 1 && !last) MbarWait(bar_free + 8 * ((i + 1) & 1), ((i - 1) >> 1) & 1);
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const int r = m * 128 + tid;
+        const int t = r / S, s = r - t * S;
+        const int b = group * S + s;
+        const bool valid = r < rows_valid && b < p.B;
+        MbarWait(bar_acc + 8 * m, i & 1);
+        TcFenceAfter();
+        if (m == MT - 1 && tid == 0) atomicAdd(const_cast<uint32_t*>(acc_cnt), 1u);   // conv i's MMAs have all retired
+        const uint32_t tcol = t_lane + (is_c1 ? (MT + m) * C : m * C);
+        const uint32_t srow = d_base + static_cast<uint32_t>(d_hmax * S + r) * 16;
+        float* orow = br.out + (static_cast<size_t>(b) * br.out_slots * T + (frame % br.out_slots) * T + t) * C;
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
+          uint32_t raw[16];
+          TmemLd16(tcol + 16 * g, raw);
+          float v[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]) + bias[16 * g + e];
+          if (!is_c1) {
+            if (!last) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) raw[e] = __float_as_uint(v[e]);
+              TmemSt16(tcol + 16 * g, raw);
+            } else if (valid) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(orow + 16 * g + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+          }
+          if (!last) {
+            if (!valid) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = 0.0f;
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.0f ? v[e] : 0.1f * v[e];
+            uint4 h0, l0, h1, l1;
+            Pack8<kSplit>(v, &h0, &l0);
+            Pack8<kSplit>(v + 8, &h1, &l1);
+            const uint32_t a0 = srow + (2 * g) * d_pstride;
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(h0.x), "r"(h0.y), "r"(h0.z), "r"(h0.w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + d_pstride), "r"(h1.x), "r"(h1.y), "r"(h1.z), "r"(h1.w) : "memory");
+            if (kSplit) {
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + d_plane), "r"(l0.x), "r"(l0.y), "r"(l0.z), "r"(l0.w) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + d_plane + d_pstride), "r"(l1.x), "r"(l1.y), "r"(l1.z), "r"(l1.w) : "memory");
+            }
+            if (!is_c1) TmemStWait();
+            FenceProxyAsync();
+            TcFenceBefore();
+            __syncwarp();
+            if (lane == 0) MbarArrive(bar_in + 8 * (m * G + g));
+          }
+        }
+      }
+      if (!last) {
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atomicAdd(const_cast<uint32_t*>(in_cnt), 1u);
+      }
+    }
+  } else if (warp == kWarpMma) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc = MakeIdesc(C);
+      uint32_t cc = 0;
+#pragma unroll 1
+      for (int i = 0; i < 6; ++i) {
+        const int buf = i & 1, dil = ConvDil(i);
+        const int hmax = buf ? HY : HX;
+        const uint32_t bbase = buf ? y_base : x_base, pstride = buf ? y_pstride : x_pstride, plane = buf ? y_plane : x_plane;
+        MbarWait(bar_hist + 8 * buf, (i >> 1) & 1);
+#pragma unroll 1
+        for (int m = 0; m < MT; ++m) {
+          const uint32_t dcol = tmem_base + (buf == 0 ? (MT + m) * C : m * C);
+          int ks = 0;
+#pragma unroll 1
+          for (int g = 0; g < G; ++g) {
+            MbarWait(bar_in + 8 * (m * G + g), i & 1);
+            TcFenceAfter();
+#pragma unroll 1
+            for (int j = 0; j < k; ++j) {
+              const int within = ks % NK;
+              const uint32_t stage = cc % kNst;
+              if (within == 0) {
+                MbarWait(bar_w_full + 8 * stage, (cc / kNst) & 1);
+                TcFenceAfter();
+              }
+              const int row0 = (hmax - (k - 1 - j) * dil) * S + 128 * m;
+              const uint32_t a_hi = bbase + (2 * g) * pstride + static_cast<uint32_t>(row0) * 16;
+              const uint32_t w_hi = w_base + stage * kChunkBytes + within * kKstepBytes;
+              const uint64_t ah = MakeDesc(a_hi, pstride, 128);
+              const uint64_t wh = MakeDesc(w_hi, C * 16, 128);
+              const uint32_t acc = buf == 0 ? (ks > 0 ? 1u : 0u) : 1u;
+              Mma(dcol, ah, wh, idesc, acc);
+              if (kSplit) {
+                const uint64_t al = MakeDesc(a_hi + plane, pstride, 128);
+                const uint64_t wl = MakeDesc(w_hi + C * 32, C * 16, 128);
+                Mma(dcol, ah, wl, idesc, 1u);
+                Mma(dcol, al, wh, idesc, 1u);
+              }
+              ++ks;
+              if (within == NK - 1 || ks == k * G) {
+                MmaCommit(bar_w_empty + 8 * stage);
+                ++cc;
+              }
+            }
+          }
+          MmaCommit(bar_acc + 8 * m);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kWarpW) {
+    // =========================== weight producer ===========================
+    if (lane == 0) {
+      const int ksteps = k * G;
+      const int chunks = (ksteps + NK - 1) / NK;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(br.w);
+      uint32_t cc = 0;
+#pragma unroll 1
+      for (int i = 0; i < 6; ++i) {
+        const uint8_t* wconv = wsrc + static_cast<size_t>(i) * ksteps * kKstepBytes;
+#pragma unroll 1
+        for (int m = 0; m < MT; ++m) {
+#pragma unroll 1
+          for (int c = 0; c < chunks; ++c) {
+            const uint32_t stage = cc % kNst, round = cc / kNst;
+            if (round > 0) MbarWait(bar_w_empty + 8 * stage, (round - 1) & 1);
+            const int n = min(NK, ksteps - c * NK);
+            const uint32_t bytes = n * kKstepBytes;
+            MbarExpectTx(bar_w_full + 8 * stage, bytes);
+            TmaBulkLoad(w_base + stage * kChunkBytes, wconv + static_cast<size_t>(c) * kChunkBytes, bytes, bar_w_full + 8 * stage);
+            ++cc;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kWarpH) {
+    // =========================== history mover ===========================
+    if (lane == 0) {
+      auto hist_ptr = [&](int i, int H) {
+        // conv i block: [group][plane][panel][H*S rows][8]
+        return br.hist + hist_unit * DilPrefix(i) + static_cast<size_t>(group) * P * PAN * H * S * 8;
+      };
+      auto load_hist = [&](int i) {
+        const int buf = i & 1, H = (k - 1) * ConvDil(i);
+        const int hmax = buf ? HY : HX;
+        const uint32_t bbase = buf ? y_base : x_base, pstride = buf ? y_pstride : x_pstride, plane = buf ? y_plane : x_plane;
+        const uint32_t bytes = static_cast<uint32_t>(H) * S * 16;
+        const uint16_t* src = hist_ptr(i, H);
+        MbarExpectTx(bar_hist + 8 * buf, bytes * P * PAN);
+        for (int pl = 0; pl < P; ++pl)
+          for (int pn = 0; pn < PAN; ++pn)
+            TmaBulkLoad(bbase + pl * plane + pn * pstride + static_cast<uint32_t>((hmax - H) * S) * 16,
+                        src + static_cast<size_t>(pl * PAN + pn) * H * S * 8, bytes, bar_hist + 8 * buf);
+      };
+      load_hist(0);
+      load_hist(1);
+#pragma unroll 1
+      for (int i = 0; i < 6; ++i) {
+        const int buf = i & 1, H = (k - 1) * ConvDil(i);
+        const int hmax = buf ? HY : HX;
+        const uint32_t bbase = buf ? y_base : x_base, pstride = buf ? y_pstride : x_pstride, plane = buf ? y_plane : x_plane;
+        // input of conv i complete: history landed + every new row written by the epilogue warps
+        MbarWait(bar_hist + 8 * buf, (i >> 1) & 1);
+        SpinUntil(in_cnt, static_cast<uint32_t>(kEpiWarps * (i + 1)));
+        __threadfence_block();
+        FenceProxyAsync();
+        {
+          const uint32_t bytes = static_cast<uint32_t>(H) * S * 16;
+          uint16_t* dst = const_cast<uint16_t*>(hist_ptr(i, H));
+          for (int pl = 0; pl < P; ++pl)
+            for (int pn = 0; pn < PAN; ++pn)
+              TmaBulkStore(dst + static_cast<size_t>(pl * PAN + pn) * H * S * 8,
+                           bbase + pl * plane + pn * pstride + static_cast<uint32_t>((hmax + T - H) * S) * 16, bytes);
+          BulkCommit();
+          BulkWaitRead0();
+        }
+        // conv i's MMAs done reading the buffer
+        SpinUntil(acc_cnt, static_cast<uint32_t>(i + 1));
+        if (i + 2 < 6) load_hist(i + 2);
+        MbarArrive(bar_free + 8 * buf);
+      }
+      BulkWait0();
+    }
+    __syncwarp();
+  }
+
+  TcFenceBefore();
+  __syncthreads();
+  if (warp == kWarpMma) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+__global__ void mrf_zero_stream_kernel(const MrfHistBlock* __restrict__ blocks, int b) {
+  const MrfHistBlock hb = blocks[blockIdx.x];
+  const int group = b / hb.S, s = b - group * hb.S;
+  // [group][plane*panel][H rows][S][8]
+  uint4* base = reinterpret_cast<uint4*>(hb.base) + static_cast<size_t>(group) * hb.planes_panels * hb.H * hb.S;
+  const int n = hb.planes_panels * hb.H;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) base[static_cast<size_t>(i) * hb.S + s] = make_uint4(0, 0, 0, 0);
+}
+
+template <int C, bool kSplit>
+void LaunchMrfT(const MrfStageParams& p, size_t smem, cudaStream_t s) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  B200_CHECK(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    B200_CHECK(cudaFuncSetAttribute(mrf_branch_kernel<C, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[dev & 63] = true;
+  }
+  mrf_branch_kernel<C, kSplit><<<dim3(p.n_groups, 3, 1), kThreads, smem, s>>>(p);
+}
+
+int NkFor(int C) { return C <= 16 ? 4 : (C <= 64 ? 2 : 1); }
+
+}  // namespace
+
+size_t MrfSmemBytes(int C, int T, int S, bool split) {
+  const int MT = (S * T + 127) / 128;
+  const int P = split ? 2 : 1, PAN = C / 8;
+  const int k = 11;   // the launch is sized for its largest branch
+  const size_t RX = static_cast<size_t>((k - 1) * 5) * S + MT * 128, RY = static_cast<size_t>(k - 1) * S + MT * 128;
+  size_t off = (8 * 40 + 16 + 6 * C * 4 + 127) / 128 * 128;
+  off += P * PAN * RX * 16;
+  off += P * PAN * RY * 16;
+  off = (off + 127) / 128 * 128;
+  off += static_cast<size_t>(kNst) * NkFor(C) * P * C * 32;
+  return off;
+}
+
+bool MrfFusedSupported(int C, int T, int S, bool split) {
+  if (C != 16 && C != 32 && C != 64) return false;
+  const int MT = (S * T + 127) / 128;
+  if (2 * MT * C > 512) return false;
+  if (2 * 4 + 4 + MT * (C / 16) + MT > 40) return false;
+  return MrfSmemBytes(C, T, S, split) <= 227 * 1024;
+}
+
+size_t MrfHistElems(int C, int k, int S, int n_groups, bool split) {
+  return static_cast<size_t>(n_groups) * (split ? 2 : 1) * (C / 8) * S * 8 * (k - 1) * 12;
+}
+
+size_t PackMrfWeights(const float* const w[6], int k, int C, bool split, uint16_t* out) {
+  // per conv: [ks = g*k + j][plane][2 panels][C rows (n)][8]   element = W[j][16g + 8p + e][n]
+  const int G = C / 16, P = split ? 2 : 1;
+  const size_t kstep = static_cast<size_t>(P) * 2 * C * 8;
+  const size_t total = 6 * static_cast<size_t>(k) * G * kstep;
+  if (!out) return total;
+  for (int i = 0; i < 6; ++i)
+    for (int g = 0; g < G; ++g)
+      for (int j = 0; j < k; ++j) {
+        uint16_t* blk = out + (static_cast<size_t>(i) * k * G + static_cast<size_t>(g) * k + j) * kstep;
+        for (int pp = 0; pp < 2; ++pp)
+          for (int n = 0; n < C; ++n)
+            for (int e = 0; e < 8; ++e) {
+              const int ci = 16 * g + 8 * pp + e;
+              const float val = w[i][(static_cast<size_t>(j) * C + ci) * C + n];
+              const uint16_t h = Bf16Rn(val);
+              const size_t o = (static_cast<size_t>(pp) * C + n) * 8 + e;
+              blk[o] = h;
+              if (split) blk[static_cast<size_t>(2) * C * 8 + o] = Bf16Rn(val - Bf16ToF(h));
+            }
+      }
+  return total;
+}
+
+void LaunchMrfStage(const MrfStageParams& p, int C, bool split, cudaStream_t s) {
+  const size_t smem = MrfSmemBytes(C, p.T, p.S, split);
+#define B200_MRF_CASE(CC)                                  \
+  case CC:                                                 \
+    if (split) LaunchMrfT<CC, true>(p, smem, s);           \
+    else LaunchMrfT<CC, false>(p, smem, s);                \
+    break
+  switch (C) {
+    B200_MRF_CASE(16);
+    B200_MRF_CASE(32);
+    B200_MRF_CASE(64);
+    default:
+      std::fprintf(stderr, "[libbeatrice_b200] FATAL: fused MRF kernel has no C = %d form\n", C);
+      std::abort();
+  }
+#undef B200_MRF_CASE
+  B200_CHECK(cudaGetLastError());
+}
+
+void LaunchMrfZeroStream(const MrfHistBlock* d_blocks, int n_blocks, int b, cudaStream_t s) {
+  if (n_blocks <= 0) return;
+  mrf_zero_stream_kernel<<<n_blocks, 128, 0, s>>>(d_blocks, b);
+  B200_CHECK(cudaGetLastError());
+}
+
+}  // namespace b200

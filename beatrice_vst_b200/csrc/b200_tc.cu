@@ -25,6 +25,7 @@
 
 #include "b200_common.h"
 #include "b200_kernels.h"
+#include "b200_tc_common.cuh"
 
 namespace b200 {
 namespace {
@@ -32,117 +33,6 @@ namespace {
 constexpr int kTcM = 128;   // rows per CTA == TMEM lanes
 constexpr int kTcKC = 64;   // K elements per chunk
 constexpr int kPanelA = kTcM * 16;  // bytes of one 8-element K panel of the activation tile
-
-__device__ __forceinline__ uint32_t SmemAddr(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void MbarInit(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void MbarExpectTx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void MbarArrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void MbarWait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void TmaBulkLoad(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void FenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void TcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void TcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave"):
-// bits [0,14) start>>4, [16,30) LBO>>4 (next K panel), [32,46) SBO>>4 (next 8-row group),
-// [46,48) version = 1 on sm_100, [61,64) layout type = 0.
-__device__ __forceinline__ uint64_t MakeDesc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  return d;
-}
-// Instruction descriptor, kind::f16: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1),
-// both K-major (bits 15, 16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
-__device__ __forceinline__ uint32_t MakeIdesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(kTcM >> 4) << 24);
-}
-__device__ __forceinline__ void Mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void MmaCommit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void TmemLd16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// transcendental activations out of line (code size; see b200_kernels.cu)
-__device__ __noinline__ float SlowActTc(float v, int act) {
-  if (act == kActGelu) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
-  return tanhf(v);
-}
-__device__ __forceinline__ float ActTc(float v, int act) {
-  if (act == kActLrelu) return v > 0.0f ? v : 0.1f * v;
-  return SlowActTc(v, act);
-}
-
-// 8 fp32 -> 8 bf16 (round to nearest even) packed in a uint4; optionally the bf16 of the residual.
-template <bool kSplit>
-__device__ __forceinline__ void Pack8(const float* v, uint4* hi, uint4* lo) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 a = __float2bfloat16_rn(v[2 * i]), b = __float2bfloat16_rn(v[2 * i + 1]);
-    h[i] = static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
-    if (kSplit) {
-      const __nv_bfloat16 ra = __float2bfloat16_rn(v[2 * i] - __bfloat162float(a));
-      const __nv_bfloat16 rb = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(b));
-      l[i] = static_cast<uint32_t>(__bfloat16_as_ushort(ra)) | (static_cast<uint32_t>(__bfloat16_as_ushort(rb)) << 16);
-    }
-  }
-  *hi = make_uint4(h[0], h[1], h[2], h[3]);
-  if (kSplit) *lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-__device__ __forceinline__ void CpAsync16(uint32_t dst_smem, const void* src, bool valid) {
-  const uint32_t n = valid ? 16u : 0u;   // src-size 0 -> the 16 destination bytes are zero-filled
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
-}
-__device__ __forceinline__ void CpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int kPending>
-__device__ __forceinline__ void CpAsyncWait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
-}
 
 // kGather = false compiles the cp.async-only producer (no fp32 gather code): ~half the registers,
 // so three to four CTAs fit on an SM for the small-tile layers.
@@ -465,21 +355,6 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
-}
-
-uint16_t Bf16Rn(float f) {
-  uint32_t u;
-  std::memcpy(&u, &f, 4);
-  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);  // NaN
-  const uint32_t lsb = (u >> 16) & 1u;
-  u += 0x7fffu + lsb;
-  return static_cast<uint16_t>(u >> 16);
-}
-float Bf16ToF(uint16_t h) {
-  const uint32_t u = static_cast<uint32_t>(h) << 16;
-  float f;
-  std::memcpy(&f, &u, 4);
-  return f;
 }
 
 size_t TcStageBytes(bool split, int bn) {

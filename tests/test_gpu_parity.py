@@ -334,3 +334,31 @@ def test_tensor_core_precisions_against_oracle(product, oracle, model_dir, preci
         assert q_raw[s] == qs[-1][0]
         worst = max(worst, rms(got[s], ref))
     assert worst <= tol, worst
+
+
+@pytest.mark.parametrize("precision,tol", [(2, TOL_WAVE), (1, 2e-2)])
+def test_fused_mrf_stream_groups_and_reset(product, oracle, model_dir, precision, tol):
+    """The fused MRF kernel keeps its conv histories per GROUP of streams (6 / 3 / 1 streams per
+    CTA): 20 streams leave partial groups in two stages, and resetting ONE stream mid-run must
+    clear exactly that stream's history (ResetContext semantics, processor_core_2.cc:258-266)."""
+    n, hops, reset_at, victim = 20, 8, 5, 7
+    xs = signals.batch_16k(n, hops, seed0=700)
+    eng = bbatch.Engine(product, n, precision=precision)
+    assert eng.load(model_dir) == 0
+    got = []
+    for h in range(hops):
+        if h == reset_at:
+            eng.reset_stream(victim)
+        got.append(eng.process_frames(xs[h]).copy())
+    got = np.stack(got, axis=1)
+    eng.close()
+    worst = 0.0
+    for s in (0, 5, 6, 7, 8, 17, 18, 19):
+        if s == victim:
+            a, _ = _oracle_stream(oracle, model_dir, xs[:reset_at, s, :].reshape(-1))
+            b, _ = _oracle_stream(oracle, model_dir, xs[reset_at:, s, :].reshape(-1))
+            ref = np.concatenate([a, b])
+        else:
+            ref, _ = _oracle_stream(oracle, model_dir, xs[:, s, :].reshape(-1))
+        worst = max(worst, rms(got[s], ref))
+    assert worst <= tol, worst
