@@ -349,7 +349,7 @@ int WaveModel::LoadFromImage(const void* data, size_t size, int on_device) {
     bool have[4] = {};
     for (int s = 0; s < 4; ++s) {
       const int co = spec::kStageCh[s + 1];
-      if (co != 16 && co != 32 && co != 64) continue;
+      if (co != 16 && co != 32 && co != 64 && co != 128) continue;
       have[s] = true;
       for (int ki = 0; ki < 3; ++ki) {
         const float* wsrc[6];
@@ -768,24 +768,33 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
   int ring_u[4], ring_uh[4], ring_a[4][3][3], ring_y[4][3][4], ring_yh[4][3][4];
   // stages the fused MRF kernel covers (b200_mrf.cu): S streams per CTA, histories in mrf_hist
   bool fused[4] = {};
-  int fused_S[4] = {}, fused_groups[4] = {};
+  int fused_S[4] = {}, fused_groups[4] = {}, fused_nc[4] = {};
   int t = 1;
   for (int s = 0; s < 4; ++s) {
     const int c = spec::kStageCh[s + 1];
     t *= spec::kRates[s];
     {
-      int S = c >= 64 ? 6 : (c == 32 ? 3 : 1);
-      // developer overrides: BEATRICE_B200_MRF_S="s1,s2,s3" (streams per CTA of stages 1..3),
-      // BEATRICE_B200_MRF_STAGES=bitmask of stages allowed to use the fused kernel
+      // streams per CTA / cluster and cluster size (1 = the single-CTA kernel of b200_mrf.cu, > 1 = the
+      // K-split cluster kernel of b200_mrfc.cu)
+      int S = c >= 128 ? 16 : (c == 64 ? 6 : (c == 32 ? 3 : 1));
+      int NC = c >= 128 ? 4 : 1;
+      // developer overrides: BEATRICE_B200_MRF_S="s0,s1,s2,s3" (streams per CTA / cluster of stages 0..3),
+      // BEATRICE_B200_MRF_NC="n0,n1,n2,n3" (cluster sizes), BEATRICE_B200_MRF_STAGES=bitmask of stages
+      // allowed to use a fused kernel
       int mask = 0xF;
       if (const char* ev = std::getenv("BEATRICE_B200_MRF_STAGES")) mask = std::atoi(ev);
       if (const char* ev = std::getenv("BEATRICE_B200_MRF_S")) {
-        int v[3] = {0, 0, 0};
-        if (std::sscanf(ev, "%d,%d,%d", &v[0], &v[1], &v[2]) == 3 && s >= 1 && v[s - 1] > 0) S = v[s - 1];
+        int v[4] = {0, 0, 0, 0};
+        if (std::sscanf(ev, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4 && v[s] > 0) S = v[s];
       }
-      fused[s] = tcm && FusedMrfEnabled() && ((mask >> s) & 1) && m->mrf_w_ptr[with_lo ? 1 : 0][s][0] != nullptr &&
-                 MrfFusedSupported(c, t, S, with_lo);
+      if (const char* ev = std::getenv("BEATRICE_B200_MRF_NC")) {
+        int v[4] = {0, 0, 0, 0};
+        if (std::sscanf(ev, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4 && v[s] > 0) NC = v[s];
+      }
+      const bool form_ok = NC > 1 ? MrfClusterSupported(c, NC, t, S, with_lo) : MrfFusedSupported(c, t, S, with_lo);
+      fused[s] = tcm && FusedMrfEnabled() && ((mask >> s) & 1) && m->mrf_w_ptr[with_lo ? 1 : 0][s][0] != nullptr && form_ok;
       fused_S[s] = S;
+      fused_nc[s] = NC;
       fused_groups[s] = (B + S - 1) / S;
     }
     if (fused[s]) {
@@ -974,7 +983,9 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
       op.flops = 2.0 * c * c * t_stage * B * 6.0 * (3 + 7 + 11);
       op.bytes = 2.0 * 6 * 21 * c * c + 4.0 * B * t_stage * c * 4;
       op.is_mrf = true;
-      op.launch = [=](cudaStream_t st) { LaunchMrfStage(mp, c, with_lo, st); };
+      const int nc = fused_nc[s];
+      if (nc > 1) op.launch = [=](cudaStream_t st) { LaunchMrfStageCluster(mp, c, nc, with_lo, st); };
+      else op.launch = [=](cudaStream_t st) { LaunchMrfStage(mp, c, with_lo, st); };
       program.push_back(op);
       continue;
     }

@@ -36,35 +36,6 @@ constexpr int kEpiWarps = 4;     // warps 0-3: epilogue (TMEM lane quarter == wa
 constexpr int kWarpMma = 4, kWarpW = 5, kWarpH = 6;
 constexpr int kThreads = 7 * 32;
 
-__device__ __forceinline__ void TmemSt16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void TmemStWait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void TmaBulkStore(void* dst, uint32_t src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void BulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void BulkWaitRead0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void BulkWait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-__device__ __forceinline__ void SpinUntil(volatile uint32_t* cnt, uint32_t target) {
-  uint32_t spins = 0;
-  while (*cnt < target) {
-    if (++spins > (1u << 28)) __trap();
-  }
-}
-__device__ __forceinline__ int ConvDil(int i) { return (i & 1) ? 1 : (i == 0 ? 1 : (i == 2 ? 3 : 5)); }
-// sum of the dilations of convs 0..i-1 (1,1,3,1,5,1)
-__device__ __forceinline__ int DilPrefix(int i) {
-  const int pre[7] = {0, 1, 2, 5, 6, 11, 12};
-  return pre[i];
-}
-
 template <int C>
 struct MrfCfg {
   static constexpr int kG = C / 16;                       // 16-channel groups == K steps per tap

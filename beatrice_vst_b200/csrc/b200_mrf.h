@@ -45,6 +45,10 @@ size_t MrfHistElems(int C, int k, int S, int n_groups, bool split);
 // w[i] = fp32 [k][C][C] (tap, in, out) of conv i; returns bf16 elements written (out may be null)
 size_t PackMrfWeights(const float* const w[6], int k, int C, bool split, uint16_t* out);
 void LaunchMrfStage(const MrfStageParams& p, int C, bool split, cudaStream_t s);
+// K-split cluster form (b200_mrfc.cu): NC CTAs per (group, branch), same weight / history images
+bool MrfClusterSupported(int C, int NC, int T, int S, bool split);
+size_t MrfClusterSmemBytes(int C, int NC, int T, int S, bool split);
+void LaunchMrfStageCluster(const MrfStageParams& p, int C, int NC, bool split, cudaStream_t s);
 void LaunchMrfZeroStream(const MrfHistBlock* d_blocks, int n_blocks, int b, cudaStream_t s);
 
 }  // namespace b200

@@ -1,0 +1,499 @@
+// Cluster form of the fused MRF branch kernel (b200_mrf.cu): one thread-block CLUSTER of NC CTAs
+// runs one branch of one vocoder stage for a group of S streams, K-SPLIT across the cluster.
+//
+// Why: at C = 128 (stage 0, 5 rows per stream per hop, dilated history of 50 steps) the bf16
+// hi+lo input panels of one 128-row group are ~0.6 MB -- no single CTA can hold them, and one CTA
+// per (group, branch) would leave 118 of 148 SMs idle.  Here CTA `rank` of the cluster owns the
+// channel slice [rank*C/NC, (rank+1)*C/NC) of every activation:
+//   * its X / Y shared-memory panels, its conv histories and its slice of the weight stream hold
+//     only those input channels, so the implicit GEMM of a conv is split along K;
+//   * every CTA accumulates a PARTIAL D[128 rows x C] over its K slice in TMEM (tcgen05.mma, taps
+//     are descriptor row shifts exactly as in the single-CTA kernel);
+//   * the partials are reduce-scattered through DISTRIBUTED SHARED MEMORY: the epilogue warps read
+//     the columns that belong to peer q from TMEM and push them (st.shared::cluster, fp32) into
+//     q's inbox, signal q's mbarrier (release.cluster) and wait for their own inbox; the sum is
+//     taken in rank order (deterministic), bias / residual / LeakyReLU applied, and the result is
+//     -- by construction -- exactly the K slice this CTA needs as input of the next conv.
+// Nothing but the stage input u, the branch output and the conv histories touches HBM.
+#include <cstring>
+#include <vector>
+
+#include "b200_common.h"
+#include "b200_mrf.h"
+#include "b200_tc_common.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int kNst = 4;          // weight ring stages
+constexpr int kEpiWarps = 4;     // warps 0-3: epilogue (TMEM lane quarter == warp)
+constexpr int kWarpMma = 4, kWarpW = 5, kWarpH = 6;
+constexpr int kThreads = 7 * 32;
+constexpr int kBars = 48;        // mbarrier slots reserved at the front of shared memory
+constexpr int kHdr = 8 * kBars + 16;
+
+__host__ __device__ constexpr int NkForC(int C) { return C >= 128 ? 1 : (C >= 64 ? 2 : 4); }
+
+template <int C, int NC, bool kSplit>
+__global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_constant__ MrfStageParams p) {
+  constexpr int Cs = C / NC;                  // channels owned by this CTA (K slice and output slice)
+  constexpr int Gs = Cs / 16;                 // own 16-channel groups == K steps per tap
+  constexpr int PANs = Cs / 8;                // own 8-channel K panels
+  constexpr int PAN = C / 8;                  // panels of the whole activation (history image)
+  constexpr int NK = NkForC(C);               // K steps per weight chunk
+  constexpr int P = kSplit ? 2 : 1;
+  constexpr uint32_t kKstepBytes = P * C * 32;
+  constexpr uint32_t kChunkBytes = NK * kKstepBytes;
+  constexpr uint32_t kBoxRow = (Cs + 4) * 4;  // inbox row pitch (bytes); +16 keeps 16-byte row accesses conflict free
+  static_assert(Cs % 16 == 0, "channel slice must be a multiple of one K step");
+  extern __shared__ __align__(1024) uint8_t smem[];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = static_cast<int>(ClusterCtaRank());
+  const MrfBranchDesc& br = p.br[2 - blockIdx.y];   // longest branch (k = 11) is scheduled first
+  const int k = br.k, T = p.T, S = p.S, MT = p.MT;
+  const int group = blockIdx.x / NC;
+  const int HX = (k - 1) * 5, HY = k - 1;            // history rows (time steps) in front of X / Y
+  const int rows_valid = S * T;
+  const int rows8 = (rows_valid + 7) & ~7;
+  const int RX = HX * S + rows8, RY = HY * S + rows8;
+  const int frame = *p.frame;
+
+  // ---- shared memory carve-up ----
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t bar0 = SmemAddr(bars);
+  const uint32_t bar_w_full = bar0, bar_w_empty = bar0 + 8 * kNst, bar_hist = bar0 + 16 * kNst, bar_free = bar_hist + 16,
+                 bar_box_full = bar_free + 16, bar_box_free = bar_box_full + 8 * kEpiWarps,
+                 bar_in = bar_box_free + 8 * kEpiWarps, bar_acc = bar_in + 8 * MT * Gs;
+  const int n_bars = 2 * kNst + 4 + 2 * kEpiWarps + MT * Gs + MT;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * kBars);
+  volatile uint32_t* in_cnt = reinterpret_cast<volatile uint32_t*>(smem + 8 * kBars + 4);   // += 1 per epilogue warp per conv input
+  volatile uint32_t* acc_cnt = reinterpret_cast<volatile uint32_t*>(smem + 8 * kBars + 8);  // += 1 per conv whose MMAs retired
+  float* bias_s = reinterpret_cast<float*>(smem + kHdr);          // [6][Cs]
+  const uint32_t x_off = (kHdr + 6 * Cs * 4 + 127) / 128 * 128;
+  const uint32_t x_pstride = static_cast<uint32_t>(RX) * 16, y_pstride = static_cast<uint32_t>(RY) * 16;
+  const uint32_t x_plane = PANs * x_pstride, y_plane = PANs * y_pstride;
+  const uint32_t y_off = x_off + P * x_plane;
+  const uint32_t box_off = (y_off + P * y_plane + 127) / 128 * 128;
+  const uint32_t box_slot = static_cast<uint32_t>(rows_valid) * kBoxRow;
+  const uint32_t w_off = (box_off + (NC - 1) * box_slot + 2048 + 127) / 128 * 128;
+  const uint32_t smem_base = SmemAddr(smem);
+  const uint32_t x_base = smem_base + x_off, y_base = smem_base + y_off, box_base = smem_base + box_off,
+                 w_base = smem_base + w_off;
+
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(2 * MT * C + MT * Cs)) tmem_cols <<= 1;
+
+  for (int i = tid; i < 6 * Cs; i += kThreads) bias_s[i] = __ldg(br.bias + (i / Cs) * C + rank * Cs + (i % Cs));
+  if (tid == 0) {
+    *in_cnt = 0;
+    *acc_cnt = 0;
+    for (int i = 0; i < n_bars; ++i) {
+      const uint32_t b = bar0 + 8 * i;
+      uint32_t count = 1;
+      if (b >= bar_in && b < bar_acc) count = kEpiWarps;
+      if (b >= bar_box_full && b < bar_in) count = NC - 1;
+      MbarInit(b, count);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kWarpMma) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemAddr(tmem_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  TcFenceBefore();
+  __syncthreads();
+  ClusterSyncAll();   // every CTA's mbarriers exist before any peer signals them
+  TcFenceAfter();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const size_t hist_unit = static_cast<size_t>(p.n_groups) * P * PAN * S * 8 * (k - 1);   // elements per unit dilation
+
+  if (warp < kEpiWarps) {
+    // =========================== epilogue warps ===========================
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t x_col0 = 2 * MT * C;   // fp32 residual stream of the own channel slice
+    // ---- prologue: u -> TMEM (fp32 residual stream) and lrelu(u) -> X new rows ----
+    for (int m = 0; m < MT; ++m) {
+      const int r = m * 128 + tid;
+      const int t = r / S, s = r - t * S;
+      const int b = group * S + s;
+      const bool exists = r < rows_valid;
+      const bool valid = exists && b < p.B;
+      const float* urow = p.u + (static_cast<size_t>(b) * p.u_slots * T + (frame % p.u_slots) * T + t) * C + rank * Cs;
+      const uint32_t srow = x_base + static_cast<uint32_t>(HX * S + r) * 16;
+#pragma unroll 1
+      for (int g = 0; g < Gs; ++g) {
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) f = __ldg(reinterpret_cast<const float4*>(urow + 16 * g + 4 * q));
+          v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+        }
+        uint32_t raw[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) raw[e] = __float_as_uint(v[e]);
+        TmemSt16(t_lane + x_col0 + m * Cs + 16 * g, raw);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.0f ? v[e] : 0.1f * v[e];
+        uint4 h0, l0, h1, l1;
+        Pack8<kSplit>(v, &h0, &l0);
+        Pack8<kSplit>(v + 8, &h1, &l1);
+        if (exists) {
+          const uint32_t a0 = srow + (2 * g) * x_pstride;
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(h0.x), "r"(h0.y), "r"(h0.z), "r"(h0.w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + x_pstride), "r"(h1.x), "r"(h1.y), "r"(h1.z), "r"(h1.w) : "memory");
+          if (kSplit) {
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + x_plane), "r"(l0.x), "r"(l0.y), "r"(l0.z), "r"(l0.w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + x_plane + x_pstride), "r"(l1.x), "r"(l1.y), "r"(l1.z), "r"(l1.w) : "memory");
+          }
+        }
+        TmemStWait();
+        FenceProxyAsync();
+        TcFenceBefore();
+        __syncwarp();
+        if (lane == 0) MbarArrive(bar_in + 8 * (m * Gs + g));
+      }
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicAdd(const_cast<uint32_t*>(in_cnt), 1u);
+    // ---- the six convs ----
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i) {
+      const bool is_c1 = (i & 1) == 0;
+      const bool last = i == 5;
+      // destination of lrelu(.): the OTHER buffer (c1 -> Y, c2 -> X)
+      const uint32_t d_base = is_c1 ? y_base : x_base;
+      const uint32_t d_pstride = is_c1 ? y_pstride : x_pstride, d_plane = is_c1 ? y_plane : x_plane;
+      const int d_hmax = is_c1 ? HY : HX;
+      const float* bias = bias_s + i * Cs;
+      if (i >= 1 && !last) MbarWait(bar_free + 8 * ((i + 1) & 1), ((i - 1) >> 1) & 1);
+      // the peers have consumed what this warp pushed for conv i-1
+      if (i >= 1) MbarWaitCluster(bar_box_free + 8 * warp, (i - 1) & 1);
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const int r = m * 128 + tid;
+        const int t = r / S, s = r - t * S;
+        const int b = group * S + s;
+        const bool exists = r < rows_valid;
+        const bool valid = exists && b < p.B;
+        MbarWait(bar_acc + 8 * m, i & 1);
+        TcFenceAfter();
+        if (m == MT - 1 && tid == 0) atomicAdd(const_cast<uint32_t*>(acc_cnt), 1u);   // conv i's MMAs have all retired
+        const uint32_t dcol = t_lane + ((i & 1) * MT + m) * C;
+        // ---- reduce-scatter, push half: the columns of every peer go to that peer's inbox ----
+#pragma unroll 1
+        for (int q = 1; q < NC; ++q) {
+          const int pr = (rank + q) % NC;
+          const int slot = rank < pr ? rank : rank - 1;
+          const uint32_t dst = MapToCta(box_base + slot * box_slot + static_cast<uint32_t>(exists ? r : 0) * kBoxRow, pr);
+#pragma unroll 1
+          for (int h = 0; h < Gs; ++h) {
+            uint32_t raw[16];
+            TmemLd16(dcol + pr * Cs + 16 * h, raw);
+            if (exists) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                StCluster16(dst + 64 * h + 16 * e, __uint_as_float(raw[4 * e]), __uint_as_float(raw[4 * e + 1]),
+                            __uint_as_float(raw[4 * e + 2]), __uint_as_float(raw[4 * e + 3]));
+            }
+          }
+        }
+        FenceCluster();
+        __syncwarp();
+        if (lane == 0) {
+          for (int q = 1; q < NC; ++q) MbarArriveCluster(MapToCta(bar_box_full + 8 * warp, (rank + q) % NC));
+        }
+        // ---- pull half: own columns + the peers' partials, summed in rank order ----
+        MbarWaitCluster(bar_box_full + 8 * warp, (i * MT + m) & 1);
+        const uint32_t xcol = t_lane + x_col0 + m * Cs;
+        const uint32_t srow = d_base + static_cast<uint32_t>(d_hmax * S + r) * 16;
+        const uint8_t* box_row = smem + box_off + static_cast<size_t>(exists ? r : 0) * kBoxRow;
+        float* orow = br.out + (static_cast<size_t>(b) * br.out_slots * T + (frame % br.out_slots) * T + t) * C + rank * Cs;
+#pragma unroll 1
+        for (int g = 0; g < Gs; ++g) {
+          uint32_t raw[16];
+          TmemLd16(dcol + rank * Cs + 16 * g, raw);
+          float v[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = 0.0f;
+#pragma unroll
+          for (int src = 0; src < NC; ++src) {
+            if (src == rank) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] += __uint_as_float(raw[e]);
+            } else {
+              const int slot = src < rank ? src : src - 1;
+              const float4* bp = reinterpret_cast<const float4*>(box_row + slot * box_slot + 64 * g);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 f = bp[e];
+                v[4 * e] += f.x; v[4 * e + 1] += f.y; v[4 * e + 2] += f.z; v[4 * e + 3] += f.w;
+              }
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] += bias[16 * g + e];
+          if (!is_c1) {
+            uint32_t xr[16];
+            TmemLd16(xcol + 16 * g, xr);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] += __uint_as_float(xr[e]);
+            if (!last) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) xr[e] = __float_as_uint(v[e]);
+              TmemSt16(xcol + 16 * g, xr);
+            } else if (valid) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(orow + 16 * g + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+          }
+          if (!last) {
+            if (!valid) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = 0.0f;
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.0f ? v[e] : 0.1f * v[e];
+            uint4 h0, l0, h1, l1;
+            Pack8<kSplit>(v, &h0, &l0);
+            Pack8<kSplit>(v + 8, &h1, &l1);
+            if (exists) {
+              const uint32_t a0 = srow + (2 * g) * d_pstride;
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(h0.x), "r"(h0.y), "r"(h0.z), "r"(h0.w) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + d_pstride), "r"(h1.x), "r"(h1.y), "r"(h1.z), "r"(h1.w) : "memory");
+              if (kSplit) {
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + d_plane), "r"(l0.x), "r"(l0.y), "r"(l0.z), "r"(l0.w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + d_plane + d_pstride), "r"(l1.x), "r"(l1.y), "r"(l1.z), "r"(l1.w) : "memory");
+              }
+            }
+            if (!is_c1) TmemStWait();
+            FenceProxyAsync();
+            TcFenceBefore();
+            __syncwarp();
+            if (lane == 0) MbarArrive(bar_in + 8 * (m * Gs + g));
+          }
+        }
+      }
+      if (!last) {
+        // this warp's inbox rows are consumed: the peers may push conv i+1
+        __syncwarp();
+        if (lane == 0) {
+          for (int q = 1; q < NC; ++q) MbarArriveCluster(MapToCta(bar_box_free + 8 * warp, (rank + q) % NC));
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atomicAdd(const_cast<uint32_t*>(in_cnt), 1u);
+      }
+    }
+  } else if (warp == kWarpMma) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc = MakeIdesc(C);
+      uint32_t cc = 0;
+#pragma unroll 1
+      for (int i = 0; i < 6; ++i) {
+        const int buf = i & 1, dil = ConvDil(i);
+        const int hmax = buf ? HY : HX;
+        const uint32_t bbase = buf ? y_base : x_base, pstride = buf ? y_pstride : x_pstride, plane = buf ? y_plane : x_plane;
+        MbarWait(bar_hist + 8 * buf, (i >> 1) & 1);
+#pragma unroll 1
+        for (int m = 0; m < MT; ++m) {
+          const uint32_t dcol = tmem_base + ((i & 1) * MT + m) * C;
+          int ks = 0;
+#pragma unroll 1
+          for (int g = 0; g < Gs; ++g) {
+            MbarWait(bar_in + 8 * (m * Gs + g), i & 1);
+            TcFenceAfter();
+#pragma unroll 1
+            for (int j = 0; j < k; ++j) {
+              const int within = ks % NK;
+              const uint32_t stage = cc % kNst;
+              if (within == 0) {
+                MbarWait(bar_w_full + 8 * stage, (cc / kNst) & 1);
+                TcFenceAfter();
+              }
+              const int row0 = (hmax - (k - 1 - j) * dil) * S + 128 * m;
+              const uint32_t a_hi = bbase + (2 * g) * pstride + static_cast<uint32_t>(row0) * 16;
+              const uint32_t w_hi = w_base + stage * kChunkBytes + within * kKstepBytes;
+              const uint64_t ah = MakeDesc(a_hi, pstride, 128);
+              const uint64_t wh = MakeDesc(w_hi, C * 16, 128);
+              Mma(dcol, ah, wh, idesc, ks > 0 ? 1u : 0u);
+              if (kSplit) {
+                const uint64_t al = MakeDesc(a_hi + plane, pstride, 128);
+                const uint64_t wl = MakeDesc(w_hi + C * 32, C * 16, 128);
+                Mma(dcol, ah, wl, idesc, 1u);
+                Mma(dcol, al, wh, idesc, 1u);
+              }
+              ++ks;
+              if (within == NK - 1 || ks == k * Gs) {
+                MmaCommit(bar_w_empty + 8 * stage);
+                ++cc;
+              }
+            }
+          }
+          MmaCommit(bar_acc + 8 * m);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kWarpW) {
+    // =========================== weight producer ===========================
+    if (lane == 0) {
+      const int ksteps = k * Gs;                     // own K slice
+      const int ksteps_conv = k * (C / 16);          // whole conv
+      const int chunks = (ksteps + NK - 1) / NK;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(br.w);
+      uint32_t cc = 0;
+#pragma unroll 1
+      for (int i = 0; i < 6; ++i) {
+        const uint8_t* wconv = wsrc + (static_cast<size_t>(i) * ksteps_conv + static_cast<size_t>(rank) * ksteps) * kKstepBytes;
+#pragma unroll 1
+        for (int m = 0; m < MT; ++m) {
+#pragma unroll 1
+          for (int c = 0; c < chunks; ++c) {
+            const uint32_t stage = cc % kNst, round = cc / kNst;
+            if (round > 0) MbarWait(bar_w_empty + 8 * stage, (round - 1) & 1);
+            const int n = min(NK, ksteps - c * NK);
+            const uint32_t bytes = n * kKstepBytes;
+            MbarExpectTx(bar_w_full + 8 * stage, bytes);
+            TmaBulkLoad(w_base + stage * kChunkBytes, wconv + static_cast<size_t>(c) * kChunkBytes, bytes, bar_w_full + 8 * stage);
+            ++cc;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kWarpH) {
+    // =========================== history mover ===========================
+    if (lane == 0) {
+      auto hist_ptr = [&](int i, int H) {
+        // conv i block: [group][plane][panel][H*S rows][8]; this CTA moves its own panels only
+        return br.hist + hist_unit * DilPrefix(i) + static_cast<size_t>(group) * P * PAN * H * S * 8;
+      };
+      auto load_hist = [&](int i) {
+        const int buf = i & 1, H = (k - 1) * ConvDil(i);
+        const int hmax = buf ? HY : HX;
+        const uint32_t bbase = buf ? y_base : x_base, pstride = buf ? y_pstride : x_pstride, plane = buf ? y_plane : x_plane;
+        const uint32_t bytes = static_cast<uint32_t>(H) * S * 16;
+        const uint16_t* src = hist_ptr(i, H);
+        MbarExpectTx(bar_hist + 8 * buf, bytes * P * PANs);
+        for (int pl = 0; pl < P; ++pl)
+          for (int pn = 0; pn < PANs; ++pn)
+            TmaBulkLoad(bbase + pl * plane + pn * pstride + static_cast<uint32_t>((hmax - H) * S) * 16,
+                        src + static_cast<size_t>(pl * PAN + rank * PANs + pn) * H * S * 8, bytes, bar_hist + 8 * buf);
+      };
+      load_hist(0);
+      load_hist(1);
+#pragma unroll 1
+      for (int i = 0; i < 6; ++i) {
+        const int buf = i & 1, H = (k - 1) * ConvDil(i);
+        const int hmax = buf ? HY : HX;
+        const uint32_t bbase = buf ? y_base : x_base, pstride = buf ? y_pstride : x_pstride, plane = buf ? y_plane : x_plane;
+        // input of conv i complete: history landed + every new row written by the epilogue warps
+        MbarWait(bar_hist + 8 * buf, (i >> 1) & 1);
+        SpinUntil(in_cnt, static_cast<uint32_t>(kEpiWarps * (i + 1)));
+        __threadfence_block();
+        FenceProxyAsync();
+        {
+          const uint32_t bytes = static_cast<uint32_t>(H) * S * 16;
+          uint16_t* dst = const_cast<uint16_t*>(hist_ptr(i, H));
+          for (int pl = 0; pl < P; ++pl)
+            for (int pn = 0; pn < PANs; ++pn)
+              TmaBulkStore(dst + static_cast<size_t>(pl * PAN + rank * PANs + pn) * H * S * 8,
+                           bbase + pl * plane + pn * pstride + static_cast<uint32_t>((hmax + T - H) * S) * 16, bytes);
+          BulkCommit();
+          BulkWaitRead0();
+        }
+        // conv i's MMAs done reading the buffer
+        SpinUntil(acc_cnt, static_cast<uint32_t>(i + 1));
+        if (i + 2 < 6) load_hist(i + 2);
+        MbarArrive(bar_free + 8 * buf);
+      }
+      BulkWait0();
+    }
+    __syncwarp();
+  }
+
+  TcFenceBefore();
+  __syncthreads();
+  ClusterSyncAll();   // no CTA leaves while a peer may still write its inbox or signal its barriers
+  if (warp == kWarpMma) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+template <int C, int NC, bool kSplit>
+void LaunchClusterT(const MrfStageParams& p, size_t smem, cudaStream_t s) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  B200_CHECK(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    B200_CHECK(cudaFuncSetAttribute(mrf_cluster_kernel<C, NC, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[dev & 63] = true;
+  }
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(p.n_groups * NC, 3, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = NC;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  B200_CHECK(cudaLaunchKernelEx(&cfg, mrf_cluster_kernel<C, NC, kSplit>, p));
+}
+
+}  // namespace
+
+size_t MrfClusterSmemBytes(int C, int NC, int T, int S, bool split) {
+  const int P = split ? 2 : 1, Cs = C / NC, PANs = Cs / 8;
+  const int k = 11;   // the launch is sized for its largest branch
+  const int rows_valid = S * T, rows8 = (rows_valid + 7) & ~7;
+  const size_t RX = static_cast<size_t>((k - 1) * 5) * S + rows8, RY = static_cast<size_t>(k - 1) * S + rows8;
+  size_t off = (kHdr + 6 * Cs * 4 + 127) / 128 * 128;
+  off += P * PANs * RX * 16;
+  off += P * PANs * RY * 16;
+  off = (off + 127) / 128 * 128;
+  off += static_cast<size_t>(NC - 1) * rows_valid * (Cs + 4) * 4 + 2048;   // inbox (+ slack the last tile's MMA may read into)
+  off = (off + 127) / 128 * 128;
+  off += static_cast<size_t>(kNst) * NkForC(C) * P * C * 32;
+  return off;
+}
+
+bool MrfClusterSupported(int C, int NC, int T, int S, bool split) {
+  if (NC < 2 || NC > 8 || C % (16 * NC) != 0) return false;
+  if (!((C == 128 && NC == 4) || (C == 64 && NC == 2) || (C == 64 && NC == 4))) return false;   // instantiated forms
+  const int MT = (S * T + 127) / 128;
+  const int Cs = C / NC;
+  if (2 * MT * C + MT * Cs > 512) return false;
+  if (2 * kNst + 4 + 2 * kEpiWarps + MT * (Cs / 16) + MT > kBars) return false;
+  return MrfClusterSmemBytes(C, NC, T, S, split) <= 227 * 1024;
+}
+
+void LaunchMrfStageCluster(const MrfStageParams& p, int C, int NC, bool split, cudaStream_t s) {
+  const size_t smem = MrfClusterSmemBytes(C, NC, p.T, p.S, split);
+#define B200_MRFC_CASE(CC, NN)                                      \
+  if (C == CC && NC == NN) {                                        \
+    if (split) LaunchClusterT<CC, NN, true>(p, smem, s);            \
+    else LaunchClusterT<CC, NN, false>(p, smem, s);                 \
+    return;                                                         \
+  }
+  B200_MRFC_CASE(128, 4)
+  B200_MRFC_CASE(64, 2)
+  B200_MRFC_CASE(64, 4)
+#undef B200_MRFC_CASE
+  std::fprintf(stderr, "[libbeatrice_b200] FATAL: cluster MRF kernel has no C = %d / NC = %d form\n", C, NC);
+  std::abort();
+}
+
+}  // namespace b200

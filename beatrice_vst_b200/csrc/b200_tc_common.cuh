@@ -85,6 +85,73 @@ __device__ __forceinline__ void TmemLd16(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void TmemSt16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void TmemStWait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void TmaBulkStore(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void BulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void BulkWaitRead0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void BulkWait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void SpinUntil(volatile uint32_t* cnt, uint32_t target) {
+  uint32_t spins = 0;
+  while (*cnt < target) {
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ int ConvDil(int i) { return (i & 1) ? 1 : (i == 0 ? 1 : (i == 2 ? 3 : 5)); }
+// sum of the dilations of convs 0..i-1 (1,1,3,1,5,1)
+__device__ __forceinline__ int DilPrefix(int i) {
+  const int pre[7] = {0, 1, 2, 5, 6, 11, 12};
+  return pre[i];
+}
+
+
+// ---- thread-block cluster / distributed shared memory helpers ----
+__device__ __forceinline__ uint32_t ClusterCtaRank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t MapToCta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void StCluster16(uint32_t cluster_addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void MbarArriveCluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void MbarWaitCluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P2;\n"
+      "LAB_WAIT_CL:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P2, [%0], %1;\n"
+      "@P2 bra DONE_CL;\n"
+      "bra LAB_WAIT_CL;\n"
+      "DONE_CL:\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void FenceCluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void ClusterSyncAll() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // transcendental activations out of line (code size; see b200_kernels.cu)
 __device__ __noinline__ float SlowActTc(float v, int act) {
   if (act == kActGelu) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
