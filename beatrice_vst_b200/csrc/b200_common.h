@@ -21,6 +21,52 @@
 
 namespace b200 {
 
+// Programmatic dependent launch: the kernel may begin (prologue up to its griddepcontrol.wait)
+// while the previous kernel on `s` drains.  BEATRICE_B200_NO_PDL=1 turns the attribute off.
+inline bool PdlEnabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("BEATRICE_B200_NO_PDL");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline void LaunchPdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x,
+                      Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  unsigned n = 0;
+  if (PdlEnabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  B200_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
+#ifdef __CUDACC__
+// ---- programmatic dependent launch (PDL), device side ----
+// A kernel launched with LaunchPdl may start while its predecessor on the stream is still
+// running: everything before PdlWait() must touch only data no in-flight predecessor writes
+// (weights, biases, barrier / TMEM setup); PdlWait() returns when the predecessor grid has
+// completed and its memory is visible.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void PdlLaunchDependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void PdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 // reference lib/beatricelib/beatrice.h:10-28
 constexpr int kInHop = 160;
 constexpr int kOutHop = 240;

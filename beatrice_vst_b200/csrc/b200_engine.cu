@@ -580,6 +580,13 @@ std::function<void(cudaStream_t)> GemmLauncher(const ConvDesc* dp, const ConvDes
   return [=](cudaStream_t s) { LaunchConvGemm(dp, h, nz, B, frame, s); };
 }
 
+// developer aid: BEATRICE_B200_TC_TRACE=<substring of an op name> makes that op's kernel print a timeline
+ConvDesc Traced(ConvDesc h, const std::string& op_name) {
+  const char* e = std::getenv("BEATRICE_B200_TC_TRACE");
+  h.trace = (e && e[0] && op_name.find(e) != std::string::npos) ? 1 : 0;
+  return h;
+}
+
 Ring FlatRing(float* base, int T, int C) {
   Ring r;
   r.base = base;
@@ -672,7 +679,7 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     program.push_back(op);
   }
   for (int i = 0; i < 6; ++i) {
-    const ConvDesc h = db.host[conv_idx[i]];
+    const ConvDesc h = Traced(db.host[conv_idx[i]], std::string(tag) + ".fe" + std::to_string(i));
     const ConvDesc* dp = dd + conv_idx[i];
     Op op;
     op.name = std::string(tag) + ".fe" + std::to_string(i);
@@ -705,7 +712,7 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     on.bytes = 8.0 * B * m->width;
     on.launch = [=](cudaStream_t s) { LaunchNorm(nd, Bn, frame, s); };
     program.push_back(on);
-    const ConvDesc h = db.host[res_idx[r]];
+    const ConvDesc h = Traced(db.host[res_idx[r]], std::string(tag) + ".res" + std::to_string(r) + ".conv");
     const ConvDesc* dp = dd + res_idx[r];
     Op oc;
     oc.name = std::string(tag) + ".res" + std::to_string(r) + ".conv";
@@ -715,7 +722,7 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     program.push_back(oc);
   }
   {
-    const ConvDesc h = db.host[head_idx];
+    const ConvDesc h = Traced(db.host[head_idx], std::string(tag) + ".head");
     const ConvDesc* dp = dd + head_idx;
     Op op;
     op.name = std::string(tag) + ".head";
@@ -946,7 +953,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
       op.bytes += ConvBytes(db.host[idx + z], B);
     }
     op.is_mrf = mrf;
-    const ConvDesc h = db.host[idx];
+    const ConvDesc h = Traced(db.host[idx], name);
     const ConvDesc* dp = dd + idx;
     op.launch = GemmLauncher(dp, h, nz, Bn, frame, tc, true);
     program.push_back(op);
@@ -978,6 +985,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
       mp.B = B;
       mp.n_groups = fused_groups[s];
       mp.frame = frame;
+      if (const char* ev = std::getenv("BEATRICE_B200_MRF_TRACE")) mp.trace = std::atoi(ev);
       Op op;
       op.name = "wave.mrf" + std::to_string(s) + ".fused";
       op.flops = 2.0 * c * c * t_stage * B * 6.0 * (3 + 7 + 11);

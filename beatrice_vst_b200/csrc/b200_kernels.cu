@@ -221,6 +221,8 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const ConvDesc* __restri
 // One thread per output element; for the two layers that are not GEMM shaped
 // (front-end conv with C_in = 1, post conv with C_out = 1).
 __global__ void direct_conv_kernel(const ConvDesc* __restrict__ descs, int B, const int* __restrict__ frame_ptr) {
+  PdlWait();
+  PdlLaunchDependents();
   const ConvDesc d = descs[0];
   const int frame = *frame_ptr;
   const long long total = static_cast<long long>(B) * d.T * d.N;
@@ -261,6 +263,8 @@ __global__ void direct_conv_kernel(const ConvDesc* __restrict__ descs, int B, co
 // are 64 bytes so every load is a float4; neighbouring threads share 6 of their 7 rows (L1).
 __global__ void __launch_bounds__(128) post_conv_kernel(const ConvDesc* __restrict__ descs, int B,
                                                          const int* __restrict__ frame_ptr) {
+  PdlWait();
+  PdlLaunchDependents();
   __shared__ float ws[7 * 16];
   const ConvDesc d = descs[0];
   if (threadIdx.x < 7 * 16) ws[threadIdx.x] = __ldg(d.w + threadIdx.x);
@@ -311,6 +315,8 @@ __device__ __forceinline__ float WarpSum(float v) {
 // y = GELU(ChanNorm(x)*gamma+beta); one warp per (stream, row); channel statistics by
 // warp-shuffle reduction, two-pass like the oracle (mean, then centred variance).
 __global__ void channorm_gelu_kernel(NormDesc d, int B, const int* __restrict__ frame_ptr) {
+  PdlWait();
+  PdlLaunchDependents();
   const int frame = *frame_ptr;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -355,6 +361,8 @@ __global__ void channorm_gelu_kernel(NormDesc d, int B, const int* __restrict__ 
 
 __global__ void ingest_kernel(const float* __restrict__ staging, float* __restrict__ ring, int slots, int TC,
                               long long total, const int* __restrict__ frame_ptr) {
+  PdlWait();
+  PdlLaunchDependents();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int frame = *frame_ptr;
@@ -364,6 +372,8 @@ __global__ void ingest_kernel(const float* __restrict__ staging, float* __restri
 }
 
 __global__ void advance_kernel(int* frame) {
+  PdlWait();
+  PdlLaunchDependents();
   // wrap at a multiple of every slot count in use (slots <= 64 by construction: lcm-free
   // choice 2^20 * 3*5*7*9*11*13 would overflow; slots are recomputed modulo so any wrap point
   // that is a common multiple works -- use 720720 * 1024 (lcm(1..16) * 1024) < 2^31)
@@ -374,6 +384,8 @@ __global__ void advance_kernel(int* frame) {
 __global__ void pitch_argmax_kernel(const float* __restrict__ head, int bins, const int* __restrict__ min_q,
                                     const int* __restrict__ max_q, int* __restrict__ q, float* __restrict__ feat,
                                     int B) {
+  PdlWait();
+  PdlLaunchDependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= B) return;
@@ -407,6 +419,8 @@ __global__ void pitch_argmax_kernel(const float* __restrict__ head, int bins, co
 // round-to-nearest mul/add so that no FMA contraction changes a rounding the CPU makes.
 __global__ void pitch_transform_kernel(const int* __restrict__ q_in, const PitchParams* __restrict__ params,
                                        int bins, int* __restrict__ q_out, int B) {
+  PdlWait();
+  PdlLaunchDependents();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const PitchParams p = params[b];
@@ -449,6 +463,8 @@ __global__ void __launch_bounds__(256) cond_kernel(const float* __restrict__ pho
                                                    const float* __restrict__ spk, const float* __restrict__ formant,
                                                    float* __restrict__ ring, int slots,
                                                    const int* __restrict__ frame_ptr) {
+  PdlWait();
+  PdlLaunchDependents();
   __shared__ float ph[256];
   __shared__ float ft[kPitchFeatures];
   const int b = blockIdx.x, c = threadIdx.x;
@@ -475,6 +491,8 @@ __global__ void __launch_bounds__(kCodebookSize) vq_kernel(const float* __restri
                                                            float* __restrict__ phone_out,
                                                            const float* const* __restrict__ codebooks,
                                                            const int* __restrict__ n_neighbors, int C) {
+  PdlWait();
+  PdlLaunchDependents();
   __shared__ float ph[256];
   __shared__ float dist[kCodebookSize];
   __shared__ float red_v[kCodebookSize / 32];
@@ -636,7 +654,7 @@ void LaunchConvGemm(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B, 
 
 void LaunchDirectConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int* d_frame, cudaStream_t s) {
   const long long total = static_cast<long long>(B) * h0.T * h0.N;
-  direct_conv_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, s>>>(d_desc, B, d_frame);
+  LaunchPdl(direct_conv_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, s, 1, d_desc, B, d_frame);
   B200_CHECK(cudaGetLastError());
 }
 
@@ -646,49 +664,49 @@ void LaunchPostConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int
     return;
   }
   const int total = B * h0.T;
-  post_conv_kernel<<<(total + 127) / 128, 128, 0, s>>>(d_desc, B, d_frame);
+  LaunchPdl(post_conv_kernel, dim3((total + 127) / 128), dim3(128), 0, s, 1, d_desc, B, d_frame);
   B200_CHECK(cudaGetLastError());
 }
 
 void LaunchNorm(const NormDesc& d, int B, const int* d_frame, cudaStream_t s) {
   const int warps = B * d.T;
-  channorm_gelu_kernel<<<(warps * 32 + 127) / 128, 128, 0, s>>>(d, B, d_frame);
+  LaunchPdl(channorm_gelu_kernel, dim3((warps * 32 + 127) / 128), dim3(128), 0, s, 1, d, B, d_frame);
   B200_CHECK(cudaGetLastError());
 }
 
 void LaunchIngest(const float* staging, float* ring, int slots, int T, int C, int B, const int* d_frame,
                   cudaStream_t s) {
   const long long total = static_cast<long long>(B) * T * C;
-  ingest_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(staging, ring, slots, T * C, total, d_frame);
+  LaunchPdl(ingest_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, 1, staging, ring, slots, T * C, total, d_frame);
   B200_CHECK(cudaGetLastError());
 }
 
 void LaunchAdvance(int* d_frame, cudaStream_t s) {
-  advance_kernel<<<1, 1, 0, s>>>(d_frame);
+  LaunchPdl(advance_kernel, dim3(1), dim3(1), 0, s, 1, d_frame);
   B200_CHECK(cudaGetLastError());
 }
 
 void LaunchPitchArgmax(const float* head, int bins, const int* min_q, const int* max_q, int* q, float* feat, int B,
                        cudaStream_t s) {
-  pitch_argmax_kernel<<<(B * 32 + 127) / 128, 128, 0, s>>>(head, bins, min_q, max_q, q, feat, B);
+  LaunchPdl(pitch_argmax_kernel, dim3((B * 32 + 127) / 128), dim3(128), 0, s, 1, head, bins, min_q, max_q, q, feat, B);
   B200_CHECK(cudaGetLastError());
 }
 
 void LaunchPitchTransform(const int* q_in, const PitchParams* params, int bins, int* q_out, int B, cudaStream_t s) {
-  pitch_transform_kernel<<<(B + 127) / 128, 128, 0, s>>>(q_in, params, bins, q_out, B);
+  LaunchPdl(pitch_transform_kernel, dim3((B + 127) / 128), dim3(128), 0, s, 1, q_in, params, bins, q_out, B);
   B200_CHECK(cudaGetLastError());
 }
 
 void LaunchCond(const float* phone, int P, const int* q, int bins, const float* feat, const float* We,
                 const float* be, const float* pitch_emb, const float* Wf, const float* spk, const float* formant,
                 float* ring, int slots, int B, const int* d_frame, cudaStream_t s) {
-  cond_kernel<<<B, kHidden, 0, s>>>(phone, P, q, bins, feat, We, be, pitch_emb, Wf, spk, formant, ring, slots, d_frame);
+  LaunchPdl(cond_kernel, dim3(B), dim3(kHidden), 0, s, 1, phone, P, q, bins, feat, We, be, pitch_emb, Wf, spk, formant, ring, slots, d_frame);
   B200_CHECK(cudaGetLastError());
 }
 
 void LaunchVq(const float* phone_in, float* phone_out, const float* const* codebooks, const int* n_neighbors, int C,
               int B, cudaStream_t s) {
-  vq_kernel<<<B, kCodebookSize, 0, s>>>(phone_in, phone_out, codebooks, n_neighbors, C);
+  LaunchPdl(vq_kernel, dim3(B), dim3(kCodebookSize), 0, s, 1, phone_in, phone_out, codebooks, n_neighbors, C);
   B200_CHECK(cudaGetLastError());
 }
 

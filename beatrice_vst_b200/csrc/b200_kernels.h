@@ -54,6 +54,7 @@ struct ConvDesc {
   uint16_t* yl;
   int yh_slots;
   int yh_act;
+  int trace;          // developer aid (BEATRICE_B200_TC_TRACE=<op name>): CTA (0,0,0) prints its timeline
 };
 
 struct NormDesc {  // y = GELU(ChanNorm(x) * gamma + beta), one row per warp

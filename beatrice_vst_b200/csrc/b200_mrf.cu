@@ -111,6 +111,10 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
   if (warp < kEpiWarps) {
     // =========================== epilogue warps ===========================
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    // Everything up to here (barriers, TMEM, bias, and in the other warps the weight ring and the
+    // history loads) touches nothing the preceding kernel -- the upsampler that writes u -- produces.
+    PdlWait();
+    PdlLaunchDependents();
     // ---- prologue: u -> TMEM (fp32 residual stream) and lrelu(u) -> X new rows ----
     for (int m = 0; m < MT; ++m) {
       const int r = m * 128 + tid;
@@ -380,7 +384,7 @@ void LaunchMrfT(const MrfStageParams& p, size_t smem, cudaStream_t s) {
     B200_CHECK(cudaFuncSetAttribute(mrf_branch_kernel<C, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev & 63] = true;
   }
-  mrf_branch_kernel<C, kSplit><<<dim3(p.n_groups, 3, 1), kThreads, smem, s>>>(p);
+  LaunchPdl(mrf_branch_kernel<C, kSplit>, dim3(p.n_groups, 3, 1), dim3(kThreads, 1, 1), smem, s, 1, p);
 }
 
 int NkFor(int C) { return C <= 16 ? 4 : (C <= 64 ? 2 : 1); }

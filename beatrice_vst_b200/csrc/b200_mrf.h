@@ -29,6 +29,7 @@ struct MrfStageParams {
   int B;               // streams
   int n_groups;        // ceil(B / S)
   const int* frame;    // device hop counter
+  int trace;           // developer aid: 1 + blockIdx.x of the CTA whose timeline is printed (0 = off)
 };
 
 // One history block, for per-stream reset: [group][planes * panels][H][S][8] bf16

@@ -15,6 +15,7 @@
 //     taken in rank order (deterministic), bias / residual / LeakyReLU applied, and the result is
 //     -- by construction -- exactly the K slice this CTA needs as input of the next conv.
 // Nothing but the stage input u, the branch output and the conv histories touches HBM.
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -81,6 +82,11 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
   const uint32_t x_base = smem_base + x_off, y_base = smem_base + y_off, box_base = smem_base + box_off,
                  w_base = smem_base + w_off;
 
+  // developer trace (BEATRICE_B200_MRF_TRACE=1): clock64 stamps of one CTA, printed at exit
+  long long* trace = reinterpret_cast<long long*>(smem + w_off + kNst * kChunkBytes);
+  const bool tracing = p.trace != 0 && blockIdx.x == static_cast<unsigned>(p.trace - 1) && blockIdx.y == 0;
+#define B200_TR(i, slot) do { if (tracing) trace[(i) * 16 + (slot)] = clock64(); } while (0)
+
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(2 * MT * C + MT * Cs)) tmem_cols <<= 1;
 
@@ -103,8 +109,10 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (tracing && tid < 128) trace[tid] = 0;
   TcFenceBefore();
   __syncthreads();
+  if (tracing && tid == 0) trace[7 * 16] = clock64();
   ClusterSyncAll();   // every CTA's mbarriers exist before any peer signals them
   TcFenceAfter();
   const uint32_t tmem_base = *tmem_slot;
@@ -115,6 +123,10 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
     // =========================== epilogue warps ===========================
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     const uint32_t x_col0 = 2 * MT * C;   // fp32 residual stream of the own channel slice
+    // Everything up to here (barriers, TMEM, bias, and in the other warps the weight ring and the
+    // history loads) touches nothing the preceding kernel -- the upsampler that writes u -- produces.
+    PdlWait();
+    PdlLaunchDependents();
     // ---- prologue: u -> TMEM (fp32 residual stream) and lrelu(u) -> X new rows ----
     for (int m = 0; m < MT; ++m) {
       const int r = m * 128 + tid;
@@ -161,6 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
     __threadfence_block();
     __syncwarp();
     if (lane == 0) atomicAdd(const_cast<uint32_t*>(in_cnt), 1u);
+    if (tid == 0) B200_TR(7, 1);
     // ---- the six convs ----
 #pragma unroll 1
     for (int i = 0; i < 6; ++i) {
@@ -183,6 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         const bool valid = exists && b < p.B;
         MbarWait(bar_acc + 8 * m, i & 1);
         TcFenceAfter();
+        if (tid == 0 && m == 0) B200_TR(i, 0);
         if (m == MT - 1 && tid == 0) atomicAdd(const_cast<uint32_t*>(acc_cnt), 1u);   // conv i's MMAs have all retired
         const uint32_t dcol = t_lane + ((i & 1) * MT + m) * C;
         // ---- reduce-scatter, push half: the columns of every peer go to that peer's inbox ----
@@ -208,8 +222,10 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         if (lane == 0) {
           for (int q = 1; q < NC; ++q) MbarArriveCluster(MapToCta(bar_box_full + 8 * warp, (rank + q) % NC));
         }
+        if (tid == 0 && m == 0) B200_TR(i, 1);
         // ---- pull half: own columns + the peers' partials, summed in rank order ----
         MbarWaitCluster(bar_box_full + 8 * warp, (i * MT + m) & 1);
+        if (tid == 0 && m == 0) B200_TR(i, 2);
         const uint32_t xcol = t_lane + x_col0 + m * Cs;
         const uint32_t srow = d_base + static_cast<uint32_t>(d_hmax * S + r) * 16;
         const uint8_t* box_row = smem + box_off + static_cast<size_t>(exists ? r : 0) * kBoxRow;
@@ -280,6 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
           }
         }
       }
+      if (tid == 0) B200_TR(i, 3);
       if (!last) {
         // this warp's inbox rows are consumed: the peers may push conv i+1
         __syncwarp();
@@ -302,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         const int hmax = buf ? HY : HX;
         const uint32_t bbase = buf ? y_base : x_base, pstride = buf ? y_pstride : x_pstride, plane = buf ? y_plane : x_plane;
         MbarWait(bar_hist + 8 * buf, (i >> 1) & 1);
+        B200_TR(i, 4);
 #pragma unroll 1
         for (int m = 0; m < MT; ++m) {
           const uint32_t dcol = tmem_base + ((i & 1) * MT + m) * C;
@@ -310,6 +328,8 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
           for (int g = 0; g < Gs; ++g) {
             MbarWait(bar_in + 8 * (m * Gs + g), i & 1);
             TcFenceAfter();
+            if (m == 0 && g == 0) B200_TR(i, 5);
+            if (m == 0 && g == Gs - 1) B200_TR(i, 6);
 #pragma unroll 1
             for (int j = 0; j < k; ++j) {
               const int within = ks % NK;
@@ -338,6 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
             }
           }
           MmaCommit(bar_acc + 8 * m);
+          if (m == MT - 1) B200_TR(i, 7);
         }
       }
     }
@@ -410,18 +431,30 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
           BulkCommit();
           BulkWaitRead0();
         }
+        B200_TR(i, 8);
         // conv i's MMAs done reading the buffer
         SpinUntil(acc_cnt, static_cast<uint32_t>(i + 1));
         if (i + 2 < 6) load_hist(i + 2);
         MbarArrive(bar_free + 8 * buf);
+        B200_TR(i, 9);
       }
       BulkWait0();
+      B200_TR(7, 2);
     }
     __syncwarp();
   }
 
   TcFenceBefore();
   __syncthreads();
+  if (tracing && tid == 0) {
+    const long long t0 = trace[7 * 16];
+    printf("[mrfc trace] C=%d NC=%d rank=%d k=%d S=%d MT=%d  prologue_done=%lld hist_drained=%lld end=%lld (cycles after init)\n", C, NC, rank, k, S,
+           MT, trace[7 * 16 + 1] - t0, trace[7 * 16 + 2] - t0, clock64() - t0);
+    for (int i = 0; i < 6; ++i)
+      printf("[mrfc trace]  conv %d: hist_ready %lld in_g0 %lld in_gLast %lld mma_issued %lld | acc %lld pushed %lld box_full %lld epi_done %lld | tail_stored %lld hist_next %lld\n",
+             i, trace[i * 16 + 4] - t0, trace[i * 16 + 5] - t0, trace[i * 16 + 6] - t0, trace[i * 16 + 7] - t0, trace[i * 16 + 0] - t0,
+             trace[i * 16 + 1] - t0, trace[i * 16 + 2] - t0, trace[i * 16 + 3] - t0, trace[i * 16 + 8] - t0, trace[i * 16 + 9] - t0);
+  }
   ClusterSyncAll();   // no CTA leaves while a peer may still write its inbox or signal its barriers
   if (warp == kWarpMma) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -437,20 +470,7 @@ void LaunchClusterT(const MrfStageParams& p, size_t smem, cudaStream_t s) {
     B200_CHECK(cudaFuncSetAttribute(mrf_cluster_kernel<C, NC, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev & 63] = true;
   }
-  cudaLaunchConfig_t cfg;
-  std::memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(p.n_groups * NC, 3, 1);
-  cfg.blockDim = dim3(kThreads, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = NC;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  B200_CHECK(cudaLaunchKernelEx(&cfg, mrf_cluster_kernel<C, NC, kSplit>, p));
+  LaunchPdl(mrf_cluster_kernel<C, NC, kSplit>, dim3(p.n_groups * NC, 3, 1), dim3(kThreads, 1, 1), smem, s, NC, p);
 }
 
 }  // namespace
@@ -467,6 +487,7 @@ size_t MrfClusterSmemBytes(int C, int NC, int T, int S, bool split) {
   off += static_cast<size_t>(NC - 1) * rows_valid * (Cs + 4) * 4 + 2048;   // inbox (+ slack the last tile's MMA may read into)
   off = (off + 127) / 128 * 128;
   off += static_cast<size_t>(kNst) * NkForC(C) * P * C * 32;
+  off += 1024;   // developer trace area
   return off;
 }
 

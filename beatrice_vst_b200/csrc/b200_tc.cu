@@ -20,6 +20,7 @@
 // hi*hi + hi*lo + lo*hi per K step recover ~16 mantissa bits with fp32 accumulation.
 #include <cuda_bf16.h>
 
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -37,15 +38,18 @@ constexpr int kPanelA = kTcM * 16;  // bytes of one 8-element K panel of the act
 // kGather = false compiles the cp.async-only producer (no fp32 gather code): ~half the registers,
 // so three to four CTAs fit on an SM for the small-tile layers.
 template <bool kSplit, int kStages, bool kGather>
-__global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(const ConvDesc* __restrict__ descs, int B,
+__global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(const __grid_constant__ ConvDesc d0,
+                                                           const ConvDesc* __restrict__ descs, int B,
                                                            const int* __restrict__ frame_ptr) {
   constexpr int kOperands = kSplit ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];
 
-  const ConvDesc d = descs[blockIdx.z];
+  // descriptor of z = 0 rides in the kernel parameters (no global round trip before the pipeline
+  // can start); the rare z-batched launch reads the others from the device array (constant data)
+  ConvDesc d = d0;
+  if (blockIdx.z != 0) d = descs[blockIdx.z];
   const int BN = d.tc_bn;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int frame = *frame_ptr;
   const int M = B * d.T;
   const int m0 = blockIdx.x * kTcM, n0 = blockIdx.y * BN;
   const int C_in = d.C_in, N = d.N;
@@ -58,6 +62,11 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
   float* bias_s = reinterpret_cast<float*>(tail + 128);   // BN floats
   const uint32_t bar_full = SmemAddr(bars), bar_empty = SmemAddr(bars + kStages), bar_done = SmemAddr(bars + 2 * kStages);
+  // developer timeline (d.trace): [0..7] phases, [8+4c..] per chunk: producer issue / landed, MMA full / commit
+  long long* trace = reinterpret_cast<long long*>(tail + 128 + 1024);
+  const bool tracing = d0.trace != 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define B200_TR(slot) do { if (tracing) trace[slot] = clock64(); } while (0)
+  if (tracing && tid == 0) trace[0] = clock64();
   const uint32_t smem_base = SmemAddr(smem);
 
   // TMEM columns: power of two >= 32 covering BN fp32 accumulator columns
@@ -86,6 +95,29 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   __syncthreads();
   TcFenceAfter();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) B200_TR(1);
+
+  // ---- weights of the first kStages chunks: constants, fetched while the predecessor drains ----
+  {
+    const int n_sub0 = d.C_in >= kTcKC ? d.C_in / kTcKC : 1;
+    const int tpc0 = d.C_in >= kTcKC ? 1 : kTcKC / d.C_in;
+    const int n_chunks0 = d.C_in >= kTcKC ? d.k * n_sub0 : (d.k + tpc0 - 1) / tpc0;
+    if (tid == 0) {
+      const uint8_t* w_hi0 = static_cast<const uint8_t*>(d.w_tc) + static_cast<size_t>(blockIdx.y) * n_chunks0 * w_bytes;
+      const uint8_t* w_lo0 = kSplit ? static_cast<const uint8_t*>(d.w_tc_lo) + static_cast<size_t>(blockIdx.y) * n_chunks0 * w_bytes
+                                    : nullptr;
+      for (int c = 0; c < kStages && c < n_chunks0; ++c) {
+        const uint32_t w_s = smem_base + c * stage_bytes + a_bytes * kOperands;
+        MbarExpectTx(bar_full + 8 * c, w_bytes * kOperands);
+        TmaBulkLoad(w_s, w_hi0 + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * c);
+        if (kSplit) TmaBulkLoad(w_s + w_bytes, w_lo0 + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * c);
+      }
+    }
+  }
+  PdlWait();   // from here on: data written by the predecessor (activations, hop counter)
+  PdlLaunchDependents();   // the successor's prologue may overlap this kernel's main loop
+  if (tid == 0) B200_TR(2);
+  const int frame = *frame_ptr;
 
   // ---- this thread's activation row ----
   const int x_L = d.x_slots * d.x_T;
@@ -132,7 +164,7 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
     if (round > 0) MbarWait(bar_empty + 8 * s, (round - 1) & 1);
     const uint32_t st_base = smem_base + s * stage_bytes;
     const uint32_t w_hi_s = st_base + a_bytes * kOperands;
-    if (tid == 0) {
+    if (tid == 0 && round > 0) {   // round 0 was issued before PdlWait()
       MbarExpectTx(bar_full + 8 * s, w_bytes * kOperands);
       TmaBulkLoad(w_hi_s, w_hi + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * s);
       if (kSplit) TmaBulkLoad(w_hi_s + w_bytes, w_lo + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * s);
@@ -163,12 +195,14 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
     for (int c = 0; c < n_chunks; ++c) {
       const int s = c % kStages;
       issue(c);
+      if (tid == 0 && c < 24) B200_TR(8 + 4 * c);
       if constexpr (!kGather) {
         CpAsyncCommit();
         if (c >= kRetire) {
           CpAsyncWait<kRetire>();   // this thread's part of chunk c-kRetire has landed
           FenceProxyAsync();        // ... and is visible to the tensor core (async proxy)
           MbarArrive(bar_full + 8 * ((c - kRetire) % kStages));
+          if (tid == 0 && c - kRetire < 24) B200_TR(8 + 4 * (c - kRetire) + 1);
         }
       } else {
         // register path: gather this thread's row from the fp32 ring(s): 64 K-elements -> eight
@@ -221,6 +255,7 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
         }
         FenceProxyAsync();
         MbarArrive(bar_full + 8 * s);
+        if (tid == 0 && c < 24) B200_TR(8 + 4 * c + 1);
       }
     }
     if (!kGather && kRetire > 0) {   // drain: the last kRetire chunks
@@ -239,6 +274,7 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       const uint32_t a_lo = st_base + a_bytes, w_lo_s = w_hi_s + w_bytes;
       MbarWait(bar_full + 8 * s, round & 1);   // 128 row arrivals + the weight TMA's bytes
       TcFenceAfter();
+      if (c < 24) B200_TR(8 + 4 * c + 2);
       const int ksteps = (taps * cw) >> 4;
       for (int kk = 0; kk < ksteps; ++kk) {
         const uint64_t ah = MakeDesc(a_hi + 2 * kk * kPanelA, kPanelA, 128);
@@ -253,6 +289,7 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
         }
       }
       MmaCommit(bar_empty + 8 * s);            // frees the stage when these MMAs retire
+      if (c < 24) B200_TR(8 + 4 * c + 3);
       if (c == n_chunks - 1) MmaCommit(bar_done);
     }
   }
@@ -284,8 +321,10 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   const int res_ld = BN + 4;   // floats; +4 keeps the per-thread 16-byte reads conflict free
   const bool res_in_smem = d.res != nullptr && static_cast<uint32_t>(kTcM * res_ld * 4) <= kStages * stage_bytes;
 
+  if (tid == 0) B200_TR(3);
   MbarWait(bar_done, 0);
   TcFenceAfter();
+  if (tid == 0) B200_TR(4);
   float* res_s = reinterpret_cast<float*>(smem) + row * res_ld;
   if (res_in_smem) {
     const uint32_t dst = smem_base + row * res_ld * 4;
@@ -293,6 +332,7 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
     CpAsyncCommit();
     CpAsyncWait<0>();   // own row only: no block-level barrier needed
   }
+  if (tid == 0) B200_TR(5);
   const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
   for (int c0 = 0; c0 < BN; c0 += 16) {
     uint32_t rr[16];
@@ -349,9 +389,19 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       }
     }
   }
+  if (tid == 0) B200_TR(6);
   }
   TcFenceBefore();
   __syncthreads();
+  if (tracing && tid == 0) {
+    const long long t0 = trace[0];
+    printf("[tc trace] grid (%d,%d,%d) BN %d C_in %d k %d N %d T %d stages %d gather %d chunks %d | setup %lld pdl_wait %lld producers_done %lld mma_done %lld res_loaded %lld epi_done %lld end %lld\n",
+           gridDim.x, gridDim.y, gridDim.z, BN, C_in, d.k, N, d.T, kStages, kGather ? 1 : 0, n_chunks, trace[1] - t0, trace[2] - t0,
+           trace[3] - t0, trace[4] - t0, trace[5] - t0, trace[6] - t0, clock64() - t0);
+    for (int c = 0; c < n_chunks && c < 24; ++c)
+      printf("[tc trace]   chunk %d: issued %lld landed %lld | mma_full %lld mma_committed %lld\n", c, trace[8 + 4 * c] - t0,
+             trace[9 + 4 * c] - t0, trace[10 + 4 * c] - t0, trace[11 + 4 * c] - t0);
+  }
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
@@ -374,7 +424,7 @@ int TcStages(bool split, int bn, int n_chunks) {
 }
 
 template <bool kSplit, int kStages, bool kGather>
-void LaunchTcT(const ConvDesc* d_descs, dim3 grid, size_t smem, int B, const int* d_frame, cudaStream_t s) {
+void LaunchTcT(const ConvDesc& h0, const ConvDesc* d_descs, dim3 grid, size_t smem, int B, const int* d_frame, cudaStream_t s) {
   static bool attr_set[64] = {};
   int dev = 0;
   B200_CHECK(cudaGetDevice(&dev));
@@ -383,7 +433,7 @@ void LaunchTcT(const ConvDesc* d_descs, dim3 grid, size_t smem, int B, const int
                                     227 * 1024));
     attr_set[dev & 63] = true;
   }
-  conv_gemm_tc_kernel<kSplit, kStages, kGather><<<grid, 160, smem, s>>>(d_descs, B, d_frame);
+  LaunchPdl(conv_gemm_tc_kernel<kSplit, kStages, kGather>, grid, dim3(160, 1, 1), smem, s, 1, h0, d_descs, B, d_frame);
 }
 
 }  // namespace
@@ -439,14 +489,14 @@ void LaunchConvGemmTc(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B
   const int kmax = nz > 1 ? 11 : h0.k;   // z-batched launches are the MRF branches k = 3, 7, 11
   const int n_chunks = h0.C_in >= kTcKC ? kmax * (h0.C_in / kTcKC) : (kmax + kTcKC / h0.C_in - 1) / (kTcKC / h0.C_in);
   const int stages = TcStages(split, bn, n_chunks);
-  const size_t smem = stages * TcStageBytes(split, bn) + 128 + static_cast<size_t>(bn) * 4;
+  const size_t smem = stages * TcStageBytes(split, bn) + 128 + 1024 + 1024;   // barriers, bias (<= 256 floats), trace
   dim3 grid((M + kTcM - 1) / kTcM, n_tiles, nz);
   const bool gather = h0.xh == nullptr;
 #define B200_TC_DISPATCH(SPLIT, GATHER)                                                    \
   do {                                                                                     \
-    if (stages == 4) LaunchTcT<SPLIT, 4, GATHER>(d_descs, grid, smem, B, d_frame, s);      \
-    else if (stages == 3) LaunchTcT<SPLIT, 3, GATHER>(d_descs, grid, smem, B, d_frame, s); \
-    else LaunchTcT<SPLIT, 2, GATHER>(d_descs, grid, smem, B, d_frame, s);                  \
+    if (stages == 4) LaunchTcT<SPLIT, 4, GATHER>(h0, d_descs, grid, smem, B, d_frame, s);      \
+    else if (stages == 3) LaunchTcT<SPLIT, 3, GATHER>(h0, d_descs, grid, smem, B, d_frame, s); \
+    else LaunchTcT<SPLIT, 2, GATHER>(h0, d_descs, grid, smem, B, d_frame, s);                  \
   } while (0)
   if (split) {
     if (gather) B200_TC_DISPATCH(true, true);

@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+L=gpurun_out/e.log
+: > $L
+run() { echo "== $*" >> $L; ( timeout 300 env "$@" ) >> $L 2>&1; echo "rc=$?" >> $L; }
+run python tools/mrf_probe.py 2 40 4
+(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15) >> $L
+run python bench.py --steps 200 --warmup 20 --no-cpu-baseline
+run BEATRICE_B200_NO_PDL=1 python bench.py --steps 200 --warmup 20 --no-cpu-baseline
+run python tools/op_profile.py 2 256
+grep -v "^\[ops\] p" $L | cut -c1-400
