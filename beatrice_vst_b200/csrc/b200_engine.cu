@@ -618,11 +618,11 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     t /= m->stride[i];
     t_out[i] = t;
   }
-  // ring_in[i] = input of front-end layer i.  Tensor-core mode: layers 2..5 read bf16 rings.
+  // ring_in[i] = input of front-end layer i.  Tensor-core mode: layers 1..5 read bf16 rings.
   int ring_in[6];
   for (int i = 0; i < 6; ++i) {
     const int hist = m->front[i].k - m->stride[i];
-    ring_in[i] = (tcm && i >= 2) ? arena.PlanH(hist, t_in[i], m->front[i].cin, true)
+    ring_in[i] = (tcm && i >= 1) ? arena.PlanH(hist, t_in[i], m->front[i].cin, true)
                                  : arena.Plan(hist, t_in[i], m->front[i].cin);
   }
   std::vector<int> ring_x(m->n_res + 1), ring_g(m->n_res);
@@ -631,6 +631,7 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     ring_g[r] = tcm ? arena.PlanH(2 * m->dil[r], 1, m->width, true) : arena.Plan(2 * m->dil[r], 1, m->width);
     ring_x[r + 1] = arena.Plan(0, 1, m->width);
   }
+  const int ring_xh = tcm ? arena.PlanH(0, 1, m->width, true) : -1;   // bf16 copy of the last x for the head
   arena.Commit(device, B);
   if (external_stage) {
     in_stage.Free();
@@ -657,10 +658,13 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     ConvDesc d = MakeConv(g, m->res[r], m->dil[r], 1, 1, arena.ring(ring_x[r + 1]), kActNone, kActNone);
     if (g.is_bf16) SetInH(&d, g);
     SetRes(&d, arena.ring(ring_x[r]));
+    if (ring_xh >= 0 && r == m->n_res - 1) SetOutH(&d, arena.ring(ring_xh), kActNone);
     res_idx.push_back(db.Add(d));
   }
   const Ring head_ring = FlatRing(head_out.as<float>(), 1, m->head_out);
-  const int head_idx = db.Add(MakeConv(arena.ring(ring_x[m->n_res]), m->head, 1, 1, 1, head_ring, kActNone, kActNone));
+  ConvDesc hd = MakeConv(arena.ring(ring_x[m->n_res]), m->head, 1, 1, 1, head_ring, kActNone, kActNone);
+  if (ring_xh >= 0) SetInH(&hd, arena.ring(ring_xh));
+  const int head_idx = db.Add(hd);
 
   descs.Alloc(device, sizeof(ConvDesc) * db.host.size(), false);
   B200_CHECK(cudaMemcpy(descs.p, db.host.data(), sizeof(ConvDesc) * db.host.size(), cudaMemcpyHostToDevice));
@@ -769,6 +773,10 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
 
   ring_hidden = arena.Plan(spec::kPreK - 1, 1, kHidden);
   ring_pre = arena.Plan(1, 1, kHidden);
+  // tensor-core mode: cond and pre also emit bf16 (hi [+ lo]) rings, so pre and ups0 move their input
+  // with cp.async instead of gathering fp32 through registers
+  const int ring_hidden_h = tcm ? arena.PlanH(spec::kPreK - 1, 1, kHidden, with_lo) : -1;
+  const int ring_pre_h = tcm ? arena.PlanH(1, 1, kHidden, with_lo) : -1;
   // fp32 rings: u (upsampler output), y (residual stream of each MRF branch), a (CUDA-core
   // path only).  Tensor-core mode keeps fp32 only where a residual / the branch sum needs it
   // (current rows) and adds bf16 rings -- already LeakyReLU'd -- that carry the conv history.
@@ -870,7 +878,12 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
   }
 
   DescBuilder db;
-  const int pre_idx = db.Add(MakeConv(arena.ring(ring_hidden), m->pre, 1, 1, 1, arena.ring(ring_pre), kActNone, kActNone));
+  ConvDesc pre_d = MakeConv(arena.ring(ring_hidden), m->pre, 1, 1, 1, arena.ring(ring_pre), kActNone, kActNone);
+  if (tcm) {
+    SetInH(&pre_d, arena.ring(ring_hidden_h));
+    SetOutH(&pre_d, arena.ring(ring_pre_h), kActLrelu);   // ups0 reads lrelu(pre) as bf16
+  }
+  const int pre_idx = db.Add(pre_d);
   int ups_idx[4], c1_idx[4][3], c2_idx[4][3];
   t = 1;
   for (int s = 0; s < 4; ++s) {
@@ -887,6 +900,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
       u.film_C = c;
     }
     if (tcm && !fused[s]) SetOutH(&u, arena.ring(ring_uh[s]), kActLrelu);
+    if (tcm && s == 0) SetInH(&u, arena.ring(ring_pre_h));
     ups_idx[s] = db.Add(u);
     t *= spec::kRates[s];
     for (int di = 0; di < 3 && !fused[s]; ++di) {
@@ -929,6 +943,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
 
   {
     const Ring hr = arena.ring(ring_hidden);
+    const Ring hh = tcm ? arena.ring(ring_hidden_h) : Ring();
     const float* ph = phone_in.as<float>();
     const int* q = q_in.as<int>();
     const float* ft = feat_in.as<float>();
@@ -941,7 +956,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
     op.bytes = 4.0 * (m->dims.phone_channels * kHidden + B * (m->dims.phone_channels + 4 * kHidden));
     op.launch = [=](cudaStream_t s) {
       LaunchCond(ph, mm->dims.phone_channels, q, mm->dims.pitch_bins, ft, mm->embed.w, mm->embed.b, mm->pitch_emb,
-                 mm->feat_proj, sp, fm, hr.base, hr.slots, Bn, frame, s);
+                 mm->feat_proj, sp, fm, hr.base, hh.hi, hh.lo, hr.slots, Bn, frame, s);   // hh has hr's geometry
     };
     program.push_back(op);
   }

@@ -255,7 +255,16 @@ __global__ void direct_conv_kernel(const ConvDesc* __restrict__ descs, int B, co
   acc = ActApply(acc, d.out_act);
   const int y_L = d.y_slots * d.y_T;
   const int y_cur = (frame % d.y_slots) * d.y_T;
-  d.y[(static_cast<long long>(b) * y_L + y_cur) * d.y_C + static_cast<long long>(t) * d.N + n] = acc;
+  if (d.y) d.y[(static_cast<long long>(b) * y_L + y_cur) * d.y_C + static_cast<long long>(t) * d.N + n] = acc;
+  if (d.yh) {   // bf16 copy (hi [+ lo] planes) for a tensor-core consumer
+    const int yh_L = d.yh_slots * d.y_T;
+    const int yh_cur = (frame % d.yh_slots) * d.y_T;
+    const long long o = (static_cast<long long>(b) * yh_L + yh_cur) * d.y_C + static_cast<long long>(t) * d.N + n;
+    const float hv = ActApply(acc, d.yh_act);
+    const __nv_bfloat16 h = __float2bfloat16_rn(hv);
+    d.yh[o] = __bfloat16_as_ushort(h);
+    if (d.yl) d.yl[o] = __bfloat16_as_ushort(__float2bfloat16_rn(hv - __bfloat162float(h)));
+  }
 }
 
 // Vocoder post conv: out[b][t] = tanh(b0 + sum_{j<7} sum_{ci<16} lrelu(x[b][t-(6-j)][ci]) * w[j][ci]) with
@@ -461,7 +470,8 @@ __global__ void __launch_bounds__(256) cond_kernel(const float* __restrict__ pho
                                                    const float* __restrict__ We, const float* __restrict__ be,
                                                    const float* __restrict__ pitch_emb, const float* __restrict__ Wf,
                                                    const float* __restrict__ spk, const float* __restrict__ formant,
-                                                   float* __restrict__ ring, int slots,
+                                                   float* __restrict__ ring, uint16_t* __restrict__ ring_hi,
+                                                   uint16_t* __restrict__ ring_lo, int slots,
                                                    const int* __restrict__ frame_ptr) {
   PdlWait();
   PdlLaunchDependents();
@@ -482,7 +492,13 @@ __global__ void __launch_bounds__(256) cond_kernel(const float* __restrict__ pho
   if (spk) v += spk[static_cast<long long>(b) * kHidden + c];
   if (formant) v += formant[static_cast<long long>(b) * kHidden + c];
   const int frame = *frame_ptr;
-  ring[(static_cast<long long>(b) * slots + (frame % slots)) * kHidden + c] = v;
+  const long long o = (static_cast<long long>(b) * slots + (frame % slots)) * kHidden + c;
+  if (ring) ring[o] = v;
+  if (ring_hi) {   // bf16 hi [+ lo] planes for the tensor-core pre conv
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    ring_hi[o] = __bfloat16_as_ushort(h);
+    if (ring_lo) ring_lo[o] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+  }
 }
 
 // kNN-VQ against a 512 x C codebook: out = mean of the n nearest rows (squared L2, ties to
@@ -699,8 +715,8 @@ void LaunchPitchTransform(const int* q_in, const PitchParams* params, int bins, 
 
 void LaunchCond(const float* phone, int P, const int* q, int bins, const float* feat, const float* We,
                 const float* be, const float* pitch_emb, const float* Wf, const float* spk, const float* formant,
-                float* ring, int slots, int B, const int* d_frame, cudaStream_t s) {
-  LaunchPdl(cond_kernel, dim3(B), dim3(kHidden), 0, s, 1, phone, P, q, bins, feat, We, be, pitch_emb, Wf, spk, formant, ring, slots, d_frame);
+                float* ring, uint16_t* ring_hi, uint16_t* ring_lo, int slots, int B, const int* d_frame, cudaStream_t s) {
+  LaunchPdl(cond_kernel, dim3(B), dim3(kHidden), 0, s, 1, phone, P, q, bins, feat, We, be, pitch_emb, Wf, spk, formant, ring, ring_hi, ring_lo, slots, d_frame);
   B200_CHECK(cudaGetLastError());
 }
 

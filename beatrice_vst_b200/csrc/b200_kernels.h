@@ -110,7 +110,8 @@ void LaunchPitchTransform(const int* q_in, const PitchParams* params, int bins, 
 // conditioning: phone 1x1 + pitch embedding gather + feature projection + speaker (+ formant)
 void LaunchCond(const float* phone, int P, const int* q, int bins, const float* feat, const float* We,
                 const float* be, const float* pitch_emb, const float* Wf, const float* spk /*[B][256]|null*/,
-                const float* formant /*[B][256]|null*/, float* ring, int slots, int B, const int* d_frame,
+                const float* formant /*[B][256]|null*/, float* ring, uint16_t* ring_hi /*null|bf16 copy*/,
+                uint16_t* ring_lo, int slots, int B, const int* d_frame,
                 cudaStream_t s);
 // kNN-VQ: phone_in [B][C] -> phone_out [B][C]; codebooks[b] -> 512 x C device table (or null), n[b] neighbours
 void LaunchVq(const float* phone_in, float* phone_out, const float* const* codebooks, const int* n_neighbors,

@@ -21,6 +21,7 @@
 //    after its input is complete.
 //  * Precision: plain bf16 (1 MMA per K step) or split bf16 (x = hi + lo for both operands,
 //    hi*hi + hi*lo + lo*hi, fp32 accumulate): same scheme as b200_tc.cu.
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -80,6 +81,12 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
   const uint32_t smem_base = SmemAddr(smem);
   const uint32_t x_base = smem_base + x_off, y_base = smem_base + y_off, w_base = smem_base + w_off;
 
+  // developer trace (BEATRICE_B200_MRF_TRACE=1 + blockIdx.x): clock64 stamps of one CTA, printed at exit
+  long long* trace = reinterpret_cast<long long*>(smem + w_off + kNst * kChunkBytes);
+  const bool tracing = p.trace != 0 && blockIdx.x == static_cast<unsigned>(p.trace - 1) && blockIdx.y == 0;
+#define B200_TR(i, slot) do { if (tracing) trace[(i) * 16 + (slot)] = clock64(); } while (0)
+  if (tracing && tid < 128) trace[tid] = 0;
+
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(2 * MT * C)) tmem_cols <<= 1;
 
@@ -104,6 +111,7 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
   __syncthreads();
   TcFenceAfter();
   const uint32_t tmem_base = *tmem_slot;
+  if (tracing && tid == 0) trace[7 * 16] = clock64();
 
   const int rows_valid = S * T;
   const size_t hist_unit = static_cast<size_t>(p.n_groups) * P * PAN * S * 8 * (k - 1);   // elements per unit dilation
@@ -158,6 +166,7 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
     __threadfence_block();
     __syncwarp();
     if (lane == 0) atomicAdd(const_cast<uint32_t*>(in_cnt), 1u);
+    if (tid == 0) B200_TR(7, 1);
     // ---- the six convs ----
 #pragma unroll 1
     for (int i = 0; i < 6; ++i) {
@@ -177,6 +186,8 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
         const bool valid = r < rows_valid && b < p.B;
         MbarWait(bar_acc + 8 * m, i & 1);
         TcFenceAfter();
+        if (tid == 0 && m == 0) B200_TR(i, 0);
+        if (tid == 0 && m == MT - 1) B200_TR(i, 1);
         if (m == MT - 1 && tid == 0) atomicAdd(const_cast<uint32_t*>(acc_cnt), 1u);   // conv i's MMAs have all retired
         const uint32_t tcol = t_lane + (is_c1 ? (MT + m) * C : m * C);
         const uint32_t srow = d_base + static_cast<uint32_t>(d_hmax * S + r) * 16;
@@ -224,6 +235,7 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
           }
         }
       }
+      if (tid == 0) B200_TR(i, 3);
       if (!last) {
         __threadfence_block();
         __syncwarp();
@@ -241,6 +253,7 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
         const int hmax = buf ? HY : HX;
         const uint32_t bbase = buf ? y_base : x_base, pstride = buf ? y_pstride : x_pstride, plane = buf ? y_plane : x_plane;
         MbarWait(bar_hist + 8 * buf, (i >> 1) & 1);
+        B200_TR(i, 4);
 #pragma unroll 1
         for (int m = 0; m < MT; ++m) {
           const uint32_t dcol = tmem_base + (buf == 0 ? (MT + m) * C : m * C);
@@ -249,6 +262,8 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
           for (int g = 0; g < G; ++g) {
             MbarWait(bar_in + 8 * (m * G + g), i & 1);
             TcFenceAfter();
+            if (m == 0 && g == 0) B200_TR(i, 5);
+            if (m == 0 && g == G - 1) B200_TR(i, 6);
 #pragma unroll 1
             for (int j = 0; j < k; ++j) {
               const int within = ks % NK;
@@ -278,6 +293,8 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
             }
           }
           MmaCommit(bar_acc + 8 * m);
+          if (m == 0) B200_TR(i, 2);
+          if (m == MT - 1) B200_TR(i, 7);
         }
       }
     }
@@ -349,18 +366,30 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
           BulkCommit();
           BulkWaitRead0();
         }
+        B200_TR(i, 8);
         // conv i's MMAs done reading the buffer
         SpinUntil(acc_cnt, static_cast<uint32_t>(i + 1));
         if (i + 2 < 6) load_hist(i + 2);
         MbarArrive(bar_free + 8 * buf);
+        B200_TR(i, 9);
       }
       BulkWait0();
+      B200_TR(7, 2);
     }
     __syncwarp();
   }
 
   TcFenceBefore();
   __syncthreads();
+  if (tracing && tid == 0) {
+    const long long t0 = trace[7 * 16];
+    printf("[mrf trace] C=%d k=%d S=%d MT=%d  prologue_done=%lld hist_drained=%lld end=%lld (cycles after init)\n", C, k, S, MT,
+           trace[7 * 16 + 1] - t0, trace[7 * 16 + 2] - t0, clock64() - t0);
+    for (int i = 0; i < 6; ++i)
+      printf("[mrf trace]  conv %d: hist_ready %lld in_g0 %lld in_gLast %lld mma_issued_m0 %lld mma_issued %lld | acc_m0 %lld acc_mLast %lld epi_done %lld | tail_stored %lld hist_next %lld\n",
+             i, trace[i * 16 + 4] - t0, trace[i * 16 + 5] - t0, trace[i * 16 + 6] - t0, trace[i * 16 + 2] - t0, trace[i * 16 + 7] - t0,
+             trace[i * 16 + 0] - t0, trace[i * 16 + 1] - t0, trace[i * 16 + 3] - t0, trace[i * 16 + 8] - t0, trace[i * 16 + 9] - t0);
+  }
   if (warp == kWarpMma) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
@@ -401,6 +430,7 @@ size_t MrfSmemBytes(int C, int T, int S, bool split) {
   off += P * PAN * RY * 16;
   off = (off + 127) / 128 * 128;
   off += static_cast<size_t>(kNst) * NkFor(C) * P * C * 32;
+  off += 1024;   // developer trace area
   return off;
 }
 

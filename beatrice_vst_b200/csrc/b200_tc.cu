@@ -33,7 +33,10 @@ namespace {
 
 constexpr int kTcM = 128;   // rows per CTA == TMEM lanes
 constexpr int kTcKC = 64;   // K elements per chunk
-constexpr int kPanelA = kTcM * 16;  // bytes of one 8-element K panel of the activation tile
+// bytes of one 8-element K panel of the activation tile: 128 rows x 16 B, +16 so that the eight
+// panels of one row fall into different shared-memory bank groups (the cp.async producer writes
+// the eight 16-byte pieces of a row from eight adjacent lanes)
+constexpr int kPanelA = kTcM * 16 + 16;
 
 // kGather = false compiles the cp.async-only producer (no fp32 gather code): ~half the registers,
 // so three to four CTAs fit on an SM for the small-tile layers.
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   const int m0 = blockIdx.x * kTcM, n0 = blockIdx.y * BN;
   const int C_in = d.C_in, N = d.N;
 
-  const uint32_t a_bytes = kTcM * kTcKC * 2;          // 16 KiB
+  const uint32_t a_bytes = 8 * kPanelA;               // one bf16 plane of the activation tile
   const uint32_t w_bytes = static_cast<uint32_t>(BN) * kTcKC * 2;
   const uint32_t stage_bytes = (a_bytes + w_bytes) * kOperands;
   uint8_t* tail = smem + kStages * stage_bytes;
@@ -119,7 +122,10 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   if (tid == 0) B200_TR(2);
   const int frame = *frame_ptr;
 
-  // ---- this thread's activation row ----
+  // ---- activation rows ----
+  // gather mode: thread == row (fp32 loads, conversion in registers).
+  // cp.async mode: lane group of 8 == one row, lane & 7 == K panel, so one warp instruction moves
+  // four whole 128-byte row segments (coalesced); every thread serves rows rg + 16 i, i < 8.
   const int x_L = d.x_slots * d.x_T;
   const int x_cur = (frame % d.x_slots) * d.x_T;
   const int m = m0 + tid;
@@ -130,6 +136,22 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
     const int b = m / d.T, t = m - b * d.T;
     xbase = static_cast<long long>(b) * x_L * C_in;
     xu0 = t * d.stride + d.stride - 1;
+  }
+  const int a_pl = tid & 7, a_rg = tid >> 3;
+  long long a_base[8];
+  int a_u0[8];
+  if constexpr (!kGather) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int mi = m0 + a_rg + 16 * i;
+      a_base[i] = -1;
+      a_u0[i] = 0;
+      if (mi < M) {
+        const int b = mi / d.T, t = mi - b * d.T;
+        a_base[i] = static_cast<long long>(b) * x_L * C_in;
+        a_u0[i] = t * d.stride + d.stride - 1;
+      }
+    }
   }
 
   // ---- chunk enumeration (must match PackWeightsTc) ----
@@ -170,16 +192,20 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       if (kSplit) TmaBulkLoad(w_hi_s + w_bytes, w_lo + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * s);
     }
     if constexpr (!kGather) {
-      long long ro[4];
-      tap_offsets(c, ro);
-      const uint32_t dst = st_base + tid * 16;
+      const int j0 = C_in >= kTcKC ? c / n_sub : c * tpc;
+      const int ci0 = C_in >= kTcKC ? (c - j0 * n_sub) * kTcKC : 0;
+      const int ch = a_pl * 8;
+      const int tl = ch >> lcw, cc = ch & (cw - 1);
+      const int back = (d.k - 1 - min(j0 + tl, d.k - 1)) * d.dil;
+      const uint32_t dst = st_base + a_pl * kPanelA + a_rg * 16;
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const int ch = p * 8;
-        const int tl = ch >> lcw, cc = ch & (cw - 1);
-        const long long a = (tl == 0 ? ro[0] : tl == 1 ? ro[1] : tl == 2 ? ro[2] : ro[3]) + cc;
-        CpAsync16(dst + p * kPanelA, d.xh + a, row_ok);
-        if (kSplit) CpAsync16(dst + a_bytes + p * kPanelA, d.xl + a, row_ok);
+      for (int i = 0; i < 8; ++i) {
+        int r = x_cur + a_u0[i] - back;
+        if (r < 0) r += x_L;
+        const bool ok = a_base[i] >= 0;
+        const long long a = (ok ? a_base[i] : 0) + static_cast<long long>(r) * C_in + ci0 + cc;
+        CpAsync16(dst + i * 256, d.xh + a, ok);
+        if (kSplit) CpAsync16(dst + a_bytes + i * 256, d.xl + a, ok);
       }
     }
   };
@@ -408,18 +434,26 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
 }
 
 size_t TcStageBytes(bool split, int bn) {
-  return (static_cast<size_t>(kTcM) * kTcKC * 2 + static_cast<size_t>(bn) * kTcKC * 2) * (split ? 2 : 1);
+  return (static_cast<size_t>(8) * kPanelA + static_cast<size_t>(bn) * kTcKC * 2) * (split ? 2 : 1);
 }
-// Pipeline depth: as deep as the K loop is long (<= 4), within ~100 KB of shared memory so that
-// two CTAs fit on an SM when the tiles are small (latency hiding across CTAs).
-int TcStages(bool split, int bn, int n_chunks) {
+// Pipeline depth.  A launch that fits in one wave (<= 148 CTAs) is latency bound: as deep as the K
+// loop is long (<= 4) within the SM's shared memory.  Multi-wave launches (the C = 16 / 32 stages:
+// hundreds of CTAs, 3-6 chunks) prefer occupancy: keep the CTA small enough for 2-3 per SM.
+int TcStages(bool split, int bn, int n_chunks, int n_ctas) {
   const size_t stage = TcStageBytes(split, bn);
-  // short K loops (the C = 16 / 32 stages: 3-6 chunks, hundreds of CTAs): occupancy beats depth,
-  // keep the CTA under ~74 KB so three fit on an SM
-  if (n_chunks <= 6) return (3 * stage <= 74 * 1024) ? 3 : 2;
-  int s = static_cast<int>((110 * 1024) / stage);
-  if (s < 3) s = static_cast<int>((200 * 1024) / stage) >= 3 ? 3 : 2;
+  const size_t cap = 222 * 1024;
+  int s;
+  if (n_ctas <= 148) {
+    s = static_cast<int>(cap / stage);
+  } else if (n_chunks <= 6) {
+    s = (3 * stage <= 74 * 1024) ? 3 : 2;
+  } else {
+    s = static_cast<int>((110 * 1024) / stage);
+    if (s < 3) s = static_cast<int>(cap / stage) >= 3 ? 3 : 2;
+  }
   if (s > 4) s = 4;
+  if (s > n_chunks) s = n_chunks;
+  if (s < 2) s = 2;
   return s;
 }
 
@@ -488,9 +522,9 @@ void LaunchConvGemmTc(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B
   const int n_tiles = (h0.N + bn - 1) / bn;
   const int kmax = nz > 1 ? 11 : h0.k;   // z-batched launches are the MRF branches k = 3, 7, 11
   const int n_chunks = h0.C_in >= kTcKC ? kmax * (h0.C_in / kTcKC) : (kmax + kTcKC / h0.C_in - 1) / (kTcKC / h0.C_in);
-  const int stages = TcStages(split, bn, n_chunks);
-  const size_t smem = stages * TcStageBytes(split, bn) + 128 + 1024 + 1024;   // barriers, bias (<= 256 floats), trace
   dim3 grid((M + kTcM - 1) / kTcM, n_tiles, nz);
+  const int stages = TcStages(split, bn, n_chunks, static_cast<int>(grid.x * grid.y * grid.z));
+  const size_t smem = stages * TcStageBytes(split, bn) + 128 + 1024 + 1024;   // barriers, bias (<= 256 floats), trace
   const bool gather = h0.xh == nullptr;
 #define B200_TC_DISPATCH(SPLIT, GATHER)                                                    \
   do {                                                                                     \
