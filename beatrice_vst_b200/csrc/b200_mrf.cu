@@ -53,7 +53,10 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
   constexpr uint32_t kChunkBytes = NK * kKstepBytes;
   extern __shared__ __align__(1024) uint8_t smem[];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // warp index broadcast from lane 0: provably warp-uniform, so the role branches below are uniform
+  // control flow and the single-thread MMA / TMA loops can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const MrfBranchDesc& br = p.br[2 - blockIdx.y];   // longest branch (k = 11) is scheduled first
   const int k = br.k, T = p.T, S = p.S, MT = p.MT;
   const int group = blockIdx.x;
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
   TcFenceBefore();
   __syncthreads();
   TcFenceAfter();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // same value in every lane, provably
   if (tracing && tid == 0) trace[7 * 16] = clock64();
 
   const int rows_valid = S * T;
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
     }
   } else if (warp == kWarpMma) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    {
       const uint32_t idesc = MakeIdesc(C);
       uint32_t cc = 0;
 #pragma unroll 1
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
         const int hmax = buf ? HY : HX;
         const uint32_t bbase = buf ? y_base : x_base, pstride = buf ? y_pstride : x_pstride, plane = buf ? y_plane : x_plane;
         MbarWait(bar_hist + 8 * buf, (i >> 1) & 1);
-        B200_TR(i, 4);
+        if (lane == 0) B200_TR(i, 4);
 #pragma unroll 1
         for (int m = 0; m < MT; ++m) {
           const uint32_t dcol = tmem_base + (buf == 0 ? (MT + m) * C : m * C);
@@ -262,8 +265,8 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
           for (int g = 0; g < G; ++g) {
             MbarWait(bar_in + 8 * (m * G + g), i & 1);
             TcFenceAfter();
-            if (m == 0 && g == 0) B200_TR(i, 5);
-            if (m == 0 && g == G - 1) B200_TR(i, 6);
+            if (m == 0 && g == 0) if (lane == 0) B200_TR(i, 5);
+            if (m == 0 && g == G - 1) if (lane == 0) B200_TR(i, 6);
 #pragma unroll 1
             for (int j = 0; j < k; ++j) {
               const int within = ks % NK;
@@ -278,30 +281,30 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
               const uint64_t ah = MakeDesc(a_hi, pstride, 128);
               const uint64_t wh = MakeDesc(w_hi, C * 16, 128);
               const uint32_t acc = buf == 0 ? (ks > 0 ? 1u : 0u) : 1u;
-              Mma(dcol, ah, wh, idesc, acc);
+              MmaW(dcol, ah, wh, idesc, acc);
               if (kSplit) {
                 const uint64_t al = MakeDesc(a_hi + plane, pstride, 128);
                 const uint64_t wl = MakeDesc(w_hi + C * 32, C * 16, 128);
-                Mma(dcol, ah, wl, idesc, 1u);
-                Mma(dcol, al, wh, idesc, 1u);
+                MmaW(dcol, ah, wl, idesc, 1u);
+                MmaW(dcol, al, wh, idesc, 1u);
               }
               ++ks;
               if (within == NK - 1 || ks == k * G) {
-                MmaCommit(bar_w_empty + 8 * stage);
+                MmaCommitW(bar_w_empty + 8 * stage);
                 ++cc;
               }
             }
           }
-          MmaCommit(bar_acc + 8 * m);
-          if (m == 0) B200_TR(i, 2);
-          if (m == MT - 1) B200_TR(i, 7);
+          MmaCommitW(bar_acc + 8 * m);
+          if (m == 0) if (lane == 0) B200_TR(i, 2);
+          if (m == MT - 1) if (lane == 0) B200_TR(i, 7);
         }
       }
     }
     __syncwarp();
   } else if (warp == kWarpW) {
     // =========================== weight producer ===========================
-    if (lane == 0) {
+    if (ElectOneSync()) {
       const int ksteps = k * G;
       const int chunks = (ksteps + NK - 1) / NK;
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(br.w);
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
             const int n = min(NK, ksteps - c * NK);
             const uint32_t bytes = n * kKstepBytes;
             MbarExpectTx(bar_w_full + 8 * stage, bytes);
-            TmaBulkLoad(w_base + stage * kChunkBytes, wconv + static_cast<size_t>(c) * kChunkBytes, bytes, bar_w_full + 8 * stage);
+            TmaBulkLoadKeep(w_base + stage * kChunkBytes, wconv + static_cast<size_t>(c) * kChunkBytes, bytes, bar_w_full + 8 * stage);
             ++cc;
           }
         }
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
     __syncwarp();
   } else if (warp == kWarpH) {
     // =========================== history mover ===========================
-    if (lane == 0) {
+    if (ElectOneSync()) {
       auto hist_ptr = [&](int i, int H) {
         // conv i block: [group][plane][panel][H*S rows][8]
         return br.hist + hist_unit * DilPrefix(i) + static_cast<size_t>(group) * P * PAN * H * S * 8;

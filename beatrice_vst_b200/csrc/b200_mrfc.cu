@@ -49,7 +49,10 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
   static_assert(Cs % 16 == 0, "channel slice must be a multiple of one K step");
   extern __shared__ __align__(1024) uint8_t smem[];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // warp index broadcast from lane 0: provably warp-uniform, so the role branches below are uniform
+  // control flow and the single-thread MMA / TMA loops can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int rank = static_cast<int>(ClusterCtaRank());
   const MrfBranchDesc& br = p.br[2 - blockIdx.y];   // longest branch (k = 11) is scheduled first
   const int k = br.k, T = p.T, S = p.S, MT = p.MT;
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
   if (tracing && tid == 0) trace[7 * 16] = clock64();
   ClusterSyncAll();   // every CTA's mbarriers exist before any peer signals them
   TcFenceAfter();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // same value in every lane, provably
 
   const size_t hist_unit = static_cast<size_t>(p.n_groups) * P * PAN * S * 8 * (k - 1);   // elements per unit dilation
 
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
     }
   } else if (warp == kWarpMma) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    {
       const uint32_t idesc = MakeIdesc(C);
       uint32_t cc = 0;
 #pragma unroll 1
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         const int hmax = buf ? HY : HX;
         const uint32_t bbase = buf ? y_base : x_base, pstride = buf ? y_pstride : x_pstride, plane = buf ? y_plane : x_plane;
         MbarWait(bar_hist + 8 * buf, (i >> 1) & 1);
-        B200_TR(i, 4);
+        if (lane == 0) B200_TR(i, 4);
 #pragma unroll 1
         for (int m = 0; m < MT; ++m) {
           const uint32_t dcol = tmem_base + ((i & 1) * MT + m) * C;
@@ -328,8 +331,8 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
           for (int g = 0; g < Gs; ++g) {
             MbarWait(bar_in + 8 * (m * Gs + g), i & 1);
             TcFenceAfter();
-            if (m == 0 && g == 0) B200_TR(i, 5);
-            if (m == 0 && g == Gs - 1) B200_TR(i, 6);
+            if (m == 0 && g == 0) if (lane == 0) B200_TR(i, 5);
+            if (m == 0 && g == Gs - 1) if (lane == 0) B200_TR(i, 6);
 #pragma unroll 1
             for (int j = 0; j < k; ++j) {
               const int within = ks % NK;
@@ -343,29 +346,29 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
               const uint32_t w_hi = w_base + stage * kChunkBytes + within * kKstepBytes;
               const uint64_t ah = MakeDesc(a_hi, pstride, 128);
               const uint64_t wh = MakeDesc(w_hi, C * 16, 128);
-              Mma(dcol, ah, wh, idesc, ks > 0 ? 1u : 0u);
+              MmaW(dcol, ah, wh, idesc, ks > 0 ? 1u : 0u);
               if (kSplit) {
                 const uint64_t al = MakeDesc(a_hi + plane, pstride, 128);
                 const uint64_t wl = MakeDesc(w_hi + C * 32, C * 16, 128);
-                Mma(dcol, ah, wl, idesc, 1u);
-                Mma(dcol, al, wh, idesc, 1u);
+                MmaW(dcol, ah, wl, idesc, 1u);
+                MmaW(dcol, al, wh, idesc, 1u);
               }
               ++ks;
               if (within == NK - 1 || ks == k * Gs) {
-                MmaCommit(bar_w_empty + 8 * stage);
+                MmaCommitW(bar_w_empty + 8 * stage);
                 ++cc;
               }
             }
           }
-          MmaCommit(bar_acc + 8 * m);
-          if (m == MT - 1) B200_TR(i, 7);
+          MmaCommitW(bar_acc + 8 * m);
+          if (m == MT - 1) if (lane == 0) B200_TR(i, 7);
         }
       }
     }
     __syncwarp();
   } else if (warp == kWarpW) {
     // =========================== weight producer ===========================
-    if (lane == 0) {
+    if (ElectOneSync()) {
       const int ksteps = k * Gs;                     // own K slice
       const int ksteps_conv = k * (C / 16);          // whole conv
       const int chunks = (ksteps + NK - 1) / NK;
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
             const int n = min(NK, ksteps - c * NK);
             const uint32_t bytes = n * kKstepBytes;
             MbarExpectTx(bar_w_full + 8 * stage, bytes);
-            TmaBulkLoad(w_base + stage * kChunkBytes, wconv + static_cast<size_t>(c) * kChunkBytes, bytes, bar_w_full + 8 * stage);
+            TmaBulkLoadKeep(w_base + stage * kChunkBytes, wconv + static_cast<size_t>(c) * kChunkBytes, bytes, bar_w_full + 8 * stage);
             ++cc;
           }
         }
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
     __syncwarp();
   } else if (warp == kWarpH) {
     // =========================== history mover ===========================
-    if (lane == 0) {
+    if (ElectOneSync()) {
       auto hist_ptr = [&](int i, int H) {
         // conv i block: [group][plane][panel][H*S rows][8]; this CTA moves its own panels only
         return br.hist + hist_unit * DilPrefix(i) + static_cast<size_t>(group) * P * PAN * H * S * 8;

@@ -52,7 +52,10 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   ConvDesc d = d0;
   if (blockIdx.z != 0) d = descs[blockIdx.z];
   const int BN = d.tc_bn;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // warp index broadcast from lane 0: provably warp-uniform, so the role branches below are uniform
+  // control flow and the single-thread MMA / TMA loops can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int M = B * d.T;
   const int m0 = blockIdx.x * kTcM, n0 = blockIdx.y * BN;
   const int C_in = d.C_in, N = d.N;
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   TcFenceBefore();
   __syncthreads();
   TcFenceAfter();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // same value in every lane, provably
   if (tid == 0) B200_TR(1);
 
   // ---- weights of the first kStages chunks: constants, fetched while the predecessor drains ----
@@ -112,8 +115,8 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       for (int c = 0; c < kStages && c < n_chunks0; ++c) {
         const uint32_t w_s = smem_base + c * stage_bytes + a_bytes * kOperands;
         MbarExpectTx(bar_full + 8 * c, w_bytes * kOperands);
-        TmaBulkLoad(w_s, w_hi0 + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * c);
-        if (kSplit) TmaBulkLoad(w_s + w_bytes, w_lo0 + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * c);
+        TmaBulkLoadKeep(w_s, w_hi0 + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * c);
+        if (kSplit) TmaBulkLoadKeep(w_s + w_bytes, w_lo0 + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * c);
       }
     }
   }
@@ -188,8 +191,8 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
     const uint32_t w_hi_s = st_base + a_bytes * kOperands;
     if (tid == 0 && round > 0) {   // round 0 was issued before PdlWait()
       MbarExpectTx(bar_full + 8 * s, w_bytes * kOperands);
-      TmaBulkLoad(w_hi_s, w_hi + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * s);
-      if (kSplit) TmaBulkLoad(w_hi_s + w_bytes, w_lo + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * s);
+      TmaBulkLoadKeep(w_hi_s, w_hi + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * s);
+      if (kSplit) TmaBulkLoadKeep(w_hi_s + w_bytes, w_lo + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * s);
     }
     if constexpr (!kGather) {
       const int j0 = C_in >= kTcKC ? c / n_sub : c * tpc;
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       for (int c = (n_chunks > kRetire ? n_chunks - kRetire : 0); c < n_chunks; ++c)
         MbarArrive(bar_full + 8 * (c % kStages));
     }
-  } else if (lane == 0) {
+  } else {   // warp 4 walks the issue loop converged; one elected lane issues each MMA
     for (int c = 0; c < n_chunks; ++c) {
       const int s = c % kStages, round = c / kStages;
       const int j0 = C_in >= kTcKC ? c / n_sub : c * tpc;
@@ -300,23 +303,23 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       const uint32_t a_lo = st_base + a_bytes, w_lo_s = w_hi_s + w_bytes;
       MbarWait(bar_full + 8 * s, round & 1);   // 128 row arrivals + the weight TMA's bytes
       TcFenceAfter();
-      if (c < 24) B200_TR(8 + 4 * c + 2);
+      if (c < 24 && lane == 0) B200_TR(8 + 4 * c + 2);
       const int ksteps = (taps * cw) >> 4;
       for (int kk = 0; kk < ksteps; ++kk) {
         const uint64_t ah = MakeDesc(a_hi + 2 * kk * kPanelA, kPanelA, 128);
         const uint64_t wh = MakeDesc(w_hi_s + 2 * kk * BN * 16, BN * 16, 128);
         const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
-        Mma(tmem_base, ah, wh, idesc, acc);
+        MmaW(tmem_base, ah, wh, idesc, acc);
         if (kSplit) {
           const uint64_t al = MakeDesc(a_lo + 2 * kk * kPanelA, kPanelA, 128);
           const uint64_t wl = MakeDesc(w_lo_s + 2 * kk * BN * 16, BN * 16, 128);
-          Mma(tmem_base, ah, wl, idesc, 1u);
-          Mma(tmem_base, al, wh, idesc, 1u);
+          MmaW(tmem_base, ah, wl, idesc, 1u);
+          MmaW(tmem_base, al, wh, idesc, 1u);
         }
       }
-      MmaCommit(bar_empty + 8 * s);            // frees the stage when these MMAs retire
-      if (c < 24) B200_TR(8 + 4 * c + 3);
-      if (c == n_chunks - 1) MmaCommit(bar_done);
+      MmaCommitW(bar_empty + 8 * s);            // frees the stage when these MMAs retire
+      if (c < 24 && lane == 0) B200_TR(8 + 4 * c + 3);
+      if (c == n_chunks - 1) MmaCommitW(bar_done);
     }
   }
   __syncwarp();   // re-converge the MMA warp (its other 31 lanes skipped the loop)

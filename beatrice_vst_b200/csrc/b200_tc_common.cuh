@@ -12,6 +12,20 @@
 namespace b200 {
 namespace {
 
+// One lane of a converged warp.  Unlike `lane == 0`, elect.sync tells the compiler that exactly one
+// thread runs the guarded region, so tcgen05 / TMA instructions (which take warp-uniform operands)
+// are issued directly instead of inside a compiler-generated per-thread election loop.
+__device__ __forceinline__ bool ElectOneSync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P_el;\n"
+      "elect.sync _|P_el, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P_el;\n"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t SmemAddr(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -41,6 +55,15 @@ __device__ __forceinline__ void TmaBulkLoad(uint32_t dst_smem, const void* src, 
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// Weight tiles: the same bytes are re-read by every CTA and on every hop, while ~160 MB of stream
+// state cycles through the 126 MB L2 in between -- ask L2 to keep them (evict-last policy).
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void TmaBulkLoadKeep(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar), "l"(kL2EvictLast)
+      : "memory");
 }
 __device__ __forceinline__ void FenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void TcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -72,6 +95,15 @@ __device__ __forceinline__ void Mma(uint32_t d_tmem, uint64_t adesc, uint64_t bd
       "}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
+}
+// Warp-converged forms: the whole MMA warp walks the (uniform) issue loop so that descriptors and
+// loop state stay in uniform registers; only the instruction itself is issued by one elected lane.
+__device__ __forceinline__ void MmaW(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (ElectOneSync()) Mma(d_tmem, adesc, bdesc, idesc, accum);
+}
+__device__ __forceinline__ void MmaCommit(uint32_t bar);
+__device__ __forceinline__ void MmaCommitW(uint32_t bar) {
+  if (ElectOneSync()) MmaCommit(bar);
 }
 __device__ __forceinline__ void MmaCommit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
