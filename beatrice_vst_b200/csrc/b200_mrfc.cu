@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
       const uint32_t b = bar0 + 8 * i;
       uint32_t count = 1;
       if (b >= bar_in && b < bar_acc) count = kEpiWarps;
-      if (b >= bar_box_full && b < bar_in) count = NC - 1;
+      if (b >= bar_box_free && b < bar_in) count = NC - 1;   // box_full: one local arrive.expect_tx per phase
       MbarInit(b, count);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -202,12 +202,18 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         if (tid == 0 && m == 0) B200_TR(i, 0);
         if (m == MT - 1 && tid == 0) atomicAdd(const_cast<uint32_t*>(acc_cnt), 1u);   // conv i's MMAs have all retired
         const uint32_t dcol = t_lane + ((i & 1) * MT + m) * C;
-        // ---- reduce-scatter, push half: the columns of every peer go to that peer's inbox ----
+        // ---- reduce-scatter, push half: the columns of every peer go to that peer's inbox; the peer's
+        //      mbarrier counts the bytes (st.async complete_tx), so no fence and no arrive is needed ----
+        {
+          const int w_rows = min(max(rows_valid - (m * 128 + warp * 32), 0), 32);   // rows this warp owns in tile m
+          if (lane == 0) MbarExpectTx(bar_box_full + 8 * warp, static_cast<uint32_t>(NC - 1) * w_rows * Cs * 4);
+        }
 #pragma unroll 1
         for (int q = 1; q < NC; ++q) {
           const int pr = (rank + q) % NC;
           const int slot = rank < pr ? rank : rank - 1;
           const uint32_t dst = MapToCta(box_base + slot * box_slot + static_cast<uint32_t>(exists ? r : 0) * kBoxRow, pr);
+          const uint32_t rbar = MapToCta(bar_box_full + 8 * warp, pr);
 #pragma unroll 1
           for (int h = 0; h < Gs; ++h) {
             uint32_t raw[16];
@@ -215,19 +221,14 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
             if (exists) {
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                StCluster16(dst + 64 * h + 16 * e, __uint_as_float(raw[4 * e]), __uint_as_float(raw[4 * e + 1]),
-                            __uint_as_float(raw[4 * e + 2]), __uint_as_float(raw[4 * e + 3]));
+                StAsync16(dst + 64 * h + 16 * e, __uint_as_float(raw[4 * e]), __uint_as_float(raw[4 * e + 1]),
+                          __uint_as_float(raw[4 * e + 2]), __uint_as_float(raw[4 * e + 3]), rbar);
             }
           }
         }
-        FenceCluster();
-        __syncwarp();
-        if (lane == 0) {
-          for (int q = 1; q < NC; ++q) MbarArriveCluster(MapToCta(bar_box_full + 8 * warp, (rank + q) % NC));
-        }
         if (tid == 0 && m == 0) B200_TR(i, 1);
         // ---- pull half: own columns + the peers' partials, summed in rank order ----
-        MbarWaitCluster(bar_box_full + 8 * warp, (i * MT + m) & 1);
+        MbarWait(bar_box_full + 8 * warp, (i * MT + m) & 1);
         if (tid == 0 && m == 0) B200_TR(i, 2);
         const uint32_t xcol = t_lane + x_col0 + m * Cs;
         const uint32_t srow = d_base + static_cast<uint32_t>(d_hmax * S + r) * 16;
@@ -458,7 +459,9 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
              i, trace[i * 16 + 4] - t0, trace[i * 16 + 5] - t0, trace[i * 16 + 6] - t0, trace[i * 16 + 7] - t0, trace[i * 16 + 0] - t0,
              trace[i * 16 + 1] - t0, trace[i * 16 + 2] - t0, trace[i * 16 + 3] - t0, trace[i * 16 + 8] - t0, trace[i * 16 + 9] - t0);
   }
-  ClusterSyncAll();   // no CTA leaves while a peer may still write its inbox or signal its barriers
+  // (no exit-time cluster barrier: every byte and every signal addressed to this CTA has been consumed by
+  //  its epilogue warps before they get here -- inbox bytes are counted by box_full, and the last
+  //  box_free arrivals, for conv 4, were awaited before the pushes of conv 5)
   if (warp == kWarpMma) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }

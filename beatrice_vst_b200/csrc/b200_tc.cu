@@ -43,7 +43,7 @@ constexpr int kPanelA = kTcM * 16 + 16;
 template <bool kSplit, int kStages, bool kGather>
 __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(const __grid_constant__ ConvDesc d0,
                                                            const ConvDesc* __restrict__ descs, int B,
-                                                           const int* __restrict__ frame_ptr) {
+                                                           const int* __restrict__ frame_ptr, int KS) {
   constexpr int kOperands = kSplit ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];
 
@@ -57,7 +57,11 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   // control flow and the single-thread MMA / TMA loops can live in uniform registers
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int M = B * d.T;
-  const int m0 = blockIdx.x * kTcM, n0 = blockIdx.y * BN;
+  // K split: a cluster of KS CTAs (consecutive blockIdx.x) shares one output tile; CTA `rank` walks the
+  // chunk range [rank, rank + 1) * n_chunks / KS, then the partial accumulators are reduce-scattered
+  // through distributed shared memory and each CTA finishes BN / KS columns of the tile.
+  const int rank = KS > 1 ? static_cast<int>(ClusterCtaRank()) : 0;
+  const int m0 = (blockIdx.x / KS) * kTcM, n0 = blockIdx.y * BN;
   const int C_in = d.C_in, N = d.N;
 
   const uint32_t a_bytes = 8 * kPanelA;               // one bf16 plane of the activation tile
@@ -65,9 +69,11 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   const uint32_t stage_bytes = (a_bytes + w_bytes) * kOperands;
   uint8_t* tail = smem + kStages * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);  // full[kStages], empty[kStages], done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
   float* bias_s = reinterpret_cast<float*>(tail + 128);   // BN floats
-  const uint32_t bar_full = SmemAddr(bars), bar_empty = SmemAddr(bars + kStages), bar_done = SmemAddr(bars + 2 * kStages);
+  const uint32_t bar_full = SmemAddr(bars), bar_empty = SmemAddr(bars + kStages), bar_done = SmemAddr(bars + 2 * kStages),
+                 bar_box = SmemAddr(bars + 2 * kStages + 1);   // peers' partial sums have landed in the inbox
+  const uint32_t box_off = static_cast<uint32_t>(tail - smem) + 128 + 1024 + 1024;   // [KS-1][128 rows][BN/KS + 4] fp32
   // developer timeline (d.trace): [0..7] phases, [8+4c..] per chunk: producer issue / landed, MMA full / commit
   long long* trace = reinterpret_cast<long long*>(tail + 128 + 1024);
   const bool tracing = d0.trace != 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
@@ -89,6 +95,7 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       MbarInit(bar_empty + 8 * i, 1);
     }
     MbarInit(bar_done, 1);
+    MbarInit(bar_box, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -99,25 +106,26 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   }
   TcFenceBefore();
   __syncthreads();
+  if (KS > 1) ClusterSyncAll();   // every CTA's barriers exist before a peer may signal them
   TcFenceAfter();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // same value in every lane, provably
   if (tid == 0) B200_TR(1);
 
   // ---- weights of the first kStages chunks: constants, fetched while the predecessor drains ----
-  {
-    const int n_sub0 = d.C_in >= kTcKC ? d.C_in / kTcKC : 1;
-    const int tpc0 = d.C_in >= kTcKC ? 1 : kTcKC / d.C_in;
-    const int n_chunks0 = d.C_in >= kTcKC ? d.k * n_sub0 : (d.k + tpc0 - 1) / tpc0;
-    if (tid == 0) {
-      const uint8_t* w_hi0 = static_cast<const uint8_t*>(d.w_tc) + static_cast<size_t>(blockIdx.y) * n_chunks0 * w_bytes;
-      const uint8_t* w_lo0 = kSplit ? static_cast<const uint8_t*>(d.w_tc_lo) + static_cast<size_t>(blockIdx.y) * n_chunks0 * w_bytes
-                                    : nullptr;
-      for (int c = 0; c < kStages && c < n_chunks0; ++c) {
-        const uint32_t w_s = smem_base + c * stage_bytes + a_bytes * kOperands;
-        MbarExpectTx(bar_full + 8 * c, w_bytes * kOperands);
-        TmaBulkLoadKeep(w_s, w_hi0 + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * c);
-        if (kSplit) TmaBulkLoadKeep(w_s + w_bytes, w_lo0 + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * c);
-      }
+  const int n_sub = d.C_in >= kTcKC ? d.C_in / kTcKC : 1;
+  const int tpc = d.C_in >= kTcKC ? 1 : kTcKC / d.C_in;       // taps per chunk
+  const int n_chunks = d.C_in >= kTcKC ? d.k * n_sub : (d.k + tpc - 1) / tpc;
+  const int c_begin = rank * n_chunks / KS, c_end = (rank + 1) * n_chunks / KS;   // this CTA's K range
+  const uint8_t* w_hi = static_cast<const uint8_t*>(d.w_tc) + static_cast<size_t>(blockIdx.y) * n_chunks * w_bytes;
+  const uint8_t* w_lo = kSplit ? static_cast<const uint8_t*>(d.w_tc_lo) + static_cast<size_t>(blockIdx.y) * n_chunks * w_bytes
+                               : nullptr;
+  if (tid == 0) {
+    for (int c = c_begin; c < c_begin + kStages && c < c_end; ++c) {
+      const int st = c - c_begin;
+      const uint32_t w_s = smem_base + st * stage_bytes + a_bytes * kOperands;
+      MbarExpectTx(bar_full + 8 * st, w_bytes * kOperands);
+      TmaBulkLoadKeep(w_s, w_hi + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * st);
+      if (kSplit) TmaBulkLoadKeep(w_s + w_bytes, w_lo + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * st);
     }
   }
   PdlWait();   // from here on: data written by the predecessor (activations, hop counter)
@@ -158,16 +166,9 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   }
 
   // ---- chunk enumeration (must match PackWeightsTc) ----
-  const int n_sub = C_in >= kTcKC ? C_in / kTcKC : 1;
-  const int tpc = C_in >= kTcKC ? 1 : kTcKC / C_in;       // taps per chunk
   const int cw = C_in >= kTcKC ? kTcKC : C_in;            // channels gathered per tap
-  const int n_chunks = C_in >= kTcKC ? d.k * n_sub : (d.k + tpc - 1) / tpc;
   const int lcw = 31 - __clz(cw);                         // cw is 16, 32 or 64
   const uint32_t idesc = MakeIdesc(BN);
-  const uint8_t* w_hi = static_cast<const uint8_t*>(d.w_tc) +
-                        static_cast<size_t>(blockIdx.y) * n_chunks * w_bytes;
-  const uint8_t* w_lo = kSplit ? static_cast<const uint8_t*>(d.w_tc_lo) + static_cast<size_t>(blockIdx.y) * n_chunks * w_bytes
-                               : nullptr;
   const bool async_a = !kGather;          // activations pre-rounded to bf16 by their producer (d.xh)
 
   // element offsets of the (up to four) taps of chunk c for this thread's row
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   // stage c % kStages: wait until its previous MMAs retired, then start the weight TMA and
   // (async mode) the 16-byte cp.async's that drop this thread's row straight into the panels
   auto issue = [&](int c) {
-    const int s = c % kStages, round = c / kStages;
+    const int s = (c - c_begin) % kStages, round = (c - c_begin) / kStages;
     if (round > 0) MbarWait(bar_empty + 8 * s, (round - 1) & 1);
     const uint32_t st_base = smem_base + s * stage_bytes;
     const uint32_t w_hi_s = st_base + a_bytes * kOperands;
@@ -221,17 +222,18 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   // the tensor pipe is fed back-to-back while the producers run up to kStages chunks ahead.
   constexpr int kRetire = kStages >= 3 ? kStages - 2 : 0;   // cp.async groups left in flight
   if (warp < 4) {
-    for (int c = 0; c < n_chunks; ++c) {
-      const int s = c % kStages;
+    for (int c = c_begin; c < c_end; ++c) {
+      const int lc = c - c_begin;
+      const int s = lc % kStages;
       issue(c);
-      if (tid == 0 && c < 24) B200_TR(8 + 4 * c);
+      if (tid == 0 && lc < 24) B200_TR(8 + 4 * lc);
       if constexpr (!kGather) {
         CpAsyncCommit();
-        if (c >= kRetire) {
+        if (lc >= kRetire) {
           CpAsyncWait<kRetire>();   // this thread's part of chunk c-kRetire has landed
           FenceProxyAsync();        // ... and is visible to the tensor core (async proxy)
-          MbarArrive(bar_full + 8 * ((c - kRetire) % kStages));
-          if (tid == 0 && c - kRetire < 24) B200_TR(8 + 4 * (c - kRetire) + 1);
+          MbarArrive(bar_full + 8 * ((lc - kRetire) % kStages));
+          if (tid == 0 && lc - kRetire < 24) B200_TR(8 + 4 * (lc - kRetire) + 1);
         }
       } else {
         // register path: gather this thread's row from the fp32 ring(s): 64 K-elements -> eight
@@ -284,18 +286,19 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
         }
         FenceProxyAsync();
         MbarArrive(bar_full + 8 * s);
-        if (tid == 0 && c < 24) B200_TR(8 + 4 * c + 1);
+        if (tid == 0 && lc < 24) B200_TR(8 + 4 * lc + 1);
       }
     }
     if (!kGather && kRetire > 0) {   // drain: the last kRetire chunks
       CpAsyncWait<0>();
       FenceProxyAsync();
-      for (int c = (n_chunks > kRetire ? n_chunks - kRetire : 0); c < n_chunks; ++c)
-        MbarArrive(bar_full + 8 * (c % kStages));
+      const int nl = c_end - c_begin;
+      for (int lc = (nl > kRetire ? nl - kRetire : 0); lc < nl; ++lc) MbarArrive(bar_full + 8 * (lc % kStages));
     }
   } else {   // warp 4 walks the issue loop converged; one elected lane issues each MMA
-    for (int c = 0; c < n_chunks; ++c) {
-      const int s = c % kStages, round = c / kStages;
+    for (int c = c_begin; c < c_end; ++c) {
+      const int lc = c - c_begin;
+      const int s = lc % kStages, round = lc / kStages;
       const int j0 = C_in >= kTcKC ? c / n_sub : c * tpc;
       const int taps = C_in >= kTcKC ? 1 : min(tpc, d.k - j0);
       const uint32_t st_base = smem_base + s * stage_bytes;
@@ -303,12 +306,12 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       const uint32_t a_lo = st_base + a_bytes, w_lo_s = w_hi_s + w_bytes;
       MbarWait(bar_full + 8 * s, round & 1);   // 128 row arrivals + the weight TMA's bytes
       TcFenceAfter();
-      if (c < 24 && lane == 0) B200_TR(8 + 4 * c + 2);
+      if (lc < 24 && lane == 0) B200_TR(8 + 4 * lc + 2);
       const int ksteps = (taps * cw) >> 4;
       for (int kk = 0; kk < ksteps; ++kk) {
         const uint64_t ah = MakeDesc(a_hi + 2 * kk * kPanelA, kPanelA, 128);
         const uint64_t wh = MakeDesc(w_hi_s + 2 * kk * BN * 16, BN * 16, 128);
-        const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
+        const uint32_t acc = (lc > 0 || kk > 0) ? 1u : 0u;
         MmaW(tmem_base, ah, wh, idesc, acc);
         if (kSplit) {
           const uint64_t al = MakeDesc(a_lo + 2 * kk * kPanelA, kPanelA, 128);
@@ -318,8 +321,8 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
         }
       }
       MmaCommitW(bar_empty + 8 * s);            // frees the stage when these MMAs retire
-      if (c < 24 && lane == 0) B200_TR(8 + 4 * c + 3);
-      if (c == n_chunks - 1) MmaCommitW(bar_done);
+      if (lc < 24 && lane == 0) B200_TR(8 + 4 * lc + 3);
+      if (c == c_end - 1) MmaCommitW(bar_done);
     }
   }
   __syncwarp();   // re-converge the MMA warp (its other 31 lanes skipped the loop)
@@ -354,18 +357,64 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   MbarWait(bar_done, 0);
   TcFenceAfter();
   if (tid == 0) B200_TR(4);
+  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  // the BN / KS columns this CTA finishes
+  const int CW = BN / KS;
+  const int col_begin = rank * CW, col_end = col_begin + CW;
+  const uint32_t box_row_bytes = static_cast<uint32_t>(CW + 4) * 4;   // +16 B: conflict-free 16-byte row accesses
   float* res_s = reinterpret_cast<float*>(smem) + row * res_ld;
   if (res_in_smem) {
     const uint32_t dst = smem_base + row * res_ld * 4;
-    for (int cc = 0; cc < BN; cc += 4) CpAsync16(dst + cc * 4, res_row + n0 + cc, out_ok && (n0 + cc) < N);
+    for (int cc = col_begin; cc < col_end; cc += 4) CpAsync16(dst + cc * 4, res_row + n0 + cc, out_ok && (n0 + cc) < N);
     CpAsyncCommit();
-    CpAsyncWait<0>();   // own row only: no block-level barrier needed
   }
+  if (KS > 1) {
+    // reduce-scatter, push half: the columns peer q finishes go to q's inbox; q's mbarrier counts the bytes
+    if (tid == 0) MbarExpectTx(bar_box, static_cast<uint32_t>(KS - 1) * kTcM * CW * 4);
+    for (int q = 1; q < KS; ++q) {
+      const int pr = (rank + q) % KS;
+      const int slot = rank < pr ? rank : rank - 1;
+      const uint32_t dst = MapToCta(smem_base + box_off + (slot * kTcM + row) * box_row_bytes, pr);
+      const uint32_t rbar = MapToCta(bar_box, pr);
+      for (int h = 0; h < CW; h += 16) {
+        uint32_t raw[16];
+        TmemLd16(t_lane + pr * CW + h, raw);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          StAsync16(dst + (h + 4 * e) * 4, __uint_as_float(raw[4 * e]), __uint_as_float(raw[4 * e + 1]),
+                    __uint_as_float(raw[4 * e + 2]), __uint_as_float(raw[4 * e + 3]), rbar);
+      }
+    }
+    MbarWait(bar_box, 0);
+  }
+  if (res_in_smem) CpAsyncWait<0>();   // own row only: no block-level barrier needed
   if (tid == 0) B200_TR(5);
-  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  for (int c0 = 0; c0 < BN; c0 += 16) {
+  const uint8_t* box_mine = smem + box_off + static_cast<size_t>(row) * box_row_bytes;
+  for (int c0 = col_begin; c0 < col_end; c0 += 16) {
     uint32_t rr[16];
     TmemLd16(t_lane + c0, rr);   // whole warp, even when some rows are past M
+    if (KS > 1) {   // own partial + the peers' partials, in rank order (deterministic)
+      float acc[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
+      for (int src = 0; src < KS; ++src) {
+        if (src == rank) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(rr[e]);
+        } else {
+          const int slot = src < rank ? src : src - 1;
+          const float4* bp = reinterpret_cast<const float4*>(box_mine + static_cast<size_t>(slot) * kTcM * box_row_bytes +
+                                                             (c0 - col_begin) * 4);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float4 f = bp[e];
+            acc[4 * e] += f.x; acc[4 * e + 1] += f.y; acc[4 * e + 2] += f.z; acc[4 * e + 3] += f.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) rr[e] = __float_as_uint(acc[e]);
+    }
     if (!out_ok || n0 + c0 >= N) continue;
     float hv[16];
 #pragma unroll
@@ -422,18 +471,28 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   }
   TcFenceBefore();
   __syncthreads();
+  // (no exit-time cluster barrier: a CTA leaves only after every byte addressed to its inbox has been
+  //  counted by its own mbarrier, and it sends nothing after its last st.async)
   if (tracing && tid == 0) {
     const long long t0 = trace[0];
-    printf("[tc trace] grid (%d,%d,%d) BN %d C_in %d k %d N %d T %d stages %d gather %d chunks %d | setup %lld pdl_wait %lld producers_done %lld mma_done %lld res_loaded %lld epi_done %lld end %lld\n",
-           gridDim.x, gridDim.y, gridDim.z, BN, C_in, d.k, N, d.T, kStages, kGather ? 1 : 0, n_chunks, trace[1] - t0, trace[2] - t0,
+    printf("[tc trace] KS %d grid (%d,%d,%d) BN %d C_in %d k %d N %d T %d stages %d gather %d chunks %d | setup %lld pdl_wait %lld producers_done %lld mma_done %lld res_loaded %lld epi_done %lld end %lld\n",
+           KS, gridDim.x, gridDim.y, gridDim.z, BN, C_in, d.k, N, d.T, kStages, kGather ? 1 : 0, n_chunks, trace[1] - t0, trace[2] - t0,
            trace[3] - t0, trace[4] - t0, trace[5] - t0, trace[6] - t0, clock64() - t0);
-    for (int c = 0; c < n_chunks && c < 24; ++c)
+    for (int c = 0; c < c_end - c_begin && c < 24; ++c)
       printf("[tc trace]   chunk %d: issued %lld landed %lld | mma_full %lld mma_committed %lld\n", c, trace[8 + 4 * c] - t0,
              trace[9 + 4 * c] - t0, trace[10 + 4 * c] - t0, trace[11 + 4 * c] - t0);
   }
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
+}
+
+bool KSplitDisabled() {
+  static const bool off = [] {
+    const char* e = std::getenv("BEATRICE_B200_NO_KSPLIT");
+    return e && e[0] == '1';
+  }();
+  return off;
 }
 
 size_t TcStageBytes(bool split, int bn) {
@@ -461,7 +520,8 @@ int TcStages(bool split, int bn, int n_chunks, int n_ctas) {
 }
 
 template <bool kSplit, int kStages, bool kGather>
-void LaunchTcT(const ConvDesc& h0, const ConvDesc* d_descs, dim3 grid, size_t smem, int B, const int* d_frame, cudaStream_t s) {
+void LaunchTcT(const ConvDesc& h0, const ConvDesc* d_descs, dim3 grid, size_t smem, int B, const int* d_frame, int ks,
+               cudaStream_t s) {
   static bool attr_set[64] = {};
   int dev = 0;
   B200_CHECK(cudaGetDevice(&dev));
@@ -470,7 +530,7 @@ void LaunchTcT(const ConvDesc& h0, const ConvDesc* d_descs, dim3 grid, size_t sm
                                     227 * 1024));
     attr_set[dev & 63] = true;
   }
-  LaunchPdl(conv_gemm_tc_kernel<kSplit, kStages, kGather>, grid, dim3(160, 1, 1), smem, s, 1, h0, d_descs, B, d_frame);
+  LaunchPdl(conv_gemm_tc_kernel<kSplit, kStages, kGather>, grid, dim3(160, 1, 1), smem, s, ks, h0, d_descs, B, d_frame, ks);
 }
 
 }  // namespace
@@ -525,15 +585,30 @@ void LaunchConvGemmTc(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B
   const int n_tiles = (h0.N + bn - 1) / bn;
   const int kmax = nz > 1 ? 11 : h0.k;   // z-batched launches are the MRF branches k = 3, 7, 11
   const int n_chunks = h0.C_in >= kTcKC ? kmax * (h0.C_in / kTcKC) : (kmax + kTcKC / h0.C_in - 1) / (kTcKC / h0.C_in);
-  dim3 grid((M + kTcM - 1) / kTcM, n_tiles, nz);
-  const int stages = TcStages(split, bn, n_chunks, static_cast<int>(grid.x * grid.y * grid.z));
-  const size_t smem = stages * TcStageBytes(split, bn) + 128 + 1024 + 1024;   // barriers, bias (<= 256 floats), trace
+  const int m_tiles = (M + kTcM - 1) / kTcM;
+  // K split over a cluster (see the kernel): worth it when the launch is a handful of CTAs walking a
+  // long K loop -- the latency-bound layers with few rows per hop
+  int ks = 1;
+  if (nz == 1 && !KSplitDisabled()) {
+    for (int cand : {4, 2}) {
+      if (n_chunks >= 2 * cand && (bn / cand) % 16 == 0 && m_tiles * n_tiles * cand <= 132) {
+        ks = cand;
+        break;
+      }
+    }
+  }
+  dim3 grid(m_tiles * ks, n_tiles, nz);
+  const int local_chunks = (n_chunks + ks - 1) / ks;
+  const size_t inbox = ks > 1 ? static_cast<size_t>(ks - 1) * kTcM * (bn / ks + 4) * 4 : 0;
+  int stages = TcStages(split, bn, local_chunks, static_cast<int>(grid.x * grid.y * grid.z));
+  while (stages > 2 && stages * TcStageBytes(split, bn) + 128 + 2048 + inbox > 227 * 1024) --stages;
+  const size_t smem = stages * TcStageBytes(split, bn) + 128 + 1024 + 1024 + inbox;   // barriers, bias, trace, inbox
   const bool gather = h0.xh == nullptr;
 #define B200_TC_DISPATCH(SPLIT, GATHER)                                                    \
   do {                                                                                     \
-    if (stages == 4) LaunchTcT<SPLIT, 4, GATHER>(h0, d_descs, grid, smem, B, d_frame, s);      \
-    else if (stages == 3) LaunchTcT<SPLIT, 3, GATHER>(h0, d_descs, grid, smem, B, d_frame, s); \
-    else LaunchTcT<SPLIT, 2, GATHER>(h0, d_descs, grid, smem, B, d_frame, s);                  \
+    if (stages == 4) LaunchTcT<SPLIT, 4, GATHER>(h0, d_descs, grid, smem, B, d_frame, ks, s);      \
+    else if (stages == 3) LaunchTcT<SPLIT, 3, GATHER>(h0, d_descs, grid, smem, B, d_frame, ks, s); \
+    else LaunchTcT<SPLIT, 2, GATHER>(h0, d_descs, grid, smem, B, d_frame, ks, s);                  \
   } while (0)
   if (split) {
     if (gather) B200_TC_DISPATCH(true, true);

@@ -162,6 +162,13 @@ __device__ __forceinline__ uint32_t MapToCta(uint32_t smem_addr, uint32_t rank) 
 __device__ __forceinline__ void StCluster16(uint32_t cluster_addr, float a, float b, float c, float d) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// 16 bytes into a peer CTA's shared memory; the peer's mbarrier counts the bytes (complete_tx), so the
+// receiver needs no fence: its wait on that barrier makes the data visible, exactly as for TMA.
+__device__ __forceinline__ void StAsync16(uint32_t cluster_addr, float a, float b, float c, float d, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(cluster_addr),
+               "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_bar)
+               : "memory");
+}
 __device__ __forceinline__ void MbarArriveCluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
