@@ -895,7 +895,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
       u.n_x = 3;
       u.in_scale = 1.0f / 3.0f;
     }
-    if (rc0) {
+    if (rc0 && !fused[s]) {   // fused stages apply the FiLM in the MRF kernel's prologue instead
       u.film = film[s].as<float>();
       u.film_C = c;
     }
@@ -993,6 +993,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
       }
       const Ring& ur = arena.ring(ring_u[s]);
       mp.u = ur.base;
+      mp.film = rc0 ? film[s].as<float>() : nullptr;
       mp.u_slots = ur.slots;
       mp.T = t_stage;
       mp.S = fused_S[s];

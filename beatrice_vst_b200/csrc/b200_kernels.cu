@@ -22,6 +22,18 @@ __device__ __noinline__ float SlowAct(float v, int act) {
   if (act == kActGelu) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
   return tanhf(v);
 }
+// inline GELU for the tensor-core modes (same form as b200_tc_common.cuh): erf by Abramowitz & Stegun
+// 7.1.26, |error| <= 1.5e-7; the fp32 parity mode keeps the exact erff above
+__device__ __forceinline__ float GeluFastK(float v) {
+  const float x = fabsf(v) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-x * x);
+  return 0.5f * v * (1.0f + copysignf(e, v));
+}
 __device__ __forceinline__ float ActApply(float v, int act) {
   if (act == kActNone) return v;
   if (act == kActLrelu) return v > 0.0f ? v : 0.1f * v;
@@ -324,11 +336,19 @@ __device__ __forceinline__ float WarpSum(float v) {
 // y = GELU(ChanNorm(x)*gamma+beta); one warp per (stream, row); channel statistics by
 // warp-shuffle reduction, two-pass like the oracle (mean, then centred variance).
 __global__ void channorm_gelu_kernel(NormDesc d, int B, const int* __restrict__ frame_ptr) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  // gamma / beta are constants: fetched before the dependency wait
+  float gm[8], bt[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + 32 * i;
+    gm[i] = c < d.C ? __ldg(d.gamma + c) : 0.0f;
+    bt[i] = c < d.C ? __ldg(d.beta + c) : 0.0f;
+  }
   PdlWait();
   PdlLaunchDependents();
   const int frame = *frame_ptr;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
   if (warp >= B * d.T) return;
   const int b = warp / d.T, t = warp - b * d.T;
   const float* x = d.x + (static_cast<long long>(b) * d.x_slots * d.T + (frame % d.x_slots) * d.T + t) * d.C;
@@ -357,7 +377,8 @@ __global__ void channorm_gelu_kernel(NormDesc d, int B, const int* __restrict__ 
   for (int i = 0; i < kMaxPerLane; ++i)
     if (i < per) {
       const int c = lane + 32 * i;
-      const float o = ActApply((v[i] - mean) * rstd * __ldg(d.gamma + c) + __ldg(d.beta + c), kActGelu);
+      const float z = (v[i] - mean) * rstd * gm[i] + bt[i];
+      const float o = d.yh ? GeluFastK(z) : ActApply(z, kActGelu);   // exact erff only on the fp32 parity path
       if (d.y) y[c] = o;
       if (d.yh) {
         const long long off = (static_cast<long long>(b) * d.yh_slots * d.T + (frame % d.yh_slots) * d.T + t) * d.C + c;

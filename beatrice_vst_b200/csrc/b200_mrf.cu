@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
       const bool valid = r < rows_valid && b < p.B;
       const float* urow = p.u + (static_cast<size_t>(b) * p.u_slots * T + (frame % p.u_slots) * T + t) * C;
       const uint32_t srow = x_base + static_cast<uint32_t>(HX * S + r) * 16;
+      const float* frow = p.film ? p.film + static_cast<size_t>(b) * 2 * C : nullptr;
 #pragma unroll 1
       for (int g = 0; g < G; ++g) {
         float v[16];
@@ -141,6 +142,14 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
         for (int q = 0; q < 4; ++q) {
           float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
           if (valid) f = __ldg(reinterpret_cast<const float4*>(urow + 16 * g + 4 * q));
+          if (valid && frow) {   // FiLM of this vocoder stage (per stream): u * (1 + gamma) + beta
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(frow + 16 * g + 4 * q));
+            const float4 be = __ldg(reinterpret_cast<const float4*>(frow + C + 16 * g + 4 * q));
+            f.x = f.x * (1.0f + ga.x) + be.x;
+            f.y = f.y * (1.0f + ga.y) + be.y;
+            f.z = f.z * (1.0f + ga.z) + be.z;
+            f.w = f.w * (1.0f + ga.w) + be.w;
+          }
           v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
         }
         uint32_t raw[16];

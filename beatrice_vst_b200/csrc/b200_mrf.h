@@ -21,7 +21,8 @@ struct MrfBranchDesc {
 
 struct MrfStageParams {
   MrfBranchDesc br[3];
-  const float* u;      // stage input (upsampler + FiLM output), fp32 ring [B][u_slots * T][C]
+  const float* u;      // stage input (upsampler output), fp32 ring [B][u_slots * T][C]
+  const float* film;   // [B][2C] = gamma | beta applied to u as u*(1+gamma)+beta in the prologue, or nullptr
   int u_slots;
   int T;               // rows per stream per hop
   int S;               // streams per CTA (rows inside a CTA are time-major: row = t * S + s)

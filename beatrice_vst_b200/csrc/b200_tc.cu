@@ -67,7 +67,10 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   const uint32_t a_bytes = 8 * kPanelA;               // one bf16 plane of the activation tile
   const uint32_t w_bytes = static_cast<uint32_t>(BN) * kTcKC * 2;
   const uint32_t stage_bytes = (a_bytes + w_bytes) * kOperands;
-  uint8_t* tail = smem + kStages * stage_bytes;
+  // pipeline area; never smaller than the epilogue's staging tile [128][BN / KS + 4] fp32 (see the launcher)
+  const uint32_t tile_bytes = (static_cast<uint32_t>(kTcM) * (BN / KS + 4) * 4 + 127) / 128 * 128;
+  const uint32_t pipe_bytes = kStages * stage_bytes > tile_bytes ? kStages * stage_bytes : tile_bytes;
+  uint8_t* tail = smem + pipe_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);  // full[kStages], empty[kStages], done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
   float* bias_s = reinterpret_cast<float*>(tail + 128);   // BN floats
@@ -111,34 +114,11 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // same value in every lane, provably
   if (tid == 0) B200_TR(1);
 
-  // ---- weights of the first kStages chunks: constants, fetched while the predecessor drains ----
-  const int n_sub = d.C_in >= kTcKC ? d.C_in / kTcKC : 1;
-  const int tpc = d.C_in >= kTcKC ? 1 : kTcKC / d.C_in;       // taps per chunk
-  const int n_chunks = d.C_in >= kTcKC ? d.k * n_sub : (d.k + tpc - 1) / tpc;
-  const int c_begin = rank * n_chunks / KS, c_end = (rank + 1) * n_chunks / KS;   // this CTA's K range
-  const uint8_t* w_hi = static_cast<const uint8_t*>(d.w_tc) + static_cast<size_t>(blockIdx.y) * n_chunks * w_bytes;
-  const uint8_t* w_lo = kSplit ? static_cast<const uint8_t*>(d.w_tc_lo) + static_cast<size_t>(blockIdx.y) * n_chunks * w_bytes
-                               : nullptr;
-  if (tid == 0) {
-    for (int c = c_begin; c < c_begin + kStages && c < c_end; ++c) {
-      const int st = c - c_begin;
-      const uint32_t w_s = smem_base + st * stage_bytes + a_bytes * kOperands;
-      MbarExpectTx(bar_full + 8 * st, w_bytes * kOperands);
-      TmaBulkLoadKeep(w_s, w_hi + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * st);
-      if (kSplit) TmaBulkLoadKeep(w_s + w_bytes, w_lo + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * st);
-    }
-  }
-  PdlWait();   // from here on: data written by the predecessor (activations, hop counter)
-  PdlLaunchDependents();   // the successor's prologue may overlap this kernel's main loop
-  if (tid == 0) B200_TR(2);
-  const int frame = *frame_ptr;
-
-  // ---- activation rows ----
+  // ---- activation rows (index arithmetic only: done before the dependency wait) ----
   // gather mode: thread == row (fp32 loads, conversion in registers).
   // cp.async mode: lane group of 8 == one row, lane & 7 == K panel, so one warp instruction moves
   // four whole 128-byte row segments (coalesced); every thread serves rows rg + 16 i, i < 8.
   const int x_L = d.x_slots * d.x_T;
-  const int x_cur = (frame % d.x_slots) * d.x_T;
   const int m = m0 + tid;
   const bool row_ok = m < M;
   long long xbase = 0;
@@ -164,6 +144,30 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       }
     }
   }
+
+  // ---- weights of the first kStages chunks: constants, fetched while the predecessor drains ----
+  const int n_sub = d.C_in >= kTcKC ? d.C_in / kTcKC : 1;
+  const int tpc = d.C_in >= kTcKC ? 1 : kTcKC / d.C_in;       // taps per chunk
+  const int n_chunks = d.C_in >= kTcKC ? d.k * n_sub : (d.k + tpc - 1) / tpc;
+  const int c_begin = rank * n_chunks / KS, c_end = (rank + 1) * n_chunks / KS;   // this CTA's K range
+  const uint8_t* w_hi = static_cast<const uint8_t*>(d.w_tc) + static_cast<size_t>(blockIdx.y) * n_chunks * w_bytes;
+  const uint8_t* w_lo = kSplit ? static_cast<const uint8_t*>(d.w_tc_lo) + static_cast<size_t>(blockIdx.y) * n_chunks * w_bytes
+                               : nullptr;
+  if (tid == 0) {
+    for (int c = c_begin; c < c_begin + kStages && c < c_end; ++c) {
+      const int st = c - c_begin;
+      const uint32_t w_s = smem_base + st * stage_bytes + a_bytes * kOperands;
+      MbarExpectTx(bar_full + 8 * st, w_bytes * kOperands);
+      TmaBulkLoadKeep(w_s, w_hi + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * st);
+      if (kSplit) TmaBulkLoadKeep(w_s + w_bytes, w_lo + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * st);
+    }
+  }
+  PdlWait();   // from here on: data written by the predecessor (activations, hop counter)
+  PdlLaunchDependents();   // the successor's prologue may overlap this kernel's main loop
+  if (tid == 0) B200_TR(2);
+  const int frame = *frame_ptr;
+
+  const int x_cur = (frame % d.x_slots) * d.x_T;
 
   // ---- chunk enumeration (must match PackWeightsTc) ----
   const int cw = C_in >= kTcKC ? kTcKC : C_in;            // channels gathered per tap
@@ -350,8 +354,12 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   const long long oh = (static_cast<long long>(ob) * yh_L + yh_cur) * d.y_C + static_cast<long long>(ot) * N;
   const float* res_row = d.res ? d.res + (static_cast<long long>(ob) * res_L + res_cur + ot) * N : nullptr;
   const float* film_row = d.film ? d.film + static_cast<long long>(ob) * 2 * d.film_C : nullptr;
-  const int res_ld = BN + 4;   // floats; +4 keeps the per-thread 16-byte reads conflict free
-  const bool res_in_smem = d.res != nullptr && static_cast<uint32_t>(kTcM * res_ld * 4) <= kStages * stage_bytes;
+  // The (now idle) pipeline buffers become an fp32 staging tile [128 rows][CW + 4] of this CTA's own
+  // columns: the residual lands there by cp.async, each thread replaces it in place with its finished
+  // values, and the rows then leave for HBM as whole contiguous segments (coalesced), not as one
+  // 16-byte piece per thread.  The launcher sizes shared memory so the tile always fits.
+  const int res_ld = BN / KS + 4;   // floats; +4 keeps the per-thread 16-byte accesses conflict free
+  const bool res_in_smem = d.res != nullptr;
 
   if (tid == 0) B200_TR(3);
   MbarWait(bar_done, 0);
@@ -365,17 +373,21 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   float* res_s = reinterpret_cast<float*>(smem) + row * res_ld;
   if (res_in_smem) {
     const uint32_t dst = smem_base + row * res_ld * 4;
-    for (int cc = col_begin; cc < col_end; cc += 4) CpAsync16(dst + cc * 4, res_row + n0 + cc, out_ok && (n0 + cc) < N);
+#pragma unroll 1
+    for (int cc = 0; cc < CW; cc += 4)
+      CpAsync16(dst + cc * 4, res_row + n0 + col_begin + cc, out_ok && (n0 + col_begin + cc) < N);
     CpAsyncCommit();
   }
   if (KS > 1) {
     // reduce-scatter, push half: the columns peer q finishes go to q's inbox; q's mbarrier counts the bytes
     if (tid == 0) MbarExpectTx(bar_box, static_cast<uint32_t>(KS - 1) * kTcM * CW * 4);
+#pragma unroll 1
     for (int q = 1; q < KS; ++q) {
       const int pr = (rank + q) % KS;
       const int slot = rank < pr ? rank : rank - 1;
       const uint32_t dst = MapToCta(smem_base + box_off + (slot * kTcM + row) * box_row_bytes, pr);
       const uint32_t rbar = MapToCta(bar_box, pr);
+#pragma unroll 1
       for (int h = 0; h < CW; h += 16) {
         uint32_t raw[16];
         TmemLd16(t_lane + pr * CW + h, raw);
@@ -390,13 +402,19 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   if (res_in_smem) CpAsyncWait<0>();   // own row only: no block-level barrier needed
   if (tid == 0) B200_TR(5);
   const uint8_t* box_mine = smem + box_off + static_cast<size_t>(row) * box_row_bytes;
+  // (epilogue loops are deliberately NOT unrolled: this code runs once per launch with a cold
+  //  instruction cache, so every extra copy of the body is another exposed fetch from L2)
+#pragma unroll 1
   for (int c0 = col_begin; c0 < col_end; c0 += 16) {
     uint32_t rr[16];
     TmemLd16(t_lane + c0, rr);   // whole warp, even when some rows are past M
+    if (tid == 0 && c0 == col_begin) B200_TR(7);
+    if (tid == 0 && c0 == col_begin + 16) B200_TR(106);
     if (KS > 1) {   // own partial + the peers' partials, in rank order (deterministic)
       float acc[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
+#pragma unroll 1
       for (int src = 0; src < KS; ++src) {
         if (src == rank) {
 #pragma unroll
@@ -416,7 +434,6 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       for (int e = 0; e < 16; ++e) rr[e] = __float_as_uint(acc[e]);
     }
     if (!out_ok || n0 + c0 >= N) continue;
-    float hv[16];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const int col = n0 + c0 + 4 * g;
@@ -435,8 +452,7 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
           v.w = v.w * (1.0f + ga.w) + be.w;
         }
         if (res_row) {
-          const float4 rz = res_in_smem ? *reinterpret_cast<const float4*>(res_s + c0 + 4 * g)
-                                        : __ldg(reinterpret_cast<const float4*>(res_row + col));
+          const float4 rz = *reinterpret_cast<const float4*>(res_s + (c0 - col_begin) + 4 * g);
           v.x += rz.x; v.y += rz.y; v.z += rz.z; v.w += rz.w;
         }
         if (d.out_act != kActNone) {
@@ -445,25 +461,55 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
           v.z = ActTc(v.z, d.out_act);
           v.w = ActTc(v.w, d.out_act);
         }
-        if (out_row) *reinterpret_cast<float4*>(out_row + col) = v;
       }
-      hv[4 * g] = v.x; hv[4 * g + 1] = v.y; hv[4 * g + 2] = v.z; hv[4 * g + 3] = v.w;
+      *reinterpret_cast<float4*>(res_s + (c0 - col_begin) + 4 * g) = v;   // staged; leaves below
     }
-    if (d.yh && n0 + c0 + 16 <= N) {   // bf16 consumer copy (N is a multiple of 16 wherever one exists)
-      if (d.yh_act == kActLrelu) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) hv[e] = hv[e] > 0.0f ? hv[e] : 0.1f * hv[e];
+    if (tid == 0 && c0 == col_begin) B200_TR(105);
+  }
+  // ---- write-out: each warp streams its own 32 staged rows, a whole row segment per lane group ----
+  __syncwarp();
+  if (tid == 0) B200_TR(104);
+  {
+    const float* wst = reinterpret_cast<const float*>(smem) + static_cast<size_t>(warp * 32) * res_ld;
+    const int colg = n0 + col_begin;
+    if (d.y) {
+      const int lpr = CW >> 2;                   // lanes per row (16 bytes each); CW <= 128
+      const int rpp = 32 / lpr;                  // rows per pass
+      const int sub = lane / lpr, c4 = (lane - sub * lpr) * 4;
+      const unsigned long long my = reinterpret_cast<unsigned long long>(out_row);
+#pragma unroll 1
+      for (int r0 = 0; r0 < 32; r0 += rpp) {
+        const int j = (r0 + sub) & 31;
+        const unsigned long long base = __shfl_sync(0xffffffffu, my, j);
+        const int ok = __shfl_sync(0xffffffffu, out_ok ? 1 : 0, j);
+        if (ok && sub < rpp && colg + c4 < N)   // sub >= rpp: spare lanes when CW / 4 does not divide 32
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + colg + c4) =
+              *reinterpret_cast<const float4*>(wst + j * res_ld + c4);
       }
-      uint4 h0, l0, h1, l1;
-      Pack8<true>(hv, &h0, &l0);
-      Pack8<true>(hv + 8, &h1, &l1);
-      uint4* ph = reinterpret_cast<uint4*>(d.yh + oh + n0 + c0);
-      ph[0] = h0;
-      ph[1] = h1;
-      if (d.yl) {
-        uint4* pl = reinterpret_cast<uint4*>(d.yl + oh + n0 + c0);
-        pl[0] = l0;
-        pl[1] = l1;
+    }
+    if (d.yh) {   // bf16 consumer copy (hi [+ lo] planes), N a multiple of 8 wherever one exists
+      const int lpr = CW >> 3;                   // lanes per row (8 channels = 16 bytes of bf16 each)
+      const int rpp = 32 / lpr;
+      const int sub = lane / lpr, c8 = (lane - sub * lpr) * 8;
+#pragma unroll 1
+      for (int r0 = 0; r0 < 32; r0 += rpp) {
+        const int j = (r0 + sub) & 31;
+        const long long off = __shfl_sync(0xffffffffu, oh, j);
+        const int ok = __shfl_sync(0xffffffffu, out_ok ? 1 : 0, j);
+        if (ok && sub < rpp && colg + c8 + 8 <= N) {
+          float hv[8];
+          const float4 a = *reinterpret_cast<const float4*>(wst + j * res_ld + c8);
+          const float4 b = *reinterpret_cast<const float4*>(wst + j * res_ld + c8 + 4);
+          hv[0] = a.x; hv[1] = a.y; hv[2] = a.z; hv[3] = a.w; hv[4] = b.x; hv[5] = b.y; hv[6] = b.z; hv[7] = b.w;
+          if (d.yh_act == kActLrelu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) hv[e] = hv[e] > 0.0f ? hv[e] : 0.1f * hv[e];
+          }
+          uint4 h0, l0;
+          Pack8<true>(hv, &h0, &l0);
+          *reinterpret_cast<uint4*>(d.yh + off + colg + c8) = h0;
+          if (d.yl) *reinterpret_cast<uint4*>(d.yl + off + colg + c8) = l0;
+        }
       }
     }
   }
@@ -475,9 +521,9 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   //  counted by its own mbarrier, and it sends nothing after its last st.async)
   if (tracing && tid == 0) {
     const long long t0 = trace[0];
-    printf("[tc trace] KS %d grid (%d,%d,%d) BN %d C_in %d k %d N %d T %d stages %d gather %d chunks %d | setup %lld pdl_wait %lld producers_done %lld mma_done %lld res_loaded %lld epi_done %lld end %lld\n",
+    printf("[tc trace] KS %d grid (%d,%d,%d) BN %d C_in %d k %d N %d T %d stages %d gather %d chunks %d | setup %lld pdl_wait %lld producers_done %lld mma_done %lld res_loaded %lld first_tmem_ld %lld it0_done %lld it1_ld %lld staged %lld epi_done %lld end %lld\n",
            KS, gridDim.x, gridDim.y, gridDim.z, BN, C_in, d.k, N, d.T, kStages, kGather ? 1 : 0, n_chunks, trace[1] - t0, trace[2] - t0,
-           trace[3] - t0, trace[4] - t0, trace[5] - t0, trace[6] - t0, clock64() - t0);
+           trace[3] - t0, trace[4] - t0, trace[5] - t0, trace[7] - t0, trace[105] - t0, trace[106] - t0, trace[104] - t0, trace[6] - t0, clock64() - t0);
     for (int c = 0; c < c_end - c_begin && c < 24; ++c)
       printf("[tc trace]   chunk %d: issued %lld landed %lld | mma_full %lld mma_committed %lld\n", c, trace[8 + 4 * c] - t0,
              trace[9 + 4 * c] - t0, trace[10 + 4 * c] - t0, trace[11 + 4 * c] - t0);
@@ -602,7 +648,10 @@ void LaunchConvGemmTc(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B
   const size_t inbox = ks > 1 ? static_cast<size_t>(ks - 1) * kTcM * (bn / ks + 4) * 4 : 0;
   int stages = TcStages(split, bn, local_chunks, static_cast<int>(grid.x * grid.y * grid.z));
   while (stages > 2 && stages * TcStageBytes(split, bn) + 128 + 2048 + inbox > 227 * 1024) --stages;
-  const size_t smem = stages * TcStageBytes(split, bn) + 128 + 1024 + 1024 + inbox;   // barriers, bias, trace, inbox
+  const size_t tile = (static_cast<size_t>(kTcM) * (bn / ks + 4) * 4 + 127) / 128 * 128;   // epilogue staging tile
+  size_t pipe = stages * TcStageBytes(split, bn);
+  if (pipe < tile) pipe = tile;
+  const size_t smem = pipe + 128 + 1024 + 1024 + inbox;   // + barriers, bias, trace, inbox
   const bool gather = h0.xh == nullptr;
 #define B200_TC_DISPATCH(SPLIT, GATHER)                                                    \
   do {                                                                                     \

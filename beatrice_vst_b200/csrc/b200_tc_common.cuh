@@ -191,13 +191,26 @@ __device__ __forceinline__ void ClusterSyncAll() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// transcendental activations out of line (code size; see b200_kernels.cu)
-__device__ __noinline__ float SlowActTc(float v, int act) {
-  if (act == kActGelu) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+// GELU(v) = v/2 * (1 + erf(v / sqrt 2)), inline: erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7,
+// far below the split-bf16 GEMM noise), exp on the SFU.  An out-of-line erff call per element forces
+// the whole 16-column register tile through local memory around every call.
+__device__ __forceinline__ float GeluFast(float v) {
+  const float x = fabsf(v) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-x * x);   // erf(|v| / sqrt 2)
+  return 0.5f * v * (1.0f + copysignf(e, v));
+}
+__device__ __noinline__ float SlowActTc(float v, int act) {   // tanh: post-conv only, never on this kernel's hot path
+  if (act == kActGelu) return GeluFast(v);
   return tanhf(v);
 }
 __device__ __forceinline__ float ActTc(float v, int act) {
   if (act == kActLrelu) return v > 0.0f ? v : 0.1f * v;
+  if (act == kActGelu) return GeluFast(v);
   return SlowActTc(v, act);
 }
 
