@@ -33,6 +33,11 @@ namespace {
 
 constexpr int kTcM = 128;   // rows per CTA == TMEM lanes
 constexpr int kTcKC = 64;   // K elements per chunk
+// 8 worker warps (producers, then epilogue) + 1 MMA-issuing warp.  Two workers per SM sub-partition:
+// the producer and epilogue code is latency bound per warp (one warp per scheduler cannot hide its
+// own dependent-issue stalls), so splitting it over twice the warps nearly halves it.
+constexpr int kTcWorkers = 256;
+constexpr int kTcThreads = kTcWorkers + 32;
 // bytes of one 8-element K panel of the activation tile: 128 rows x 16 B, +16 so that the eight
 // panels of one row fall into different shared-memory bank groups (the cp.async producer writes
 // the eight 16-byte pieces of a row from eight adjacent lanes)
@@ -41,7 +46,7 @@ constexpr int kPanelA = kTcM * 16 + 16;
 // kGather = false compiles the cp.async-only producer (no fp32 gather code): ~half the registers,
 // so three to four CTAs fit on an SM for the small-tile layers.
 template <bool kSplit, int kStages, bool kGather>
-__global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(const __grid_constant__ ConvDesc d0,
+__global__ void __launch_bounds__(kTcThreads, kGather ? 1 : 2) conv_gemm_tc_kernel(const __grid_constant__ ConvDesc d0,
                                                            const ConvDesc* __restrict__ descs, int B,
                                                            const int* __restrict__ frame_ptr, int KS) {
   constexpr int kOperands = kSplit ? 2 : 1;
@@ -88,13 +93,13 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(BN)) tmem_cols <<= 1;
 
-  for (int i = tid; i < BN; i += 160) {
+  for (int i = tid; i < BN; i += kTcThreads) {
     const int col = blockIdx.y * BN + i;
     bias_s[i] = (d.bias && col < d.N) ? __ldg(d.bias + col) : 0.0f;
   }
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
-      MbarInit(bar_full + 8 * i, kTcM + 1);   // 128 producer rows + the weight TMA's expect_tx arrive
+      MbarInit(bar_full + 8 * i, kTcWorkers + 1);   // every worker thread + the weight TMA's expect_tx arrive
       MbarInit(bar_empty + 8 * i, 1);
     }
     MbarInit(bar_done, 1);
@@ -117,10 +122,11 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   // ---- activation rows (index arithmetic only: done before the dependency wait) ----
   // gather mode: thread == row (fp32 loads, conversion in registers).
   // cp.async mode: lane group of 8 == one row, lane & 7 == K panel, so one warp instruction moves
-  // four whole 128-byte row segments (coalesced); every thread serves rows rg + 16 i, i < 8.
+  // four whole 128-byte row segments (coalesced); every worker serves rows rg + 32 i, i < 4.
   const int x_L = d.x_slots * d.x_T;
-  const int m = m0 + tid;
+  const int m = m0 + (tid & 127);
   const bool row_ok = m < M;
+  const int whalf = (tid >> 7) & 1;   // which half of the split work (K half / column half) a worker takes
   long long xbase = 0;
   int xu0 = 0;
   if (row_ok) {
@@ -128,13 +134,13 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
     xbase = static_cast<long long>(b) * x_L * C_in;
     xu0 = t * d.stride + d.stride - 1;
   }
-  const int a_pl = tid & 7, a_rg = tid >> 3;
-  long long a_base[8];
-  int a_u0[8];
+  const int a_pl = tid & 7, a_rg = (tid >> 3) & 31;
+  long long a_base[4];
+  int a_u0[4];
   if constexpr (!kGather) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int mi = m0 + a_rg + 16 * i;
+    for (int i = 0; i < 4; ++i) {
+      const int mi = m0 + a_rg + 32 * i;
       a_base[i] = -1;
       a_u0[i] = 0;
       if (mi < M) {
@@ -207,25 +213,25 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       const int back = (d.k - 1 - min(j0 + tl, d.k - 1)) * d.dil;
       const uint32_t dst = st_base + a_pl * kPanelA + a_rg * 16;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         int r = x_cur + a_u0[i] - back;
         if (r < 0) r += x_L;
         const bool ok = a_base[i] >= 0;
         const long long a = (ok ? a_base[i] : 0) + static_cast<long long>(r) * C_in + ci0 + cc;
-        CpAsync16(dst + i * 256, d.xh + a, ok);
-        if (kSplit) CpAsync16(dst + a_bytes + i * 256, d.xl + a, ok);
+        CpAsync16(dst + i * 512, d.xh + a, ok);
+        if (kSplit) CpAsync16(dst + a_bytes + i * 512, d.xl + a, ok);
       }
     }
   };
 
   // ---- warp-specialised main loop ----
-  // warps 0-3 (128 threads, one activation row each) are PRODUCERS: they fill pipeline stages and
+  // warps 0-7 are PRODUCERS: they fill pipeline stages and
   // arrive on the stage's "full" mbarrier when their own bytes have landed -- no block barrier.
-  // warp 4 is the MMA ISSUER: one elected lane waits on "full", issues the tcgen05.mma's of the
+  // warp 8 is the MMA ISSUER: one elected lane waits on "full", issues the tcgen05.mma's of the
   // chunk and commits the stage's "empty" mbarrier.  The roles only meet through mbarriers, so
   // the tensor pipe is fed back-to-back while the producers run up to kStages chunks ahead.
   constexpr int kRetire = kStages >= 3 ? kStages - 2 : 0;   // cp.async groups left in flight
-  if (warp < 4) {
+  if (warp < 8) {
     for (int c = c_begin; c < c_end; ++c) {
       const int lc = c - c_begin;
       const int s = lc % kStages;
@@ -242,12 +248,12 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       } else {
         // register path: gather this thread's row from the fp32 ring(s): 64 K-elements -> eight
         // bf16 panels.  All loads of a half-chunk are issued before the first use.
-        uint8_t* a_hi_p = smem + s * stage_bytes + tid * 16;
+        uint8_t* a_hi_p = smem + s * stage_bytes + (tid & 127) * 16;
         uint8_t* a_lo_p = a_hi_p + a_bytes;
         long long ro[4];
         tap_offsets(c, ro);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        {
+          const int half = whalf;   // workers 0-127 convert K elements 0-31 of the chunk, 128-255 the rest
           float4 x0[8], x1[8], x2[8];
           if (row_ok) {
 #pragma unroll
@@ -299,7 +305,7 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       const int nl = c_end - c_begin;
       for (int lc = (nl > kRetire ? nl - kRetire : 0); lc < nl; ++lc) MbarArrive(bar_full + 8 * (lc % kStages));
     }
-  } else {   // warp 4 walks the issue loop converged; one elected lane issues each MMA
+  } else {   // warp 8 walks the issue loop converged; one elected lane issues each MMA
     for (int c = c_begin; c < c_end; ++c) {
       const int lc = c - c_begin;
       const int s = lc % kStages, round = lc / kStages;
@@ -335,8 +341,10 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   // Every row of the tile is owned by one thread (TMEM lane == thread).  Bias sits in shared
   // memory since kernel start; the residual tile is pulled into the (now idle) pipeline
   // buffers with one batch of cp.async so its DRAM latency is paid once, not per 16 columns.
-  if (warp < 4) {   // the four producer warps own TMEM lanes 0-127 == the tile's rows
-  const int row = tid;
+  // Worker warps w and w + 4 share TMEM lane quarter w & 3 (== tile rows 32 (w & 3) ..) and split that
+  // quarter's columns between them: whalf 0 takes the first half of the 16-column groups, whalf 1 the rest.
+  if (warp < 8) {
+  const int row = tid & 127;
   const int mm = m0 + row;
   const bool out_ok = mm < M;
   int ob = 0, ot = 0;
@@ -365,16 +373,18 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   MbarWait(bar_done, 0);
   TcFenceAfter();
   if (tid == 0) B200_TR(4);
-  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  // the BN / KS columns this CTA finishes
+  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  // the BN / KS columns this CTA finishes, and this worker's share [c_lo, c_hi) of them
   const int CW = BN / KS;
   const int col_begin = rank * CW, col_end = col_begin + CW;
+  const int n16 = CW >> 4, n16_lo = (n16 + 1) >> 1;
+  const int c_lo = col_begin + (whalf ? n16_lo * 16 : 0), c_hi = whalf ? col_end : col_begin + n16_lo * 16;
   const uint32_t box_row_bytes = static_cast<uint32_t>(CW + 4) * 4;   // +16 B: conflict-free 16-byte row accesses
   float* res_s = reinterpret_cast<float*>(smem) + row * res_ld;
   if (res_in_smem) {
     const uint32_t dst = smem_base + row * res_ld * 4;
 #pragma unroll 1
-    for (int cc = 0; cc < CW; cc += 4)
+    for (int cc = c_lo - col_begin; cc < c_hi - col_begin; cc += 4)
       CpAsync16(dst + cc * 4, res_row + n0 + col_begin + cc, out_ok && (n0 + col_begin + cc) < N);
     CpAsyncCommit();
   }
@@ -389,6 +399,7 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       const uint32_t rbar = MapToCta(bar_box, pr);
 #pragma unroll 1
       for (int h = 0; h < CW; h += 16) {
+        if ((((q - 1) * n16 + (h >> 4)) & 1) != whalf) continue;   // (peer, group) pairs alternate between the two workers of a row
         uint32_t raw[16];
         TmemLd16(t_lane + pr * CW + h, raw);
 #pragma unroll
@@ -405,11 +416,10 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   // (epilogue loops are deliberately NOT unrolled: this code runs once per launch with a cold
   //  instruction cache, so every extra copy of the body is another exposed fetch from L2)
 #pragma unroll 1
-  for (int c0 = col_begin; c0 < col_end; c0 += 16) {
+  for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
     uint32_t rr[16];
     TmemLd16(t_lane + c0, rr);   // whole warp, even when some rows are past M
     if (tid == 0 && c0 == col_begin) B200_TR(7);
-    if (tid == 0 && c0 == col_begin + 16) B200_TR(106);
     if (KS > 1) {   // own partial + the peers' partials, in rank order (deterministic)
       float acc[16];
 #pragma unroll
@@ -464,13 +474,15 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       }
       *reinterpret_cast<float4*>(res_s + (c0 - col_begin) + 4 * g) = v;   // staged; leaves below
     }
-    if (tid == 0 && c0 == col_begin) B200_TR(105);
+
   }
-  // ---- write-out: each warp streams its own 32 staged rows, a whole row segment per lane group ----
-  __syncwarp();
+  // ---- write-out: warps w and w + 4 stream 16 each of their quarter's 32 staged rows, a whole row
+  //      segment per lane group (both column halves of a row must be staged: worker-wide barrier) ----
+  asm volatile("bar.sync 1, 256;" ::: "memory");
   if (tid == 0) B200_TR(104);
   {
-    const float* wst = reinterpret_cast<const float*>(smem) + static_cast<size_t>(warp * 32) * res_ld;
+    const float* wst = reinterpret_cast<const float*>(smem) + static_cast<size_t>((warp & 3) * 32) * res_ld;
+    const int r_begin = (warp >> 2) * 16, r_end = r_begin + 16;
     const int colg = n0 + col_begin;
     if (d.y) {
       const int lpr = CW >> 2;                   // lanes per row (16 bytes each); CW <= 128
@@ -478,11 +490,11 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       const int sub = lane / lpr, c4 = (lane - sub * lpr) * 4;
       const unsigned long long my = reinterpret_cast<unsigned long long>(out_row);
 #pragma unroll 1
-      for (int r0 = 0; r0 < 32; r0 += rpp) {
+      for (int r0 = r_begin; r0 < r_end; r0 += rpp) {
         const int j = (r0 + sub) & 31;
         const unsigned long long base = __shfl_sync(0xffffffffu, my, j);
         const int ok = __shfl_sync(0xffffffffu, out_ok ? 1 : 0, j);
-        if (ok && sub < rpp && colg + c4 < N)   // sub >= rpp: spare lanes when CW / 4 does not divide 32
+        if (ok && sub < rpp && r0 + sub < r_end && colg + c4 < N)   // sub >= rpp: spare lanes when CW / 4 does not divide 32
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + colg + c4) =
               *reinterpret_cast<const float4*>(wst + j * res_ld + c4);
       }
@@ -492,11 +504,11 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
       const int rpp = 32 / lpr;
       const int sub = lane / lpr, c8 = (lane - sub * lpr) * 8;
 #pragma unroll 1
-      for (int r0 = 0; r0 < 32; r0 += rpp) {
+      for (int r0 = r_begin; r0 < r_end; r0 += rpp) {
         const int j = (r0 + sub) & 31;
         const long long off = __shfl_sync(0xffffffffu, oh, j);
         const int ok = __shfl_sync(0xffffffffu, out_ok ? 1 : 0, j);
-        if (ok && sub < rpp && colg + c8 + 8 <= N) {
+        if (ok && sub < rpp && r0 + sub < r_end && colg + c8 + 8 <= N) {
           float hv[8];
           const float4 a = *reinterpret_cast<const float4*>(wst + j * res_ld + c8);
           const float4 b = *reinterpret_cast<const float4*>(wst + j * res_ld + c8 + 4);
@@ -521,9 +533,9 @@ __global__ void __launch_bounds__(160, kGather ? 1 : 3) conv_gemm_tc_kernel(cons
   //  counted by its own mbarrier, and it sends nothing after its last st.async)
   if (tracing && tid == 0) {
     const long long t0 = trace[0];
-    printf("[tc trace] KS %d grid (%d,%d,%d) BN %d C_in %d k %d N %d T %d stages %d gather %d chunks %d | setup %lld pdl_wait %lld producers_done %lld mma_done %lld res_loaded %lld first_tmem_ld %lld it0_done %lld it1_ld %lld staged %lld epi_done %lld end %lld\n",
+    printf("[tc trace] KS %d grid (%d,%d,%d) BN %d C_in %d k %d N %d T %d stages %d gather %d chunks %d | setup %lld pdl_wait %lld producers_done %lld mma_done %lld res_loaded %lld first_tmem_ld %lld staged %lld epi_done %lld end %lld\n",
            KS, gridDim.x, gridDim.y, gridDim.z, BN, C_in, d.k, N, d.T, kStages, kGather ? 1 : 0, n_chunks, trace[1] - t0, trace[2] - t0,
-           trace[3] - t0, trace[4] - t0, trace[5] - t0, trace[7] - t0, trace[105] - t0, trace[106] - t0, trace[104] - t0, trace[6] - t0, clock64() - t0);
+           trace[3] - t0, trace[4] - t0, trace[5] - t0, trace[7] - t0, trace[104] - t0, trace[6] - t0, clock64() - t0);
     for (int c = 0; c < c_end - c_begin && c < 24; ++c)
       printf("[tc trace]   chunk %d: issued %lld landed %lld | mma_full %lld mma_committed %lld\n", c, trace[8 + 4 * c] - t0,
              trace[9 + 4 * c] - t0, trace[10 + 4 * c] - t0, trace[11 + 4 * c] - t0);
@@ -576,7 +588,7 @@ void LaunchTcT(const ConvDesc& h0, const ConvDesc* d_descs, dim3 grid, size_t sm
                                     227 * 1024));
     attr_set[dev & 63] = true;
   }
-  LaunchPdl(conv_gemm_tc_kernel<kSplit, kStages, kGather>, grid, dim3(160, 1, 1), smem, s, ks, h0, d_descs, B, d_frame, ks);
+  LaunchPdl(conv_gemm_tc_kernel<kSplit, kStages, kGather>, grid, dim3(kTcThreads, 1, 1), smem, s, ks, h0, d_descs, B, d_frame, ks);
 }
 
 }  // namespace
