@@ -33,9 +33,13 @@ namespace b200 {
 namespace {
 
 constexpr int kNst = 4;          // weight ring stages
-constexpr int kEpiWarps = 4;     // warps 0-3: epilogue (TMEM lane quarter == warp)
-constexpr int kWarpMma = 4, kWarpW = 5, kWarpH = 6;
-constexpr int kThreads = 7 * 32;
+// Epilogue warps: 8 where a tile has more than one work item -- (tile, 16-channel group) pairs --
+// per conv, else 4.  Warps w and w + 4 share TMEM lane quarter w & 3 (tile rows 32 (w & 3) ..) and take
+// the items of one parity each: the epilogue is latency bound per warp, two warps per SM
+// sub-partition nearly halve it.  Then one MMA-issuing, one weight and one history warp.
+__host__ __device__ constexpr int EpiWarpsFor(int C) { return C >= 32 ? 8 : 4; }
+__host__ __device__ constexpr int ThreadsFor(int C) { return (EpiWarpsFor(C) + 3) * 32; }
+constexpr int kQuarters = 4;
 
 template <int C>
 struct MrfCfg {
@@ -45,7 +49,9 @@ struct MrfCfg {
 };
 
 template <int C, bool kSplit>
-__global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf_branch_kernel(const __grid_constant__ MrfStageParams p) {
+__global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf_branch_kernel(const __grid_constant__ MrfStageParams p) {
+  constexpr int kEpiWarps = EpiWarpsFor(C), kThreads = ThreadsFor(C);
+  constexpr int kWarpMma = kEpiWarps, kWarpW = kEpiWarps + 1, kWarpH = kEpiWarps + 2;
   using Cfg = MrfCfg<C>;
   constexpr int G = Cfg::kG, PAN = Cfg::kPan, NK = Cfg::kNk;
   constexpr int P = kSplit ? 2 : 1;
@@ -53,6 +59,8 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
   constexpr uint32_t kChunkBytes = NK * kKstepBytes;
   extern __shared__ __align__(1024) uint8_t smem[];
 
+  unsigned long long t_start_ns = 0;
+  if (p.trace < 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_ns));
   const int tid = threadIdx.x, lane = tid & 31;
   // warp index broadcast from lane 0: provably warp-uniform, so the role branches below are uniform
   // control flow and the single-thread MMA / TMA loops can live in uniform registers
@@ -100,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
     for (int i = 0; i < n_bars; ++i) {
       const uint32_t b = bar0 + 8 * i;
       const bool is_in = b >= bar_in && b < bar_acc;
-      MbarInit(b, is_in ? kEpiWarps : 1);
+      MbarInit(b, is_in ? kQuarters : 1);   // the four warps that produce a group
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -121,14 +129,15 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
 
   if (warp < kEpiWarps) {
     // =========================== epilogue warps ===========================
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int q4 = warp & 3, whalf = warp >> 2, rtid = tid & 127;   // whalf is 0 when there are only 4 epilogue warps
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
     // Everything up to here (barriers, TMEM, bias, and in the other warps the weight ring and the
     // history loads) touches nothing the preceding kernel -- the upsampler that writes u -- produces.
     PdlWait();
     PdlLaunchDependents();
     // ---- prologue: u -> TMEM (fp32 residual stream) and lrelu(u) -> X new rows ----
     for (int m = 0; m < MT; ++m) {
-      const int r = m * 128 + tid;
+      const int r = m * 128 + rtid;
       const int t = r / S, s = r - t * S;
       const int b = group * S + s;
       const bool valid = r < rows_valid && b < p.B;
@@ -137,6 +146,7 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
       const float* frow = p.film ? p.film + static_cast<size_t>(b) * 2 * C : nullptr;
 #pragma unroll 1
       for (int g = 0; g < G; ++g) {
+        if (kEpiWarps == 8 && ((m * G + g) & 1) != whalf) continue;   // the partner warp's item
         float v[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -192,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
       if (i >= 1 && !last) MbarWait(bar_free + 8 * ((i + 1) & 1), ((i - 1) >> 1) & 1);
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
-        const int r = m * 128 + tid;
+        const int r = m * 128 + rtid;
         const int t = r / S, s = r - t * S;
         const int b = group * S + s;
         const bool valid = r < rows_valid && b < p.B;
@@ -206,6 +216,7 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
         float* orow = br.out + (static_cast<size_t>(b) * br.out_slots * T + (frame % br.out_slots) * T + t) * C;
 #pragma unroll 1
         for (int g = 0; g < G; ++g) {
+          if (kEpiWarps == 8 && ((m * G + g) & 1) != whalf) continue;   // the partner warp's item
           uint32_t raw[16];
           TmemLd16(tcol + 16 * g, raw);
           float v[16];
@@ -402,6 +413,13 @@ __global__ void __launch_bounds__(kThreads, C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf
              i, trace[i * 16 + 4] - t0, trace[i * 16 + 5] - t0, trace[i * 16 + 6] - t0, trace[i * 16 + 2] - t0, trace[i * 16 + 7] - t0,
              trace[i * 16 + 0] - t0, trace[i * 16 + 1] - t0, trace[i * 16 + 3] - t0, trace[i * 16 + 8] - t0, trace[i * 16 + 9] - t0);
   }
+  if (p.trace < 0 && tid == 0) {   // developer aid: residency window of every CTA (BEATRICE_B200_MRF_TRACE=-1)
+    unsigned long long t_end_ns;
+    uint32_t smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end_ns));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    printf("[%s cta] C %d bx %d by %d sm %u start_ns %llu end_ns %llu\n", "mrf", C, blockIdx.x, blockIdx.y, smid, t_start_ns, t_end_ns);
+  }
   if (warp == kWarpMma) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
@@ -425,7 +443,7 @@ void LaunchMrfT(const MrfStageParams& p, size_t smem, cudaStream_t s) {
     B200_CHECK(cudaFuncSetAttribute(mrf_branch_kernel<C, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev & 63] = true;
   }
-  LaunchPdl(mrf_branch_kernel<C, kSplit>, dim3(p.n_groups, 3, 1), dim3(kThreads, 1, 1), smem, s, 1, p);
+  LaunchPdl(mrf_branch_kernel<C, kSplit>, dim3(p.n_groups, 3, 1), dim3(ThreadsFor(C), 1, 1), smem, s, 1, p);
 }
 
 int NkFor(int C) { return C <= 16 ? 4 : (C <= 64 ? 2 : 1); }

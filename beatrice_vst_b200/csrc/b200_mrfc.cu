@@ -27,9 +27,13 @@ namespace b200 {
 namespace {
 
 constexpr int kNst = 4;          // weight ring stages
-constexpr int kEpiWarps = 4;     // warps 0-3: epilogue (TMEM lane quarter == warp)
-constexpr int kWarpMma = 4, kWarpW = 5, kWarpH = 6;
-constexpr int kThreads = 7 * 32;
+// warps 0-7: epilogue.  Warps w and w + 4 share TMEM lane quarter w & 3 (tile rows 32 (w & 3) ..) and
+// split its work items -- (tile, 16-channel group) and (peer, group) pairs -- by parity: the epilogue
+// is latency bound per warp, two warps per SM sub-partition nearly halve it.
+constexpr int kEpiWarps = 8;
+constexpr int kQuarters = 4;
+constexpr int kWarpMma = 8, kWarpW = 9, kWarpH = 10;
+constexpr int kThreads = 11 * 32;
 constexpr int kBars = 48;        // mbarrier slots reserved at the front of shared memory
 constexpr int kHdr = 8 * kBars + 16;
 
@@ -49,6 +53,8 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
   static_assert(Cs % 16 == 0, "channel slice must be a multiple of one K step");
   extern __shared__ __align__(1024) uint8_t smem[];
 
+  unsigned long long t_start_ns = 0;
+  if (p.trace < 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_ns));
   const int tid = threadIdx.x, lane = tid & 31;
   // warp index broadcast from lane 0: provably warp-uniform, so the role branches below are uniform
   // control flow and the single-thread MMA / TMA loops can live in uniform registers
@@ -67,9 +73,9 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t bar0 = SmemAddr(bars);
   const uint32_t bar_w_full = bar0, bar_w_empty = bar0 + 8 * kNst, bar_hist = bar0 + 16 * kNst, bar_free = bar_hist + 16,
-                 bar_box_full = bar_free + 16, bar_box_free = bar_box_full + 8 * kEpiWarps,
-                 bar_in = bar_box_free + 8 * kEpiWarps, bar_acc = bar_in + 8 * MT * Gs;
-  const int n_bars = 2 * kNst + 4 + 2 * kEpiWarps + MT * Gs + MT;
+                 bar_box_full = bar_free + 16, bar_box_free = bar_box_full + 8 * kQuarters,
+                 bar_in = bar_box_free + 8 * kQuarters, bar_acc = bar_in + 8 * MT * Gs;
+  const int n_bars = 2 * kNst + 4 + 2 * kQuarters + MT * Gs + MT;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * kBars);
   volatile uint32_t* in_cnt = reinterpret_cast<volatile uint32_t*>(smem + 8 * kBars + 4);   // += 1 per epilogue warp per conv input
   volatile uint32_t* acc_cnt = reinterpret_cast<volatile uint32_t*>(smem + 8 * kBars + 8);  // += 1 per conv whose MMAs retired
@@ -100,8 +106,9 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
     for (int i = 0; i < n_bars; ++i) {
       const uint32_t b = bar0 + 8 * i;
       uint32_t count = 1;
-      if (b >= bar_in && b < bar_acc) count = kEpiWarps;
-      if (b >= bar_box_free && b < bar_in) count = NC - 1;   // box_full: one local arrive.expect_tx per phase
+      if (b >= bar_in && b < bar_acc) count = kQuarters;     // the four warps that produce a group
+      if (b >= bar_box_free && b < bar_in) count = 2 * (NC - 1);   // both warps of the quarter, in every peer
+      // box_full: one local arrive.expect_tx per phase (count 1)
       MbarInit(b, count);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -124,7 +131,8 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
 
   if (warp < kEpiWarps) {
     // =========================== epilogue warps ===========================
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int q4 = warp & 3, whalf = warp >> 2, rtid = tid & 127;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
     const uint32_t x_col0 = 2 * MT * C;   // fp32 residual stream of the own channel slice
     // Everything up to here (barriers, TMEM, bias, and in the other warps the weight ring and the
     // history loads) touches nothing the preceding kernel -- the upsampler that writes u -- produces.
@@ -132,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
     PdlLaunchDependents();
     // ---- prologue: u -> TMEM (fp32 residual stream) and lrelu(u) -> X new rows ----
     for (int m = 0; m < MT; ++m) {
-      const int r = m * 128 + tid;
+      const int r = m * 128 + rtid;
       const int t = r / S, s = r - t * S;
       const int b = group * S + s;
       const bool exists = r < rows_valid;
@@ -142,6 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
       const float* frow = p.film ? p.film + static_cast<size_t>(b) * 2 * C + rank * Cs : nullptr;
 #pragma unroll 1
       for (int g = 0; g < Gs; ++g) {
+        if (((m * Gs + g) & 1) != whalf) continue;
         float v[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -198,10 +207,10 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
       const float* bias = bias_s + i * Cs;
       if (i >= 1 && !last) MbarWait(bar_free + 8 * ((i + 1) & 1), ((i - 1) >> 1) & 1);
       // the peers have consumed what this warp pushed for conv i-1
-      if (i >= 1) MbarWaitCluster(bar_box_free + 8 * warp, (i - 1) & 1);
+      if (i >= 1) MbarWaitCluster(bar_box_free + 8 * q4, (i - 1) & 1);
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
-        const int r = m * 128 + tid;
+        const int r = m * 128 + rtid;
         const int t = r / S, s = r - t * S;
         const int b = group * S + s;
         const bool exists = r < rows_valid;
@@ -214,17 +223,18 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         // ---- reduce-scatter, push half: the columns of every peer go to that peer's inbox; the peer's
         //      mbarrier counts the bytes (st.async complete_tx), so no fence and no arrive is needed ----
         {
-          const int w_rows = min(max(rows_valid - (m * 128 + warp * 32), 0), 32);   // rows this warp owns in tile m
-          if (lane == 0) MbarExpectTx(bar_box_full + 8 * warp, static_cast<uint32_t>(NC - 1) * w_rows * Cs * 4);
+          const int w_rows = min(max(rows_valid - (m * 128 + q4 * 32), 0), 32);   // rows of this lane quarter in tile m
+          if (lane == 0 && whalf == 0) MbarExpectTx(bar_box_full + 8 * q4, static_cast<uint32_t>(NC - 1) * w_rows * Cs * 4);
         }
 #pragma unroll 1
         for (int q = 1; q < NC; ++q) {
           const int pr = (rank + q) % NC;
           const int slot = rank < pr ? rank : rank - 1;
           const uint32_t dst = MapToCta(box_base + slot * box_slot + static_cast<uint32_t>(exists ? r : 0) * kBoxRow, pr);
-          const uint32_t rbar = MapToCta(bar_box_full + 8 * warp, pr);
+          const uint32_t rbar = MapToCta(bar_box_full + 8 * q4, pr);
 #pragma unroll 1
           for (int h = 0; h < Gs; ++h) {
+            if ((((q - 1) * Gs + h) & 1) != whalf) continue;
             uint32_t raw[16];
             TmemLd16(dcol + pr * Cs + 16 * h, raw);
             if (exists) {
@@ -237,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         }
         if (tid == 0 && m == 0) B200_TR(i, 1);
         // ---- pull half: own columns + the peers' partials, summed in rank order ----
-        MbarWait(bar_box_full + 8 * warp, (i * MT + m) & 1);
+        MbarWait(bar_box_full + 8 * q4, (i * MT + m) & 1);
         if (tid == 0 && m == 0) B200_TR(i, 2);
         const uint32_t xcol = t_lane + x_col0 + m * Cs;
         const uint32_t srow = d_base + static_cast<uint32_t>(d_hmax * S + r) * 16;
@@ -245,6 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         float* orow = br.out + (static_cast<size_t>(b) * br.out_slots * T + (frame % br.out_slots) * T + t) * C + rank * Cs;
 #pragma unroll 1
         for (int g = 0; g < Gs; ++g) {
+          if (((m * Gs + g) & 1) != whalf) continue;
           uint32_t raw[16];
           TmemLd16(dcol + rank * Cs + 16 * g, raw);
           float v[16];
@@ -314,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         // this warp's inbox rows are consumed: the peers may push conv i+1
         __syncwarp();
         if (lane == 0) {
-          for (int q = 1; q < NC; ++q) MbarArriveCluster(MapToCta(bar_box_free + 8 * warp, (rank + q) % NC));
+          for (int q = 1; q < NC; ++q) MbarArriveCluster(MapToCta(bar_box_free + 8 * q4, (rank + q) % NC));
         }
         __threadfence_block();
         __syncwarp();
@@ -471,6 +482,13 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
   // (no exit-time cluster barrier: every byte and every signal addressed to this CTA has been consumed by
   //  its epilogue warps before they get here -- inbox bytes are counted by box_full, and the last
   //  box_free arrivals, for conv 4, were awaited before the pushes of conv 5)
+  if (p.trace < 0 && tid == 0) {   // developer aid: residency window of every CTA (BEATRICE_B200_MRF_TRACE=-1)
+    unsigned long long t_end_ns;
+    uint32_t smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end_ns));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    printf("[%s cta] C %d bx %d by %d sm %u start_ns %llu end_ns %llu\n", "mrfc", C, blockIdx.x, blockIdx.y, smid, t_start_ns, t_end_ns);
+  }
   if (warp == kWarpMma) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
@@ -512,7 +530,7 @@ bool MrfClusterSupported(int C, int NC, int T, int S, bool split) {
   const int MT = (S * T + 127) / 128;
   const int Cs = C / NC;
   if (2 * MT * C + MT * Cs > 512) return false;
-  if (2 * kNst + 4 + 2 * kEpiWarps + MT * (Cs / 16) + MT > kBars) return false;
+  if (2 * kNst + 4 + 2 * kQuarters + MT * (Cs / 16) + MT > kBars) return false;
   return MrfClusterSmemBytes(C, NC, T, S, split) <= 227 * 1024;
 }
 
