@@ -673,7 +673,8 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
   const int Bn = B;
   const char* tag = m->is_pitch ? "pitch" : "phone";
 
-  {
+  const bool fe0_fused = Frontend0Supported(db.host[conv_idx[0]]);
+  if (!fe0_fused) {
     const Ring in0 = arena.ring(ring_in[0]);
     const float* stage = stage_ptr;
     Op op;
@@ -689,7 +690,11 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     op.name = std::string(tag) + ".fe" + std::to_string(i);
     op.flops = ConvFlops(h, B);
     op.bytes = ConvBytes(h, B);
-    if (i == 0)
+    if (i == 0 && fe0_fused) {
+      const float* stage = stage_ptr;
+      float* ring0 = arena.ring(ring_in[0]).base;
+      op.launch = [=](cudaStream_t s) { LaunchFrontend0(h, stage, ring0, Bn, frame, s); };   // ingest + conv
+    } else if (i == 0)
       op.launch = [=](cudaStream_t s) { LaunchDirectConv(dp, h, Bn, frame, s); };
     else
       op.launch = GemmLauncher(dp, h, 1, Bn, frame, tc, tcm);

@@ -280,51 +280,111 @@ __global__ void direct_conv_kernel(const ConvDesc* __restrict__ descs, int B, co
 }
 
 // Vocoder post conv: out[b][t] = tanh(b0 + sum_{j<7} sum_{ci<16} lrelu(x[b][t-(6-j)][ci]) * w[j][ci]) with
-// x = (x0 + x1 + x2) * in_scale (the three MRF branches).  One thread per output sample; rows
-// are 64 bytes so every load is a float4; neighbouring threads share 6 of their 7 rows (L1).
-__global__ void __launch_bounds__(128) post_conv_kernel(const ConvDesc* __restrict__ descs, int B,
+// x = (x0 + x1 + x2) * in_scale (the three MRF branches).  One block per stream: the hop's rows plus six
+// rows of history are combined, activated and staged in shared memory once (coalesced float4 loads),
+// then one thread per output sample walks the 7 x 16 window.  Summation order is the oracle's (tap,
+// then channel), so the result does not depend on the staging.
+constexpr int kPostRowLd = 20;   // floats per staged row (16 + 4: conflict-free 16-byte reads, rows 80 B apart)
+__global__ void __launch_bounds__(256) post_conv_kernel(const __grid_constant__ ConvDesc d, int B,
                                                          const int* __restrict__ frame_ptr) {
+  extern __shared__ float post_smem[];
+  float* ws = post_smem;                 // [7][16]
+  float* xs = post_smem + 7 * 16;        // [T + 6][kPostRowLd]
+  const int tid = threadIdx.x, b = blockIdx.x;
+  if (tid < 7 * 16) ws[tid] = __ldg(d.w + tid);            // constants: before the dependency wait
+  const float bias = d.bias ? __ldg(d.bias) : 0.f;
+  const int frame = *frame_ptr;                             // written only by the chain's advance kernel
   PdlWait();
   PdlLaunchDependents();
-  __shared__ float ws[7 * 16];
-  const ConvDesc d = descs[0];
-  if (threadIdx.x < 7 * 16) ws[threadIdx.x] = __ldg(d.w + threadIdx.x);
-  __syncthreads();
-  const int frame = *frame_ptr;
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= B * d.T) return;
-  const int b = m / d.T, t = m - b * d.T;
   const int x_L = d.x_slots * d.x_T;
   const int x_cur = (frame % d.x_slots) * d.x_T;
   const long long xb = static_cast<long long>(b) * x_L * 16;
-  float acc = d.bias ? __ldg(d.bias) : 0.f;
-#pragma unroll
-  for (int j = 0; j < 7; ++j) {
-    int r = x_cur + t - (6 - j);
+  for (int idx = tid; idx < (d.T + 6) * 4; idx += 256) {
+    const int row = idx >> 2, q = idx & 3;
+    int r = x_cur + row - 6;
     if (r < 0) r += x_L;
-    const long long a = xb + static_cast<long long>(r) * 16;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 v = Ldg4(d.x[0] + a + 4 * q);
-      if (d.n_x > 1) {
-        const float4 v1 = Ldg4(d.x[1] + a + 4 * q), v2 = Ldg4(d.x[2] + a + 4 * q);
-        v.x = ((v.x + v1.x) + v2.x) * d.in_scale;
-        v.y = ((v.y + v1.y) + v2.y) * d.in_scale;
-        v.z = ((v.z + v1.z) + v2.z) * d.in_scale;
-        v.w = ((v.w + v1.w) + v2.w) * d.in_scale;
-      }
-      v = InAct4(v, d.in_act);
-      const float* wq = ws + j * 16 + 4 * q;
-      acc = fmaf(v.x, wq[0], acc);
-      acc = fmaf(v.y, wq[1], acc);
-      acc = fmaf(v.z, wq[2], acc);
-      acc = fmaf(v.w, wq[3], acc);
+    const long long a = xb + static_cast<long long>(r) * 16 + 4 * q;
+    float4 v = Ldg4(d.x[0] + a);
+    if (d.n_x > 1) {
+      const float4 v1 = Ldg4(d.x[1] + a), v2 = Ldg4(d.x[2] + a);
+      v.x = ((v.x + v1.x) + v2.x) * d.in_scale;
+      v.y = ((v.y + v1.y) + v2.y) * d.in_scale;
+      v.z = ((v.z + v1.z) + v2.z) * d.in_scale;
+      v.w = ((v.w + v1.w) + v2.w) * d.in_scale;
     }
+    v = InAct4(v, d.in_act);
+    *reinterpret_cast<float4*>(xs + row * kPostRowLd + 4 * q) = v;
   }
-  acc = ActApply(acc, d.out_act);
+  __syncthreads();
   const int y_L = d.y_slots * d.y_T;
   const int y_cur = (frame % d.y_slots) * d.y_T;
-  d.y[(static_cast<long long>(b) * y_L + y_cur) * d.y_C + t] = acc;
+  for (int t = tid; t < d.T; t += 256) {
+    float acc = bias;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(xs + (t + j) * kPostRowLd + 4 * q);
+        const float* wq = ws + j * 16 + 4 * q;
+        acc = fmaf(v.x, wq[0], acc);
+        acc = fmaf(v.y, wq[1], acc);
+        acc = fmaf(v.z, wq[2], acc);
+        acc = fmaf(v.w, wq[3], acc);
+      }
+    }
+    acc = ActApply(acc, d.out_act);
+    d.y[(static_cast<long long>(b) * y_L + y_cur) * d.y_C + t] = acc;
+  }
+}
+
+// Front-end layer 0 of the encoders (C_in = 1, k = 10, stride 5 -> N <= 32 channels) fused with the
+// ingest of the hop: one block per stream copies the hop's samples staging -> ring (they are next
+// hop's history), stages them with the k - stride samples of history, and computes the T x N outputs
+// from shared memory.  Writes the fp32 ring and / or the bf16 (hi [+ lo]) ring of the next layer.
+__global__ void __launch_bounds__(256) frontend0_kernel(const __grid_constant__ ConvDesc d, const float* __restrict__ staging,
+                                                         float* __restrict__ ring, int B, const int* __restrict__ frame_ptr) {
+  __shared__ float xs[kInHop + 32];
+  __shared__ float ws[16 * 32];
+  __shared__ float bs[32];
+  const int tid = threadIdx.x, b = blockIdx.x;
+  for (int i = tid; i < d.k * d.N; i += 256) ws[i] = __ldg(d.w + i);   // constants: before the dependency wait
+  if (tid < d.N) bs[tid] = d.bias ? __ldg(d.bias + tid) : 0.f;
+  const int frame = *frame_ptr;                                        // written only by the chain's advance kernel
+  PdlWait();
+  PdlLaunchDependents();
+  const int hist = d.k - d.stride;
+  const int x_L = d.x_slots * d.x_T;
+  const int x_cur = (frame % d.x_slots) * d.x_T;
+  float* rb = ring + static_cast<long long>(b) * x_L;
+  for (int i = tid; i < d.x_T; i += 256) {
+    const float v = staging[static_cast<long long>(b) * d.x_T + i];
+    xs[hist + i] = v;
+    rb[x_cur + i] = v;
+  }
+  if (tid < hist) {
+    int r = x_cur - hist + tid;
+    if (r < 0) r += x_L;
+    xs[tid] = rb[r];
+  }
+  __syncthreads();
+  const int y_L = d.y_slots * d.y_T;
+  const int y_cur = (frame % d.y_slots) * d.y_T;
+  const int yh_L = d.yh_slots * d.y_T;
+  const int yh_cur = d.yh ? (frame % d.yh_slots) * d.y_T : 0;
+  for (int item = tid; item < d.T * d.N; item += 256) {
+    const int t = item / d.N, n = item - t * d.N;
+    float acc = bs[n];
+    for (int j = 0; j < d.k; ++j) acc = fmaf(xs[t * d.stride + j], ws[j * d.N + n], acc);
+    acc = (d.yh && d.out_act == kActGelu) ? GeluFastK(acc) : ActApply(acc, d.out_act);   // exact erff on the fp32 parity path
+    if (d.y) d.y[(static_cast<long long>(b) * y_L + y_cur) * d.y_C + static_cast<long long>(t) * d.N + n] = acc;
+    if (d.yh) {
+      const long long o = (static_cast<long long>(b) * yh_L + yh_cur) * d.y_C + static_cast<long long>(t) * d.N + n;
+      const float hv = ActApply(acc, d.yh_act);
+      const __nv_bfloat16 h = __float2bfloat16_rn(hv);
+      d.yh[o] = __bfloat16_as_ushort(h);
+      if (d.yl) d.yl[o] = __bfloat16_as_ushort(__float2bfloat16_rn(hv - __bfloat162float(h)));
+    }
+  }
 }
 
 __device__ __forceinline__ float WarpSum(float v) {
@@ -486,39 +546,67 @@ __global__ void pitch_transform_kernel(const int* __restrict__ q_in, const Pitch
 }
 
 // hidden[b][c] = be[c] + phone[b].We[:,c] + pitch_emb[q[b]][c] + feat[b].Wf[:,c] (+ spk + formant)
+// One block = kCondStreams streams x 256 channels: every weight fetched from L2 is used for all of the
+// block's streams, and the loads of a batch of 8 phone channels are in flight together.
+constexpr int kCondStreams = 2;
 __global__ void __launch_bounds__(256) cond_kernel(const float* __restrict__ phone, int P, const int* __restrict__ q,
                                                    int bins, const float* __restrict__ feat,
                                                    const float* __restrict__ We, const float* __restrict__ be,
                                                    const float* __restrict__ pitch_emb, const float* __restrict__ Wf,
                                                    const float* __restrict__ spk, const float* __restrict__ formant,
                                                    float* __restrict__ ring, uint16_t* __restrict__ ring_hi,
-                                                   uint16_t* __restrict__ ring_lo, int slots,
+                                                   uint16_t* __restrict__ ring_lo, int slots, int B,
                                                    const int* __restrict__ frame_ptr) {
+  __shared__ float ph[kCondStreams][256];
+  __shared__ float ft[kCondStreams][kPitchFeatures];
+  const int b0 = blockIdx.x * kCondStreams, c = threadIdx.x;
+  const float bias = __ldg(be + c);                  // constants: before the dependency wait
+  float wf[kPitchFeatures];
+#pragma unroll
+  for (int i = 0; i < kPitchFeatures; ++i) wf[i] = __ldg(Wf + i * kHidden + c);
+  const int frame = *frame_ptr;                      // written only by the chain's advance kernel
   PdlWait();
   PdlLaunchDependents();
-  __shared__ float ph[256];
-  __shared__ float ft[kPitchFeatures];
-  const int b = blockIdx.x, c = threadIdx.x;
-  if (c < P) ph[c] = phone[static_cast<long long>(b) * P + c];
-  if (c < kPitchFeatures) ft[c] = feat[b * kPitchFeatures + c];
-  __syncthreads();
-  float acc = __ldg(be + c);
-  for (int i = 0; i < P; ++i) acc = fmaf(ph[i], __ldg(We + i * kHidden + c), acc);
-  const int qq = min(max(q[b], 0), bins - 1);
-  float v = acc + __ldg(pitch_emb + static_cast<long long>(qq) * kHidden + c);
-  float fp = 0.f;
 #pragma unroll
-  for (int i = 0; i < kPitchFeatures; ++i) fp = fmaf(ft[i], __ldg(Wf + i * kHidden + c), fp);
-  v += fp;
-  if (spk) v += spk[static_cast<long long>(b) * kHidden + c];
-  if (formant) v += formant[static_cast<long long>(b) * kHidden + c];
-  const int frame = *frame_ptr;
-  const long long o = (static_cast<long long>(b) * slots + (frame % slots)) * kHidden + c;
-  if (ring) ring[o] = v;
-  if (ring_hi) {   // bf16 hi [+ lo] planes for the tensor-core pre conv
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    ring_hi[o] = __bfloat16_as_ushort(h);
-    if (ring_lo) ring_lo[o] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+  for (int s = 0; s < kCondStreams; ++s) {
+    const int b = b0 + s;
+    if (c < P) ph[s][c] = b < B ? phone[static_cast<long long>(b) * P + c] : 0.f;
+    if (c < kPitchFeatures) ft[s][c] = b < B ? feat[b * kPitchFeatures + c] : 0.f;
+  }
+  __syncthreads();
+  float acc[kCondStreams];
+#pragma unroll
+  for (int s = 0; s < kCondStreams; ++s) acc[s] = bias;
+#pragma unroll 2
+  for (int i0 = 0; i0 < P; i0 += 8) {   // P is 128 or 256 (beatrice.h:17,20,23)
+    float w[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) w[u] = __ldg(We + (i0 + u) * kHidden + c);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int s = 0; s < kCondStreams; ++s) acc[s] = fmaf(ph[s][i0 + u], w[u], acc[s]);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < kCondStreams; ++s) {
+    const int b = b0 + s;
+    if (b >= B) break;
+    const int qq = min(max(q[b], 0), bins - 1);
+    float v = acc[s] + __ldg(pitch_emb + static_cast<long long>(qq) * kHidden + c);
+    float fp = 0.f;
+#pragma unroll
+    for (int i = 0; i < kPitchFeatures; ++i) fp = fmaf(ft[s][i], wf[i], fp);
+    v += fp;
+    if (spk) v += spk[static_cast<long long>(b) * kHidden + c];
+    if (formant) v += formant[static_cast<long long>(b) * kHidden + c];
+    const long long o = (static_cast<long long>(b) * slots + (frame % slots)) * kHidden + c;
+    if (ring) ring[o] = v;
+    if (ring_hi) {   // bf16 hi [+ lo] planes for the tensor-core pre conv
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      ring_hi[o] = __bfloat16_as_ushort(h);
+      if (ring_lo) ring_lo[o] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+    }
   }
 }
 
@@ -700,8 +788,17 @@ void LaunchPostConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int
     LaunchDirectConv(d_desc, h0, B, d_frame, s);
     return;
   }
-  const int total = B * h0.T;
-  LaunchPdl(post_conv_kernel, dim3((total + 127) / 128), dim3(128), 0, s, 1, d_desc, B, d_frame);
+  const size_t smem = (7 * 16 + static_cast<size_t>(h0.T + 6) * kPostRowLd) * sizeof(float);
+  LaunchPdl(post_conv_kernel, dim3(B), dim3(256), smem, s, 1, h0, B, d_frame);
+  B200_CHECK(cudaGetLastError());
+}
+
+bool Frontend0Supported(const ConvDesc& h0) {
+  return h0.C_in == 1 && h0.N <= 32 && h0.k <= 16 && h0.dil == 1 && h0.x_T <= kInHop && h0.k - h0.stride <= 32 &&
+         h0.n_x == 1 && h0.res == nullptr;
+}
+void LaunchFrontend0(const ConvDesc& h0, const float* staging, float* ring, int B, const int* d_frame, cudaStream_t s) {
+  LaunchPdl(frontend0_kernel, dim3(B), dim3(256), 0, s, 1, h0, staging, ring, B, d_frame);
   B200_CHECK(cudaGetLastError());
 }
 
@@ -737,7 +834,8 @@ void LaunchPitchTransform(const int* q_in, const PitchParams* params, int bins, 
 void LaunchCond(const float* phone, int P, const int* q, int bins, const float* feat, const float* We,
                 const float* be, const float* pitch_emb, const float* Wf, const float* spk, const float* formant,
                 float* ring, uint16_t* ring_hi, uint16_t* ring_lo, int slots, int B, const int* d_frame, cudaStream_t s) {
-  LaunchPdl(cond_kernel, dim3(B), dim3(kHidden), 0, s, 1, phone, P, q, bins, feat, We, be, pitch_emb, Wf, spk, formant, ring, ring_hi, ring_lo, slots, d_frame);
+  LaunchPdl(cond_kernel, dim3((B + kCondStreams - 1) / kCondStreams), dim3(kHidden), 0, s, 1, phone, P, q, bins, feat, We, be,
+            pitch_emb, Wf, spk, formant, ring, ring_hi, ring_lo, slots, B, d_frame);
   B200_CHECK(cudaGetLastError());
 }
 

@@ -96,6 +96,9 @@ size_t PackWeightsTc(const float* w, int k, int C_in, int N, int bn_cap, int* bn
 // post conv of the vocoder (16 -> 1 channels, k = 7, tanh): one thread per output sample
 void LaunchPostConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int* d_frame, cudaStream_t s);
 void LaunchDirectConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int* d_frame, cudaStream_t s);
+// encoder front-end layer 0 (C_in = 1) fused with the hop's ingest: staging [B][x_T] -> ring slot + conv
+bool Frontend0Supported(const ConvDesc& h0);
+void LaunchFrontend0(const ConvDesc& h0, const float* staging, float* ring, int B, const int* d_frame, cudaStream_t s);
 void LaunchNorm(const NormDesc& d, int B, const int* d_frame, cudaStream_t s);
 // staging [B][T*C] -> ring slot of the current hop
 void LaunchIngest(const float* staging, float* ring, int slots, int T, int C, int B, const int* d_frame,
