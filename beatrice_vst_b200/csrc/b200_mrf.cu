@@ -20,7 +20,11 @@
 //    TMA bulk loads global -> shared before a conv, bulk stores of the new tail shared -> global
 //    after its input is complete.
 //  * Precision: plain bf16 (1 MMA per K step) or split bf16 (x = hi + lo for both operands,
-//    hi*hi + hi*lo + lo*hi, fp32 accumulate): same scheme as b200_tc.cu.
+//    hi*hi + hi*lo + lo*hi, fp32 accumulate).  In split mode the weight rows of a K step are packed
+//    [W_hi ; W_lo] so that ONE MMA of width N = 2C yields x_hi*W_hi (accumulator columns [0,C)) and
+//    x_hi*W_lo (columns [C,2C)), and a second MMA of width C adds x_lo*W_hi onto columns [0,C): two
+//    MMAs instead of three, and the x_hi panel -- shared-memory reads bound these narrow-N MMAs --
+//    is read once instead of twice.  The epilogue adds the two column halves.
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -32,7 +36,12 @@
 namespace b200 {
 namespace {
 
-constexpr int kNst = 4;          // weight ring stages
+// Weight ring: K steps per chunk and stages.  Every chunk costs the MMA warp one mbarrier wait (~90
+// cycles even when already complete) and one tcgen05.commit, so chunks are as large as the CTA's
+// shared-memory budget allows (C = 64: one CTA per SM, 16 KB chunks; C = 32: two per SM, 8 KB; C = 16:
+// four per SM, 6 KB) while the bytes in flight still cover the ring's ~1.6k-cycle round trip.
+__host__ __device__ constexpr int NkFor(int C) { return C <= 16 ? 6 : 4; }
+__host__ __device__ constexpr int NstFor(int C) { return C >= 64 ? 4 : 3; }
 // Epilogue warps: 8 where a tile has more than one work item -- (tile, 16-channel group) pairs --
 // per conv, else 4.  Warps w and w + 4 share TMEM lane quarter w & 3 (tile rows 32 (w & 3) ..) and take
 // the items of one parity each: the epilogue is latency bound per warp, two warps per SM
@@ -45,7 +54,7 @@ template <int C>
 struct MrfCfg {
   static constexpr int kG = C / 16;                       // 16-channel groups == K steps per tap
   static constexpr int kPan = C / 8;                      // 8-channel K panels
-  static constexpr int kNk = C <= 16 ? 4 : (C <= 64 ? 2 : 1);   // K steps per weight chunk
+  static constexpr int kNk = NkFor(C);                    // K steps per weight chunk
 };
 
 template <int C, bool kSplit>
@@ -55,8 +64,10 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
   using Cfg = MrfCfg<C>;
   constexpr int G = Cfg::kG, PAN = Cfg::kPan, NK = Cfg::kNk;
   constexpr int P = kSplit ? 2 : 1;
+  constexpr int DW = kSplit ? 2 * C : C;          // accumulator columns per 128-row tile (see "Precision")
   constexpr uint32_t kKstepBytes = P * C * 32;
   constexpr uint32_t kChunkBytes = NK * kKstepBytes;
+  constexpr int kNst = NstFor(C);
   extern __shared__ __align__(1024) uint8_t smem[];
 
   unsigned long long t_start_ns = 0;
@@ -69,7 +80,11 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
   const int k = br.k, T = p.T, S = p.S, MT = p.MT;
   const int group = blockIdx.x;
   const int HX = (k - 1) * 5, HY = k - 1;            // history rows (time steps) in front of X / Y
-  const int RX = HX * S + MT * 128, RY = HY * S + MT * 128;
+  // rows of the X / Y panels: history + the hop's rows (8-row granules).  The last tile's MMA may read up
+  // to 127 rows past that -- into the next panel, plane or buffer, all mapped shared memory; rows of an
+  // operand only ever reach the same rows of the accumulator, and those rows are never read back.
+  const int rows8 = (S * T + 7) & ~7;
+  const int RX = HX * S + rows8, RY = HY * S + rows8;
   const int frame = *p.frame;
 
   // ---- shared memory carve-up ----
@@ -99,7 +114,7 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
   if (tracing && tid < 128) trace[tid] = 0;
 
   uint32_t tmem_cols = 32;
-  while (tmem_cols < static_cast<uint32_t>(2 * MT * C)) tmem_cols <<= 1;
+  while (tmem_cols < static_cast<uint32_t>(2 * MT * DW)) tmem_cols <<= 1;
 
   for (int i = tid; i < 6 * C; i += kThreads) bias_s[i] = __ldg(br.bias + i);
   if (tid == 0) {
@@ -140,7 +155,8 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
       const int r = m * 128 + rtid;
       const int t = r / S, s = r - t * S;
       const int b = group * S + s;
-      const bool valid = r < rows_valid && b < p.B;
+      const bool exists = r < rows_valid;
+      const bool valid = exists && b < p.B;
       const float* urow = p.u + (static_cast<size_t>(b) * p.u_slots * T + (frame % p.u_slots) * T + t) * C;
       const uint32_t srow = x_base + static_cast<uint32_t>(HX * S + r) * 16;
       const float* frow = p.film ? p.film + static_cast<size_t>(b) * 2 * C : nullptr;
@@ -165,18 +181,25 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
         uint32_t raw[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) raw[e] = __float_as_uint(v[e]);
-        TmemSt16(t_lane + m * C + 16 * g, raw);
+        TmemSt16(t_lane + m * DW + 16 * g, raw);
+        if (kSplit) {   // the x_hi*W_lo half of the residual tile starts every c2 at zero
+#pragma unroll
+          for (int e = 0; e < 16; ++e) raw[e] = 0u;
+          TmemSt16(t_lane + m * DW + C + 16 * g, raw);
+        }
 #pragma unroll
         for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.0f ? v[e] : 0.1f * v[e];
         uint4 h0, l0, h1, l1;
         Pack8<kSplit>(v, &h0, &l0);
         Pack8<kSplit>(v + 8, &h1, &l1);
-        const uint32_t a0 = srow + (2 * g) * x_pstride;
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(h0.x), "r"(h0.y), "r"(h0.z), "r"(h0.w) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + x_pstride), "r"(h1.x), "r"(h1.y), "r"(h1.z), "r"(h1.w) : "memory");
-        if (kSplit) {
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + x_plane), "r"(l0.x), "r"(l0.y), "r"(l0.z), "r"(l0.w) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + x_plane + x_pstride), "r"(l1.x), "r"(l1.y), "r"(l1.z), "r"(l1.w) : "memory");
+        if (exists) {   // rows past S*T do not exist in the panels (the next panel starts there)
+          const uint32_t a0 = srow + (2 * g) * x_pstride;
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(h0.x), "r"(h0.y), "r"(h0.z), "r"(h0.w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + x_pstride), "r"(h1.x), "r"(h1.y), "r"(h1.z), "r"(h1.w) : "memory");
+          if (kSplit) {
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + x_plane), "r"(l0.x), "r"(l0.y), "r"(l0.z), "r"(l0.w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + x_plane + x_pstride), "r"(l1.x), "r"(l1.y), "r"(l1.z), "r"(l1.w) : "memory");
+          }
         }
         TmemStWait();
         FenceProxyAsync();
@@ -185,9 +208,8 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
         if (lane == 0) MbarArrive(bar_in + 8 * (m * G + g));
       }
     }
-    __threadfence_block();
     __syncwarp();
-    if (lane == 0) atomicAdd(const_cast<uint32_t*>(in_cnt), 1u);
+    if (lane == 0) SmemAddRelease(in_cnt);
     if (tid == 0) B200_TR(7, 1);
     // ---- the six convs ----
 #pragma unroll 1
@@ -205,13 +227,14 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
         const int r = m * 128 + rtid;
         const int t = r / S, s = r - t * S;
         const int b = group * S + s;
-        const bool valid = r < rows_valid && b < p.B;
+        const bool exists = r < rows_valid;
+        const bool valid = exists && b < p.B;
         MbarWait(bar_acc + 8 * m, i & 1);
         TcFenceAfter();
         if (tid == 0 && m == 0) B200_TR(i, 0);
         if (tid == 0 && m == MT - 1) B200_TR(i, 1);
         if (m == MT - 1 && tid == 0) atomicAdd(const_cast<uint32_t*>(acc_cnt), 1u);   // conv i's MMAs have all retired
-        const uint32_t tcol = t_lane + (is_c1 ? (MT + m) * C : m * C);
+        const uint32_t tcol = t_lane + (is_c1 ? (MT + m) * DW : m * DW);
         const uint32_t srow = d_base + static_cast<uint32_t>(d_hmax * S + r) * 16;
         float* orow = br.out + (static_cast<size_t>(b) * br.out_slots * T + (frame % br.out_slots) * T + t) * C;
 #pragma unroll 1
@@ -221,12 +244,24 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
           TmemLd16(tcol + 16 * g, raw);
           float v[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]) + bias[16 * g + e];
+          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]);
+          if (kSplit) {   // + the x_hi*W_lo half
+            TmemLd16(tcol + C + 16 * g, raw);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] += __uint_as_float(raw[e]);
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] += bias[16 * g + e];
           if (!is_c1) {
             if (!last) {
 #pragma unroll
               for (int e = 0; e < 16; ++e) raw[e] = __float_as_uint(v[e]);
               TmemSt16(tcol + 16 * g, raw);
+              if (kSplit) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) raw[e] = 0u;
+                TmemSt16(tcol + C + 16 * g, raw);
+              }
             } else if (valid) {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
@@ -243,12 +278,14 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
             uint4 h0, l0, h1, l1;
             Pack8<kSplit>(v, &h0, &l0);
             Pack8<kSplit>(v + 8, &h1, &l1);
-            const uint32_t a0 = srow + (2 * g) * d_pstride;
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(h0.x), "r"(h0.y), "r"(h0.z), "r"(h0.w) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + d_pstride), "r"(h1.x), "r"(h1.y), "r"(h1.z), "r"(h1.w) : "memory");
-            if (kSplit) {
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + d_plane), "r"(l0.x), "r"(l0.y), "r"(l0.z), "r"(l0.w) : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + d_plane + d_pstride), "r"(l1.x), "r"(l1.y), "r"(l1.z), "r"(l1.w) : "memory");
+            if (exists) {
+              const uint32_t a0 = srow + (2 * g) * d_pstride;
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(h0.x), "r"(h0.y), "r"(h0.z), "r"(h0.w) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + d_pstride), "r"(h1.x), "r"(h1.y), "r"(h1.z), "r"(h1.w) : "memory");
+              if (kSplit) {
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + d_plane), "r"(l0.x), "r"(l0.y), "r"(l0.z), "r"(l0.w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + d_plane + d_pstride), "r"(l1.x), "r"(l1.y), "r"(l1.z), "r"(l1.w) : "memory");
+              }
             }
             if (!is_c1) TmemStWait();
             FenceProxyAsync();
@@ -260,15 +297,14 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
       }
       if (tid == 0) B200_TR(i, 3);
       if (!last) {
-        __threadfence_block();
         __syncwarp();
-        if (lane == 0) atomicAdd(const_cast<uint32_t*>(in_cnt), 1u);
+        if (lane == 0) SmemAddRelease(in_cnt);
       }
     }
   } else if (warp == kWarpMma) {
     // =========================== MMA issuer ===========================
     {
-      const uint32_t idesc = MakeIdesc(C);
+      const uint32_t idesc = MakeIdesc(C), idesc_cat = MakeIdesc(2 * C);
       uint32_t cc = 0;
 #pragma unroll 1
       for (int i = 0; i < 6; ++i) {
@@ -279,7 +315,7 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
         if (lane == 0) B200_TR(i, 4);
 #pragma unroll 1
         for (int m = 0; m < MT; ++m) {
-          const uint32_t dcol = tmem_base + (buf == 0 ? (MT + m) * C : m * C);
+          const uint32_t dcol = tmem_base + (buf == 0 ? (MT + m) * DW : m * DW);
           int ks = 0;
 #pragma unroll 1
           for (int g = 0; g < G; ++g) {
@@ -299,14 +335,16 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
               const uint32_t a_hi = bbase + (2 * g) * pstride + static_cast<uint32_t>(row0) * 16;
               const uint32_t w_hi = w_base + stage * kChunkBytes + within * kKstepBytes;
               const uint64_t ah = MakeDesc(a_hi, pstride, 128);
-              const uint64_t wh = MakeDesc(w_hi, C * 16, 128);
               const uint32_t acc = buf == 0 ? (ks > 0 ? 1u : 0u) : 1u;
-              MmaW(dcol, ah, wh, idesc, acc);
               if (kSplit) {
+                // weight rows of the K step: [W_hi ; W_lo], 2C rows per 8-element K panel
+                const uint64_t wcat = MakeDesc(w_hi, 2 * C * 16, 128);
                 const uint64_t al = MakeDesc(a_hi + plane, pstride, 128);
-                const uint64_t wl = MakeDesc(w_hi + C * 32, C * 16, 128);
-                MmaW(dcol, ah, wl, idesc, 1u);
-                MmaW(dcol, al, wh, idesc, 1u);
+                MmaW(dcol, ah, wcat, idesc_cat, acc);   // x_hi*W_hi -> cols [0,C), x_hi*W_lo -> cols [C,2C)
+                MmaW(dcol, al, wcat, idesc, 1u);        // x_lo*W_hi -> cols [0,C) (first C rows of the same tile)
+              } else {
+                const uint64_t wh = MakeDesc(w_hi, C * 16, 128);
+                MmaW(dcol, ah, wh, idesc, acc);
               }
               ++ks;
               if (within == NK - 1 || ks == k * G) {
@@ -446,7 +484,6 @@ void LaunchMrfT(const MrfStageParams& p, size_t smem, cudaStream_t s) {
   LaunchPdl(mrf_branch_kernel<C, kSplit>, dim3(p.n_groups, 3, 1), dim3(ThreadsFor(C), 1, 1), smem, s, 1, p);
 }
 
-int NkFor(int C) { return C <= 16 ? 4 : (C <= 64 ? 2 : 1); }
 
 }  // namespace
 
@@ -454,12 +491,14 @@ size_t MrfSmemBytes(int C, int T, int S, bool split) {
   const int MT = (S * T + 127) / 128;
   const int P = split ? 2 : 1, PAN = C / 8;
   const int k = 11;   // the launch is sized for its largest branch
-  const size_t RX = static_cast<size_t>((k - 1) * 5) * S + MT * 128, RY = static_cast<size_t>(k - 1) * S + MT * 128;
+  const size_t rows8 = (static_cast<size_t>(S) * T + 7) & ~static_cast<size_t>(7);
+  const size_t RX = static_cast<size_t>((k - 1) * 5) * S + rows8, RY = static_cast<size_t>(k - 1) * S + rows8;
+  (void)MT;
   size_t off = (8 * 40 + 16 + 6 * C * 4 + 127) / 128 * 128;
   off += P * PAN * RX * 16;
   off += P * PAN * RY * 16;
   off = (off + 127) / 128 * 128;
-  off += static_cast<size_t>(kNst) * NkFor(C) * P * C * 32;
+  off += static_cast<size_t>(NstFor(C)) * NkFor(C) * P * C * 32;   // also absorbs the last tile's MMA over-read (< 2 KB)
   off += 1024;   // developer trace area
   return off;
 }
@@ -467,8 +506,8 @@ size_t MrfSmemBytes(int C, int T, int S, bool split) {
 bool MrfFusedSupported(int C, int T, int S, bool split) {
   if (C != 16 && C != 32 && C != 64) return false;
   const int MT = (S * T + 127) / 128;
-  if (2 * MT * C > 512) return false;
-  if (2 * 4 + 4 + MT * (C / 16) + MT > 40) return false;
+  if (2 * MT * (split ? 2 * C : C) > 512) return false;
+  if (2 * NstFor(C) + 4 + MT * (C / 16) + MT > 40) return false;
   return MrfSmemBytes(C, T, S, split) <= 227 * 1024;
 }
 
@@ -477,8 +516,11 @@ size_t MrfHistElems(int C, int k, int S, int n_groups, bool split) {
 }
 
 size_t PackMrfWeights(const float* const w[6], int k, int C, bool split, uint16_t* out) {
-  // per conv: [ks = g*k + j][plane][2 panels][C rows (n)][8]   element = W[j][16g + 8p + e][n]
+  // per conv, K step ks = g*k + j, element = W[j][16g + 8p + e][n]:
+  //   planar (bf16 mode, and split mode at C = 128 / the cluster kernel): [plane][2 panels][C rows (n)][8]
+  //   concatenated (split mode at C <= 64 / the single-CTA kernel):       [2 panels][2C rows: hi n, then lo n][8]
   const int G = C / 16, P = split ? 2 : 1;
+  const bool concat = split && C <= 64;
   const size_t kstep = static_cast<size_t>(P) * 2 * C * 8;
   const size_t total = 6 * static_cast<size_t>(k) * G * kstep;
   if (!out) return total;
@@ -492,9 +534,14 @@ size_t PackMrfWeights(const float* const w[6], int k, int C, bool split, uint16_
               const int ci = 16 * g + 8 * pp + e;
               const float val = w[i][(static_cast<size_t>(j) * C + ci) * C + n];
               const uint16_t h = Bf16Rn(val);
-              const size_t o = (static_cast<size_t>(pp) * C + n) * 8 + e;
-              blk[o] = h;
-              if (split) blk[static_cast<size_t>(2) * C * 8 + o] = Bf16Rn(val - Bf16ToF(h));
+              if (concat) {
+                blk[(static_cast<size_t>(pp) * 2 * C + n) * 8 + e] = h;
+                blk[(static_cast<size_t>(pp) * 2 * C + C + n) * 8 + e] = Bf16Rn(val - Bf16ToF(h));
+              } else {
+                const size_t o = (static_cast<size_t>(pp) * C + n) * 8 + e;
+                blk[o] = h;
+                if (split) blk[static_cast<size_t>(2) * C * 8 + o] = Bf16Rn(val - Bf16ToF(h));
+              }
             }
       }
   return total;

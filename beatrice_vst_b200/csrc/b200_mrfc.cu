@@ -191,9 +191,8 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         if (lane == 0) MbarArrive(bar_in + 8 * (m * Gs + g));
       }
     }
-    __threadfence_block();
     __syncwarp();
-    if (lane == 0) atomicAdd(const_cast<uint32_t*>(in_cnt), 1u);
+    if (lane == 0) SmemAddRelease(in_cnt);
     if (tid == 0) B200_TR(7, 1);
     // ---- the six convs ----
 #pragma unroll 1
@@ -327,9 +326,8 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         if (lane == 0) {
           for (int q = 1; q < NC; ++q) MbarArriveCluster(MapToCta(bar_box_free + 8 * q4, (rank + q) % NC));
         }
-        __threadfence_block();
         __syncwarp();
-        if (lane == 0) atomicAdd(const_cast<uint32_t*>(in_cnt), 1u);
+        if (lane == 0) SmemAddRelease(in_cnt);
       }
     }
   } else if (warp == kWarpMma) {
@@ -526,7 +524,9 @@ size_t MrfClusterSmemBytes(int C, int NC, int T, int S, bool split) {
 
 bool MrfClusterSupported(int C, int NC, int T, int S, bool split) {
   if (NC < 2 || NC > 8 || C % (16 * NC) != 0) return false;
-  if (!((C == 128 && NC == 4) || (C == 64 && NC == 2) || (C == 64 && NC == 4))) return false;   // instantiated forms
+  // instantiated forms; the C = 64 forms read the planar weight image, which PackMrfWeights emits only for
+  // C = 128 in split mode (C <= 64 is packed for the single-CTA kernel's concatenated-N MMAs)
+  if (!((C == 128 && NC == 4) || (!split && C == 64 && (NC == 2 || NC == 4)))) return false;
   const int MT = (S * T + 127) / 128;
   const int Cs = C / NC;
   if (2 * MT * C + MT * Cs > 512) return false;

@@ -133,6 +133,11 @@ __device__ __forceinline__ void BulkCommit() { asm volatile("cp.async.bulk.commi
 __device__ __forceinline__ void BulkWaitRead0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void BulkWait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// counter += 1 with release semantics at CTA scope (publishes this warp's earlier shared-memory writes
+// after a __syncwarp) -- cheaper than a __threadfence_block, which also drains in-flight remote stores
+__device__ __forceinline__ void SmemAddRelease(volatile uint32_t* cnt) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(SmemAddr(const_cast<uint32_t*>(cnt))) : "memory");
+}
 __device__ __forceinline__ void SpinUntil(volatile uint32_t* cnt, uint32_t target) {
   uint32_t spins = 0;
   while (*cnt < target) {

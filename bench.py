@@ -49,32 +49,88 @@ def _peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """Samples SM clock / throttle reasons DURING the timed region: NVML from a thread every 5 ms
+    (the timed region of the default run is a few hundred ms), nvidia-smi -lms as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+        self.index = index
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.proc = self.thread = None
+        self.stop = threading.Event()
+        self.nvml = None
+
+    def _nvml_loop(self):
+        nv, h = self.nvml
+        names = [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap")]
+        masks = [(n, getattr(nv, a, None) or getattr(nv, b, 0)) for n, a, b in names]
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while not self.stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                if mx:
+                    self.mx.append(mx)
+                r = int(get_reasons(h))
+                for n, m in masks:
+                    if m and (r & m):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self.stop.wait(0.005)
+
+    def _smi_loop(self):
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                self.sm.append(float(r[0]))
+                self.mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def __enter__(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.index
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[self.index])
+            self.nvml = (nv, nv.nvmlDeviceGetHandleByIndex(idx))
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread = threading.Thread(target=self._smi_loop, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *a):
+        self.stop.set()
+        if self.nvml and self.thread:
+            self.thread.join(timeout=1)
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.05)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -82,20 +138,11 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "how": "NVML every 5 ms during the device-timed region" if self.nvml else "nvidia-smi -lms 20"}
 
 
 def cpu_reference_run(model_toml: str, threads: int, frames_per_thread: int, warmup: int):
@@ -169,8 +216,8 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU (default = the named config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -308,13 +355,25 @@ def main():
     mrf_flops, mrf_ms = sum(r["flops"] for r in mrf), sum(r["ms"] for r in mrf)
     tot_ms = sum(r["ms"] for r in recs)
     achieved = mrf_flops / (mrf_ms * 1e-3) / 1e12 if mrf_ms > 0 else 0.0
+    # DRAM traffic of the same launches from the committed ncu --set full capture (profiles/), per launch
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_mrf_traffic.json")
+    if args.precision == "bf16x3" and os.path.exists(tpath):
+        try:
+            traffic = float(json.load(open(tpath))["dram_bytes_per_launch"])
+        except (ValueError, KeyError):
+            traffic = None
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["tflops"], "traffic": None,
-        "kernel": ("conv_gemm_kernel (CUDA cores)" if args.precision == "f32" else "conv_gemm_tc_kernel (tcgen05)")
+        "frac": achieved / peaks["tflops"], "traffic": traffic,
+        "kernel": ("conv_gemm_kernel (CUDA cores)" if args.precision == "f32" else
+                   "mrf_cluster_kernel<128,4> + mrf_branch_kernel<64|32|16> (tcgen05/TMEM/TMA, six convs of a branch per CTA)")
                   + ", vocoder MRF dilated Conv1d stage", "launches_per_step": len(mrf),
         "algorithmic_flops_per_step": mrf_flops, "avg_launch_us": 1e3 * mrf_ms / max(len(mrf), 1),
         "share_of_step": mrf_ms / tot_ms if tot_ms > 0 else None, "peak_source": peaks["source"] + " bf16 sustained",
+        "timing": "CUDA events around every launch of one hop on the engine's stream (BeatriceB200_ProfileHop), median of 4 hops; "
+                  "each bracket carries ~4 us of event overhead, so frac is a lower bound",
+        "mma_work_factor": 3.0 if args.precision == "bf16x3" else 1.0,
     }
     resident = eng.resident_bytes()
     eng.close()
