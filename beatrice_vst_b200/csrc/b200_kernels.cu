@@ -406,9 +406,9 @@ __global__ void channorm_gelu_kernel(NormDesc d, int B, const int* __restrict__ 
     gm[i] = c < d.C ? __ldg(d.gamma + c) : 0.0f;
     bt[i] = c < d.C ? __ldg(d.beta + c) : 0.0f;
   }
+  const int frame = *frame_ptr;   // written only by the chain's advance kernel, never the immediate predecessor
   PdlWait();
   PdlLaunchDependents();
-  const int frame = *frame_ptr;
   if (warp >= B * d.T) return;
   const int b = warp / d.T, t = warp - b * d.T;
   const float* x = d.x + (static_cast<long long>(b) * d.x_slots * d.T + (frame % d.x_slots) * d.T + t) * d.C;

@@ -134,6 +134,22 @@ __global__ void __launch_bounds__(kTcThreads, kGather ? 1 : 2) conv_gemm_tc_kern
     xbase = static_cast<long long>(b) * x_L * C_in;
     xu0 = t * d.stride + d.stride - 1;
   }
+  const int g_l16 = tid & 15, g_rg = (tid >> 4) & 15;   // gather mode: lane group of 16 == one row
+  long long g_base[8];
+  int g_u0[8];
+  if constexpr (kGather) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int mi = m0 + g_rg + 16 * i;
+      g_base[i] = -1;
+      g_u0[i] = 0;
+      if (mi < M) {
+        const int b = mi / d.T, t = mi - b * d.T;
+        g_base[i] = static_cast<long long>(b) * x_L * C_in;
+        g_u0[i] = t * d.stride + d.stride - 1;
+      }
+    }
+  }
   const int a_pl = tid & 7, a_rg = (tid >> 3) & 31;
   long long a_base[4];
   int a_u0[4];
@@ -168,10 +184,12 @@ __global__ void __launch_bounds__(kTcThreads, kGather ? 1 : 2) conv_gemm_tc_kern
       if (kSplit) TmaBulkLoadKeep(w_s + w_bytes, w_lo + static_cast<size_t>(c) * w_bytes, w_bytes, bar_full + 8 * st);
     }
   }
-  PdlWait();   // from here on: data written by the predecessor (activations, hop counter)
+  // The hop counter is written only by the advance kernel that ends a chain, and no conv kernel directly
+  // follows one (a PDL kernel overlaps at most its immediate predecessor): safe to read before the wait.
+  const int frame = *frame_ptr;
+  PdlWait();   // from here on: data written by the predecessor (activations)
   PdlLaunchDependents();   // the successor's prologue may overlap this kernel's main loop
   if (tid == 0) B200_TR(2);
-  const int frame = *frame_ptr;
 
   const int x_cur = (frame % d.x_slots) * d.x_T;
 
@@ -246,52 +264,58 @@ __global__ void __launch_bounds__(kTcThreads, kGather ? 1 : 2) conv_gemm_tc_kern
           if (tid == 0 && lc - kRetire < 24) B200_TR(8 + 4 * (lc - kRetire) + 1);
         }
       } else {
-        // register path: gather this thread's row from the fp32 ring(s): 64 K-elements -> eight
-        // bf16 panels.  All loads of a half-chunk are issued before the first use.
-        uint8_t* a_hi_p = smem + s * stage_bytes + (tid & 127) * 16;
-        uint8_t* a_lo_p = a_hi_p + a_bytes;
-        long long ro[4];
-        tap_offsets(c, ro);
-        {
-          const int half = whalf;   // workers 0-127 convert K elements 0-31 of the chunk, 128-255 the rest
-          float4 x0[8], x1[8], x2[8];
-          if (row_ok) {
+        // register path (inputs that exist only as fp32 rings, e.g. the mean of the three MRF branches):
+        // 16 lanes cover the 64 K-elements (256 B) of one row, so a warp instruction reads two whole row
+        // segments (coalesced); every worker serves rows g_rg + 16 i, i < 8, in two batches of four so
+        // that all loads of a batch are in flight before the first use.
+        const uint32_t a_dst = smem_base + s * stage_bytes + (g_l16 >> 1) * kPanelA + (g_l16 & 1) * 8;
+        const int j0 = C_in >= kTcKC ? c / n_sub : c * tpc;
+        const int ci0 = C_in >= kTcKC ? (c - j0 * n_sub) * kTcKC : 0;
+        const int ch = g_l16 * 4;
+        const int tl = ch >> lcw, cc = ch & (cw - 1);
+        const int back = (d.k - 1 - min(j0 + tl, d.k - 1)) * d.dil;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int ch = half * 32 + i * 4;          // K index inside the chunk
-              const int tl = ch >> lcw, cc = ch & (cw - 1);
-              const long long a = (tl == 0 ? ro[0] : tl == 1 ? ro[1] : tl == 2 ? ro[2] : ro[3]) + cc;
-              x0[i] = __ldg(reinterpret_cast<const float4*>(d.x[0] + a));
-              if (d.n_x > 1) {
-                x1[i] = __ldg(reinterpret_cast<const float4*>(d.x[1] + a));
-                x2[i] = __ldg(reinterpret_cast<const float4*>(d.x[2] + a));
-              }
-            }
+        for (int bt = 0; bt < 2; ++bt) {
+          float4 x0[4], x1[4], x2[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int ii = bt * 4 + i;
+            int r = x_cur + g_u0[ii] - back;
+            if (r < 0) r += x_L;
+            const bool ok = g_base[ii] >= 0;
+            const long long a = (ok ? g_base[ii] : 0) + static_cast<long long>(r) * C_in + ci0 + cc;
+            x0[i] = ok ? __ldg(reinterpret_cast<const float4*>(d.x[0] + a)) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (d.n_x > 1) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                x0[i].x = ((x0[i].x + x1[i].x) + x2[i].x) * d.in_scale;
-                x0[i].y = ((x0[i].y + x1[i].y) + x2[i].y) * d.in_scale;
-                x0[i].z = ((x0[i].z + x1[i].z) + x2[i].z) * d.in_scale;
-                x0[i].w = ((x0[i].w + x1[i].w) + x2[i].w) * d.in_scale;
-              }
+              x1[i] = ok ? __ldg(reinterpret_cast<const float4*>(d.x[1] + a)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              x2[i] = ok ? __ldg(reinterpret_cast<const float4*>(d.x[2] + a)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            float v[8] = {x0[2 * p].x, x0[2 * p].y, x0[2 * p].z, x0[2 * p].w,
-                          x0[2 * p + 1].x, x0[2 * p + 1].y, x0[2 * p + 1].z, x0[2 * p + 1].w};
+          for (int i = 0; i < 4; ++i) {
+            float v[4] = {x0[i].x, x0[i].y, x0[i].z, x0[i].w};
+            if (d.n_x > 1) {
+              v[0] = ((v[0] + x1[i].x) + x2[i].x) * d.in_scale;
+              v[1] = ((v[1] + x1[i].y) + x2[i].y) * d.in_scale;
+              v[2] = ((v[2] + x1[i].z) + x2[i].z) * d.in_scale;
+              v[3] = ((v[3] + x1[i].w) + x2[i].w) * d.in_scale;
+            }
             if (d.in_act == kActLrelu) {   // the only input activation of spec M0
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.0f ? v[e] : 0.1f * v[e];
+              for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.0f ? v[e] : 0.1f * v[e];
             }
-            uint4 hi, lo;
-            Pack8<kSplit>(v, &hi, &lo);
-            *reinterpret_cast<uint4*>(a_hi_p + (half * 4 + p) * kPanelA) = hi;
-            if (kSplit) *reinterpret_cast<uint4*>(a_lo_p + (half * 4 + p) * kPanelA) = lo;
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]),
+                                h2 = __float2bfloat16_rn(v[2]), h3 = __float2bfloat16_rn(v[3]);
+            const uint32_t hi0 = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+            const uint32_t hi1 = static_cast<uint32_t>(__bfloat16_as_ushort(h2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h3)) << 16);
+            const uint32_t dst = a_dst + (g_rg + 16 * (bt * 4 + i)) * 16;
+            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(dst), "r"(hi0), "r"(hi1) : "memory");
+            if (kSplit) {
+              const __nv_bfloat16 l0 = __float2bfloat16_rn(v[0] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v[1] - __bfloat162float(h1)),
+                                  l2 = __float2bfloat16_rn(v[2] - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v[3] - __bfloat162float(h3));
+              const uint32_t lo0 = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+              const uint32_t lo1 = static_cast<uint32_t>(__bfloat16_as_ushort(l2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l3)) << 16);
+              asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(dst + a_bytes), "r"(lo0), "r"(lo1) : "memory");
+            }
           }
         }
         FenceProxyAsync();
