@@ -363,10 +363,13 @@ int WaveModel::LoadFromImage(const void* data, size_t size, int on_device) {
           bias_all.insert(bias_all.end(), b2, b2 + co);
         }
         for (int sp = 0; sp < 2; ++sp) {
-          const size_t n = PackMrfWeights(wsrc, spec::kMrfK[ki], co, sp == 1, nullptr);
+          // rows [W_hi ; W_lo] (2-MMA split scheme) wherever the single-CTA kernel runs the branch: every
+          // branch at C <= 64, and the k = 3 branch of stage 0 (C = 128), which runs beside the clusters
+          const bool concat = co <= 64 || ki == 0;
+          const size_t n = PackMrfWeights(wsrc, spec::kMrfK[ki], co, sp == 1, concat, nullptr);
           size_t off = (packed[sp].size() + 127) / 128 * 128;   // 256-byte aligned images
           packed[sp].resize(off + n);
-          PackMrfWeights(wsrc, spec::kMrfK[ki], co, sp == 1, packed[sp].data() + off);
+          PackMrfWeights(wsrc, spec::kMrfK[ki], co, sp == 1, concat, packed[sp].data() + off);
           w_off[sp][s][ki] = off;
         }
       }
@@ -811,7 +814,10 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
         int v[4] = {0, 0, 0, 0};
         if (std::sscanf(ev, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4 && v[s] > 0) NC = v[s];
       }
-      const bool form_ok = NC > 1 ? MrfClusterSupported(c, NC, t, S, with_lo) : MrfFusedSupported(c, t, S, with_lo);
+      // NC > 1 (stage 0): the clusters run k = 11 and k = 7, the k = 3 branch runs on the single-CTA kernel
+      // beside them (16 CTAs on the SMs 32 clusters of 4 leave free), so the stage is one wave
+      const bool form_ok = NC > 1 ? (MrfClusterSupported(c, NC, t, S, with_lo) && MrfFusedSupported(c, t, S, with_lo, spec::kMrfK[0]))
+                                  : MrfFusedSupported(c, t, S, with_lo);
       fused[s] = tcm && FusedMrfEnabled() && ((mask >> s) & 1) && m->mrf_w_ptr[with_lo ? 1 : 0][s][0] != nullptr && form_ok;
       fused_S[s] = S;
       fused_nc[s] = NC;
@@ -1006,6 +1012,9 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
       mp.B = B;
       mp.n_groups = fused_groups[s];
       mp.frame = frame;
+      mp.n_branches = 3;
+      mp.br_hi = 2;
+      mp.pdl_mode = 0;
       if (const char* ev = std::getenv("BEATRICE_B200_MRF_TRACE")) mp.trace = std::atoi(ev);
       Op op;
       op.name = "wave.mrf" + std::to_string(s) + ".fused";
@@ -1013,8 +1022,19 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
       op.bytes = 2.0 * 6 * 21 * c * c + 4.0 * B * t_stage * c * 4;
       op.is_mrf = true;
       const int nc = fused_nc[s];
-      if (nc > 1) op.launch = [=](cudaStream_t st) { LaunchMrfStageCluster(mp, c, nc, with_lo, st); };
-      else op.launch = [=](cudaStream_t st) { LaunchMrfStage(mp, c, with_lo, st); };
+      if (nc > 1) {
+        MrfStageParams mc = mp, m3 = mp;
+        mc.n_branches = 2;      // blockIdx.y = 0 -> k = 11, 1 -> k = 7
+        m3.n_branches = 1;      // k = 3 on the single-CTA kernel ...
+        m3.br_hi = 0;
+        m3.pdl_mode = 1;        // ... as the second launch of the pair (see MrfStageParams::pdl_mode)
+        op.launch = [=](cudaStream_t st) {
+          LaunchMrfStageCluster(mc, c, nc, with_lo, st);
+          LaunchMrfStage(m3, c, with_lo, st);
+        };
+      } else {
+        op.launch = [=](cudaStream_t st) { LaunchMrfStage(mp, c, with_lo, st); };
+      }
       program.push_back(op);
       continue;
     }

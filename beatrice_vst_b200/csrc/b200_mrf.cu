@@ -25,6 +25,7 @@
 //    x_hi*W_lo (columns [C,2C)), and a second MMA of width C adds x_lo*W_hi onto columns [0,C): two
 //    MMAs instead of three, and the x_hi panel -- shared-memory reads bound these narrow-N MMAs --
 //    is read once instead of twice.  The epilogue adds the two column halves.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -40,7 +41,7 @@ namespace {
 // cycles even when already complete) and one tcgen05.commit, so chunks are as large as the CTA's
 // shared-memory budget allows (C = 64: one CTA per SM, 16 KB chunks; C = 32: two per SM, 8 KB; C = 16:
 // four per SM, 6 KB) while the bytes in flight still cover the ring's ~1.6k-cycle round trip.
-__host__ __device__ constexpr int NkFor(int C) { return C <= 16 ? 6 : 4; }
+__host__ __device__ constexpr int NkFor(int C) { return C >= 128 ? 1 : (C <= 16 ? 6 : 4); }
 __host__ __device__ constexpr int NstFor(int C) { return C >= 64 ? 4 : 3; }
 // Epilogue warps: 8 where a tile has more than one work item -- (tile, 16-channel group) pairs --
 // per conv, else 4.  Warps w and w + 4 share TMEM lane quarter w & 3 (tile rows 32 (w & 3) ..) and take
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
   // warp index broadcast from lane 0: provably warp-uniform, so the role branches below are uniform
   // control flow and the single-thread MMA / TMA loops can live in uniform registers
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const MrfBranchDesc& br = p.br[2 - blockIdx.y];   // longest branch (k = 11) is scheduled first
+  const MrfBranchDesc& br = p.br[p.br_hi - blockIdx.y];   // longest branch first
   const int k = br.k, T = p.T, S = p.S, MT = p.MT;
   const int group = blockIdx.x;
   const int HX = (k - 1) * 5, HY = k - 1;            // history rows (time steps) in front of X / Y
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
     // Everything up to here (barriers, TMEM, bias, and in the other warps the weight ring and the
     // history loads) touches nothing the preceding kernel -- the upsampler that writes u -- produces.
-    PdlWait();
+    if (p.pdl_mode == 0) PdlWait();   // pdl_mode 1: u is already complete, see MrfStageParams
     PdlLaunchDependents();
     // ---- prologue: u -> TMEM (fp32 residual stream) and lrelu(u) -> X new rows ----
     for (int m = 0; m < MT; ++m) {
@@ -440,6 +441,7 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
     __syncwarp();
   }
 
+  if (p.pdl_mode == 1) PdlWait();   // the stage is complete only when the first launch of the pair is, too
   TcFenceBefore();
   __syncthreads();
   if (tracing && tid == 0) {
@@ -481,16 +483,16 @@ void LaunchMrfT(const MrfStageParams& p, size_t smem, cudaStream_t s) {
     B200_CHECK(cudaFuncSetAttribute(mrf_branch_kernel<C, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev & 63] = true;
   }
-  LaunchPdl(mrf_branch_kernel<C, kSplit>, dim3(p.n_groups, 3, 1), dim3(ThreadsFor(C), 1, 1), smem, s, 1, p);
+  LaunchPdl(mrf_branch_kernel<C, kSplit>, dim3(p.n_groups, p.n_branches, 1), dim3(ThreadsFor(C), 1, 1), smem, s, 1, p);
 }
 
 
 }  // namespace
 
-size_t MrfSmemBytes(int C, int T, int S, bool split) {
+size_t MrfSmemBytes(int C, int T, int S, bool split, int kmax) {
   const int MT = (S * T + 127) / 128;
   const int P = split ? 2 : 1, PAN = C / 8;
-  const int k = 11;   // the launch is sized for its largest branch
+  const int k = kmax;   // the launch is sized for its largest branch
   const size_t rows8 = (static_cast<size_t>(S) * T + 7) & ~static_cast<size_t>(7);
   const size_t RX = static_cast<size_t>((k - 1) * 5) * S + rows8, RY = static_cast<size_t>(k - 1) * S + rows8;
   (void)MT;
@@ -503,24 +505,24 @@ size_t MrfSmemBytes(int C, int T, int S, bool split) {
   return off;
 }
 
-bool MrfFusedSupported(int C, int T, int S, bool split) {
-  if (C != 16 && C != 32 && C != 64) return false;
+bool MrfFusedSupported(int C, int T, int S, bool split, int kmax) {
+  if (C != 16 && C != 32 && C != 64 && C != 128) return false;
   const int MT = (S * T + 127) / 128;
   if (2 * MT * (split ? 2 * C : C) > 512) return false;
   if (2 * NstFor(C) + 4 + MT * (C / 16) + MT > 40) return false;
-  return MrfSmemBytes(C, T, S, split) <= 227 * 1024;
+  return MrfSmemBytes(C, T, S, split, kmax) <= 227 * 1024;
 }
 
 size_t MrfHistElems(int C, int k, int S, int n_groups, bool split) {
   return static_cast<size_t>(n_groups) * (split ? 2 : 1) * (C / 8) * S * 8 * (k - 1) * 12;
 }
 
-size_t PackMrfWeights(const float* const w[6], int k, int C, bool split, uint16_t* out) {
+size_t PackMrfWeights(const float* const w[6], int k, int C, bool split, bool concat_rows, uint16_t* out) {
   // per conv, K step ks = g*k + j, element = W[j][16g + 8p + e][n]:
   //   planar (bf16 mode, and split mode at C = 128 / the cluster kernel): [plane][2 panels][C rows (n)][8]
   //   concatenated (split mode at C <= 64 / the single-CTA kernel):       [2 panels][2C rows: hi n, then lo n][8]
   const int G = C / 16, P = split ? 2 : 1;
-  const bool concat = split && C <= 64;
+  const bool concat = split && concat_rows;
   const size_t kstep = static_cast<size_t>(P) * 2 * C * 8;
   const size_t total = 6 * static_cast<size_t>(k) * G * kstep;
   if (!out) return total;
@@ -548,7 +550,9 @@ size_t PackMrfWeights(const float* const w[6], int k, int C, bool split, uint16_
 }
 
 void LaunchMrfStage(const MrfStageParams& p, int C, bool split, cudaStream_t s) {
-  const size_t smem = MrfSmemBytes(C, p.T, p.S, split);
+  int kmax = 3;
+  for (int y = 0; y < p.n_branches; ++y) kmax = std::max(kmax, p.br[p.br_hi - y].k);
+  const size_t smem = MrfSmemBytes(C, p.T, p.S, split, kmax);
 #define B200_MRF_CASE(CC)                                  \
   case CC:                                                 \
     if (split) LaunchMrfT<CC, true>(p, smem, s);           \
@@ -558,6 +562,7 @@ void LaunchMrfStage(const MrfStageParams& p, int C, bool split, cudaStream_t s) 
     B200_MRF_CASE(16);
     B200_MRF_CASE(32);
     B200_MRF_CASE(64);
+    B200_MRF_CASE(128);
     default:
       std::fprintf(stderr, "[libbeatrice_b200] FATAL: fused MRF kernel has no C = %d form\n", C);
       std::abort();

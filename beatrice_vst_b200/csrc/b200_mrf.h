@@ -30,6 +30,13 @@ struct MrfStageParams {
   int B;               // streams
   int n_groups;        // ceil(B / S)
   const int* frame;    // device hop counter
+  int n_branches;      // grid.y: branches this launch runs, blockIdx.y = 0 -> br[br_hi], 1 -> br[br_hi - 1], ...
+  int br_hi;
+  // 0: ordinary PDL kernel (dependency wait in front of the first read of u).
+  // 1: second launch of a pair that together make up one stage: launched (programmatically) only after the
+  //    first launch's CTAs passed THEIR wait, so u is already complete -- no wait at the start; instead it
+  //    waits for the first launch at its very end, so that "this kernel complete" implies "stage complete".
+  int pdl_mode;
   int trace;           // developer aid: 1 + blockIdx.x of the CTA whose timeline is printed (0 = off)
 };
 
@@ -39,13 +46,15 @@ struct MrfHistBlock {
   int planes_panels, H, S, pad_;
 };
 
-bool MrfFusedSupported(int C, int T, int S, bool split);
-size_t MrfSmemBytes(int C, int T, int S, bool split);
+// kmax: the largest branch kernel size this launch runs (shared memory is sized for it)
+bool MrfFusedSupported(int C, int T, int S, bool split, int kmax = 11);
+size_t MrfSmemBytes(int C, int T, int S, bool split, int kmax = 11);
 // bf16 elements of one branch's history state: for conv i (dilation dil_i) a block
 // [group][plane][C/8 panels][(k-1)*dil_i * S rows][8], blocks in conv order
 size_t MrfHistElems(int C, int k, int S, int n_groups, bool split);
 // w[i] = fp32 [k][C][C] (tap, in, out) of conv i; returns bf16 elements written (out may be null)
-size_t PackMrfWeights(const float* const w[6], int k, int C, bool split, uint16_t* out);
+// concat (split mode, single-CTA kernel): weight rows of a K step packed [W_hi ; W_lo] for the 2-MMA scheme
+size_t PackMrfWeights(const float* const w[6], int k, int C, bool split, bool concat, uint16_t* out);
 void LaunchMrfStage(const MrfStageParams& p, int C, bool split, cudaStream_t s);
 // K-split cluster form (b200_mrfc.cu): NC CTAs per (group, branch), same weight / history images
 bool MrfClusterSupported(int C, int NC, int T, int S, bool split);

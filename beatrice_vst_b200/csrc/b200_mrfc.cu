@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
   // control flow and the single-thread MMA / TMA loops can live in uniform registers
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int rank = static_cast<int>(ClusterCtaRank());
-  const MrfBranchDesc& br = p.br[2 - blockIdx.y];   // longest branch (k = 11) is scheduled first
+  const MrfBranchDesc& br = p.br[p.br_hi - blockIdx.y];   // longest branch first
   const int k = br.k, T = p.T, S = p.S, MT = p.MT;
   const int group = blockIdx.x / NC;
   const int HX = (k - 1) * 5, HY = k - 1;            // history rows (time steps) in front of X / Y
@@ -501,7 +501,7 @@ void LaunchClusterT(const MrfStageParams& p, size_t smem, cudaStream_t s) {
     B200_CHECK(cudaFuncSetAttribute(mrf_cluster_kernel<C, NC, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev & 63] = true;
   }
-  LaunchPdl(mrf_cluster_kernel<C, NC, kSplit>, dim3(p.n_groups * NC, 3, 1), dim3(kThreads, 1, 1), smem, s, NC, p);
+  LaunchPdl(mrf_cluster_kernel<C, NC, kSplit>, dim3(p.n_groups * NC, p.n_branches, 1), dim3(kThreads, 1, 1), smem, s, NC, p);
 }
 
 }  // namespace

@@ -5,10 +5,8 @@ L=gpurun_out/k.log
 run() { echo "== $*" >> $L; ( timeout 300 env "$@" ) >> $L 2>&1; echo "rc=$?" >> $L; }
 run python tools/mrf_probe.py 2 40 4
 run python tools/mrf_probe.py 1 40 4
+run BEATRICE_B200_NO_PDL=1 python tools/mrf_probe.py 2 40 4
 (timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15) >> $L
 run python bench.py --steps 300 --warmup 20 --no-cpu-baseline
 run python tools/op_profile.py 2 256
-BEATRICE_B200_MRF_TRACE=1 timeout 120 python tools/op_profile.py 2 256 2 > gpurun_out/k_tmp.log 2>&1
-grep "mrf trace" gpurun_out/k_tmp.log | tail -21 | cut -c1-220 >> $L
-grep "mrfc trace" gpurun_out/k_tmp.log | tail -7 | cut -c1-250 >> $L
 cut -c1-330 $L
