@@ -367,6 +367,9 @@ BeatriceB200_Engine* BeatriceB200_CreateEngine(int device, int n_streams, int pr
   e->B = n_streams;
   e->precision = precision;
   B200_CHECK(cudaSetDevice(device));
+  if (std::getenv("BEATRICE_B200_MRF_TRACE")) {   // developer traces print one line per CTA: room for all of them
+    cudaDeviceSetLimit(cudaLimitPrintfFifoSize, 64u << 20);
+  }
   B200_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   B200_CHECK(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));

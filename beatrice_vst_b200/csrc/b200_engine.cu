@@ -1013,7 +1013,12 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
       mp.n_groups = fused_groups[s];
       mp.frame = frame;
       mp.n_branches = 3;
-      mp.br_hi = 2;
+      // CTA scheduling order of the branches.  Where the stage fits in one wave: longest chain (k = 11) first.
+      // Stage 3 (768 short CTAs for 592 slots): k = 11, then k = 3, then k = 7 -- the CTAs that have to wait
+      // for a slot then start when the k = 3 CTAs retire (~1/4 of the stage) instead of when the k = 7 ones do.
+      mp.y2br[0] = 2;
+      mp.y2br[1] = c <= 16 ? 0 : 1;
+      mp.y2br[2] = c <= 16 ? 1 : 0;
       mp.pdl_mode = 0;
       if (const char* ev = std::getenv("BEATRICE_B200_MRF_TRACE")) mp.trace = std::atoi(ev);
       Op op;
@@ -1026,7 +1031,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
         MrfStageParams mc = mp, m3 = mp;
         mc.n_branches = 2;      // blockIdx.y = 0 -> k = 11, 1 -> k = 7
         m3.n_branches = 1;      // k = 3 on the single-CTA kernel ...
-        m3.br_hi = 0;
+        m3.y2br[0] = 0;
         m3.pdl_mode = 1;        // ... as the second launch of the pair (see MrfStageParams::pdl_mode)
         op.launch = [=](cudaStream_t st) {
           LaunchMrfStageCluster(mc, c, nc, with_lo, st);

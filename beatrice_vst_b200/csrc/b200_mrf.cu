@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
   // warp index broadcast from lane 0: provably warp-uniform, so the role branches below are uniform
   // control flow and the single-thread MMA / TMA loops can live in uniform registers
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const MrfBranchDesc& br = p.br[p.br_hi - blockIdx.y];   // longest branch first
+  const MrfBranchDesc& br = p.br[p.y2br[blockIdx.y]];
   const int k = br.k, T = p.T, S = p.S, MT = p.MT;
   const int group = blockIdx.x;
   const int HX = (k - 1) * 5, HY = k - 1;            // history rows (time steps) in front of X / Y
@@ -551,7 +551,7 @@ size_t PackMrfWeights(const float* const w[6], int k, int C, bool split, bool co
 
 void LaunchMrfStage(const MrfStageParams& p, int C, bool split, cudaStream_t s) {
   int kmax = 3;
-  for (int y = 0; y < p.n_branches; ++y) kmax = std::max(kmax, p.br[p.br_hi - y].k);
+  for (int y = 0; y < p.n_branches; ++y) kmax = std::max(kmax, p.br[p.y2br[y]].k);
   const size_t smem = MrfSmemBytes(C, p.T, p.S, split, kmax);
 #define B200_MRF_CASE(CC)                                  \
   case CC:                                                 \

@@ -30,8 +30,8 @@ struct MrfStageParams {
   int B;               // streams
   int n_groups;        // ceil(B / S)
   const int* frame;    // device hop counter
-  int n_branches;      // grid.y: branches this launch runs, blockIdx.y = 0 -> br[br_hi], 1 -> br[br_hi - 1], ...
-  int br_hi;
+  int n_branches;      // grid.y: branches this launch runs; blockIdx.y = y runs br[y2br[y]] (CTAs are scheduled in y order)
+  int y2br[3];
   // 0: ordinary PDL kernel (dependency wait in front of the first read of u).
   // 1: second launch of a pair that together make up one stage: launched (programmatically) only after the
   //    first launch's CTAs passed THEIR wait, so u is already complete -- no wait at the start; instead it

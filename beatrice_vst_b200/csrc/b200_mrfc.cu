@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
   // control flow and the single-thread MMA / TMA loops can live in uniform registers
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int rank = static_cast<int>(ClusterCtaRank());
-  const MrfBranchDesc& br = p.br[p.br_hi - blockIdx.y];   // longest branch first
+  const MrfBranchDesc& br = p.br[p.y2br[blockIdx.y]];
   const int k = br.k, T = p.T, S = p.S, MT = p.MT;
   const int group = blockIdx.x / NC;
   const int HX = (k - 1) * 5, HY = k - 1;            // history rows (time steps) in front of X / Y
