@@ -1067,6 +1067,10 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
   }
 }
 
+void WaveState::ZeroAll(cudaStream_t s) {
+  arena.ZeroAll(s);
+  if (mrf_hist.p) B200_CHECK(cudaMemsetAsync(mrf_hist.p, 0, mrf_hist.bytes, s));
+}
 void WaveState::ZeroStream(int b, cudaStream_t s) {
   arena.ZeroStream(b, s);
   LaunchMrfZeroStream(mrf_blocks.as<MrfHistBlock>(), n_mrf_blocks, b, s);

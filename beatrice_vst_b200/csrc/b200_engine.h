@@ -226,6 +226,7 @@ struct WaveState {
   DeviceBuffer mrf_hist, mrf_blocks;
   int n_mrf_blocks = 0;
   void ZeroStream(int b, cudaStream_t s);   // arena + fused-kernel histories of stream b
+  void ZeroAll(cudaStream_t s);             // ... of every stream
   // conditioning buffers depend only on the family, not on the weights: the rc0 setters
   // (beatrice.h:323-343) may run before the first GenerateWaveform1 names the model
   void AllocCond(const FamilyDims& dims, int B, int device);
