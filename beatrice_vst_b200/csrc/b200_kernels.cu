@@ -577,13 +577,13 @@ __global__ void __launch_bounds__(256) cond_kernel(const float* __restrict__ pho
   float acc[kCondStreams];
 #pragma unroll
   for (int s = 0; s < kCondStreams; ++s) acc[s] = bias;
-#pragma unroll 2
-  for (int i0 = 0; i0 < P; i0 += 8) {   // P is 128 or 256 (beatrice.h:17,20,23)
-    float w[8];
+#pragma unroll 1
+  for (int i0 = 0; i0 < P; i0 += 32) {   // P is 128 or 256 (beatrice.h:17,20,23); 32 weight loads in flight per thread
+    float w[32];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) w[u] = __ldg(We + (i0 + u) * kHidden + c);
+    for (int u = 0; u < 32; ++u) w[u] = __ldg(We + (i0 + u) * kHidden + c);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 32; ++u) {
 #pragma unroll
       for (int s = 0; s < kCondStreams; ++s) acc[s] = fmaf(ph[s][i0 + u], w[u], acc[s]);
     }

@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(kTcThreads, kGather ? 1 : 2) conv_gemm_tc_kern
   PdlWait();   // from here on: data written by the predecessor (activations)
   PdlLaunchDependents();   // the successor's prologue may overlap this kernel's main loop
   if (tid == 0) B200_TR(2);
+  if (tracing && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(*reinterpret_cast<unsigned long long*>(&trace[120])));
 
   const int x_cur = (frame % d.x_slots) * d.x_T;
 
@@ -557,6 +558,10 @@ __global__ void __launch_bounds__(kTcThreads, kGather ? 1 : 2) conv_gemm_tc_kern
   //  counted by its own mbarrier, and it sends nothing after its last st.async)
   if (tracing && tid == 0) {
     const long long t0 = trace[0];
+    unsigned long long t_end_ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end_ns));
+    printf("[tc trace] wall: dependency wait returned at %llu ns, CTA 0 done at %llu ns (+%llu)\n",
+           static_cast<unsigned long long>(trace[120]), t_end_ns, t_end_ns - static_cast<unsigned long long>(trace[120]));
     printf("[tc trace] KS %d grid (%d,%d,%d) BN %d C_in %d k %d N %d T %d stages %d gather %d chunks %d | setup %lld pdl_wait %lld producers_done %lld mma_done %lld res_loaded %lld first_tmem_ld %lld staged %lld epi_done %lld end %lld\n",
            KS, gridDim.x, gridDim.y, gridDim.z, BN, C_in, d.k, N, d.T, kStages, kGather ? 1 : 0, n_chunks, trace[1] - t0, trace[2] - t0,
            trace[3] - t0, trace[4] - t0, trace[5] - t0, trace[7] - t0, trace[104] - t0, trace[6] - t0, clock64() - t0);
