@@ -4,8 +4,7 @@ L=gpurun_out/k.log
 : > $L
 run() { echo "== $*" >> $L; ( timeout 300 env "$@" ) >> $L 2>&1; echo "rc=$?" >> $L; }
 run python tools/mrf_probe.py 2 40 4
-run python tools/mrf_probe.py 1 40 4
-run BEATRICE_B200_NO_PDL=1 python tools/mrf_probe.py 2 40 4
+run BEATRICE_B200_NO_FUSED_NORM=1 python tools/mrf_probe.py 2 40 4
 (timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15) >> $L
 run python bench.py --steps 300 --warmup 20 --no-cpu-baseline
 run python tools/op_profile.py 2 256
