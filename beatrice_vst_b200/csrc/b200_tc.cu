@@ -46,7 +46,7 @@ constexpr int kPanelA = kTcM * 16 + 16;
 // kGather = false compiles the cp.async-only producer (no fp32 gather code): ~half the registers,
 // so three to four CTAs fit on an SM for the small-tile layers.
 template <bool kSplit, int kStages, bool kGather>
-__global__ void __launch_bounds__(kTcThreads, kGather ? 1 : 2) conv_gemm_tc_kernel(const __grid_constant__ ConvDesc d0,
+__global__ void __launch_bounds__(kTcThreads, 2) conv_gemm_tc_kernel(const __grid_constant__ ConvDesc d0,
                                                            const ConvDesc* __restrict__ descs, int B,
                                                            const int* __restrict__ frame_ptr, int KS) {
   constexpr int kOperands = kSplit ? 2 : 1;
