@@ -26,7 +26,9 @@
 namespace b200 {
 namespace {
 
-constexpr int kNst = 4;          // weight ring stages
+// weight ring: stages x K steps per chunk.  Every chunk costs the MMA warp an mbarrier wait and a commit,
+// so at C = 128 (8 KB per K step, shared memory nearly full) 3 stages of 2 K steps beat 4 stages of 1.
+__host__ __device__ constexpr int NstForC(int C) { return C >= 128 ? 3 : 4; }
 // warps 0-7: epilogue.  Warps w and w + 4 share TMEM lane quarter w & 3 (tile rows 32 (w & 3) ..) and
 // split its work items -- (tile, 16-channel group) and (peer, group) pairs -- by parity: the epilogue
 // is latency bound per warp, two warps per SM sub-partition nearly halve it.
@@ -37,7 +39,7 @@ constexpr int kThreads = 11 * 32;
 constexpr int kBars = 48;        // mbarrier slots reserved at the front of shared memory
 constexpr int kHdr = 8 * kBars + 16;
 
-__host__ __device__ constexpr int NkForC(int C) { return C >= 128 ? 1 : (C >= 64 ? 2 : 4); }
+__host__ __device__ constexpr int NkForC(int C) { return C >= 64 ? 2 : 4; }
 
 template <int C, int NC, bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_constant__ MrfStageParams p) {
@@ -46,6 +48,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
   constexpr int PANs = Cs / 8;                // own 8-channel K panels
   constexpr int PAN = C / 8;                  // panels of the whole activation (history image)
   constexpr int NK = NkForC(C);               // K steps per weight chunk
+  constexpr int kNst = NstForC(C);
   constexpr int P = kSplit ? 2 : 1;
   constexpr uint32_t kKstepBytes = P * C * 32;
   constexpr uint32_t kChunkBytes = NK * kKstepBytes;
@@ -517,7 +520,7 @@ size_t MrfClusterSmemBytes(int C, int NC, int T, int S, bool split) {
   off = (off + 127) / 128 * 128;
   off += static_cast<size_t>(NC - 1) * rows_valid * (Cs + 4) * 4 + 2048;   // inbox (+ slack the last tile's MMA may read into)
   off = (off + 127) / 128 * 128;
-  off += static_cast<size_t>(kNst) * NkForC(C) * P * C * 32;
+  off += static_cast<size_t>(NstForC(C)) * NkForC(C) * P * C * 32;
   off += 1024;   // developer trace area
   return off;
 }
@@ -530,7 +533,7 @@ bool MrfClusterSupported(int C, int NC, int T, int S, bool split) {
   const int MT = (S * T + 127) / 128;
   const int Cs = C / NC;
   if (2 * MT * C + MT * Cs > 512) return false;
-  if (2 * kNst + 4 + 2 * kQuarters + MT * (Cs / 16) + MT > kBars) return false;
+  if (2 * NstForC(C) + 4 + 2 * kQuarters + MT * (Cs / 16) + MT > kBars) return false;
   return MrfClusterSmemBytes(C, NC, T, S, split) <= 227 * 1024;
 }
 
