@@ -508,14 +508,14 @@ int BeatriceB200_ResetStream(BeatriceB200_Engine* e, int stream) {
   B200_CHECK(cudaSetDevice(e->device));
   B200_CHECK(cudaStreamSynchronize(e->stream));
   if (stream < 0) {   // every stream: three memsets instead of O(streams x rings) of them
-    e->phone_st.arena.ZeroAll(e->stream);
-    e->pitch_st.arena.ZeroAll(e->stream);
+    e->phone_st.ZeroAll(e->stream);
+    e->pitch_st.ZeroAll(e->stream);
     e->wave_st.ZeroAll(e->stream);
   }
   ForStreams(e, stream, [&](int b) {
     if (stream >= 0) {
-      e->phone_st.arena.ZeroStream(b, e->stream);
-      e->pitch_st.arena.ZeroStream(b, e->stream);
+      e->phone_st.ZeroStream(b, e->stream);
+      e->pitch_st.ZeroStream(b, e->stream);
       e->wave_st.ZeroStream(b, e->stream);
     }
     e->sp[b].kv_set_count = 0;

@@ -1,0 +1,482 @@
+// Fused residual stack of the encoders (content encoder: 6 blocks at C = 256, pitch estimator: 3 blocks at
+// C = 128), tcgen05 / TMEM / TMA + thread-block clusters, sm_100a only.
+//
+//     for r in blocks:  x = x + b_r + Conv_{k=3, dil=d_r}( GELU( ChanNorm(x) * gamma_r + beta_r ) )
+//
+// One hop adds ONE row per stream to this stack, so a block is a GEMM with 256 rows (streams) and
+// K = 3C: far too little work to be anything but latency bound, and as separate launches (norm + conv
+// per block) the stack was twelve dependent kernels.  Here one CLUSTER of NC = C/32 CTAs carries a tile of
+// 32 streams through all blocks without leaving the SMs:
+//
+//  * TRANSPOSED GEMM.  D^T[C_out x 32 streams] = W^T[C_out x K] * G^T[K x 32]: the output channels fill
+//    the 128 MMA rows (C/128 MMAs of M = 128, N = 32 per K step), the streams are the narrow N.
+//  * K-SPLIT over the cluster.  CTA `rank` owns input channels [32 rank, 32 rank + 32) of every
+//    activation: its slice of x (fp32, shared memory), of g (bf16 hi/lo K-panels with the block's causal
+//    history in front: a tap is a row shift of the B descriptor), of the conv histories (TMA bulk copies)
+//    and of the weight stream (TMA ring).  Its partial D^T covers all C output channels.
+//  * REDUCE-SCATTER through distributed shared memory.  TMEM lane quarter q of M tile m holds output
+//    channels 128 m + 32 q .. +32 == the slice CTA 4m + q owns: warp (m, q) reads its quarter and pushes it
+//    (st.async, the receiver's mbarrier counts the bytes) into that CTA's inbox; sums in rank order.
+//  * ChanNorm statistics: per stream over all C channels = over the cluster.  Every CTA reduces its 32
+//    channels (exact two-pass inside a thread, Chan's parallel combination above), the 8-byte partials are
+//    exchanged through DSMEM, every CTA combines them in rank order -> identical mean / rstd everywhere.
+//  * Everything else (bias, residual add, normalise, GELU, bf16 hi/lo split) is elementwise on the CTA's
+//    own [32 channels x 32 streams] slice, spread over all 256 worker threads.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "b200_common.h"
+#include "b200_enc.h"
+#include "b200_tc_common.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int kRs = 32;            // streams per cluster tile (the MMA's N)
+constexpr int kCs = 32;            // channels owned by a CTA
+constexpr int kHmax = 8;           // history time steps kept in front of the new row: 2 * max dilation
+constexpr int kGpRows = (kHmax + 1) * kRs;
+constexpr int kWorkers = 256;      // 8 warps: warp w <-> (M tile w / 4, TMEM lane quarter w % 4)
+constexpr int kWarpMma = 8, kWarpW = 9, kWarpH = 10;
+constexpr int kEncThreads = 11 * 32;
+constexpr int kNstW = 4;           // weight ring stages, one K step (16 KB at C = 256) each
+constexpr int kBoxPitch = kRs + 4; // floats per inbox row (one channel x 32 streams), +16 B against bank conflicts
+
+__device__ __forceinline__ void ChanCombine(float& n, float& mean, float& m2, float nb, float mb, float m2b) {
+  const float nt = n + nb;
+  const float delta = mb - mean;
+  mean = mean + delta * (nb / nt);
+  m2 = m2 + m2b + delta * delta * (n * nb / nt);
+  n = nt;
+}
+
+// shared-memory layout (bytes), identical on host and device
+template <int C>
+struct EncSmem {
+  static constexpr int NC = C / kCs;
+  static constexpr int P = 2;                                   // hi + lo planes (the encoders always run split-bf16)
+  static constexpr uint32_t kBars = 0;                          // 32 mbarriers
+  static constexpr uint32_t kMisc = 256;                        // tmem slot, counters
+  static constexpr uint32_t kXbuf = 512;                        // fp32 x slice [32 ch][32 streams]
+  static constexpr uint32_t kStat = kXbuf + kCs * kRs * 4;      // [8 groups][32 streams][2] local partials, then [32][2] mean/rstd
+  static constexpr uint32_t kStatBox = kStat + 8 * kRs * 8 + kRs * 8;   // [NC][32 streams][2] cluster partials
+  static constexpr uint32_t kGp = (kStatBox + NC * kRs * 8 + 1023) / 1024 * 1024;
+  static constexpr uint32_t kGpPanel = kGpRows * 16;            // one 8-channel K panel
+  static constexpr uint32_t kGpPlane = (kCs / 8) * kGpPanel;
+  static constexpr uint32_t kGpBuf = P * kGpPlane;              // one of two buffers (block parity)
+  static constexpr uint32_t kBox = kGp + 2 * kGpBuf;            // [2 parities][NC slots][32 ch][kBoxPitch] fp32
+  static constexpr uint32_t kBoxSlot = kCs * kBoxPitch * 4;
+  static constexpr uint32_t kBoxBuf = NC * kBoxSlot;
+  static constexpr uint32_t kW = (kBox + 2 * kBoxBuf + 1023) / 1024 * 1024;
+  static constexpr uint32_t kKstep = P * 2 * C * 16;            // one K step of weights: [plane][2 panels][C rows][8]
+  static constexpr uint32_t kTotal = kW + kNstW * kKstep;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __grid_constant__ ResStackParams p) {
+  using L = EncSmem<C>;
+  constexpr int NC = L::NC, P = L::P;
+  constexpr int MTc = C / 128;                 // M tiles of output channels
+  constexpr int Gs = kCs / 16;                 // K steps per tap (own slice)
+  constexpr uint32_t kTmemCols = 64;           // MTc * 32 accumulator columns (power of two >= 32)
+  extern __shared__ __align__(1024) uint8_t smem[];
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int rank = static_cast<int>(ClusterCtaRank());
+  const int tile = blockIdx.x / NC;
+  const uint32_t smem_base = SmemAddr(smem);
+
+  // barriers
+  const uint32_t bar0 = smem_base + L::kBars;
+  const uint32_t bar_w_full = bar0, bar_w_empty = bar0 + 8 * kNstW, bar_hist = bar0 + 16 * kNstW, bar_free = bar_hist + 16,
+                 bar_in = bar_free + 16, bar_acc = bar_in + 8, bar_box = bar_acc + 8, bar_stat = bar_box + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kMisc);
+  volatile uint32_t* in_cnt = reinterpret_cast<volatile uint32_t*>(smem + L::kMisc + 4);    // += 1 per worker warp per block input
+  volatile uint32_t* acc_cnt = reinterpret_cast<volatile uint32_t*>(smem + L::kMisc + 8);   // += 1 per block whose MMAs retired
+  float* xbuf = reinterpret_cast<float*>(smem + L::kXbuf);        // [lc][s]
+  float* stat_loc = reinterpret_cast<float*>(smem + L::kStat);    // [cg][s][2], then mean/rstd at + 8*32*2
+  float* stat_box = reinterpret_cast<float*>(smem + L::kStatBox); // [src rank][s][2]
+
+  if (tid == 0) {
+    *in_cnt = 0;
+    *acc_cnt = 0;
+    for (int i = 0; i < 2 * kNstW + 4; ++i) MbarInit(bar0 + 8 * i, 1);   // w_full, w_empty, hist[2], free[2]
+    MbarInit(bar_in, kWorkers / 32);
+    MbarInit(bar_acc, 1);
+    MbarInit(bar_box, 1);
+    MbarInit(bar_stat, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kWarpMma) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemAddr(tmem_slot)), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  TcFenceBefore();
+  __syncthreads();
+  ClusterSyncAll();   // every CTA's barriers exist before a peer signals them
+  TcFenceAfter();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  // per-block history geometry: block r keeps H = 2 * dil[r] time steps; image [tile][rank*P*4 + plane*4 + panel][H*32 rows][8]
+  auto hist_ptr = [&](int r) {
+    size_t off = 0;
+    for (int i = 0; i < r; ++i) off += static_cast<size_t>(p.n_tiles) * NC * P * (kCs / 8) * (2 * p.dil[i]) * kRs * 8;
+    const int H = 2 * p.dil[r];
+    return p.hist + off + (static_cast<size_t>(tile) * NC + rank) * P * (kCs / 8) * H * kRs * 8;
+  };
+
+  if (warp < kWorkers / 32) {
+    // =========================== worker warps ===========================
+    const int s = tid & 31, cg = tid >> 5;            // stream in the tile, group of 4 own channels
+    const int b = tile * kRs + s;
+    const bool valid = b < p.B;
+    const int wm = warp >> 2, wq = warp & 3;          // (M tile, lane quarter) this warp drains
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
+    PdlWait();
+    PdlLaunchDependents();
+    // x slice of this CTA: [lc][s]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int lc = cg * 4 + i;
+      xbuf[lc * kRs + s] = valid ? __ldg(p.x_in + static_cast<size_t>(b) * C + rank * kCs + lc) : 0.0f;
+    }
+#pragma unroll 1
+    for (int r = 0; r < p.n_res; ++r) {
+      const int buf = r & 1;
+      const uint32_t gp = smem_base + L::kGp + buf * L::kGpBuf;
+      // ---- ChanNorm statistics of x (block input), exact two-pass per thread, Chan above ----
+      float xv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xv[i] = xbuf[(cg * 4 + i) * kRs + s];
+      {
+        const float m4 = ((xv[0] + xv[1]) + (xv[2] + xv[3])) * 0.25f;
+        float q4 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q4 = fmaf(xv[i] - m4, xv[i] - m4, q4);
+        stat_loc[(cg * kRs + s) * 2] = m4;
+        stat_loc[(cg * kRs + s) * 2 + 1] = q4;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (cg == 0) {   // 32 threads: this CTA's partial over its 32 channels, pushed to every peer
+        float n = 4.f, mean = stat_loc[s * 2], m2 = stat_loc[s * 2 + 1];
+#pragma unroll
+        for (int g = 1; g < 8; ++g) ChanCombine(n, mean, m2, 4.f, stat_loc[(g * kRs + s) * 2], stat_loc[(g * kRs + s) * 2 + 1]);
+        stat_box[(rank * kRs + s) * 2] = mean;
+        stat_box[(rank * kRs + s) * 2 + 1] = m2;
+        if (lane == 0) MbarExpectTx(bar_stat, static_cast<uint32_t>(NC - 1) * kRs * 8);
+        const uint32_t src = smem_base + L::kStatBox + (rank * kRs + s) * 8;
+#pragma unroll 1
+        for (int q = 1; q < NC; ++q) {
+          const int pr = (rank + q) % NC;
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1,%2}, [%3];" ::"r"(MapToCta(src, pr)),
+                       "f"(mean), "f"(m2), "r"(MapToCta(bar_stat, pr))
+                       : "memory");
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // own partial visible to every worker
+      MbarWait(bar_stat, r & 1);
+      float mean, rstd;
+      {
+        float n = static_cast<float>(kCs), m2;
+        mean = stat_box[s * 2];
+        m2 = stat_box[s * 2 + 1];
+#pragma unroll 1
+        for (int src = 1; src < NC; ++src) ChanCombine(n, mean, m2, static_cast<float>(kCs), stat_box[(src * kRs + s) * 2], stat_box[(src * kRs + s) * 2 + 1]);
+        rstd = 1.0f / sqrtf(m2 / static_cast<float>(C) + 1e-5f);
+      }
+      // ---- g = GELU(norm * gamma + beta) -> bf16 hi/lo into the new rows of the B panels ----
+      if (r >= 2) MbarWait(bar_free + 8 * buf, ((r - 2) >> 1) & 1);   // the history mover is done with this buffer's block r-2
+      {
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + static_cast<size_t>(r) * C + rank * kCs + cg * 4));
+        const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + static_cast<size_t>(r) * C + rank * kCs + cg * 4));
+        float g[4];
+        g[0] = GeluFast((xv[0] - mean) * rstd * ga.x + be.x);
+        g[1] = GeluFast((xv[1] - mean) * rstd * ga.y + be.y);
+        g[2] = GeluFast((xv[2] - mean) * rstd * ga.z + be.z);
+        g[3] = GeluFast((xv[3] - mean) * rstd * ga.w + be.w);
+        if (!valid) g[0] = g[1] = g[2] = g[3] = 0.0f;
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(g[0]), h1 = __float2bfloat16_rn(g[1]), h2 = __float2bfloat16_rn(g[2]),
+                            h3 = __float2bfloat16_rn(g[3]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(g[0] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(g[1] - __bfloat162float(h1)),
+                            l2 = __float2bfloat16_rn(g[2] - __bfloat162float(h2)), l3 = __float2bfloat16_rn(g[3] - __bfloat162float(h3));
+        const uint32_t hi0 = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+        const uint32_t hi1 = static_cast<uint32_t>(__bfloat16_as_ushort(h2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h3)) << 16);
+        const uint32_t lo0 = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+        const uint32_t lo1 = static_cast<uint32_t>(__bfloat16_as_ushort(l2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l3)) << 16);
+        // channel lc = 4 cg + i -> panel cg / 2, byte (cg & 1) * 8 inside the 16-byte row entry; row = newest time step
+        const uint32_t dst = gp + (cg >> 1) * L::kGpPanel + static_cast<uint32_t>(kHmax * kRs + s) * 16 + (cg & 1) * 8;
+        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(dst), "r"(hi0), "r"(hi1) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(dst + L::kGpPlane), "r"(lo0), "r"(lo1) : "memory");
+      }
+      FenceProxyAsync();
+      __syncwarp();
+      if (lane == 0) {
+        MbarArrive(bar_in);
+        SmemAddRelease(in_cnt);
+      }
+      // ---- the block's MMAs run (warp 8); then reduce-scatter the partial D^T ----
+      MbarWait(bar_acc, r & 1);
+      TcFenceAfter();
+      if (tid == 0) {
+        SmemAddRelease(acc_cnt);
+        MbarExpectTx(bar_box, static_cast<uint32_t>(NC - 1) * kCs * kRs * 4);
+      }
+      if (wm < MTc) {
+        const int dest = wm * 4 + wq;                 // owner of output channels 128 wm + 32 wq .. + 32
+        const int slot = rank;                        // inbox slots are indexed by source rank
+        const uint32_t row = smem_base + L::kBox + buf * L::kBoxBuf + slot * L::kBoxSlot + static_cast<uint32_t>(lane) * kBoxPitch * 4;
+        uint32_t raw[32];
+        TmemLd16(t_lane + wm * kRs, raw);
+        TmemLd16(t_lane + wm * kRs + 16, raw + 16);
+        if (dest == rank) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + 16 * e), "r"(raw[4 * e]), "r"(raw[4 * e + 1]),
+                         "r"(raw[4 * e + 2]), "r"(raw[4 * e + 3])
+                         : "memory");
+        } else {
+          const uint32_t rrow = MapToCta(row, dest), rbar = MapToCta(bar_box, dest);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            StAsync16(rrow + 16 * e, __uint_as_float(raw[4 * e]), __uint_as_float(raw[4 * e + 1]), __uint_as_float(raw[4 * e + 2]),
+                      __uint_as_float(raw[4 * e + 3]), rbar);
+        }
+      }
+      TcFenceBefore();
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // own partial stored (and every TMEM read done before the next MMAs)
+      MbarWait(bar_box, r & 1);
+      // ---- x += bias + sum of the partials in rank order ----
+      {
+        const float* box = reinterpret_cast<const float*>(smem + L::kBox + buf * L::kBoxBuf);
+        const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(r) * C + rank * kCs + cg * 4));
+        const float bb[4] = {bi.x, bi.y, bi.z, bi.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int lc = cg * 4 + i;
+          float y = 0.f;
+#pragma unroll 1
+          for (int src = 0; src < NC; ++src) y += box[(src * kCs + lc) * kBoxPitch + s];
+          xbuf[lc * kRs + s] = xv[i] + (y + bb[i]);
+        }
+      }
+      // (every thread re-reads only its own xbuf entries at the top of the next block: no barrier needed here)
+    }
+    // ---- stack output: fp32 x for the record, bf16 hi/lo for the head conv ----
+    if (valid) {
+      float xo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xo[i] = xbuf[(cg * 4 + i) * kRs + s];
+      const size_t o = static_cast<size_t>(b) * C + rank * kCs + cg * 4;
+      *reinterpret_cast<float4*>(p.x_out + o) = make_float4(xo[0], xo[1], xo[2], xo[3]);
+      if (p.xh_out) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(xo[0]), h1 = __float2bfloat16_rn(xo[1]), h2 = __float2bfloat16_rn(xo[2]),
+                            h3 = __float2bfloat16_rn(xo[3]);
+        uint2 hv, lv;
+        hv.x = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+        hv.y = static_cast<uint32_t>(__bfloat16_as_ushort(h2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h3)) << 16);
+        *reinterpret_cast<uint2*>(p.xh_out + o) = hv;
+        if (p.xl_out) {
+          const __nv_bfloat16 l0 = __float2bfloat16_rn(xo[0] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(xo[1] - __bfloat162float(h1)),
+                              l2 = __float2bfloat16_rn(xo[2] - __bfloat162float(h2)), l3 = __float2bfloat16_rn(xo[3] - __bfloat162float(h3));
+          lv.x = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+          lv.y = static_cast<uint32_t>(__bfloat16_as_ushort(l2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l3)) << 16);
+          *reinterpret_cast<uint2*>(p.xl_out + o) = lv;
+        }
+      }
+    }
+  } else if (warp == kWarpMma) {
+    // =========================== MMA issuer (warp-converged, elected issue) ===========================
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kRs >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+    uint32_t cc = 0;
+#pragma unroll 1
+    for (int r = 0; r < p.n_res; ++r) {
+      const int buf = r & 1, dil = p.dil[r];
+      const uint32_t gp = smem_base + L::kGp + buf * L::kGpBuf;
+      MbarWait(bar_hist + 8 * buf, (r >> 1) & 1);
+      MbarWait(bar_in, r & 1);
+      TcFenceAfter();
+      int ks = 0;
+#pragma unroll 1
+      for (int j = 0; j < 3; ++j) {
+        const uint32_t row0 = static_cast<uint32_t>((kHmax - (2 - j) * dil) * kRs);
+#pragma unroll 1
+        for (int h = 0; h < Gs; ++h) {
+          const uint32_t stage = cc % kNstW;
+          MbarWait(bar_w_full + 8 * stage, (cc / kNstW) & 1);
+          TcFenceAfter();
+          const uint32_t w_s = smem_base + L::kW + stage * L::kKstep;
+          const uint32_t b_hi = gp + (2 * h) * L::kGpPanel + row0 * 16;
+          const uint64_t bh = MakeDesc(b_hi, L::kGpPanel, 128);
+          const uint64_t bl = MakeDesc(b_hi + L::kGpPlane, L::kGpPanel, 128);
+#pragma unroll
+          for (int m = 0; m < MTc; ++m) {
+            const uint64_t ah = MakeDesc(w_s + m * 128 * 16, C * 16, 128);
+            const uint64_t al = MakeDesc(w_s + 2 * C * 16 + m * 128 * 16, C * 16, 128);
+            const uint32_t dcol = tmem_base + m * kRs;
+            MmaW(dcol, ah, bh, idesc, ks > 0 ? 1u : 0u);
+            MmaW(dcol, ah, bl, idesc, 1u);
+            MmaW(dcol, al, bh, idesc, 1u);
+          }
+          ++ks;
+          MmaCommitW(bar_w_empty + 8 * stage);
+          ++cc;
+        }
+      }
+      MmaCommitW(bar_acc);
+    }
+    __syncwarp();
+  } else if (warp == kWarpW) {
+    // =========================== weight producer ===========================
+    if (ElectOneSync()) {
+      const int ksteps = 3 * Gs;   // own K slice of one block
+      uint32_t cc = 0;
+#pragma unroll 1
+      for (int r = 0; r < p.n_res; ++r) {
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (static_cast<size_t>(r) * NC + rank) * ksteps * L::kKstep;
+#pragma unroll 1
+        for (int c = 0; c < ksteps; ++c) {
+          const uint32_t stage = cc % kNstW, round = cc / kNstW;
+          if (round > 0) MbarWait(bar_w_empty + 8 * stage, (round - 1) & 1);
+          MbarExpectTx(bar_w_full + 8 * stage, L::kKstep);
+          TmaBulkLoadKeep(smem_base + L::kW + stage * L::kKstep, wsrc + static_cast<size_t>(c) * L::kKstep, L::kKstep, bar_w_full + 8 * stage);
+          ++cc;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kWarpH) {
+    // =========================== history mover ===========================
+    if (ElectOneSync()) {
+      auto load_hist = [&](int r) {
+        const int buf = r & 1, H = 2 * p.dil[r];
+        const uint32_t gp = smem_base + L::kGp + buf * L::kGpBuf;
+        const uint32_t bytes = static_cast<uint32_t>(H) * kRs * 16;
+        const uint16_t* src = hist_ptr(r);
+        MbarExpectTx(bar_hist + 8 * buf, bytes * P * (kCs / 8));
+        for (int pl = 0; pl < P; ++pl)
+          for (int pn = 0; pn < kCs / 8; ++pn)
+            TmaBulkLoad(gp + pl * L::kGpPlane + pn * L::kGpPanel + static_cast<uint32_t>((kHmax - H) * kRs) * 16,
+                        src + static_cast<size_t>(pl * (kCs / 8) + pn) * H * kRs * 8, bytes, bar_hist + 8 * buf);
+      };
+      load_hist(0);
+      if (p.n_res > 1) load_hist(1);
+#pragma unroll 1
+      for (int r = 0; r < p.n_res; ++r) {
+        const int buf = r & 1, H = 2 * p.dil[r];
+        const uint32_t gp = smem_base + L::kGp + buf * L::kGpBuf;
+        MbarWait(bar_hist + 8 * buf, (r >> 1) & 1);
+        SpinUntil(in_cnt, static_cast<uint32_t>((kWorkers / 32) * (r + 1)));   // the new row of block r is in the panels
+        __threadfence_block();
+        FenceProxyAsync();
+        {
+          const uint32_t bytes = static_cast<uint32_t>(H) * kRs * 16;
+          uint16_t* dst = const_cast<uint16_t*>(hist_ptr(r));
+          for (int pl = 0; pl < P; ++pl)
+            for (int pn = 0; pn < kCs / 8; ++pn)
+              TmaBulkStore(dst + static_cast<size_t>(pl * (kCs / 8) + pn) * H * kRs * 8,
+                           gp + pl * L::kGpPlane + pn * L::kGpPanel + static_cast<uint32_t>((kHmax + 1 - H) * kRs) * 16, bytes);
+          BulkCommit();
+          BulkWaitRead0();
+        }
+        SpinUntil(acc_cnt, static_cast<uint32_t>(r + 1));   // block r's MMAs are done reading the buffer
+        if (r + 2 < p.n_res) load_hist(r + 2);
+        MbarArrive(bar_free + 8 * buf);
+      }
+      BulkWait0();
+    }
+    __syncwarp();
+  }
+
+  TcFenceBefore();
+  __syncthreads();
+  if (warp == kWarpMma) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+template <int C>
+void LaunchResStackT(const ResStackParams& p, cudaStream_t s) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  B200_CHECK(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    B200_CHECK(cudaFuncSetAttribute(enc_res_stack_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[dev & 63] = true;
+  }
+  constexpr int NC = C / kCs;
+  LaunchPdl(enc_res_stack_kernel<C>, dim3(p.n_tiles * NC, 1, 1), dim3(kEncThreads, 1, 1), EncSmem<C>::kTotal, s, NC, p);
+}
+
+}  // namespace
+
+bool ResStackSupported(int C, int n_res, const int* dil) {
+  if (C != 128 && C != 256) return false;
+  if (n_res < 1 || n_res > 6) return false;
+  for (int r = 0; r < n_res; ++r)
+    if (dil[r] < 1 || 2 * dil[r] > kHmax) return false;
+  return (C == 256 ? EncSmem<256>::kTotal : EncSmem<128>::kTotal) <= 227 * 1024;
+}
+
+int ResStackTiles(int B) { return (B + kRs - 1) / kRs; }
+
+size_t ResStackHistElems(int C, int n_res, const int* dil, int B) {
+  size_t n = 0;
+  for (int r = 0; r < n_res; ++r) n += static_cast<size_t>(ResStackTiles(B)) * (C / kCs) * 2 * (kCs / 8) * (2 * dil[r]) * kRs * 8;
+  return n;
+}
+
+// One MrfHistBlock per residual block (layout [tile][rank*8 + plane*4 + panel][H][32 streams][8], which is the
+// [group][planes_panels][H][S][8] form mrf_zero_stream_kernel clears per stream).
+void ResStackHistBlocks(int C, int n_res, const int* dil, int B, uint16_t* base, std::vector<MrfHistBlock>* out) {
+  size_t off = 0;
+  for (int r = 0; r < n_res; ++r) {
+    MrfHistBlock hb;
+    hb.base = base + off;
+    hb.planes_panels = (C / kCs) * 2 * (kCs / 8);
+    hb.H = 2 * dil[r];
+    hb.S = kRs;
+    hb.pad_ = 0;
+    out->push_back(hb);
+    off += static_cast<size_t>(ResStackTiles(B)) * hb.planes_panels * hb.H * kRs * 8;
+  }
+}
+
+size_t PackResStackWeights(const float* const* w, int n_res, int C, uint16_t* out) {
+  // [block r][rank][tap j][K step h][plane][2 panels][C rows n][8]   element = W_r[j][32 rank + 16 h + 8 pp + e][n]
+  const int NC = C / kCs, Gs = kCs / 16;
+  const size_t kstep = static_cast<size_t>(2) * 2 * C * 8;
+  const size_t total = static_cast<size_t>(n_res) * NC * 3 * Gs * kstep;
+  if (!out) return total;
+  for (int r = 0; r < n_res; ++r)
+    for (int rk = 0; rk < NC; ++rk)
+      for (int j = 0; j < 3; ++j)
+        for (int h = 0; h < Gs; ++h) {
+          uint16_t* blk = out + (((static_cast<size_t>(r) * NC + rk) * 3 + j) * Gs + h) * kstep;
+          for (int pp = 0; pp < 2; ++pp)
+            for (int n = 0; n < C; ++n)
+              for (int e = 0; e < 8; ++e) {
+                const int ci = rk * kCs + 16 * h + 8 * pp + e;
+                const float val = w[r][(static_cast<size_t>(j) * C + ci) * C + n];
+                const uint16_t hi = Bf16Rn(val);
+                const size_t o = (static_cast<size_t>(pp) * C + n) * 8 + e;
+                blk[o] = hi;
+                blk[static_cast<size_t>(2) * C * 8 + o] = Bf16Rn(val - Bf16ToF(hi));
+              }
+        }
+  return total;
+}
+
+void LaunchResStack(const ResStackParams& p, int C, cudaStream_t s) {
+  if (C == 256) LaunchResStackT<256>(p, s);
+  else if (C == 128) LaunchResStackT<128>(p, s);
+  else {
+    std::fprintf(stderr, "[libbeatrice_b200] FATAL: residual-stack kernel has no C = %d form\n", C);
+    std::abort();
+  }
+  B200_CHECK(cudaGetLastError());
+}
+
+}  // namespace b200

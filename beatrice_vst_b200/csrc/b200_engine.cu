@@ -183,6 +183,14 @@ bool GraphsEnabled() {
   return on;
 }
 
+bool ResStackEnabled() {
+  static bool on = [] {
+    const char* e = std::getenv("BEATRICE_B200_NO_FUSED_RESSTACK");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
 bool FusedMrfEnabled() {
   static bool on = [] {
     const char* e = std::getenv("BEATRICE_B200_NO_FUSED_MRF");
@@ -276,6 +284,25 @@ int EncoderModel::LoadFromImage(const void* data, size_t size, int on_device) {
     convs.push_back(&head);
     for (ConvW* cv : convs) cv->tc_bn_cap = 64;   // few rows per hop (T <= 16): favour CTA count
     tc.Pack(device, img.payload, blob.as<float>(), convs);
+  }
+  rs_ok = ResStackSupported(width, n_res, dil);
+  if (rs_ok) {   // fused residual-stack kernel: weight image and contiguous per-block parameters
+    const float* wsrc[6];
+    std::vector<float> par(static_cast<size_t>(3) * n_res * width);
+    for (int i = 0; i < n_res; ++i) {
+      wsrc[i] = c.HostAt(res[i].w);
+      std::memcpy(par.data() + (0 * n_res + i) * width, c.HostAt(res[i].b), sizeof(float) * width);
+      std::memcpy(par.data() + (1 * n_res + i) * width, c.HostAt(gamma[i]), sizeof(float) * width);
+      std::memcpy(par.data() + (2 * n_res + i) * width, c.HostAt(beta[i]), sizeof(float) * width);
+    }
+    std::vector<uint16_t> packed(PackResStackWeights(wsrc, n_res, width, nullptr));
+    PackResStackWeights(wsrc, n_res, width, packed.data());
+    rs_w.Alloc(device, packed.size() * sizeof(uint16_t), false);
+    B200_CHECK(cudaMemcpy(rs_w.p, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    Upload(&rs_par, device, par.data(), par.size());
+    rs_bias = rs_par.as<float>();
+    rs_gamma = rs_bias + static_cast<size_t>(n_res) * width;
+    rs_beta = rs_gamma + static_cast<size_t>(n_res) * width;
   }
   ++generation;
   loaded = true;
@@ -628,11 +655,14 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     ring_in[i] = (tcm && i >= 1) ? arena.PlanH(hist, t_in[i], m->front[i].cin, true)
                                  : arena.Plan(hist, t_in[i], m->front[i].cin);
   }
-  std::vector<int> ring_x(m->n_res + 1), ring_g(m->n_res);
+  // tensor-core mode: the residual stack (ChanNorm + GELU + dilated conv, n_res blocks) is ONE cluster kernel
+  // (b200_enc.cu); it keeps its own conv-input histories, so only the stack's input and output rows are rings
+  const bool rs_fused = tcm && m->rs_ok && ResStackEnabled();
+  std::vector<int> ring_x(m->n_res + 1, -1), ring_g(m->n_res, -1);
   ring_x[0] = arena.Plan(0, 1, m->width);
   for (int r = 0; r < m->n_res; ++r) {
-    ring_g[r] = tcm ? arena.PlanH(2 * m->dil[r], 1, m->width, true) : arena.Plan(2 * m->dil[r], 1, m->width);
-    ring_x[r + 1] = arena.Plan(0, 1, m->width);
+    if (!rs_fused) ring_g[r] = tcm ? arena.PlanH(2 * m->dil[r], 1, m->width, true) : arena.Plan(2 * m->dil[r], 1, m->width);
+    if (!rs_fused || r == m->n_res - 1) ring_x[r + 1] = arena.Plan(0, 1, m->width);
   }
   const int ring_xh = tcm ? arena.PlanH(0, 1, m->width, true) : -1;   // bf16 copy of the last x for the head
   arena.Commit(device, B);
@@ -656,7 +686,7 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     conv_idx.push_back(db.Add(d));
   }
   std::vector<int> res_idx;
-  for (int r = 0; r < m->n_res; ++r) {
+  for (int r = 0; r < m->n_res && !rs_fused; ++r) {
     const Ring& g = arena.ring(ring_g[r]);
     ConvDesc d = MakeConv(g, m->res[r], m->dil[r], 1, 1, arena.ring(ring_x[r + 1]), kActNone, kActNone);
     if (g.is_bf16) SetInH(&d, g);
@@ -703,7 +733,39 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
       op.launch = GemmLauncher(dp, h, 1, Bn, frame, tc, tcm);
     program.push_back(op);
   }
-  for (int r = 0; r < m->n_res; ++r) {
+  n_rs_blocks = 0;
+  if (rs_fused) {
+    const size_t n_hist = ResStackHistElems(m->width, m->n_res, m->dil, B);
+    rs_hist.Alloc(device, n_hist * sizeof(uint16_t), true);
+    std::vector<MrfHistBlock> blocks;
+    ResStackHistBlocks(m->width, m->n_res, m->dil, B, rs_hist.as<uint16_t>(), &blocks);
+    n_rs_blocks = static_cast<int>(blocks.size());
+    rs_blocks.Alloc(device, sizeof(MrfHistBlock) * blocks.size(), false);
+    B200_CHECK(cudaMemcpy(rs_blocks.p, blocks.data(), sizeof(MrfHistBlock) * blocks.size(), cudaMemcpyHostToDevice));
+    ResStackParams rp;
+    std::memset(&rp, 0, sizeof(rp));
+    rp.x_in = arena.ring(ring_x[0]).base;
+    rp.x_out = arena.ring(ring_x[m->n_res]).base;
+    rp.xh_out = arena.ring(ring_xh).hi;
+    rp.xl_out = arena.ring(ring_xh).lo;
+    rp.w = m->rs_w.as<uint16_t>();
+    rp.bias = m->rs_bias;
+    rp.gamma = m->rs_gamma;
+    rp.beta = m->rs_beta;
+    rp.hist = rs_hist.as<uint16_t>();
+    rp.n_res = m->n_res;
+    for (int r = 0; r < m->n_res; ++r) rp.dil[r] = m->dil[r];
+    rp.B = B;
+    rp.n_tiles = ResStackTiles(B);
+    const int width = m->width;
+    Op op;
+    op.name = std::string(tag) + ".resstack";
+    op.flops = 2.0 * 3 * width * width * B * m->n_res;
+    op.bytes = 4.0 * 3 * width * width * m->n_res + 8.0 * B * width;
+    op.launch = [=](cudaStream_t s) { LaunchResStack(rp, width, s); };
+    program.push_back(op);
+  }
+  for (int r = 0; r < m->n_res && !rs_fused; ++r) {
     NormDesc nd;
     std::memset(&nd, 0, sizeof(nd));
     const Ring& xr = arena.ring(ring_x[r]);
@@ -750,6 +812,15 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     op.launch = [=](cudaStream_t s) { LaunchAdvance(f, s); };
     program.push_back(op);
   }
+}
+
+void EncoderState::ZeroStream(int b, cudaStream_t s) {
+  arena.ZeroStream(b, s);
+  LaunchMrfZeroStream(rs_blocks.as<MrfHistBlock>(), n_rs_blocks, b, s);
+}
+void EncoderState::ZeroAll(cudaStream_t s) {
+  arena.ZeroAll(s);
+  if (n_rs_blocks > 0 && rs_hist.p) B200_CHECK(cudaMemsetAsync(rs_hist.p, 0, rs_hist.bytes, s));
 }
 
 void WaveState::AllocCond(const FamilyDims& dims, int B_, int device_) {

@@ -12,6 +12,7 @@
 
 #include "b200_common.h"
 #include "b200_kernels.h"
+#include "b200_enc.h"
 #include "b200_mrf.h"
 
 namespace b200 {
@@ -104,6 +105,12 @@ struct EncoderModel {  // PhoneExtractor / PitchEstimator
   int dil[6];
   ConvW head;
   TcWeights tc;
+  // fused residual-stack kernel (b200_enc.cu): weight image + the blocks' bias / gamma / beta made contiguous
+  DeviceBuffer rs_w, rs_par;
+  bool rs_ok = false;
+  const float* rs_bias = nullptr;
+  const float* rs_gamma = nullptr;
+  const float* rs_beta = nullptr;
   // returns Beatrice_ErrorCode; host validation happens before any CUDA call
   int LoadFromImage(const void* data, size_t size, int on_device = -1);
   int LoadFromFile(const char* utf8_path, int on_device = -1);
@@ -199,6 +206,10 @@ struct EncoderState {
   DeviceBuffer in_stage;  // [B][160]
   DeviceBuffer head_out;  // [B][head_out]
   std::vector<Op> program;
+  DeviceBuffer rs_hist, rs_blocks;   // fused residual stack: conv-input histories + their per-stream reset table
+  int n_rs_blocks = 0;
+  void ZeroStream(int b, cudaStream_t s);   // rings + fused-stack histories of stream b
+  void ZeroAll(cudaStream_t s);
   const float* stage_ptr = nullptr;  // == in_stage unless an external staging buffer is shared
   // Builds rings + program for `m`.  `external_stage` (device, [B][160]) replaces in_stage.
   void Build(const EncoderModel* m, int B, int device, const float* external_stage = nullptr,
