@@ -40,15 +40,17 @@ constexpr int kGpRows = (kHmax + 1) * kRs;
 constexpr int kWorkers = 256;      // 8 warps: warp w <-> (M tile w / 4, TMEM lane quarter w % 4)
 constexpr int kWarpMma = 8, kWarpW = 9, kWarpH = 10;
 constexpr int kEncThreads = 11 * 32;
-constexpr int kNstW = 4;           // weight ring stages, one K step (16 KB at C = 256) each
+constexpr int kNstW = 6;           // weight ring stages, one K step (16 KB at C = 256) each: a whole block's slice in flight
 constexpr int kBoxPitch = kRs + 4; // floats per inbox row (one channel x 32 streams), +16 B against bank conflicts
 
-__device__ __forceinline__ void ChanCombine(float& n, float& mean, float& m2, float nb, float mb, float m2b) {
-  const float nt = n + nb;
+// Chan's pairwise combination of (count, mean, M2) when every partial has the same count g and the running
+// value already holds k of them: nb / nt = 1 / (k + 1), n nb / nt = g k / (k + 1) -- compile-time constants
+// once the loop over k is unrolled (no divisions on the critical path).
+__device__ __forceinline__ void ChanCombineEq(int k, float g, float& mean, float& m2, float mb, float m2b) {
+  const float inv = 1.0f / static_cast<float>(k + 1);
   const float delta = mb - mean;
-  mean = mean + delta * (nb / nt);
-  m2 = m2 + m2b + delta * delta * (n * nb / nt);
-  n = nt;
+  mean = fmaf(delta, inv, mean);
+  m2 = m2 + m2b + delta * delta * (g * static_cast<float>(k) * inv);
 }
 
 // shared-memory layout (bytes), identical on host and device
@@ -65,10 +67,12 @@ struct EncSmem {
   static constexpr uint32_t kGpPanel = kGpRows * 16;            // one 8-channel K panel
   static constexpr uint32_t kGpPlane = (kCs / 8) * kGpPanel;
   static constexpr uint32_t kGpBuf = P * kGpPlane;              // one of two buffers (block parity)
-  static constexpr uint32_t kBox = kGp + 2 * kGpBuf;            // [2 parities][NC slots][32 ch][kBoxPitch] fp32
+  // inbox [NC slots][32 ch][kBoxPitch] fp32, single-buffered: a peer can push block r+1 only after it has this
+  // CTA's statistics of block r+1, which are sent after the last read of block r's partials
+  static constexpr uint32_t kBox = kGp + 2 * kGpBuf;
   static constexpr uint32_t kBoxSlot = kCs * kBoxPitch * 4;
   static constexpr uint32_t kBoxBuf = NC * kBoxSlot;
-  static constexpr uint32_t kW = (kBox + 2 * kBoxBuf + 1023) / 1024 * 1024;
+  static constexpr uint32_t kW = (kBox + kBoxBuf + 1023) / 1024 * 1024;
   static constexpr uint32_t kKstep = P * 2 * C * 16;            // one K step of weights: [plane][2 panels][C rows][8]
   static constexpr uint32_t kTotal = kW + kNstW * kKstep;
 };
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
   if (tid == 0) {
     *in_cnt = 0;
     *acc_cnt = 0;
-    for (int i = 0; i < 2 * kNstW + 4; ++i) MbarInit(bar0 + 8 * i, 1);   // w_full, w_empty, hist[2], free[2]
+    for (int i = 0; i < 2 * kNstW + 4; ++i) MbarInit(bar0 + 8 * i, 1);   // w_full, w_empty, hist[2], free[2]  (20 + 4 more fit in 256 B)
     MbarInit(bar_in, kWorkers / 32);
     MbarInit(bar_acc, 1);
     MbarInit(bar_box, 1);
@@ -128,6 +132,11 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
     return p.hist + off + (static_cast<size_t>(tile) * NC + rank) * P * (kCs / 8) * H * kRs * 8;
   };
 
+  __shared__ long long trace[8 * 8];
+  const bool tracing = p.trace != 0 && blockIdx.x == 0;
+#define B200_ETR(r, slot) do { if (tracing && tid == 0) trace[(r) * 8 + (slot)] = clock64(); } while (0)
+  const long long t_origin = clock64();
+
   if (warp < kWorkers / 32) {
     // =========================== worker warps ===========================
     const int s = tid & 31, cg = tid >> 5;            // stream in the tile, group of 4 own channels
@@ -148,9 +157,14 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
       const int buf = r & 1;
       const uint32_t gp = smem_base + L::kGp + buf * L::kGpBuf;
       // ---- ChanNorm statistics of x (block input), exact two-pass per thread, Chan above ----
+      // per-block parameters of this thread's four channels: in flight while the statistics are exchanged
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + static_cast<size_t>(r) * C + rank * kCs + cg * 4));
+      const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + static_cast<size_t>(r) * C + rank * kCs + cg * 4));
+      const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(r) * C + rank * kCs + cg * 4));
       float xv[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) xv[i] = xbuf[(cg * 4 + i) * kRs + s];
+      B200_ETR(r, 0);
       {
         const float m4 = ((xv[0] + xv[1]) + (xv[2] + xv[3])) * 0.25f;
         float q4 = 0.f;
@@ -161,9 +175,9 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (cg == 0) {   // 32 threads: this CTA's partial over its 32 channels, pushed to every peer
-        float n = 4.f, mean = stat_loc[s * 2], m2 = stat_loc[s * 2 + 1];
+        float mean = stat_loc[s * 2], m2 = stat_loc[s * 2 + 1];
 #pragma unroll
-        for (int g = 1; g < 8; ++g) ChanCombine(n, mean, m2, 4.f, stat_loc[(g * kRs + s) * 2], stat_loc[(g * kRs + s) * 2 + 1]);
+        for (int g = 1; g < 8; ++g) ChanCombineEq(g, 4.f, mean, m2, stat_loc[(g * kRs + s) * 2], stat_loc[(g * kRs + s) * 2 + 1]);
         stat_box[(rank * kRs + s) * 2] = mean;
         stat_box[(rank * kRs + s) * 2 + 1] = m2;
         if (lane == 0) MbarExpectTx(bar_stat, static_cast<uint32_t>(NC - 1) * kRs * 8);
@@ -178,20 +192,20 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");   // own partial visible to every worker
       MbarWait(bar_stat, r & 1);
+      B200_ETR(r, 1);
       float mean, rstd;
       {
-        float n = static_cast<float>(kCs), m2;
+        float m2;
         mean = stat_box[s * 2];
         m2 = stat_box[s * 2 + 1];
-#pragma unroll 1
-        for (int src = 1; src < NC; ++src) ChanCombine(n, mean, m2, static_cast<float>(kCs), stat_box[(src * kRs + s) * 2], stat_box[(src * kRs + s) * 2 + 1]);
-        rstd = 1.0f / sqrtf(m2 / static_cast<float>(C) + 1e-5f);
+#pragma unroll
+        for (int src = 1; src < NC; ++src)
+          ChanCombineEq(src, static_cast<float>(kCs), mean, m2, stat_box[(src * kRs + s) * 2], stat_box[(src * kRs + s) * 2 + 1]);
+        rstd = rsqrtf(m2 * (1.0f / static_cast<float>(C)) + 1e-5f);
       }
       // ---- g = GELU(norm * gamma + beta) -> bf16 hi/lo into the new rows of the B panels ----
       if (r >= 2) MbarWait(bar_free + 8 * buf, ((r - 2) >> 1) & 1);   // the history mover is done with this buffer's block r-2
       {
-        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + static_cast<size_t>(r) * C + rank * kCs + cg * 4));
-        const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + static_cast<size_t>(r) * C + rank * kCs + cg * 4));
         float g[4];
         g[0] = GeluFast((xv[0] - mean) * rstd * ga.x + be.x);
         g[1] = GeluFast((xv[1] - mean) * rstd * ga.y + be.y);
@@ -217,9 +231,11 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
         MbarArrive(bar_in);
         SmemAddRelease(in_cnt);
       }
+      B200_ETR(r, 2);
       // ---- the block's MMAs run (warp 8); then reduce-scatter the partial D^T ----
       MbarWait(bar_acc, r & 1);
       TcFenceAfter();
+      B200_ETR(r, 3);
       if (tid == 0) {
         SmemAddRelease(acc_cnt);
         MbarExpectTx(bar_box, static_cast<uint32_t>(NC - 1) * kCs * kRs * 4);
@@ -227,7 +243,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
       if (wm < MTc) {
         const int dest = wm * 4 + wq;                 // owner of output channels 128 wm + 32 wq .. + 32
         const int slot = rank;                        // inbox slots are indexed by source rank
-        const uint32_t row = smem_base + L::kBox + buf * L::kBoxBuf + slot * L::kBoxSlot + static_cast<uint32_t>(lane) * kBoxPitch * 4;
+        const uint32_t row = smem_base + L::kBox + slot * L::kBoxSlot + static_cast<uint32_t>(lane) * kBoxPitch * 4;
         uint32_t raw[32];
         TmemLd16(t_lane + wm * kRs, raw);
         TmemLd16(t_lane + wm * kRs + 16, raw + 16);
@@ -247,22 +263,31 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
       }
       TcFenceBefore();
       asm volatile("bar.sync 1, 256;" ::: "memory");   // own partial stored (and every TMEM read done before the next MMAs)
+      B200_ETR(r, 4);
       MbarWait(bar_box, r & 1);
+      B200_ETR(r, 5);
       // ---- x += bias + sum of the partials in rank order ----
       {
-        const float* box = reinterpret_cast<const float*>(smem + L::kBox + buf * L::kBoxBuf);
-        const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(r) * C + rank * kCs + cg * 4));
+        const float* box = reinterpret_cast<const float*>(smem + L::kBox);
         const float bb[4] = {bi.x, bi.y, bi.z, bi.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int lc = cg * 4 + i;
           float y = 0.f;
-#pragma unroll 1
+#pragma unroll
           for (int src = 0; src < NC; ++src) y += box[(src * kCs + lc) * kBoxPitch + s];
           xbuf[lc * kRs + s] = xv[i] + (y + bb[i]);
         }
       }
       // (every thread re-reads only its own xbuf entries at the top of the next block: no barrier needed here)
+      B200_ETR(r, 6);
+    }
+    if (tracing && tid == 0) {
+      printf("[enc trace] C=%d blocks %d (cycles after kernel start)\n", C, p.n_res);
+      for (int r = 0; r < p.n_res; ++r)
+        printf("[enc trace]  block %d: start %lld stats %lld g_written %lld acc %lld pushed %lld box_full %lld summed %lld\n", r,
+               trace[r * 8] - t_origin, trace[r * 8 + 1] - t_origin, trace[r * 8 + 2] - t_origin, trace[r * 8 + 3] - t_origin,
+               trace[r * 8 + 4] - t_origin, trace[r * 8 + 5] - t_origin, trace[r * 8 + 6] - t_origin);
     }
     // ---- stack output: fp32 x for the record, bf16 hi/lo for the head conv ----
     if (valid) {
@@ -403,7 +428,7 @@ void LaunchResStackT(const ResStackParams& p, cudaStream_t s) {
   int dev = 0;
   B200_CHECK(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    B200_CHECK(cudaFuncSetAttribute(enc_res_stack_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(enc_res_stack_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EncSmem<C>::kTotal)));
     attr_set[dev & 63] = true;
   }
   constexpr int NC = C / kCs;

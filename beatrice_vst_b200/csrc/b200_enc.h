@@ -26,6 +26,7 @@ struct ResStackParams {
   int dil[6];
   int B;
   int n_tiles;          // ceil(B / 32): stream tiles == clusters
+  int trace;            // developer aid (BEATRICE_B200_ENC_TRACE=1): CTA 0 prints a per-block timeline
 };
 
 bool ResStackSupported(int C, int n_res, const int* dil);

@@ -757,6 +757,7 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     for (int r = 0; r < m->n_res; ++r) rp.dil[r] = m->dil[r];
     rp.B = B;
     rp.n_tiles = ResStackTiles(B);
+    if (const char* ev = std::getenv("BEATRICE_B200_ENC_TRACE")) rp.trace = std::atoi(ev);
     const int width = m->width;
     Op op;
     op.name = std::string(tag) + ".resstack";
