@@ -124,12 +124,16 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
   TcFenceAfter();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  // per-block history geometry: block r keeps H = 2 * dil[r] time steps; image [tile][rank*P*4 + plane*4 + panel][H*32 rows][8]
+  // ---- per-block geometry (see ResStackParams) ----
+  auto blk_taps = [&](int r) { return p.kind[r] == 0 ? 3 : (p.kind[r] == 1 ? 2 : 1); };
+  auto blk_rows = [&](int r) { return p.kind[r] == 2 ? p.head_n : C; };                  // output channels == A rows
+  auto blk_hist = [&](int r) { return p.kind[r] == 0 ? 2 * p.dil[r] : 0; };              // history time steps
+  auto blk_kstep = [&](int r) { return static_cast<uint32_t>(P * 2 * blk_rows(r) * 16); };   // bytes of one K step of weights
+  // history image of block r: [tile][rank*P*4 + plane*4 + panel][H*32 rows][8]
   auto hist_ptr = [&](int r) {
     size_t off = 0;
-    for (int i = 0; i < r; ++i) off += static_cast<size_t>(p.n_tiles) * NC * P * (kCs / 8) * (2 * p.dil[i]) * kRs * 8;
-    const int H = 2 * p.dil[r];
-    return p.hist + off + (static_cast<size_t>(tile) * NC + rank) * P * (kCs / 8) * H * kRs * 8;
+    for (int i = 0; i < r; ++i) off += static_cast<size_t>(p.n_tiles) * NC * P * (kCs / 8) * blk_hist(i) * kRs * 8;
+    return p.hist + off + (static_cast<size_t>(tile) * NC + rank) * P * (kCs / 8) * blk_hist(r) * kRs * 8;
   };
 
   __shared__ long long trace[8 * 8];
@@ -146,15 +150,16 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
     PdlWait();
     PdlLaunchDependents();
-    // x slice of this CTA: [lc][s]
+    // x slice of this CTA: [lc][s] (a kind-1 first block computes it instead)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int lc = cg * 4 + i;
-      xbuf[lc * kRs + s] = valid ? __ldg(p.x_in + static_cast<size_t>(b) * C + rank * kCs + lc) : 0.0f;
+      xbuf[lc * kRs + s] = (valid && p.kind[0] != 1) ? __ldg(p.x_in + static_cast<size_t>(b) * C + rank * kCs + lc) : 0.0f;
     }
+    int stat_phase = 0;   // bar_stat completes one phase per kind-0 block
 #pragma unroll 1
-    for (int r = 0; r < p.n_res; ++r) {
-      const int buf = r & 1;
+    for (int r = 0; r < p.n_blk; ++r) {
+      const int buf = r & 1, kind = p.kind[r];
       const uint32_t gp = smem_base + L::kGp + buf * L::kGpBuf;
       // ---- ChanNorm statistics of x (block input), exact two-pass per thread, Chan above ----
       // per-block parameters of this thread's four channels: in flight while the statistics are exchanged
@@ -165,6 +170,8 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
 #pragma unroll
       for (int i = 0; i < 4; ++i) xv[i] = xbuf[(cg * 4 + i) * kRs + s];
       B200_ETR(r, 0);
+      float mean = 0.f, rstd = 0.f;
+      if (kind == 0) {
       {
         const float m4 = ((xv[0] + xv[1]) + (xv[2] + xv[3])) * 0.25f;
         float q4 = 0.f;
@@ -191,9 +198,9 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");   // own partial visible to every worker
-      MbarWait(bar_stat, r & 1);
+      MbarWait(bar_stat, stat_phase & 1);
+      ++stat_phase;
       B200_ETR(r, 1);
-      float mean, rstd;
       {
         float m2;
         mean = stat_box[s * 2];
@@ -203,14 +210,33 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
           ChanCombineEq(src, static_cast<float>(kCs), mean, m2, stat_box[(src * kRs + s) * 2], stat_box[(src * kRs + s) * 2 + 1]);
         rstd = rsqrtf(m2 * (1.0f / static_cast<float>(C)) + 1e-5f);
       }
+      }   // kind == 0
       // ---- g = GELU(norm * gamma + beta) -> bf16 hi/lo into the new rows of the B panels ----
       if (r >= 2) MbarWait(bar_free + 8 * buf, ((r - 2) >> 1) & 1);   // the history mover is done with this buffer's block r-2
-      {
+      if (kind == 1) {
+        // last front-end layer: tap j reads input row j of the hop (k = 2, stride 2): rows -> time blocks kHmax-1, kHmax
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint2 hv = make_uint2(0u, 0u), lv = make_uint2(0u, 0u);
+          if (valid) {
+            const size_t o = (static_cast<size_t>(b) * 2 + j) * C + rank * kCs + cg * 4;
+            hv = __ldg(reinterpret_cast<const uint2*>(p.fin_h + o));
+            lv = __ldg(reinterpret_cast<const uint2*>(p.fin_l + o));
+          }
+          const uint32_t dst = gp + (cg >> 1) * L::kGpPanel + static_cast<uint32_t>((kHmax - 1 + j) * kRs + s) * 16 + (cg & 1) * 8;
+          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(dst), "r"(hv.x), "r"(hv.y) : "memory");
+          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(dst + L::kGpPlane), "r"(lv.x), "r"(lv.y) : "memory");
+        }
+      } else {
         float g[4];
-        g[0] = GeluFast((xv[0] - mean) * rstd * ga.x + be.x);
-        g[1] = GeluFast((xv[1] - mean) * rstd * ga.y + be.y);
-        g[2] = GeluFast((xv[2] - mean) * rstd * ga.z + be.z);
-        g[3] = GeluFast((xv[3] - mean) * rstd * ga.w + be.w);
+        if (kind == 0) {
+          g[0] = GeluFast((xv[0] - mean) * rstd * ga.x + be.x);
+          g[1] = GeluFast((xv[1] - mean) * rstd * ga.y + be.y);
+          g[2] = GeluFast((xv[2] - mean) * rstd * ga.z + be.z);
+          g[3] = GeluFast((xv[3] - mean) * rstd * ga.w + be.w);
+        } else {   // head: the operand is x itself
+          g[0] = xv[0]; g[1] = xv[1]; g[2] = xv[2]; g[3] = xv[3];
+        }
         if (!valid) g[0] = g[1] = g[2] = g[3] = 0.0f;
         const __nv_bfloat16 h0 = __float2bfloat16_rn(g[0]), h1 = __float2bfloat16_rn(g[1]), h2 = __float2bfloat16_rn(g[2]),
                             h3 = __float2bfloat16_rn(g[3]);
@@ -236,11 +262,13 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
       MbarWait(bar_acc, r & 1);
       TcFenceAfter();
       B200_ETR(r, 3);
+      const int m_tiles = blk_rows(r) / 128;
+      const int owners = blk_rows(r) / kCs;           // ranks that own 32 of this block's output channels
       if (tid == 0) {
         SmemAddRelease(acc_cnt);
-        MbarExpectTx(bar_box, static_cast<uint32_t>(NC - 1) * kCs * kRs * 4);
+        MbarExpectTx(bar_box, rank < owners ? static_cast<uint32_t>(NC - 1) * kCs * kRs * 4 : 0u);
       }
-      if (wm < MTc) {
+      if (wm < m_tiles) {
         const int dest = wm * 4 + wq;                 // owner of output channels 128 wm + 32 wq .. + 32
         const int slot = rank;                        // inbox slots are indexed by source rank
         const uint32_t row = smem_base + L::kBox + slot * L::kBoxSlot + static_cast<uint32_t>(lane) * kBoxPitch * 4;
@@ -270,27 +298,33 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
       {
         const float* box = reinterpret_cast<const float*>(smem + L::kBox);
         const float bb[4] = {bi.x, bi.y, bi.z, bi.w};
+        float yo[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int lc = cg * 4 + i;
           float y = 0.f;
 #pragma unroll
           for (int src = 0; src < NC; ++src) y += box[(src * kCs + lc) * kBoxPitch + s];
-          xbuf[lc * kRs + s] = xv[i] + (y + bb[i]);
+          yo[i] = y + bb[i];
+          if (kind == 0) xbuf[lc * kRs + s] = xv[i] + yo[i];
+          else if (kind == 1) xbuf[lc * kRs + s] = GeluFast(yo[i]);
         }
+        if (kind == 2 && rank < owners && valid)
+          *reinterpret_cast<float4*>(p.head_out + static_cast<size_t>(b) * p.head_n + rank * kCs + cg * 4) =
+              make_float4(yo[0], yo[1], yo[2], yo[3]);
       }
       // (every thread re-reads only its own xbuf entries at the top of the next block: no barrier needed here)
       B200_ETR(r, 6);
     }
     if (tracing && tid == 0) {
-      printf("[enc trace] C=%d blocks %d (cycles after kernel start)\n", C, p.n_res);
-      for (int r = 0; r < p.n_res; ++r)
+      printf("[enc trace] C=%d blocks %d (cycles after kernel start)\n", C, p.n_blk);
+      for (int r = 0; r < p.n_blk; ++r)
         printf("[enc trace]  block %d: start %lld stats %lld g_written %lld acc %lld pushed %lld box_full %lld summed %lld\n", r,
                trace[r * 8] - t_origin, trace[r * 8 + 1] - t_origin, trace[r * 8 + 2] - t_origin, trace[r * 8 + 3] - t_origin,
                trace[r * 8 + 4] - t_origin, trace[r * 8 + 5] - t_origin, trace[r * 8 + 6] - t_origin);
     }
     // ---- stack output: fp32 x for the record, bf16 hi/lo for the head conv ----
-    if (valid) {
+    if (valid && p.x_out) {
       float xo[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) xo[i] = xbuf[(cg * 4 + i) * kRs + s];
@@ -317,16 +351,19 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kRs >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
     uint32_t cc = 0;
 #pragma unroll 1
-    for (int r = 0; r < p.n_res; ++r) {
-      const int buf = r & 1, dil = p.dil[r];
+    for (int r = 0; r < p.n_blk; ++r) {
+      const int buf = r & 1, kind = p.kind[r], dil = p.dil[r];
+      const int taps = blk_taps(r), rows_a = blk_rows(r), m_tiles = rows_a / 128;
       const uint32_t gp = smem_base + L::kGp + buf * L::kGpBuf;
       MbarWait(bar_hist + 8 * buf, (r >> 1) & 1);
       MbarWait(bar_in, r & 1);
       TcFenceAfter();
       int ks = 0;
 #pragma unroll 1
-      for (int j = 0; j < 3; ++j) {
-        const uint32_t row0 = static_cast<uint32_t>((kHmax - (2 - j) * dil) * kRs);
+      for (int j = 0; j < taps; ++j) {
+        // time block the tap reads: residual block t - (2 - j) dil; front conv: hop row j; head: the current row
+        const int tb = kind == 0 ? kHmax - (2 - j) * dil : (kind == 1 ? kHmax - 1 + j : kHmax);
+        const uint32_t row0 = static_cast<uint32_t>(tb * kRs);
 #pragma unroll 1
         for (int h = 0; h < Gs; ++h) {
           const uint32_t stage = cc % kNstW;
@@ -336,10 +373,10 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
           const uint32_t b_hi = gp + (2 * h) * L::kGpPanel + row0 * 16;
           const uint64_t bh = MakeDesc(b_hi, L::kGpPanel, 128);
           const uint64_t bl = MakeDesc(b_hi + L::kGpPlane, L::kGpPanel, 128);
-#pragma unroll
-          for (int m = 0; m < MTc; ++m) {
-            const uint64_t ah = MakeDesc(w_s + m * 128 * 16, C * 16, 128);
-            const uint64_t al = MakeDesc(w_s + 2 * C * 16 + m * 128 * 16, C * 16, 128);
+#pragma unroll 1
+          for (int m = 0; m < m_tiles; ++m) {
+            const uint64_t ah = MakeDesc(w_s + m * 128 * 16, rows_a * 16, 128);
+            const uint64_t al = MakeDesc(w_s + 2 * rows_a * 16 + m * 128 * 16, rows_a * 16, 128);
             const uint32_t dcol = tmem_base + m * kRs;
             MmaW(dcol, ah, bh, idesc, ks > 0 ? 1u : 0u);
             MmaW(dcol, ah, bl, idesc, 1u);
@@ -356,19 +393,22 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
   } else if (warp == kWarpW) {
     // =========================== weight producer ===========================
     if (ElectOneSync()) {
-      const int ksteps = 3 * Gs;   // own K slice of one block
       uint32_t cc = 0;
+      size_t w_off = 0;   // byte offset of block r in the image: [block][rank][tap][K step]
 #pragma unroll 1
-      for (int r = 0; r < p.n_res; ++r) {
-        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (static_cast<size_t>(r) * NC + rank) * ksteps * L::kKstep;
+      for (int r = 0; r < p.n_blk; ++r) {
+        const int ksteps = blk_taps(r) * Gs;   // own K slice of the block
+        const uint32_t kb = blk_kstep(r);
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + w_off + static_cast<size_t>(rank) * ksteps * kb;
 #pragma unroll 1
         for (int c = 0; c < ksteps; ++c) {
           const uint32_t stage = cc % kNstW, round = cc / kNstW;
           if (round > 0) MbarWait(bar_w_empty + 8 * stage, (round - 1) & 1);
-          MbarExpectTx(bar_w_full + 8 * stage, L::kKstep);
-          TmaBulkLoadKeep(smem_base + L::kW + stage * L::kKstep, wsrc + static_cast<size_t>(c) * L::kKstep, L::kKstep, bar_w_full + 8 * stage);
+          MbarExpectTx(bar_w_full + 8 * stage, kb);
+          TmaBulkLoadKeep(smem_base + L::kW + stage * L::kKstep, wsrc + static_cast<size_t>(c) * kb, kb, bar_w_full + 8 * stage);
           ++cc;
         }
+        w_off += static_cast<size_t>(NC) * ksteps * kb;
       }
     }
     __syncwarp();
@@ -376,7 +416,11 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
     // =========================== history mover ===========================
     if (ElectOneSync()) {
       auto load_hist = [&](int r) {
-        const int buf = r & 1, H = 2 * p.dil[r];
+        const int buf = r & 1, H = blk_hist(r);
+        if (H == 0) {   // no history (front conv, head): just complete the buffer's phase
+          MbarArrive(bar_hist + 8 * buf);
+          return;
+        }
         const uint32_t gp = smem_base + L::kGp + buf * L::kGpBuf;
         const uint32_t bytes = static_cast<uint32_t>(H) * kRs * 16;
         const uint16_t* src = hist_ptr(r);
@@ -387,16 +431,16 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
                         src + static_cast<size_t>(pl * (kCs / 8) + pn) * H * kRs * 8, bytes, bar_hist + 8 * buf);
       };
       load_hist(0);
-      if (p.n_res > 1) load_hist(1);
+      if (p.n_blk > 1) load_hist(1);
 #pragma unroll 1
-      for (int r = 0; r < p.n_res; ++r) {
-        const int buf = r & 1, H = 2 * p.dil[r];
+      for (int r = 0; r < p.n_blk; ++r) {
+        const int buf = r & 1, H = blk_hist(r);
         const uint32_t gp = smem_base + L::kGp + buf * L::kGpBuf;
         MbarWait(bar_hist + 8 * buf, (r >> 1) & 1);
         SpinUntil(in_cnt, static_cast<uint32_t>((kWorkers / 32) * (r + 1)));   // the new row of block r is in the panels
         __threadfence_block();
         FenceProxyAsync();
-        {
+        if (H > 0) {
           const uint32_t bytes = static_cast<uint32_t>(H) * kRs * 16;
           uint16_t* dst = const_cast<uint16_t*>(hist_ptr(r));
           for (int pl = 0; pl < P; ++pl)
@@ -407,7 +451,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
           BulkWaitRead0();
         }
         SpinUntil(acc_cnt, static_cast<uint32_t>(r + 1));   // block r's MMAs are done reading the buffer
-        if (r + 2 < p.n_res) load_hist(r + 2);
+        if (r + 2 < p.n_blk) load_hist(r + 2);
         MbarArrive(bar_free + 8 * buf);
       }
       BulkWait0();
@@ -469,28 +513,33 @@ void ResStackHistBlocks(int C, int n_res, const int* dil, int B, uint16_t* base,
   }
 }
 
-size_t PackResStackWeights(const float* const* w, int n_res, int C, uint16_t* out) {
-  // [block r][rank][tap j][K step h][plane][2 panels][C rows n][8]   element = W_r[j][32 rank + 16 h + 8 pp + e][n]
+size_t PackChainWeights(const ChainLayer* layers, int n_layers, int C, uint16_t* out) {
+  // [block r][rank][tap j][K step h][plane][2 panels][n_out rows n][8]   element = W_r[j][32 rank + 16 h + 8 pp + e][n]
   const int NC = C / kCs, Gs = kCs / 16;
-  const size_t kstep = static_cast<size_t>(2) * 2 * C * 8;
-  const size_t total = static_cast<size_t>(n_res) * NC * 3 * Gs * kstep;
+  size_t total = 0;
+  for (int r = 0; r < n_layers; ++r) total += static_cast<size_t>(NC) * layers[r].taps * Gs * (static_cast<size_t>(2) * 2 * layers[r].n_out * 8);
   if (!out) return total;
-  for (int r = 0; r < n_res; ++r)
+  size_t base = 0;
+  for (int r = 0; r < n_layers; ++r) {
+    const int taps = layers[r].taps, N = layers[r].n_out;
+    const size_t kstep = static_cast<size_t>(2) * 2 * N * 8;
     for (int rk = 0; rk < NC; ++rk)
-      for (int j = 0; j < 3; ++j)
+      for (int j = 0; j < taps; ++j)
         for (int h = 0; h < Gs; ++h) {
-          uint16_t* blk = out + (((static_cast<size_t>(r) * NC + rk) * 3 + j) * Gs + h) * kstep;
+          uint16_t* blk = out + base + ((static_cast<size_t>(rk) * taps + j) * Gs + h) * kstep;
           for (int pp = 0; pp < 2; ++pp)
-            for (int n = 0; n < C; ++n)
+            for (int n = 0; n < N; ++n)
               for (int e = 0; e < 8; ++e) {
                 const int ci = rk * kCs + 16 * h + 8 * pp + e;
-                const float val = w[r][(static_cast<size_t>(j) * C + ci) * C + n];
+                const float val = layers[r].w[(static_cast<size_t>(j) * C + ci) * N + n];
                 const uint16_t hi = Bf16Rn(val);
-                const size_t o = (static_cast<size_t>(pp) * C + n) * 8 + e;
+                const size_t o = (static_cast<size_t>(pp) * N + n) * 8 + e;
                 blk[o] = hi;
-                blk[static_cast<size_t>(2) * C * 8 + o] = Bf16Rn(val - Bf16ToF(hi));
+                blk[static_cast<size_t>(2) * N * 8 + o] = Bf16Rn(val - Bf16ToF(hi));
               }
         }
+    base += static_cast<size_t>(NC) * taps * Gs * kstep;
+  }
   return total;
 }
 

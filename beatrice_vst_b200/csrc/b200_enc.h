@@ -12,29 +12,44 @@
 
 namespace b200 {
 
+// One launch runs a CHAIN of blocks on every tile of 32 streams:
+//   kind 1 (optional, first):  x = GELU(b + Conv_{k=2, stride 2}(fin))        -- the last front-end layer
+//   kind 0 (n times):          x = x + b + Conv_{k=3, dil}(GELU(ChanNorm(x) * gamma + beta))
+//   kind 2 (optional, last):   head_out = b + W x                            -- the 1x1 head
 struct ResStackParams {
-  const float* x_in;    // [B][C] fp32: output of the last front-end layer (current hop's row of every stream)
-  float* x_out;         // [B][C] fp32: the stack's output
-  uint16_t* xh_out;     // [B][C] bf16 hi (+ lo) copy of x_out for the head conv, or nullptr
+  const float* x_in;    // [B][C] fp32 input of the first block when there is no kind-1 block
+  float* x_out;         // [B][C] fp32: x after the last kind-0 block (nullptr when the head is fused)
+  uint16_t* xh_out;     // [B][C] bf16 hi (+ lo) copy of x_out for a separate head conv, or nullptr
   uint16_t* xl_out;
-  const uint16_t* w;    // PackResStackWeights image
-  const float* bias;    // [n_res][C]
-  const float* gamma;   // [n_res][C]
-  const float* beta;    // [n_res][C]
-  uint16_t* hist;       // conv-input histories of all blocks, see ResStackHistElems
-  int n_res;
-  int dil[6];
+  const uint16_t* fin_h;  // kind 1: input rows, bf16 hi / lo planes [B][2][C]
+  const uint16_t* fin_l;
+  float* head_out;      // kind 2: [B][head_n] fp32
+  int head_n;           // 128 or 256
+  const uint16_t* w;    // PackChainWeights image
+  const float* bias;    // [n_blk][C]
+  const float* gamma;   // [n_blk][C] (kind 0 rows used)
+  const float* beta;    // [n_blk][C]
+  uint16_t* hist;       // conv-input histories of the kind-0 blocks, see ResStackHistElems
+  int n_blk;
+  int kind[8];
+  int dil[8];           // kind 0 only
   int B;
   int n_tiles;          // ceil(B / 32): stream tiles == clusters
   int trace;            // developer aid (BEATRICE_B200_ENC_TRACE=1): CTA 0 prints a per-block timeline
+};
+
+struct ChainLayer {     // host description of one block's conv for PackChainWeights
+  const float* w;       // fp32 [taps][C][n_out]
+  int taps;
+  int n_out;
 };
 
 bool ResStackSupported(int C, int n_res, const int* dil);
 int ResStackTiles(int B);
 size_t ResStackHistElems(int C, int n_res, const int* dil, int B);
 void ResStackHistBlocks(int C, int n_res, const int* dil, int B, uint16_t* base, std::vector<MrfHistBlock>* out);
-// w[r] = fp32 [3][C][C] (tap, in, out) of block r; returns bf16 elements written (out may be null)
-size_t PackResStackWeights(const float* const* w, int n_res, int C, uint16_t* out);
+// returns bf16 elements written (out may be null)
+size_t PackChainWeights(const ChainLayer* layers, int n_layers, int C, uint16_t* out);
 void LaunchResStack(const ResStackParams& p, int C, cudaStream_t s);
 
 }  // namespace b200

@@ -285,24 +285,39 @@ int EncoderModel::LoadFromImage(const void* data, size_t size, int on_device) {
     for (ConvW* cv : convs) cv->tc_bn_cap = 64;   // few rows per hop (T <= 16): favour CTA count
     tc.Pack(device, img.payload, blob.as<float>(), convs);
   }
-  rs_ok = ResStackSupported(width, n_res, dil);
-  if (rs_ok) {   // fused residual-stack kernel: weight image and contiguous per-block parameters
-    const float* wsrc[6];
-    std::vector<float> par(static_cast<size_t>(3) * n_res * width);
+  rs_ok = ResStackSupported(width, n_res, dil) && front[5].k == 2 && stride[5] == 2 && front[5].cin == width && front[5].cout == width;
+  if (rs_ok) {   // fused encoder chain (b200_enc.cu): front layer 5, the residual blocks, and the head where it fits
+    rs_head = !is_pitch && head.k == 1 && (head_out == 128 || head_out == 256) && head_out <= width;
+    std::vector<ChainLayer> layers;
+    rs_n_blk = 0;
+    auto add = [&](int kind, const ConvW& cw, int d) {
+      layers.push_back({c.HostAt(cw.w), cw.k, cw.cout});
+      rs_kind[rs_n_blk] = kind;
+      rs_dil[rs_n_blk] = d;
+      ++rs_n_blk;
+    };
+    add(1, front[5], 1);
+    for (int i = 0; i < n_res; ++i) add(0, res[i], dil[i]);
+    if (rs_head) add(2, head, 1);
+    std::vector<float> par(static_cast<size_t>(3) * rs_n_blk * width, 0.0f);
+    auto put = [&](int which, int blk, const float* dev_ptr, int n) {
+      std::memcpy(par.data() + (static_cast<size_t>(which) * rs_n_blk + blk) * width, c.HostAt(dev_ptr), sizeof(float) * n);
+    };
+    put(0, 0, front[5].b, width);
     for (int i = 0; i < n_res; ++i) {
-      wsrc[i] = c.HostAt(res[i].w);
-      std::memcpy(par.data() + (0 * n_res + i) * width, c.HostAt(res[i].b), sizeof(float) * width);
-      std::memcpy(par.data() + (1 * n_res + i) * width, c.HostAt(gamma[i]), sizeof(float) * width);
-      std::memcpy(par.data() + (2 * n_res + i) * width, c.HostAt(beta[i]), sizeof(float) * width);
+      put(0, 1 + i, res[i].b, width);
+      put(1, 1 + i, gamma[i], width);
+      put(2, 1 + i, beta[i], width);
     }
-    std::vector<uint16_t> packed(PackResStackWeights(wsrc, n_res, width, nullptr));
-    PackResStackWeights(wsrc, n_res, width, packed.data());
+    if (rs_head) put(0, 1 + n_res, head.b, head_out);
+    std::vector<uint16_t> packed(PackChainWeights(layers.data(), rs_n_blk, width, nullptr));
+    PackChainWeights(layers.data(), rs_n_blk, width, packed.data());
     rs_w.Alloc(device, packed.size() * sizeof(uint16_t), false);
     B200_CHECK(cudaMemcpy(rs_w.p, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     Upload(&rs_par, device, par.data(), par.size());
     rs_bias = rs_par.as<float>();
-    rs_gamma = rs_bias + static_cast<size_t>(n_res) * width;
-    rs_beta = rs_gamma + static_cast<size_t>(n_res) * width;
+    rs_gamma = rs_bias + static_cast<size_t>(rs_n_blk) * width;
+    rs_beta = rs_gamma + static_cast<size_t>(rs_n_blk) * width;
   }
   ++generation;
   loaded = true;
@@ -731,7 +746,7 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
       op.launch = [=](cudaStream_t s) { LaunchDirectConv(dp, h, Bn, frame, s); };
     else
       op.launch = GemmLauncher(dp, h, 1, Bn, frame, tc, tcm);
-    program.push_back(op);
+    if (!(rs_fused && i == 5)) program.push_back(op);   // layer 5 is the first block of the fused chain
   }
   n_rs_blocks = 0;
   if (rs_fused) {
@@ -744,24 +759,34 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     B200_CHECK(cudaMemcpy(rs_blocks.p, blocks.data(), sizeof(MrfHistBlock) * blocks.size(), cudaMemcpyHostToDevice));
     ResStackParams rp;
     std::memset(&rp, 0, sizeof(rp));
-    rp.x_in = arena.ring(ring_x[0]).base;
-    rp.x_out = arena.ring(ring_x[m->n_res]).base;
-    rp.xh_out = arena.ring(ring_xh).hi;
-    rp.xl_out = arena.ring(ring_xh).lo;
+    const Ring& fin = arena.ring(ring_in[5]);           // front layer 5 reads the hop's two rows of layer 4's output
+    rp.fin_h = fin.hi;
+    rp.fin_l = fin.lo;
+    if (!m->rs_head) {                                  // a separate head conv reads the stack's output
+      rp.x_out = arena.ring(ring_x[m->n_res]).base;
+      rp.xh_out = arena.ring(ring_xh).hi;
+      rp.xl_out = arena.ring(ring_xh).lo;
+    } else {
+      rp.head_out = head_out.as<float>();
+      rp.head_n = m->head_out;
+    }
     rp.w = m->rs_w.as<uint16_t>();
     rp.bias = m->rs_bias;
     rp.gamma = m->rs_gamma;
     rp.beta = m->rs_beta;
     rp.hist = rs_hist.as<uint16_t>();
-    rp.n_res = m->n_res;
-    for (int r = 0; r < m->n_res; ++r) rp.dil[r] = m->dil[r];
+    rp.n_blk = m->rs_n_blk;
+    for (int r = 0; r < m->rs_n_blk; ++r) {
+      rp.kind[r] = m->rs_kind[r];
+      rp.dil[r] = m->rs_dil[r];
+    }
     rp.B = B;
     rp.n_tiles = ResStackTiles(B);
     if (const char* ev = std::getenv("BEATRICE_B200_ENC_TRACE")) rp.trace = std::atoi(ev);
     const int width = m->width;
     Op op;
-    op.name = std::string(tag) + ".resstack";
-    op.flops = 2.0 * 3 * width * width * B * m->n_res;
+    op.name = std::string(tag) + ".chain";   // fe5 + residual stack (+ head)
+    op.flops = 2.0 * 3 * width * width * B * m->n_res + 2.0 * 2 * width * width * B + (m->rs_head ? 2.0 * width * m->head_out * B : 0.0);
     op.bytes = 4.0 * 3 * width * width * m->n_res + 8.0 * B * width;
     op.launch = [=](cudaStream_t s) { LaunchResStack(rp, width, s); };
     program.push_back(op);
@@ -804,7 +829,7 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     op.flops = ConvFlops(h, B);
     op.bytes = ConvBytes(h, B);
     op.launch = GemmLauncher(dp, h, 1, Bn, frame, tc, tcm);
-    program.push_back(op);
+    if (!(rs_fused && m->rs_head)) program.push_back(op);   // the head is the last block of the fused chain
   }
   {
     int* f = arena.frame();

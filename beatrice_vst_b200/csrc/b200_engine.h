@@ -108,6 +108,8 @@ struct EncoderModel {  // PhoneExtractor / PitchEstimator
   // fused residual-stack kernel (b200_enc.cu): weight image + the blocks' bias / gamma / beta made contiguous
   DeviceBuffer rs_w, rs_par;
   bool rs_ok = false;
+  int rs_n_blk = 0, rs_kind[8] = {}, rs_dil[8] = {};   // the chain: [front layer 5] + residual blocks + [head]
+  bool rs_head = false;                                 // head (k = 1) is the chain's last block
   const float* rs_bias = nullptr;
   const float* rs_gamma = nullptr;
   const float* rs_beta = nullptr;
