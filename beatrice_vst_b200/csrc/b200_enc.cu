@@ -125,9 +125,9 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   // ---- per-block geometry (see ResStackParams) ----
-  auto blk_taps = [&](int r) { return p.kind[r] == 0 ? 3 : (p.kind[r] == 1 ? 2 : 1); };
+  auto blk_taps = [&](int r) { return p.kind[r] == 0 ? 3 : (p.kind[r] == 1 ? 2 : (p.kind[r] == 2 ? 1 : 7)); };
   auto blk_rows = [&](int r) { return p.kind[r] == 2 ? p.head_n : C; };                  // output channels == A rows
-  auto blk_hist = [&](int r) { return p.kind[r] == 0 ? 2 * p.dil[r] : 0; };              // history time steps
+  auto blk_hist = [&](int r) { return p.kind[r] == 0 ? 2 * p.dil[r] : (p.kind[r] == 3 ? 6 : 0); };   // history time steps
   auto blk_kstep = [&](int r) { return static_cast<uint32_t>(P * 2 * blk_rows(r) * 16); };   // bytes of one K step of weights
   // history image of block r: [tile][rank*P*4 + plane*4 + panel][H*32 rows][8]
   auto hist_ptr = [&](int r) {
@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
           yo[i] = y + bb[i];
           if (kind == 0) xbuf[lc * kRs + s] = xv[i] + yo[i];
           else if (kind == 1) xbuf[lc * kRs + s] = GeluFast(yo[i]);
+          else if (kind == 3) xbuf[lc * kRs + s] = yo[i];
         }
         if (kind == 2 && rank < owners && valid)
           *reinterpret_cast<float4*>(p.head_out + static_cast<size_t>(b) * p.head_n + rank * kCs + cg * 4) =
@@ -328,8 +329,14 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
       float xo[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) xo[i] = xbuf[(cg * 4 + i) * kRs + s];
-      const size_t o = static_cast<size_t>(b) * C + rank * kCs + cg * 4;
+      const int n_slots = p.out_slots > 1 ? p.out_slots : 1;
+      const int cur = n_slots > 1 ? (*p.frame % n_slots) : 0;
+      const size_t o = (static_cast<size_t>(b) * n_slots + cur) * C + rank * kCs + cg * 4;
       *reinterpret_cast<float4*>(p.x_out + o) = make_float4(xo[0], xo[1], xo[2], xo[3]);
+      if (p.out_act == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xo[i] = xo[i] > 0.0f ? xo[i] : 0.1f * xo[i];
+      }
       if (p.xh_out) {
         const __nv_bfloat16 h0 = __float2bfloat16_rn(xo[0]), h1 = __float2bfloat16_rn(xo[1]), h2 = __float2bfloat16_rn(xo[2]),
                             h3 = __float2bfloat16_rn(xo[3]);
@@ -362,7 +369,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
 #pragma unroll 1
       for (int j = 0; j < taps; ++j) {
         // time block the tap reads: residual block t - (2 - j) dil; front conv: hop row j; head: the current row
-        const int tb = kind == 0 ? kHmax - (2 - j) * dil : (kind == 1 ? kHmax - 1 + j : kHmax);
+        const int tb = kind == 0 ? kHmax - (2 - j) * dil : (kind == 1 ? kHmax - 1 + j : (kind == 2 ? kHmax : kHmax - (6 - j)));
         const uint32_t row0 = static_cast<uint32_t>(tb * kRs);
 #pragma unroll 1
         for (int h = 0; h < Gs; ++h) {

@@ -16,11 +16,15 @@ namespace b200 {
 //   kind 1 (optional, first):  x = GELU(b + Conv_{k=2, stride 2}(fin))        -- the last front-end layer
 //   kind 0 (n times):          x = x + b + Conv_{k=3, dil}(GELU(ChanNorm(x) * gamma + beta))
 //   kind 2 (optional, last):   head_out = b + W x                            -- the 1x1 head
+//   kind 3:                    x = b + Conv_{k=7}(x)                         -- the vocoder's pre conv
 struct ResStackParams {
   const float* x_in;    // [B][C] fp32 input of the first block when there is no kind-1 block
-  float* x_out;         // [B][C] fp32: x after the last kind-0 block (nullptr when the head is fused)
-  uint16_t* xh_out;     // [B][C] bf16 hi (+ lo) copy of x_out for a separate head conv, or nullptr
+  float* x_out;         // [B][out_slots][C] fp32: x after the last block (nullptr when the head is fused)
+  uint16_t* xh_out;     // [B][out_slots][C] bf16 hi (+ lo) copy of out_act(x) for the consumer conv, or nullptr
   uint16_t* xl_out;
+  int out_slots;        // ring slots of the outputs (row frame % out_slots is written); 0 or 1: flat
+  int out_act;          // activation applied to the bf16 copy only: 0 none, 1 LeakyReLU(0.1)
+  const int* frame;     // device hop counter (needed when out_slots > 1)
   const uint16_t* fin_h;  // kind 1: input rows, bf16 hi / lo planes [B][2][C]
   const uint16_t* fin_l;
   float* head_out;      // kind 2: [B][head_n] fp32

@@ -383,6 +383,20 @@ int WaveModel::LoadFromImage(const void* data, size_t size, int on_device) {
   }
   for (int s = 0; s < 4; ++s) ups[s].b = ups_bias.as<float>() + rep_off[s];
   {
+    const int d3 = 3;   // the chain kernel sizes a k = 7 block's history like a residual block of dilation 3 (6 rows)
+    pre_chain_ok = pre.k == 7 && pre.cin == kHidden && pre.cout == kHidden && ResStackSupported(kHidden, 1, &d3);
+    if (pre_chain_ok) {
+      const ChainLayer layer = {c.HostAt(pre.w), 7, kHidden};
+      std::vector<uint16_t> packed(PackChainWeights(&layer, 1, kHidden, nullptr));
+      PackChainWeights(&layer, 1, kHidden, packed.data());
+      pre_w.Alloc(device, packed.size() * sizeof(uint16_t), false);
+      B200_CHECK(cudaMemcpy(pre_w.p, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      std::vector<float> par(static_cast<size_t>(3) * kHidden, 0.0f);   // bias | gamma (unused) | beta (unused)
+      std::memcpy(par.data(), c.HostAt(pre.b), sizeof(float) * kHidden);
+      Upload(&pre_par, device, par.data(), par.size());
+    }
+  }
+  {
     // fused MRF kernel images: for every stage the kernel has a form for, both precisions
     std::vector<float> bias_all;
     size_t bias_off[4][3] = {};
@@ -876,11 +890,14 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
   const bool tcm = tc != kTcOff;
   const bool with_lo = tc == kTcSplit;
 
-  ring_hidden = arena.Plan(spec::kPreK - 1, 1, kHidden);
+  // tensor-core mode: the pre conv runs as a one-block chain of the encoder cluster kernel (b200_enc.cu), which
+  // keeps the six-row input history itself: cond then writes only the hop's fp32 row
+  const bool pre_fused = tcm && m->pre_chain_ok && ResStackEnabled();
+  ring_hidden = arena.Plan(pre_fused ? 0 : spec::kPreK - 1, 1, kHidden);
   ring_pre = arena.Plan(1, 1, kHidden);
   // tensor-core mode: cond and pre also emit bf16 (hi [+ lo]) rings, so pre and ups0 move their input
   // with cp.async instead of gathering fp32 through registers
-  const int ring_hidden_h = tcm ? arena.PlanH(spec::kPreK - 1, 1, kHidden, with_lo) : -1;
+  const int ring_hidden_h = (tcm && !pre_fused) ? arena.PlanH(spec::kPreK - 1, 1, kHidden, with_lo) : -1;
   const int ring_pre_h = tcm ? arena.PlanH(1, 1, kHidden, with_lo) : -1;
   // fp32 rings: u (upsampler output), y (residual stream of each MRF branch), a (CUDA-core
   // path only).  Tensor-core mode keeps fp32 only where a residual / the branch sum needs it
@@ -987,7 +1004,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
 
   DescBuilder db;
   ConvDesc pre_d = MakeConv(arena.ring(ring_hidden), m->pre, 1, 1, 1, arena.ring(ring_pre), kActNone, kActNone);
-  if (tcm) {
+  if (tcm && !pre_fused) {
     SetInH(&pre_d, arena.ring(ring_hidden_h));
     SetOutH(&pre_d, arena.ring(ring_pre_h), kActLrelu);   // ups0 reads lrelu(pre) as bf16
   }
@@ -1051,7 +1068,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
 
   {
     const Ring hr = arena.ring(ring_hidden);
-    const Ring hh = tcm ? arena.ring(ring_hidden_h) : Ring();
+    const Ring hh = (tcm && !pre_fused) ? arena.ring(ring_hidden_h) : Ring();
     const float* ph = phone_in.as<float>();
     const int* q = q_in.as<int>();
     const float* ft = feat_in.as<float>();
@@ -1081,7 +1098,45 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
     op.launch = GemmLauncher(dp, h, nz, Bn, frame, tc, true);
     program.push_back(op);
   };
-  add_gemm("wave.pre", pre_idx, 1, false);
+  n_pre_blocks = 0;
+  if (pre_fused) {
+    const int d3 = 3;
+    pre_hist.Alloc(device, ResStackHistElems(kHidden, 1, &d3, B) * sizeof(uint16_t), true);
+    std::vector<MrfHistBlock> blocks;
+    ResStackHistBlocks(kHidden, 1, &d3, B, pre_hist.as<uint16_t>(), &blocks);
+    n_pre_blocks = static_cast<int>(blocks.size());
+    pre_blocks.Alloc(device, sizeof(MrfHistBlock) * blocks.size(), false);
+    B200_CHECK(cudaMemcpy(pre_blocks.p, blocks.data(), sizeof(MrfHistBlock) * blocks.size(), cudaMemcpyHostToDevice));
+    ResStackParams rp;
+    std::memset(&rp, 0, sizeof(rp));
+    rp.x_in = arena.ring(ring_hidden).base;             // [B][256]: the hop's conditioning row (one slot)
+    const Ring& pr = arena.ring(ring_pre);
+    const Ring& ph = arena.ring(ring_pre_h);
+    rp.x_out = pr.base;
+    rp.xh_out = ph.hi;
+    rp.xl_out = ph.lo;
+    rp.out_slots = pr.slots;                            // == ph.slots: ups0 reads one row of history
+    rp.out_act = 1;                                     // ups0 consumes lrelu(pre) as bf16
+    rp.frame = frame;
+    rp.w = m->pre_w.as<uint16_t>();
+    rp.bias = m->pre_par.as<float>();
+    rp.gamma = rp.bias + kHidden;
+    rp.beta = rp.gamma + kHidden;
+    rp.hist = pre_hist.as<uint16_t>();
+    rp.n_blk = 1;
+    rp.kind[0] = 3;
+    rp.dil[0] = 1;
+    rp.B = B;
+    rp.n_tiles = ResStackTiles(B);
+    Op op;
+    op.name = "wave.pre";
+    op.flops = ConvFlops(db.host[pre_idx], B);
+    op.bytes = ConvBytes(db.host[pre_idx], B);
+    op.launch = [=](cudaStream_t s) { LaunchResStack(rp, kHidden, s); };
+    program.push_back(op);
+  } else {
+    add_gemm("wave.pre", pre_idx, 1, false);
+  }
   int t_stage = 1;
   for (int s = 0; s < 4; ++s) {
     add_gemm("wave.ups" + std::to_string(s), ups_idx[s], 1, false);
@@ -1167,10 +1222,12 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
 void WaveState::ZeroAll(cudaStream_t s) {
   arena.ZeroAll(s);
   if (mrf_hist.p) B200_CHECK(cudaMemsetAsync(mrf_hist.p, 0, mrf_hist.bytes, s));
+  if (n_pre_blocks > 0 && pre_hist.p) B200_CHECK(cudaMemsetAsync(pre_hist.p, 0, pre_hist.bytes, s));
 }
 void WaveState::ZeroStream(int b, cudaStream_t s) {
   arena.ZeroStream(b, s);
   LaunchMrfZeroStream(mrf_blocks.as<MrfHistBlock>(), n_mrf_blocks, b, s);
+  LaunchMrfZeroStream(pre_blocks.as<MrfHistBlock>(), n_pre_blocks, b, s);
 }
 
 void RunProgram(const std::vector<Op>& program, cudaStream_t s) {

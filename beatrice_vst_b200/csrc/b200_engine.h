@@ -135,6 +135,9 @@ struct WaveModel {
   // fused MRF kernel (b200_mrf.cu): weight images per precision [0] bf16, [1] split bf16, and
   // the six biases of a branch made contiguous
   DeviceBuffer mrf_w[2], mrf_bias;
+  // pre conv (k = 7) as a one-block chain of the cluster kernel in b200_enc.cu
+  DeviceBuffer pre_w, pre_par;
+  bool pre_chain_ok = false;
   const uint16_t* mrf_w_ptr[2][4][3] = {};
   const float* mrf_bias_ptr[4][3] = {};
   int LoadFromImage(const void* data, size_t size, int on_device = -1);
@@ -238,6 +241,8 @@ struct WaveState {
   // fused MRF stages: conv-input histories (bf16, stream-group layout) + reset table
   DeviceBuffer mrf_hist, mrf_blocks;
   int n_mrf_blocks = 0;
+  DeviceBuffer pre_hist, pre_blocks;   // fused pre conv: its six-row input history + per-stream reset table
+  int n_pre_blocks = 0;
   void ZeroStream(int b, cudaStream_t s);   // arena + fused-kernel histories of stream b
   void ZeroAll(cudaStream_t s);             // ... of every stream
   // conditioning buffers depend only on the family, not on the weights: the rc0 setters
