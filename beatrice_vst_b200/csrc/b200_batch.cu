@@ -184,7 +184,11 @@ void BuildHop(Engine* e) {
     e->hop_ops.push_back(op);
     e->hop_lane.push_back(lane);
   };
-  for (const Op& op : e->phone_st.program) push(op, 0);
+  // with the advance folded into the post conv the encoders' own advance launches are dropped
+  auto is_advance = [](const Op& op) { return op.name.size() > 8 && op.name.compare(op.name.size() - 8, 8, ".advance") == 0; };
+  const bool folded = e->wave_st.advance_folded;
+  for (const Op& op : e->phone_st.program)
+    if (!(folded && is_advance(op))) push(op, 0);
   {
     Op op;
     op.name = "phone.vq";
@@ -197,7 +201,8 @@ void BuildHop(Engine* e) {
     op.launch = [=](cudaStream_t s) { LaunchVq(in, out, cbs, n, C, B, s); };
     push(op, 0);
   }
-  for (const Op& op : e->pitch_st.program) push(op, 1);
+  for (const Op& op : e->pitch_st.program)
+    if (!(folded && is_advance(op))) push(op, 1);
   {
     Op op;
     op.name = "pitch.argmax";
@@ -224,14 +229,25 @@ void EnqueueHop(Engine* e, cudaStream_t s) {
   B200_CHECK(cudaEventRecord(e->ev_fork, s));
   B200_CHECK(cudaStreamWaitEvent(e->aux, e->ev_fork, 0));
   bool joined = false;
+  // developer ablation: BEATRICE_B200_LANES = bit mask of the lanes to launch (1 content, 2 pitch, 4 vocoder);
+  // timing only, the audio is meaningless with a lane missing
+  static const int lane_mask = [] {
+    const char* ev = std::getenv("BEATRICE_B200_LANES");
+    return ev ? std::atoi(ev) : 7;
+  }();
   for (size_t i = 0; i < e->hop_ops.size(); ++i) {
     const int lane = e->hop_lane[i];
+    if (!((lane_mask >> lane) & 1)) continue;
     if (lane == 2 && !joined) {
       B200_CHECK(cudaEventRecord(e->ev_join, e->aux));
       B200_CHECK(cudaStreamWaitEvent(s, e->ev_join, 0));
       joined = true;
     }
     e->hop_ops[i].launch(lane == 1 ? e->aux : s);
+  }
+  if (!joined) {   // only under the lane ablation: a capture must not end with the side stream unjoined
+    B200_CHECK(cudaEventRecord(e->ev_join, e->aux));
+    B200_CHECK(cudaStreamWaitEvent(s, e->ev_join, 0));
   }
 }
 
@@ -294,6 +310,9 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
   e->phone_st.Build(&e->phone_m, B, e->device, e->in16.as<float>(), tc);
   e->pitch_st.Build(&e->pitch_m, B, e->device, e->in16.as<float>(), tc);
   e->wave_st.cond_ready = false;
+  // one hop = one graph: the vocoder's last kernel advances all three hop counters (no advance launches)
+  e->wave_st.fold_frames[0] = e->phone_st.arena.frame();
+  e->wave_st.fold_frames[1] = e->pitch_st.arena.frame();
   e->wave_st.Build(&e->wave_m, B, e->device, tc);
   e->q_raw.Alloc(e->device, sizeof(int) * B, true);
   e->min_q.Alloc(e->device, sizeof(int) * B, true);

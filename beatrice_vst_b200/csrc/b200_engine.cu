@@ -1207,10 +1207,19 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
     op.name = "wave.post";
     op.flops = ConvFlops(h, B);
     op.bytes = ConvBytes(h, B);
-    op.launch = [=](cudaStream_t s) { LaunchPostConv(dp, h, Bn, frame, s); };
+    AdvanceFold fold;
+    advance_folded = fold_frames[0] != nullptr && fold_frames[1] != nullptr && PostConvFused(h);
+    if (advance_folded) {
+      fold_done.Alloc(device, sizeof(int), true);
+      fold.done = fold_done.as<int>();
+      fold.frames[0] = arena.frame();
+      fold.frames[1] = fold_frames[0];
+      fold.frames[2] = fold_frames[1];
+    }
+    op.launch = [=](cudaStream_t s) { LaunchPostConv(dp, h, Bn, frame, fold, s); };
     program.push_back(op);
   }
-  {
+  if (!advance_folded) {
     int* f = arena.frame();
     Op op;
     op.name = "wave.advance";

@@ -238,6 +238,11 @@ struct WaveState {
   std::vector<Op> program;
   int ring_hidden = -1, ring_pre = -1, ring_stage_out[4][3];
   bool cond_ready = false;
+  // batched engine: the post conv, last kernel of a hop, advances this state's hop counter and the two encoders'
+  // (set before Build; see AdvanceFold in b200_kernels.h).  advance_folded: Build took the offer.
+  int* fold_frames[2] = {nullptr, nullptr};
+  bool advance_folded = false;
+  DeviceBuffer fold_done;
   // fused MRF stages: conv-input histories (bf16, stream-group layout) + reset table
   DeviceBuffer mrf_hist, mrf_blocks;
   int n_mrf_blocks = 0;

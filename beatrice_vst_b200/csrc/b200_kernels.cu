@@ -285,8 +285,10 @@ __global__ void direct_conv_kernel(const ConvDesc* __restrict__ descs, int B, co
 // then one thread per output sample walks the 7 x 16 window.  Summation order is the oracle's (tap,
 // then channel), so the result does not depend on the staging.
 constexpr int kPostRowLd = 20;   // floats per staged row (16 + 4: conflict-free 16-byte reads, rows 80 B apart)
+__device__ __forceinline__ int NextFrame(int f) { return (f + 1 >= 738017280) ? 0 : f + 1; }   // see advance_kernel
+
 __global__ void __launch_bounds__(256) post_conv_kernel(const __grid_constant__ ConvDesc d, int B,
-                                                         const int* __restrict__ frame_ptr) {
+                                                         const int* __restrict__ frame_ptr, const AdvanceFold fold) {
   extern __shared__ float post_smem[];
   float* ws = post_smem;                 // [7][16]
   float* xs = post_smem + 7 * 16;        // [T + 6][kPostRowLd]
@@ -299,7 +301,8 @@ __global__ void __launch_bounds__(256) post_conv_kernel(const __grid_constant__ 
   const int x_L = d.x_slots * d.x_T;
   const int x_cur = (frame % d.x_slots) * d.x_T;
   const long long xb = static_cast<long long>(b) * x_L * 16;
-  for (int idx = tid; idx < (d.T + 6) * 4; idx += 256) {
+#pragma unroll 4
+  for (int idx = tid; idx < (d.T + 6) * 4; idx += 256) {   // T = 240: four rounds, their twelve loads in flight together
     const int row = idx >> 2, q = idx & 3;
     int r = x_cur + row - 6;
     if (r < 0) r += x_L;
@@ -335,6 +338,16 @@ __global__ void __launch_bounds__(256) post_conv_kernel(const __grid_constant__ 
     acc = ActApply(acc, d.out_act);
     d.y[(static_cast<long long>(b) * y_L + y_cur) * d.y_C + t] = acc;
   }
+  if (fold.done != nullptr && tid == 0) {
+    // the hop ends here: the last block to arrive advances the hop counters (every block read them on entry)
+    __threadfence();
+    if (atomicAdd(fold.done, 1) == static_cast<int>(gridDim.x) - 1) {
+      *fold.done = 0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        if (fold.frames[i] != nullptr) *fold.frames[i] = NextFrame(*fold.frames[i]);
+    }
+  }
 }
 
 // Front-end layer 0 of the encoders (C_in = 1, k = 10, stride 5 -> N <= 32 channels) fused with the
@@ -349,9 +362,11 @@ __global__ void __launch_bounds__(256) frontend0_kernel(const __grid_constant__ 
   const int tid = threadIdx.x, b = blockIdx.x;
   for (int i = tid; i < d.k * d.N; i += 256) ws[i] = __ldg(d.w + i);   // constants: before the dependency wait
   if (tid < d.N) bs[tid] = d.bias ? __ldg(d.bias + tid) : 0.f;
-  const int frame = *frame_ptr;                                        // written only by the chain's advance kernel
   PdlWait();
   PdlLaunchDependents();
+  // first kernel of a hop: its stream predecessor may be the previous hop's last kernel, which advances the
+  // counter when the advance is folded (AdvanceFold) -- so read it only after the dependency wait
+  const int frame = *frame_ptr;
   const int hist = d.k - d.stride;
   const int x_L = d.x_slots * d.x_T;
   const int x_cur = (frame % d.x_slots) * d.x_T;
@@ -467,8 +482,7 @@ __global__ void advance_kernel(int* frame) {
   // wrap at a multiple of every slot count in use (slots <= 64 by construction: lcm-free
   // choice 2^20 * 3*5*7*9*11*13 would overflow; slots are recomputed modulo so any wrap point
   // that is a common multiple works -- use 720720 * 1024 (lcm(1..16) * 1024) < 2^31)
-  const int f = *frame + 1;
-  *frame = (f >= 738017280) ? 0 : f;
+  *frame = NextFrame(*frame);
 }
 
 __global__ void pitch_argmax_kernel(const float* __restrict__ head, int bins, const int* __restrict__ min_q,
@@ -783,13 +797,15 @@ void LaunchDirectConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const i
   B200_CHECK(cudaGetLastError());
 }
 
-void LaunchPostConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int* d_frame, cudaStream_t s) {
-  if (h0.k != 7 || h0.C_in != 16 || h0.N != 1 || h0.stride != 1 || h0.dil != 1) {
+bool PostConvFused(const ConvDesc& h0) { return h0.k == 7 && h0.C_in == 16 && h0.N == 1 && h0.stride == 1 && h0.dil == 1; }
+void LaunchPostConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int* d_frame, const AdvanceFold& fold,
+                    cudaStream_t s) {
+  if (!PostConvFused(h0)) {
     LaunchDirectConv(d_desc, h0, B, d_frame, s);
     return;
   }
   const size_t smem = (7 * 16 + static_cast<size_t>(h0.T + 6) * kPostRowLd) * sizeof(float);
-  LaunchPdl(post_conv_kernel, dim3(B), dim3(256), smem, s, 1, h0, B, d_frame);
+  LaunchPdl(post_conv_kernel, dim3(B), dim3(256), smem, s, 1, h0, B, d_frame, fold);
   B200_CHECK(cudaGetLastError());
 }
 

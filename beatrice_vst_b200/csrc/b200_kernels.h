@@ -94,7 +94,15 @@ void LaunchConvGemmTc(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B
 size_t PackWeightsTc(const float* w, int k, int C_in, int N, int bn_cap, int* bn_out, int* kc_out, uint16_t* hi,
                      uint16_t* lo);
 // post conv of the vocoder (16 -> 1 channels, k = 7, tanh): one thread per output sample
-void LaunchPostConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int* d_frame, cudaStream_t s);
+// Hop counters the LAST kernel of a hop advances itself (its last block to finish, when every block has long
+// read them), instead of one single-thread advance launch per counter; done == nullptr: nothing to advance.
+struct AdvanceFold {
+  int* done = nullptr;                               // zero-initialised block counter, left at zero again
+  int* frames[3] = {nullptr, nullptr, nullptr};
+};
+void LaunchPostConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int* d_frame, const AdvanceFold& fold,
+                    cudaStream_t s);
+bool PostConvFused(const ConvDesc& h0);   // the shape post_conv_kernel handles (else the generic direct conv runs)
 void LaunchDirectConv(const ConvDesc* d_desc, const ConvDesc& h0, int B, const int* d_frame, cudaStream_t s);
 // encoder front-end layer 0 (C_in = 1) fused with the hop's ingest: staging [B][x_T] -> ring slot + conv
 bool Frontend0Supported(const ConvDesc& h0);

@@ -101,6 +101,24 @@ __device__ __forceinline__ void Mma(uint32_t d_tmem, uint64_t adesc, uint64_t bd
 __device__ __forceinline__ void MmaW(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   if (ElectOneSync()) Mma(d_tmem, adesc, bdesc, idesc, accum);
 }
+// Same, descriptors passed as (low, high) words: issue loops keep the high words constant and bump the low
+// word's start-address field.
+__device__ __forceinline__ void MmaW2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                      uint32_t idesc, uint32_t accum) {
+  if (ElectOneSync()) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+        "}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
 __device__ __forceinline__ void MmaCommit(uint32_t bar);
 __device__ __forceinline__ void MmaCommitW(uint32_t bar) {
   if (ElectOneSync()) MmaCommit(bar);

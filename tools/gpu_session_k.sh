@@ -2,11 +2,9 @@
 mkdir -p gpurun_out
 L=gpurun_out/k.log
 : > $L
-run() { echo "== $*" >> $L; ( timeout 300 env "$@" ) >> $L 2>&1; echo "rc=$?" >> $L; }
+run() { echo "== $*" >> $L; ( timeout 300 env "$@" ) 2>&1 | cut -c1-400 >> $L; echo "rc=$?" >> $L; }
 run python tools/mrf_probe.py 2 40 6
-run BEATRICE_B200_NO_FUSED_RESSTACK=1 python tools/mrf_probe.py 2 40 6
-run python tools/mrf_probe.py 2 3 6
+run BEATRICE_B200_NO_GRAPH=1 python tools/mrf_probe.py 2 40 6
 (timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15) >> $L
 run python bench.py --steps 300 --warmup 20 --no-cpu-baseline
-run python tools/op_profile.py 2 256
-cut -c1-330 $L
+cat $L
