@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
       const uint64_t w_tmpl = MakeDesc(0, kWLbo, 128);
       const uint32_t w_tmpl_lo = static_cast<uint32_t>(w_tmpl), w_hi32 = static_cast<uint32_t>(w_tmpl >> 32);
       uint32_t stage = 0, within = 0, wphase = 0;
-      uint32_t w_lo = w_tmpl_lo + (w_base >> 4);
+      uint32_t w_lo = w_tmpl_lo + ((w_base >> 4) & 0x3FFFu);
 #pragma unroll 1
       for (int i = 0; i < 6; ++i) {
         const int buf = i & 1, dil = ConvDil(i);
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
           const uint32_t dcol = tmem_base + (buf == 0 ? (MT + m) * DW : m * DW);
           uint32_t acc = buf == 0 ? 0u : 1u;
           // tap 0 of channel group 0: rows (hmax - (k-1) dil) S + 128 m of panel 0
-          uint32_t a_group = a_tmpl_lo + (bbase >> 4) + static_cast<uint32_t>((hmax - (k - 1) * dil) * S + 128 * m);
+          uint32_t a_group = a_tmpl_lo + ((bbase >> 4) & 0x3FFFu) + static_cast<uint32_t>((hmax - (k - 1) * dil) * S + 128 * m);
 #pragma unroll 1
           for (int g = 0; g < G; ++g) {
             MbarWait(bar_in + 8 * (m * G + g), i & 1);
@@ -359,11 +359,11 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
                 MmaCommitW(bar_w_empty + 8 * stage);
                 within = 0;
                 ++stage;
-                w_lo = w_tmpl_lo + ((w_base + stage * kChunkBytes) >> 4);
+                w_lo = w_tmpl_lo + (((w_base + stage * kChunkBytes) >> 4) & 0x3FFFu);
                 if (stage == kNst) {
                   stage = 0;
                   wphase ^= 1u;
-                  w_lo = w_tmpl_lo + (w_base >> 4);
+                  w_lo = w_tmpl_lo + ((w_base >> 4) & 0x3FFFu);
                 }
               }
             }

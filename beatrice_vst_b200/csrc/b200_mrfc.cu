@@ -336,51 +336,63 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
   } else if (warp == kWarpMma) {
     // =========================== MMA issuer ===========================
     {
+      // lean issue loop (see b200_mrf.cu): constant descriptor high words, running low words, ring counters
       const uint32_t idesc = MakeIdesc(C);
-      uint32_t cc = 0;
+      const uint64_t w_tmpl = MakeDesc(0, C * 16, 128);
+      const uint32_t w_tmpl_lo = static_cast<uint32_t>(w_tmpl), w_hi32 = static_cast<uint32_t>(w_tmpl >> 32);
+      uint32_t stage = 0, within = 0, wphase = 0;
+      uint32_t w_lo = w_tmpl_lo + ((w_base >> 4) & 0x3FFFu);   // a CTA of a cluster sees its window at a rank-dependent base: keep 14 bits
 #pragma unroll 1
       for (int i = 0; i < 6; ++i) {
         const int buf = i & 1, dil = ConvDil(i);
         const int hmax = buf ? HY : HX;
         const uint32_t bbase = buf ? y_base : x_base, pstride = buf ? y_pstride : x_pstride, plane = buf ? y_plane : x_plane;
+        const uint64_t a_tmpl = MakeDesc(0, pstride, 128);
+        const uint32_t a_tmpl_lo = static_cast<uint32_t>(a_tmpl), a_hi32 = static_cast<uint32_t>(a_tmpl >> 32);
+        const uint32_t tap_step = static_cast<uint32_t>(dil * S);
+        const uint32_t plane16 = plane >> 4, group_step = (2 * pstride) >> 4;
         MbarWait(bar_hist + 8 * buf, (i >> 1) & 1);
         if (lane == 0) B200_TR(i, 4);
 #pragma unroll 1
         for (int m = 0; m < MT; ++m) {
           const uint32_t dcol = tmem_base + ((i & 1) * MT + m) * C;
-          int ks = 0;
+          uint32_t acc = 0u;
+          uint32_t a_group = a_tmpl_lo + ((bbase >> 4) & 0x3FFFu) + static_cast<uint32_t>((hmax - (k - 1) * dil) * S + 128 * m);
 #pragma unroll 1
           for (int g = 0; g < Gs; ++g) {
             MbarWait(bar_in + 8 * (m * Gs + g), i & 1);
             TcFenceAfter();
             if (m == 0 && g == 0) if (lane == 0) B200_TR(i, 5);
             if (m == 0 && g == Gs - 1) if (lane == 0) B200_TR(i, 6);
+            uint32_t a_lo = a_group;
 #pragma unroll 1
             for (int j = 0; j < k; ++j) {
-              const int within = ks % NK;
-              const uint32_t stage = cc % kNst;
               if (within == 0) {
-                MbarWait(bar_w_full + 8 * stage, (cc / kNst) & 1);
+                MbarWait(bar_w_full + 8 * stage, wphase);
                 TcFenceAfter();
               }
-              const int row0 = (hmax - (k - 1 - j) * dil) * S + 128 * m;
-              const uint32_t a_hi = bbase + (2 * g) * pstride + static_cast<uint32_t>(row0) * 16;
-              const uint32_t w_hi = w_base + stage * kChunkBytes + within * kKstepBytes;
-              const uint64_t ah = MakeDesc(a_hi, pstride, 128);
-              const uint64_t wh = MakeDesc(w_hi, C * 16, 128);
-              MmaW(dcol, ah, wh, idesc, ks > 0 ? 1u : 0u);
+              MmaW2(dcol, a_lo, a_hi32, w_lo, w_hi32, idesc, acc);
               if (kSplit) {
-                const uint64_t al = MakeDesc(a_hi + plane, pstride, 128);
-                const uint64_t wl = MakeDesc(w_hi + C * 32, C * 16, 128);
-                MmaW(dcol, ah, wl, idesc, 1u);
-                MmaW(dcol, al, wh, idesc, 1u);
+                MmaW2(dcol, a_lo, a_hi32, w_lo + ((C * 32) >> 4), w_hi32, idesc, 1u);    // x_hi * W_lo
+                MmaW2(dcol, a_lo + plane16, a_hi32, w_lo, w_hi32, idesc, 1u);            // x_lo * W_hi
               }
-              ++ks;
-              if (within == NK - 1 || ks == k * Gs) {
+              acc = 1u;
+              a_lo += tap_step;
+              w_lo += kKstepBytes >> 4;
+              ++within;
+              if (within == NK || (g == Gs - 1 && j == k - 1)) {
                 MmaCommitW(bar_w_empty + 8 * stage);
-                ++cc;
+                within = 0;
+                ++stage;
+                w_lo = w_tmpl_lo + (((w_base + stage * kChunkBytes) >> 4) & 0x3FFFu);
+                if (stage == kNst) {
+                  stage = 0;
+                  wphase ^= 1u;
+                  w_lo = w_tmpl_lo + ((w_base >> 4) & 0x3FFFu);
+                }
               }
             }
+            a_group += group_step;
           }
           MmaCommitW(bar_acc + 8 * m);
           if (m == MT - 1) if (lane == 0) B200_TR(i, 7);
