@@ -339,8 +339,9 @@ __global__ void __launch_bounds__(256) post_conv_kernel(const __grid_constant__ 
     d.y[(static_cast<long long>(b) * y_L + y_cur) * d.y_C + t] = acc;
   }
   if (fold.done != nullptr && tid == 0) {
-    // the hop ends here: the last block to arrive advances the hop counters (every block read them on entry)
-    __threadfence();
+    // the hop ends here: the last block to arrive advances the hop counters.  Every block read them on entry
+    // (its output addresses depend on the value), so no fence is needed: the last arrival publishes nothing
+    // another block reads.
     if (atomicAdd(fold.done, 1) == static_cast<int>(gridDim.x) - 1) {
       *fold.done = 0;
 #pragma unroll
