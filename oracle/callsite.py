@@ -6,6 +6,10 @@ Those executables are the reference's unmodified ``src/common`` call site
 oracle (``which="oracle"``) or the CUDA product library (``which="b200"``).
 They run as a separate process so the reference's C++ never shares a symbol
 namespace with Python extension modules (doing so crashed inside libstdc++).
+
+``oracle/_ref/vst_harness_*`` (``run_vst``) go one layer further out: the reference's
+unmodified VST3 processor ``src/vst/processor.cc`` plus the vendored vst3sdk, driven by a
+headless host (``oracle/vst_harness.cc``) -- SURVEY.md section 8 row (f-2).
 """
 from __future__ import annotations
 
@@ -55,6 +59,46 @@ def run(which: str, toml_path, x: np.ndarray, sample_rate: float = 48000.0, bloc
         if "=" in tok:
             k, v = tok.split("=")
             info[k] = int(v)
+    return y, info
+
+
+def vst_exe_path(which: str) -> str:
+    return os.path.join(_HERE, "_ref", f"vst_harness_{which}")
+
+
+def vst_available(which: str) -> bool:
+    return os.path.exists(vst_exe_path(which))
+
+
+def run_vst(which: str, toml_path, x: np.ndarray, sample_rate: float = 48000.0, block: int = 480,
+            events=(), timeout: float = 600.0):
+    """Same contract as :func:`run`, but through the reference's unmodified VST3 processor
+    (``src/vst/processor.cc`` + vendored vst3sdk) driven by the headless host ``oracle/vst_harness.cc``:
+    parameters travel as normalised values in ``IParameterChanges``, the model path as the controller's
+    ``param_change`` message, audio through ``IAudioProcessor::process``.
+
+    Returns ``(y, info)``; ``info["applied"]`` lists ``(name, plain_value)`` as the processor de-normalised
+    them (feed these to :func:`run` for a bit-exact comparison), ``info["load"]`` / ``info["process"]`` are
+    the ``tresult`` codes (0 = kResultOk).
+    """
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.f32"), os.path.join(d, "out.f32")
+        np.ascontiguousarray(x, "<f4").tofile(fin)
+        cmd = [vst_exe_path(which), "run", toml_path or "-", fin, fout, repr(float(sample_rate)), str(int(block))]
+        cmd += [f"{int(b)}:{n}={float(v)!r}" for b, n, v in events]
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        if p.returncode != 0:
+            raise RuntimeError(f"vst_harness failed ({p.returncode}): {p.stderr[-2000:]}")
+        y = np.fromfile(fout, "<f4")
+    info = {"applied": []}
+    for line in p.stdout.splitlines():
+        if line.startswith("applied "):
+            k, v = line[len("applied "):].split("=")
+            info["applied"].append((k, float(v)))
+        elif line.startswith("status:"):
+            for tok in line.split()[1:]:
+                k, v = tok.split("=")
+                info[k] = int(v)
     return y, info
 
 

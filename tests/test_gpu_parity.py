@@ -282,6 +282,23 @@ def test_dropin_through_reference_callsite(model_dir):
     assert rms(ya, yb) <= TOL_WAVE, rms(ya, yb)
 
 
+@pytest.mark.skipif(not (callsite.vst_available("oracle") and callsite.vst_available("b200")),
+                    reason="oracle/_ref VST harness not built")
+def test_dropin_through_reference_vst_processor(model_dir):
+    """the reference's unmodified VST3 processor (src/vst/processor.cc + vst3sdk), driven by a
+    headless host through IAudioProcessor::process with parameter queues and the model-load message, produces
+    the same audio linked against the CUDA library as linked against the CPU oracle."""
+    x = signals.voice_like(480 * 40, 48000.0, seed=78)
+    events = [(-1, "pitch_shift", 4.0), (5, "voice", 3), (12, "vq_num_neighbors", 4), (19, "reset", 1),
+              (24, "formant_shift", -1.5), (30, "output_gain", -2.0)]
+    toml = os.path.join(model_dir, "model.toml")
+    ya, ia = callsite.run_vst("b200", toml, x, events=events, block=256)
+    yb, ib = callsite.run_vst("oracle", toml, x, events=events, block=256)
+    assert ia["load"] == ib["load"] == 0 and ia["process"] == ib["process"] == 0
+    assert ia["applied"] == ib["applied"]
+    assert yb.std() > 0.01 and rms(ya, yb) <= TOL_WAVE, rms(ya, yb)
+
+
 def test_full_size_batch_properties(product, model_dir):
     """256 streams (BASELINE.json configs[1]): determinism, stream independence (a stream's
     output does not depend on what the other 255 carry) and equality with the batch-of-1 path."""
