@@ -68,7 +68,8 @@ struct EncSmem {
   static constexpr uint32_t kGpPlane = (kCs / 8) * kGpPanel;
   static constexpr uint32_t kGpBuf = P * kGpPlane;              // one of two buffers (block parity)
   // inbox [NC slots][32 ch][kBoxPitch] fp32, single-buffered: a peer can push block r+1 only after it has this
-  // CTA's statistics of block r+1, which are sent after the last read of block r's partials
+  // CTA's statistics of block r+1, which are sent after the last read of block r's partials (a block without
+  // ChanNorm that is not the first of its chain runs the exchange for this hand-shake alone)
   static constexpr uint32_t kBox = kGp + 2 * kGpBuf;
   static constexpr uint32_t kBoxSlot = kCs * kBoxPitch * 4;
   static constexpr uint32_t kBoxBuf = NC * kBoxSlot;
@@ -171,7 +172,11 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
       for (int i = 0; i < 4; ++i) xv[i] = xbuf[(cg * 4 + i) * kRs + s];
       B200_ETR(r, 0);
       float mean = 0.f, rstd = 0.f;
-      if (kind == 0) {
+      // The exchange doubles as the cluster-wide hand-shake that makes the single inbox safe: a CTA sends its
+      // partials of block r only after every peer's statistics of block r arrived, and a peer sends those only
+      // after its last read of block r-1's inbox.  A head that follows another block has no statistics of its
+      // own, so it runs the same exchange for the hand-shake alone.
+      if (kind == 0 || (kind == 2 && r > 0)) {
       {
         const float m4 = ((xv[0] + xv[1]) + (xv[2] + xv[3])) * 0.25f;
         float q4 = 0.f;
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
           ChanCombineEq(src, static_cast<float>(kCs), mean, m2, stat_box[(src * kRs + s) * 2], stat_box[(src * kRs + s) * 2 + 1]);
         rstd = rsqrtf(m2 * (1.0f / static_cast<float>(C)) + 1e-5f);
       }
-      }   // kind == 0
+      }   // statistics / hand-shake
       // ---- g = GELU(norm * gamma + beta) -> bf16 hi/lo into the new rows of the B panels ----
       if (r >= 2) MbarWait(bar_free + 8 * buf, ((r - 2) >> 1) & 1);   // the history mover is done with this buffer's block r-2
       if (kind == 1) {
@@ -551,6 +556,13 @@ size_t PackChainWeights(const ChainLayer* layers, int n_layers, int C, uint16_t*
 }
 
 void LaunchResStack(const ResStackParams& p, int C, cudaStream_t s) {
+  // the single-inbox hand-shake (see the kernel) covers residual blocks and heads anywhere, front / pre convs
+  // only as the first block of a chain
+  for (int r = 1; r < p.n_blk; ++r)
+    if (p.kind[r] == 1 || p.kind[r] == 3) {
+      std::fprintf(stderr, "[libbeatrice_b200] FATAL: chain block %d of kind %d must be the first of its chain\n", r, p.kind[r]);
+      std::abort();
+    }
   if (C == 256) LaunchResStackT<256>(p, s);
   else if (C == 128) LaunchResStackT<128>(p, s);
   else {
