@@ -39,7 +39,8 @@ int NoteToBin(double note, int bins) {  // processor_core_2.cc:561-583
 struct BeatriceB200_Engine {
   int device = 0, B = 0, precision = 0;
   cudaStream_t stream = nullptr, aux = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side = nullptr;                        // host-buffer path: early output block + its D2H copy
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_side = nullptr;
   bool loaded = false;
   FamilyDims dims = kFamilies[2];
 
@@ -61,7 +62,7 @@ struct BeatriceB200_Engine {
   std::vector<int> pending_speaker, pending_formant;  // stream ids whose projection must be refreshed
   std::vector<Op> hop_ops;                            // flat op list of one model-rate hop
   std::vector<int> hop_lane;                          // 0 = main stream, 1 = aux (pitch branch)
-  GraphRunner graph16, graph48;
+  GraphRunner graph16, graph48, graph48s;
   uint64_t launches = 0;
   uint64_t hops = 0;
 
@@ -267,6 +268,7 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
   e->loaded = false;
   e->graph16.Reset();
   e->graph48.Reset();
+  e->graph48s.Reset();
   e->phone_m.dims = e->pitch_m.dims = e->wave_m.dims = e->setter_m.dims = e->dims;
   e->pitch_m.is_pitch = true;
   if (const int err = e->phone_m.LoadFromImage(images[0], sizes[0], e->device)) return err;
@@ -367,7 +369,31 @@ void RunHop48(Engine* e, bool allow_graph) {
         e->hostrate.EnqueueOut(e->wave_st.out.as<float>(), s);
       },
       allow_graph && GraphsEnabled());
+  e->hostrate.HopDone();
   e->launches += e->hop_ops.size() + HostRateState::kKernelsPerHop;
+  ++e->hops;
+}
+
+// Host-buffer form of the same hop.  The block a 48 kHz hop hands back is built from the model outputs of the
+// two previous hops (the adapter's block FIFO), so it is computed and copied to the host on a side stream
+// WHILE this hop's model call runs; the hop graph itself only stores its model output for the next call.
+void RunHop48Split(Engine* e, float* out_host, size_t bytes) {
+  FlushPending(e);
+  e->hostrate.PrepareHop(e->stream);
+  B200_CHECK(cudaEventRecord(e->ev_side, e->stream));          // gain segments uploaded, previous hop complete
+  B200_CHECK(cudaStreamWaitEvent(e->side, e->ev_side, 0));
+  e->hostrate.EnqueueOutEarly(e->side);
+  B200_CHECK(cudaMemcpyAsync(out_host, e->hostrate.out48(), bytes, cudaMemcpyDeviceToHost, e->side));
+  e->graph48s.Run(
+      e->stream,
+      [&](cudaStream_t s) {
+        e->hostrate.EnqueueIn(e->in16.as<float>(), s);
+        EnqueueHop(e, s);
+        e->hostrate.EnqueueStore(e->wave_st.out.as<float>(), s);
+      },
+      GraphsEnabled());
+  e->hostrate.HopDone();
+  e->launches += e->hop_ops.size() + HostRateState::kKernelsPerHop + 1;
   ++e->hops;
 }
 
@@ -391,6 +417,8 @@ BeatriceB200_Engine* BeatriceB200_CreateEngine(int device, int n_streams, int pr
   }
   B200_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   B200_CHECK(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
+  B200_CHECK(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+  B200_CHECK(cudaEventCreateWithFlags(&e->ev_side, cudaEventDisableTiming));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   return e;
@@ -403,8 +431,12 @@ void BeatriceB200_DestroyEngine(BeatriceB200_Engine* e) {
   cudaStreamSynchronize(e->aux);
   e->graph16.Reset();
   e->graph48.Reset();
+  e->graph48s.Reset();
   if (e->pin_in) cudaFreeHost(e->pin_in);
   if (e->pin_out) cudaFreeHost(e->pin_out);
+  cudaStreamSynchronize(e->side);
+  cudaEventDestroy(e->ev_side);
+  cudaStreamDestroy(e->side);
   cudaEventDestroy(e->ev_fork);
   cudaEventDestroy(e->ev_join);
   cudaStreamDestroy(e->stream);
@@ -586,8 +618,8 @@ int BeatriceB200_Process48k(BeatriceB200_Engine* e, const float* in_host, float*
   B200_CHECK(cudaSetDevice(e->device));
   const size_t n = sizeof(float) * e->B * kHostHop48k;
   B200_CHECK(cudaMemcpyAsync(e->hostrate.in48(), in_host, n, cudaMemcpyHostToDevice, e->stream));
-  RunHop48(e, true);
-  B200_CHECK(cudaMemcpyAsync(out_host, e->hostrate.out48(), n, cudaMemcpyDeviceToHost, e->stream));
+  RunHop48Split(e, out_host, n);
+  B200_CHECK(cudaStreamSynchronize(e->side));
   B200_CHECK(cudaStreamSynchronize(e->stream));
   return 0;
 }

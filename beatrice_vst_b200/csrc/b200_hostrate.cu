@@ -65,22 +65,35 @@ __global__ void __launch_bounds__(160) hostrate_in_kernel(const float* __restric
 }
 
 // zero-stuffed interpolating FIR over the PREVIOUS hop's model output -> gain_out.
+// The block handed back by hop c is built from the model outputs of hops c-1 and c-2 only (the block FIFO of
+// resample.h:343-363), so the two halves of this kernel can run apart: `compute` (out48 from the ring; may run
+// before the hop's model call, with the hop index passed by value in frame_value >= 0) and `store` (this hop's
+// model output into the ring for hop c+1; the last block to finish then advances the hop counter).
 __global__ void __launch_bounds__(kHop) hostrate_out_kernel(const float* __restrict__ o24, float* __restrict__ o_ring,
                                                             const GainSeg* __restrict__ seg,
                                                             const float* __restrict__ cu, float* __restrict__ out48,
-                                                            const int* __restrict__ frame_ptr) {
+                                                            int* __restrict__ frame_ptr, int frame_value, int compute,
+                                                            int store, int* __restrict__ done) {
   __shared__ float z[kZHist + kOutHop];
   __shared__ double amp[kHop];
   __shared__ float c[kTaps];
   const int b = blockIdx.x, tid = threadIdx.x;
-  const int frame = *frame_ptr;
+  const int frame = frame_value >= 0 ? frame_value : *frame_ptr;
   const int cur = frame % 3, p1 = (frame + 2) % 3, p2 = (frame + 1) % 3;
-  const GainSeg s = seg[b];
   float* ring_b = o_ring + static_cast<long long>(b) * 3 * kOutHop;
+  if (store) {
+    if (tid < kOutHop) ring_b[cur * kOutHop + tid] = o24[b * kOutHop + tid];  // becomes hop c+1's input
+    if (tid == 0 && atomicAdd(done, 1) == static_cast<int>(gridDim.x) - 1) {
+      // every block read the counter on entry; the last one out advances it (wrap: see advance_kernel)
+      *done = 0;
+      *frame_ptr = (frame + 1 >= 738017280) ? 0 : frame + 1;
+    }
+  }
+  if (!compute) return;
+  const GainSeg s = seg[b];
   if (tid < kTaps) c[tid] = cu[tid];
   if (tid < kOutHop) {
     z[kZHist + tid] = ring_b[p1 * kOutHop + tid];
-    ring_b[cur * kOutHop + tid] = o24[b * kOutHop + tid];  // becomes hop c+1's input
   } else if (tid < kOutHop + kZHist) {
     const int j = tid - kOutHop;
     z[j] = ring_b[p2 * kOutHop + (kOutHop - kZHist) + j];
@@ -117,6 +130,8 @@ void HostRateState::Init(int device, int B) {
   g_ring_.Alloc(device, sizeof(float) * B * 2 * kHop, true);
   o_ring_.Alloc(device, sizeof(float) * B * 3 * kOutHop, true);
   frame_.Alloc(device, sizeof(int), true);
+  done_.Alloc(device, sizeof(int), true);
+  host_frame_ = 0;
   seg_in_.Alloc(device, sizeof(GainSeg) * B, true);
   seg_out_.Alloc(device, sizeof(GainSeg) * B, true);
   // filter tables: DownUpSamplerImpl::Reset (resample.h:209-230) for outer = inner = 48 kHz,
@@ -215,10 +230,23 @@ void HostRateState::EnqueueIn(float* x16, cudaStream_t s) {
 }
 
 void HostRateState::EnqueueOut(const float* o24, cudaStream_t s) {
-  hostrate_out_kernel<<<B_, kHop, 0, s>>>(o24, o_ring_.as<float>(), seg_out_.as<GainSeg>(),
-                                          coef_.as<float>() + kTaps, out48_.as<float>(), frame_.as<int>());
+  hostrate_out_kernel<<<B_, kHop, 0, s>>>(o24, o_ring_.as<float>(), seg_out_.as<GainSeg>(), coef_.as<float>() + kTaps,
+                                          out48_.as<float>(), frame_.as<int>(), -1, 1, 1, done_.as<int>());
   B200_CHECK(cudaGetLastError());
-  LaunchAdvance(frame_.as<int>(), s);
 }
+
+void HostRateState::EnqueueOutEarly(cudaStream_t s) {
+  hostrate_out_kernel<<<B_, kHop, 0, s>>>(nullptr, o_ring_.as<float>(), seg_out_.as<GainSeg>(), coef_.as<float>() + kTaps,
+                                          out48_.as<float>(), frame_.as<int>(), host_frame_, 1, 0, done_.as<int>());
+  B200_CHECK(cudaGetLastError());
+}
+
+void HostRateState::EnqueueStore(const float* o24, cudaStream_t s) {
+  hostrate_out_kernel<<<B_, kHop, 0, s>>>(o24, o_ring_.as<float>(), seg_out_.as<GainSeg>(), coef_.as<float>() + kTaps,
+                                          out48_.as<float>(), frame_.as<int>(), -1, 0, 1, done_.as<int>());
+  B200_CHECK(cudaGetLastError());
+}
+
+void HostRateState::HopDone() { host_frame_ = (host_frame_ + 1 >= 738017280) ? 0 : host_frame_ + 1; }
 
 }  // namespace b200

@@ -44,9 +44,15 @@ class HostRateState {
   void EnqueueIn(float* x16, cudaStream_t s);
   // model output o24 (device, [B][240]) -> out48 (device, [B][480]); graph-capturable
   void EnqueueOut(const float* o24, cudaStream_t s);
+  // The same in two halves.  The block a hop hands back depends on the model outputs of the two PREVIOUS hops
+  // only (the block FIFO), so EnqueueOutEarly may run -- on another stream, outside the hop graph: the hop index
+  // is a launch argument -- before this hop's model call, and EnqueueStore after it.
+  void EnqueueOutEarly(cudaStream_t s);
+  void EnqueueStore(const float* o24, cudaStream_t s);   // graph-capturable
+  void HopDone();   // host mirror of the device hop counter: call once per enqueued hop
   float* in48() const { return in48_.as<float>(); }
   float* out48() const { return out48_.as<float>(); }
-  static constexpr int kKernelsPerHop = 3;
+  static constexpr int kKernelsPerHop = 2;
 
  private:
   struct HostGain {
@@ -54,7 +60,8 @@ class HostRateState {
     bool settled = false;
   };
   int device_ = -1, B_ = 0;
-  DeviceBuffer in48_, out48_, g_ring_, o_ring_, frame_, coef_, seg_in_, seg_out_;
+  DeviceBuffer in48_, out48_, g_ring_, o_ring_, frame_, done_, coef_, seg_in_, seg_out_;
+  int host_frame_ = 0;
   std::vector<HostGain> gin_, gout_;
   std::vector<GainSeg> hseg_in_, hseg_out_, up_in_, up_out_;
   bool uploaded_ = false;
