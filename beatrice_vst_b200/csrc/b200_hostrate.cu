@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(kHop) hostrate_out_kernel(const float* __restr
   const int cur = frame % 3, p1 = (frame + 2) % 3, p2 = (frame + 1) % 3;
   float* ring_b = o_ring + static_cast<long long>(b) * 3 * kOutHop;
   if (store) {
+    PdlWait();   // o24 is the previous kernel's output (no-op unless launched with the PDL attribute)
     if (tid < kOutHop) ring_b[cur * kOutHop + tid] = o24[b * kOutHop + tid];  // becomes hop c+1's input
     if (tid == 0 && atomicAdd(done, 1) == static_cast<int>(gridDim.x) - 1) {
       // every block read the counter on entry; the last one out advances it (wrap: see advance_kernel)
@@ -242,8 +243,8 @@ void HostRateState::EnqueueOutEarly(cudaStream_t s) {
 }
 
 void HostRateState::EnqueueStore(const float* o24, cudaStream_t s) {
-  hostrate_out_kernel<<<B_, kHop, 0, s>>>(o24, o_ring_.as<float>(), seg_out_.as<GainSeg>(), coef_.as<float>() + kTaps,
-                                          out48_.as<float>(), frame_.as<int>(), -1, 0, 1, done_.as<int>());
+  LaunchPdl(hostrate_out_kernel, dim3(B_), dim3(kHop), 0, s, 1, o24, o_ring_.as<float>(), seg_out_.as<GainSeg>(),
+            coef_.as<float>() + kTaps, out48_.as<float>(), frame_.as<int>(), -1, 0, 1, done_.as<int>());
   B200_CHECK(cudaGetLastError());
 }
 

@@ -250,6 +250,35 @@ def test_batched_48k_matches_reference_callsite(product, model_dir):
         assert e <= TOL_WAVE, (s, e)
 
 
+def test_48k_host_and_device_entries_interleave(product, model_dir):
+    """The host-buffer entry computes the block it hands back on a side stream, with the hop index mirrored on
+    the host; the device-buffer entry does it inside the hop graph with the device counter.  Alternating the
+    two must give exactly what either gives alone (same ring slots, same counters), gain slew included."""
+    n, hops = 2, 14
+    x = signals.batch_48k(n, hops, seed0=90)
+    ref_eng = bbatch.Engine(product, n)
+    assert ref_eng.load(model_dir) == 0
+    mix = bbatch.Engine(product, n)
+    assert mix.load(model_dir) == 0
+    d_in, d_out = mix.dev_alloc("t_in48", n * 480), mix.dev_alloc("t_out48", n * 480)
+    for h in range(hops):
+        if h == 3:
+            for e in (ref_eng, mix):
+                assert e.set("OutputGain", -4.0, 1) == 0 and e.set("InputGain", 2.0, 0) == 0
+        want = ref_eng.process_48k(x[h]).copy()
+        if h % 3 == 1:
+            mix.to_device(d_in, x[h])
+            assert mix.process_48k_device(d_in, d_out) == 0
+            mix.synchronize()
+            got = mix.to_host(d_out, (n, 480))
+        else:
+            got = mix.process_48k(x[h]).copy()
+        assert np.array_equal(got, want), h
+    assert want.std() > 0.01
+    ref_eng.close()
+    mix.close()
+
+
 def test_batched_48k_matches_committed_callsite_golden(product, model_dir):
     g = np.load(os.path.join(GOLDEN, "callsite_48k.npz"))
     events = [tuple(e) for e in json.loads(str(g["events"]))]
