@@ -381,8 +381,7 @@ void RunHop48Split(Engine* e, float* out_host, size_t bytes) {
   FlushPending(e);
   e->hostrate.PrepareHop(e->stream);
   B200_CHECK(cudaEventRecord(e->ev_side, e->stream));          // gain segments uploaded, previous hop complete
-  B200_CHECK(cudaStreamWaitEvent(e->side, e->ev_side, 0));
-  e->hostrate.EnqueueOutEarly(e->side);
+  // the hop graph goes out first: the host work below then overlaps the input copy and the first kernels
   e->graph48s.Run(
       e->stream,
       [&](cudaStream_t s) {
@@ -391,7 +390,9 @@ void RunHop48Split(Engine* e, float* out_host, size_t bytes) {
         e->hostrate.EnqueueStore(e->wave_st.out.as<float>(), s);
       },
       GraphsEnabled());
-  // after the graph launch: with a pageable destination this copy blocks the host, and the hop is then already running
+  B200_CHECK(cudaStreamWaitEvent(e->side, e->ev_side, 0));
+  e->hostrate.EnqueueOutEarly(e->side);
+  // (with a pageable destination this copy blocks the host; the hop is already running by then)
   B200_CHECK(cudaMemcpyAsync(out_host, e->hostrate.out48(), bytes, cudaMemcpyDeviceToHost, e->side));
   e->hostrate.HopDone();
   e->launches += e->hop_ops.size() + HostRateState::kKernelsPerHop + 1;
