@@ -54,17 +54,28 @@ def full(tag, rep):
     name = os.path.splitext(os.path.basename(rep))[0]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr = rows[0]
+    hdr, units = rows[0], rows[1]
     idx = [(m, hdr.index(m)) for m in METRICS if m in hdr]
+
+    def norm(i, v):
+        """ncu scales the unit per report (byte / Kbyte / Mbyte, ns / us ...): bring bytes to MB and times to us."""
+        scale = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[i])
+        if scale is None:
+            return v
+        try:
+            return f"{float(v.replace(',', '')) * scale:.6f}"
+        except ValueError:
+            return v
+
     stall = [(i, h.replace("smsp__pcsamp_warps_issue_stalled_", "")) for i, h in enumerate(hdr)
              if "pcsamp_warps_issue_stalled" in h and "not_issued" not in h]
     with open(os.path.join(OUT, f"{tag}_{name}.md"), "w") as f:
         f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` -- {name}\n\n")
-        f.write("Units as ncu prints them (time us, DRAM bytes MB, percentages).  `traffic` = dram read + write per launch.\n\n")
+        f.write("Units normalised (time us, bytes MB, percentages).  `traffic` = dram read + write per launch.\n\n")
         for r in rows[2:]:
             f.write("## " + r[hdr.index("Kernel Name")][:110] + "\n\n| metric | value |\n|---|---|\n")
             for m, i in idx[1:]:
-                f.write(f"| {m} | {r[i]} |\n")
+                f.write(f"| {m} | {norm(i, r[i])} |\n")
             st = []
             for i, h in stall:
                 try:
