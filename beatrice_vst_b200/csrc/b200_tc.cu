@@ -676,9 +676,13 @@ void LaunchConvGemmTc(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B
   // K split over a cluster (see the kernel): worth it when the launch is a handful of CTAs walking a
   // long K loop -- the latency-bound layers with few rows per hop
   int ks = 1;
+  const bool gather = h0.xh == nullptr;
   if (nz == 1 && !KSplitDisabled()) {
+    // a gathered chunk (fp32 rings of three branches, summed and rounded in registers) costs ~2.7 us per CTA,
+    // a cp.async chunk ~0.6 us: gathered launches split down to one chunk per CTA
+    const int min_chunks = gather ? 1 : 2;
     for (int cand : {4, 2}) {
-      if (n_chunks >= 2 * cand && (bn / cand) % 16 == 0 && m_tiles * n_tiles * cand <= 132) {
+      if (n_chunks >= min_chunks * cand && (bn / cand) % 16 == 0 && m_tiles * n_tiles * cand <= 132) {
         ks = cand;
         break;
       }
@@ -693,7 +697,6 @@ void LaunchConvGemmTc(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B
   size_t pipe = stages * TcStageBytes(split, bn);
   if (pipe < tile) pipe = tile;
   const size_t smem = pipe + 128 + 1024 + 1024 + inbox;   // + barriers, bias, trace, inbox
-  const bool gather = h0.xh == nullptr;
 #define B200_TC_DISPATCH(SPLIT, GATHER)                                                    \
   do {                                                                                     \
     if (stages == 4) LaunchTcT<SPLIT, 4, GATHER>(h0, d_descs, grid, smem, B, d_frame, ks, s);      \
