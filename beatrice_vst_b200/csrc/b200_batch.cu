@@ -701,8 +701,12 @@ int BeatriceB200_ProfileHop(BeatriceB200_Engine* e, const float* in_dev, float* 
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& x : ev) B200_CHECK(cudaEventCreate(&x));
   B200_CHECK(cudaEventRecord(ev[0], s));
+  // developer aid: BEATRICE_B200_REPEAT_OP=<substring> launches the matching (idempotent) ops twice, back to back,
+  // so that a traced kernel prints a cold and a warm (instruction cache, L2) timeline
+  const char* rep = std::getenv("BEATRICE_B200_REPEAT_OP");
   for (size_t i = 0; i < n; ++i) {
     e->hop_ops[i].launch(s);  // serialised on the main stream: each kernel timed alone
+    if (rep && rep[0] && e->hop_ops[i].name.find(rep) != std::string::npos) e->hop_ops[i].launch(s);
     B200_CHECK(cudaEventRecord(ev[i + 1], s));
   }
   B200_CHECK(cudaMemcpyAsync(out_dev, e->wave_st.out.p, nout, cudaMemcpyDeviceToDevice, s));
