@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   // ---- per-block geometry (see ResStackParams) ----
-  auto blk_taps = [&](int r) { return p.kind[r] == 0 ? 3 : (p.kind[r] == 1 ? 2 : (p.kind[r] == 2 ? 1 : 7)); };
+  auto blk_taps = [&](int r) { return p.kind[r] == 0 ? 3 : (p.kind[r] == 1 ? 2 : (p.kind[r] == 3 ? 7 : 1)); };
   auto blk_rows = [&](int r) { return p.kind[r] == 2 ? p.head_n : C; };                  // output channels == A rows
   auto blk_hist = [&](int r) { return p.kind[r] == 0 ? 2 * p.dil[r] : (p.kind[r] == 3 ? 6 : 0); };   // history time steps
   auto blk_kstep = [&](int r) { return static_cast<uint32_t>(P * 2 * blk_rows(r) * 16); };   // bytes of one K step of weights
@@ -155,7 +155,9 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int lc = cg * 4 + i;
-      xbuf[lc * kRs + s] = (valid && p.kind[0] != 1) ? __ldg(p.x_in + static_cast<size_t>(b) * C + rank * kCs + lc) : 0.0f;
+      const int xc = p.x_in_C > 0 ? p.x_in_C : C;     // a kind-4 first block may have fewer input channels than C
+      const int ch = rank * kCs + lc;
+      xbuf[lc * kRs + s] = (valid && p.kind[0] != 1 && ch < xc) ? __ldg(p.x_in + static_cast<size_t>(b) * xc + ch) : 0.0f;
     }
     int stat_phase = 0;   // bar_stat completes one phase per kind-0 block
 #pragma unroll 1
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
       // partials of block r only after every peer's statistics of block r arrived, and a peer sends those only
       // after its last read of block r-1's inbox.  A head that follows another block has no statistics of its
       // own, so it runs the same exchange for the hand-shake alone.
-      if (kind == 0 || (kind == 2 && r > 0)) {
+      if (kind == 0 || ((kind == 2 || kind == 3) && r > 0)) {
       {
         const float m4 = ((xv[0] + xv[1]) + (xv[2] + xv[3])) * 0.25f;
         float q4 = 0.f;
@@ -315,6 +317,33 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
           else if (kind == 1) xbuf[lc * kRs + s] = GeluFast(yo[i]);
           else if (kind == 3) xbuf[lc * kRs + s] = yo[i];
         }
+        if (kind == 4) {   // conditioning: + pitch embedding row + feature projection + speaker (+ formant) embeddings
+          const int ch = rank * kCs + cg * 4;
+          float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) {
+            const int qq = min(max(__ldg(p.emb_q + b), 0), p.emb_bins - 1);
+            add = __ldg(reinterpret_cast<const float4*>(p.emb_pitch + static_cast<size_t>(qq) * C + ch));
+            float4 fp = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+              const float ft = __ldg(p.emb_feat + b * 4 + f);
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.emb_wf + static_cast<size_t>(f) * C + ch));
+              fp.x = fmaf(ft, w4.x, fp.x); fp.y = fmaf(ft, w4.y, fp.y); fp.z = fmaf(ft, w4.z, fp.z); fp.w = fmaf(ft, w4.w, fp.w);
+            }
+            add.x += fp.x; add.y += fp.y; add.z += fp.z; add.w += fp.w;   // (acc + pitch) + feat, like cond_kernel
+          }
+          float v4[4] = {yo[0] + add.x, yo[1] + add.y, yo[2] + add.z, yo[3] + add.w};
+          if (valid && p.emb_spk) {
+            const float4 sp = *reinterpret_cast<const float4*>(p.emb_spk + static_cast<size_t>(b) * C + ch);
+            v4[0] += sp.x; v4[1] += sp.y; v4[2] += sp.z; v4[3] += sp.w;
+          }
+          if (valid && p.emb_formant) {
+            const float4 fm = *reinterpret_cast<const float4*>(p.emb_formant + static_cast<size_t>(b) * C + ch);
+            v4[0] += fm.x; v4[1] += fm.y; v4[2] += fm.z; v4[3] += fm.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xbuf[(cg * 4 + i) * kRs + s] = v4[i];
+        }
         if (kind == 2 && rank < owners && valid)
           *reinterpret_cast<float4*>(p.head_out + static_cast<size_t>(b) * p.head_n + rank * kCs + cg * 4) =
               make_float4(yo[0], yo[1], yo[2], yo[3]);
@@ -374,7 +403,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
 #pragma unroll 1
       for (int j = 0; j < taps; ++j) {
         // time block the tap reads: residual block t - (2 - j) dil; front conv: hop row j; head: the current row
-        const int tb = kind == 0 ? kHmax - (2 - j) * dil : (kind == 1 ? kHmax - 1 + j : (kind == 2 ? kHmax : kHmax - (6 - j)));
+        const int tb = kind == 0 ? kHmax - (2 - j) * dil : (kind == 1 ? kHmax - 1 + j : (kind == 3 ? kHmax - (6 - j) : kHmax));
         const uint32_t row0 = static_cast<uint32_t>(tb * kRs);
 #pragma unroll 1
         for (int h = 0; h < Gs; ++h) {
@@ -556,10 +585,10 @@ size_t PackChainWeights(const ChainLayer* layers, int n_layers, int C, uint16_t*
 }
 
 void LaunchResStack(const ResStackParams& p, int C, cudaStream_t s) {
-  // the single-inbox hand-shake (see the kernel) covers residual blocks and heads anywhere, front / pre convs
-  // only as the first block of a chain
+  // the single-inbox hand-shake (see the kernel) covers residual blocks, heads and the pre conv anywhere, the
+  // front conv and the conditioning block only as the first block of a chain
   for (int r = 1; r < p.n_blk; ++r)
-    if (p.kind[r] == 1 || p.kind[r] == 3) {
+    if (p.kind[r] == 1 || p.kind[r] == 4) {
       std::fprintf(stderr, "[libbeatrice_b200] FATAL: chain block %d of kind %d must be the first of its chain\n", r, p.kind[r]);
       std::abort();
     }

@@ -17,8 +17,21 @@ namespace b200 {
 //   kind 0 (n times):          x = x + b + Conv_{k=3, dil}(GELU(ChanNorm(x) * gamma + beta))
 //   kind 2 (optional, last):   head_out = b + W x                            -- the 1x1 head
 //   kind 3:                    x = b + Conv_{k=7}(x)                         -- the vocoder's pre conv
+//   kind 4 (first):            x = b + W x_in + pitch_emb[q] + Wf feat + spk (+ formant)
+//                                                                            -- the vocoder's conditioning
+//                                 (1x1 phone embedding; x_in has x_in_C <= C channels, W zero-padded to C)
 struct ResStackParams {
-  const float* x_in;    // [B][C] fp32 input of the first block when there is no kind-1 block
+  const float* x_in;    // [B][x_in_C] fp32 input of the first block when there is no kind-1 block
+  int x_in_C;           // channels of x_in (0: C)
+  // kind 4 only (reference semantics: oracle Generate(), conditioning): per-stream pitch bin, pitch features,
+  // additive speaker embedding and (rc0) formant embedding
+  const int* emb_q;         // [B]
+  int emb_bins;
+  const float* emb_pitch;   // [bins][C]
+  const float* emb_feat;    // [B][4]
+  const float* emb_wf;      // [4][C]
+  const float* emb_spk;     // [B][C] or nullptr
+  const float* emb_formant; // [B][C] or nullptr
   float* x_out;         // [B][out_slots][C] fp32: x after the last block (nullptr when the head is fused)
   uint16_t* xh_out;     // [B][out_slots][C] bf16 hi (+ lo) copy of out_act(x) for the consumer conv, or nullptr
   uint16_t* xl_out;

@@ -394,6 +394,21 @@ int WaveModel::LoadFromImage(const void* data, size_t size, int on_device) {
       std::vector<float> par(static_cast<size_t>(3) * kHidden, 0.0f);   // bias | gamma (unused) | beta (unused)
       std::memcpy(par.data(), c.HostAt(pre.b), sizeof(float) * kHidden);
       Upload(&pre_par, device, par.data(), par.size());
+      // two-block chain: conditioning (phone embedding, rows past the phone channels zero) + pre conv
+      cond_chain_ok = embed.k == 1 && embed.cout == kHidden && embed.cin <= kHidden && embed.cin % 4 == 0;
+      if (cond_chain_ok) {
+        std::vector<float> we(static_cast<size_t>(kHidden) * kHidden, 0.0f);
+        std::memcpy(we.data(), c.HostAt(embed.w), sizeof(float) * embed.cin * kHidden);
+        const ChainLayer layers[2] = {{we.data(), 1, kHidden}, {c.HostAt(pre.w), 7, kHidden}};
+        std::vector<uint16_t> packed2(PackChainWeights(layers, 2, kHidden, nullptr));
+        PackChainWeights(layers, 2, kHidden, packed2.data());
+        cond_pre_w.Alloc(device, packed2.size() * sizeof(uint16_t), false);
+        B200_CHECK(cudaMemcpy(cond_pre_w.p, packed2.data(), packed2.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        std::vector<float> par2(static_cast<size_t>(3) * 2 * kHidden, 0.0f);   // bias[2][C] | gamma[2][C] | beta[2][C]
+        std::memcpy(par2.data(), c.HostAt(embed.b), sizeof(float) * kHidden);
+        std::memcpy(par2.data() + kHidden, c.HostAt(pre.b), sizeof(float) * kHidden);
+        Upload(&cond_pre_par, device, par2.data(), par2.size());
+      }
     }
   }
   {
@@ -893,6 +908,11 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
   // tensor-core mode: the pre conv runs as a one-block chain of the encoder cluster kernel (b200_enc.cu), which
   // keeps the six-row input history itself: cond then writes only the hop's fp32 row
   const bool pre_fused = tcm && m->pre_chain_ok && ResStackEnabled();
+  static const bool no_cond_chain = [] {
+    const char* ev = std::getenv("BEATRICE_B200_NO_COND_CHAIN");
+    return ev && ev[0] == '1';
+  }();
+  const bool cond_fused = pre_fused && m->cond_chain_ok && !no_cond_chain;
   ring_hidden = arena.Plan(pre_fused ? 0 : spec::kPreK - 1, 1, kHidden);
   ring_pre = arena.Plan(1, 1, kHidden);
   // tensor-core mode: cond and pre also emit bf16 (hi [+ lo]) rings, so pre and ups0 move their input
@@ -1083,7 +1103,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
       LaunchCond(ph, mm->dims.phone_channels, q, mm->dims.pitch_bins, ft, mm->embed.w, mm->embed.b, mm->pitch_emb,
                  mm->feat_proj, sp, fm, hr.base, hh.hi, hh.lo, hr.slots, Bn, frame, s);   // hh has hr's geometry
     };
-    program.push_back(op);
+    if (!cond_fused) program.push_back(op);   // fused: first block of the "wave.cond+pre" chain below
   }
   auto add_gemm = [&](const std::string& name, int idx, int nz, bool mrf) {
     Op op;
@@ -1132,6 +1152,27 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
     op.name = "wave.pre";
     op.flops = ConvFlops(db.host[pre_idx], B);
     op.bytes = ConvBytes(db.host[pre_idx], B);
+    if (cond_fused) {   // conditioning + pre conv as one chain: no cond launch, no hidden ring
+      rp.x_in = phone_in.as<float>();
+      rp.x_in_C = m->dims.phone_channels;
+      rp.emb_q = q_in.as<int>();
+      rp.emb_bins = m->dims.pitch_bins;
+      rp.emb_pitch = m->pitch_emb;
+      rp.emb_feat = feat_in.as<float>();
+      rp.emb_wf = m->feat_proj;
+      rp.emb_spk = spk.as<float>();
+      rp.emb_formant = rc0 ? formant.as<float>() : nullptr;
+      rp.w = m->cond_pre_w.as<uint16_t>();
+      rp.bias = m->cond_pre_par.as<float>();
+      rp.gamma = rp.bias + 2 * kHidden;
+      rp.beta = rp.gamma + 2 * kHidden;
+      rp.n_blk = 2;
+      rp.kind[0] = 4;
+      rp.kind[1] = 3;
+      rp.dil[1] = 1;
+      op.name = "wave.cond+pre";
+      op.flops += 2.0 * B * (m->dims.phone_channels + kPitchFeatures) * kHidden;
+    }
     op.launch = [=](cudaStream_t s) { LaunchResStack(rp, kHidden, s); };
     program.push_back(op);
   } else {

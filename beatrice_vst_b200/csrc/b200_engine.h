@@ -138,6 +138,9 @@ struct WaveModel {
   // pre conv (k = 7) as a one-block chain of the cluster kernel in b200_enc.cu
   DeviceBuffer pre_w, pre_par;
   bool pre_chain_ok = false;
+  // the same with the conditioning (1x1 phone embedding + pitch / feature / speaker terms) as the chain's first block
+  DeviceBuffer cond_pre_w, cond_pre_par;
+  bool cond_chain_ok = false;
   const uint16_t* mrf_w_ptr[2][4][3] = {};
   const float* mrf_bias_ptr[4][3] = {};
   int LoadFromImage(const void* data, size_t size, int on_device = -1);
