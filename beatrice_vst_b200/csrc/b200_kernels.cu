@@ -301,19 +301,54 @@ __global__ void __launch_bounds__(256) post_conv_kernel(const __grid_constant__ 
   const int x_L = d.x_slots * d.x_T;
   const int x_cur = (frame % d.x_slots) * d.x_T;
   const long long xb = static_cast<long long>(b) * x_L * 16;
-#pragma unroll 4
-  for (int idx = tid; idx < (d.T + 6) * 4; idx += 256) {   // T = 240: four rounds, their twelve loads in flight together
+  // T = 240: four rounds per thread.  The branch rings are read through unconditional pointers (the single-input
+  // form aliases all three to the first) so that the twelve loads of a thread are in flight together.
+  const bool mean3 = d.n_x > 1;
+  const float* x0 = d.x[0];
+  const float* x1 = mean3 ? d.x[1] : d.x[0];
+  const float* x2 = mean3 ? d.x[2] : d.x[0];
+  constexpr int kRounds = 4;
+  float4 v0[kRounds], v1[kRounds], v2[kRounds];
+  const int n_items = (d.T + 6) * 4;
+#pragma unroll
+  for (int j = 0; j < kRounds; ++j) {
+    const int idx = tid + 256 * j;
     const int row = idx >> 2, q = idx & 3;
     int r = x_cur + row - 6;
     if (r < 0) r += x_L;
     const long long a = xb + static_cast<long long>(r) * 16 + 4 * q;
-    float4 v = Ldg4(d.x[0] + a);
-    if (d.n_x > 1) {
-      const float4 v1 = Ldg4(d.x[1] + a), v2 = Ldg4(d.x[2] + a);
-      v.x = ((v.x + v1.x) + v2.x) * d.in_scale;
-      v.y = ((v.y + v1.y) + v2.y) * d.in_scale;
-      v.z = ((v.z + v1.z) + v2.z) * d.in_scale;
-      v.w = ((v.w + v1.w) + v2.w) * d.in_scale;
+    const bool ok = idx < n_items;
+    v0[j] = ok ? Ldg4(x0 + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v1[j] = ok ? Ldg4(x1 + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v2[j] = ok ? Ldg4(x2 + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int j = 0; j < kRounds; ++j) {
+    const int idx = tid + 256 * j;
+    if (idx >= n_items) break;
+    const int row = idx >> 2, q = idx & 3;
+    float4 v = v0[j];
+    if (mean3) {
+      v.x = ((v.x + v1[j].x) + v2[j].x) * d.in_scale;
+      v.y = ((v.y + v1[j].y) + v2[j].y) * d.in_scale;
+      v.z = ((v.z + v1[j].z) + v2[j].z) * d.in_scale;
+      v.w = ((v.w + v1[j].w) + v2[j].w) * d.in_scale;
+    }
+    v = InAct4(v, d.in_act);
+    *reinterpret_cast<float4*>(xs + row * kPostRowLd + 4 * q) = v;
+  }
+  for (int idx = tid + 256 * kRounds; idx < n_items; idx += 256) {   // T > 250 (not spec M0): plain rounds
+    const int row = idx >> 2, q = idx & 3;
+    int r = x_cur + row - 6;
+    if (r < 0) r += x_L;
+    const long long a = xb + static_cast<long long>(r) * 16 + 4 * q;
+    float4 v = Ldg4(x0 + a);
+    if (mean3) {
+      const float4 w1 = Ldg4(x1 + a), w2 = Ldg4(x2 + a);
+      v.x = ((v.x + w1.x) + w2.x) * d.in_scale;
+      v.y = ((v.y + w1.y) + w2.y) * d.in_scale;
+      v.z = ((v.z + w1.z) + w2.z) * d.in_scale;
+      v.w = ((v.w + w1.w) + w2.w) * d.in_scale;
     }
     v = InAct4(v, d.in_act);
     *reinterpret_cast<float4*>(xs + row * kPostRowLd + 4 * q) = v;
