@@ -53,3 +53,11 @@ def test_vst_unloaded_and_silence(model_dir):
     z = np.zeros(480 * 4, np.float32)
     y, info = callsite.run_vst("oracle", _toml(model_dir), z)   # silent input: processor.cc:205-218 skips the core
     assert info["load"] == 0 and not y.any()
+
+
+def test_vst_bad_model_path_keeps_running(tmp_path):
+    """processor.cc:274-300 keeps whatever the controller sent, even when the model cannot be loaded: the message is
+    acknowledged, the core stays unloaded and the processor hands back silence instead of failing."""
+    x = signals.voice_like(480 * 3, 48000.0, 14)
+    y, info = callsite.run_vst("oracle", str(tmp_path / "missing" / "model.toml"), x)
+    assert info["load"] == 0 and info["process"] == 0 and not y.any()
