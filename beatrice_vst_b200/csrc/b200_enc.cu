@@ -22,6 +22,15 @@
 //    exchanged through DSMEM, every CTA combines them in rank order -> identical mean / rstd everywhere.
 //  * Everything else (bias, residual add, normalise, GELU, bf16 hi/lo split) is elementwise on the CTA's
 //    own [32 channels x 32 streams] slice, spread over all 256 worker threads.
+//
+// The same machinery runs every other one-row-per-hop conv of the model as further block kinds of the chain
+// (ResStackParams in b200_enc.h): the last front-end layer in front of the stack (kind 1: k = 2, stride 2,
+// GELU), the content encoder's 1x1 head behind it (kind 2), and -- as a chain of its own at C = 256 -- the
+// vocoder's conditioning (kind 4: 1x1 phone embedding, then pitch-embedding row + feature projection +
+// speaker / formant embeddings in the epilogue) followed by its `pre` conv (kind 3: k = 7, six history rows).
+// The inbox is single-buffered; what keeps a fast CTA from pushing block r+1 into a peer that still reads
+// block r is the statistics exchange of block r+1, which blocks without a ChanNorm run for that purpose alone
+// (see the worker loop).
 #include <cstdio>
 #include <cstring>
 #include <vector>
