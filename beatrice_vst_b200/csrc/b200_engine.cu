@@ -283,6 +283,17 @@ int EncoderModel::LoadFromImage(const void* data, size_t size, int on_device) {
     for (int i = 0; i < n_res; ++i) convs.push_back(&res[i]);
     convs.push_back(&head);
     for (ConvW* cv : convs) cv->tc_bn_cap = 64;   // few rows per hop (T <= 16): favour CTA count
+    // front-end layers 1-2 (16 / 8 rows per stream, N = 64 / 128 at the content encoder): 32-column tiles -- twice the
+    // CTAs, half the epilogue (bias + GELU + bf16 split) per thread: 15 -> 13 us each
+    front[1].tc_bn_cap = front[2].tc_bn_cap = 32;
+    if (const char* ev = std::getenv("BEATRICE_B200_FE_BN")) {   // developer overrides: layers 1-2 / layers 3-4
+      const int cap = std::atoi(ev);
+      if (cap == 64 || cap == 32 || cap == 16) front[1].tc_bn_cap = front[2].tc_bn_cap = cap;
+    }
+    if (const char* ev = std::getenv("BEATRICE_B200_FE_BN34")) {
+      const int cap = std::atoi(ev);
+      if (cap == 64 || cap == 32) front[3].tc_bn_cap = front[4].tc_bn_cap = cap;
+    }
     tc.Pack(device, img.payload, blob.as<float>(), convs);
   }
   rs_ok = ResStackSupported(width, n_res, dil) && front[5].k == 2 && stride[5] == 2 && front[5].cin == width && front[5].cout == width;
