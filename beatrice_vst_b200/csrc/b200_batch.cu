@@ -62,6 +62,8 @@ struct BeatriceB200_Engine {
   std::vector<int> pending_speaker, pending_formant;  // stream ids whose projection must be refreshed
   std::vector<Op> hop_ops;                            // flat op list of one model-rate hop
   std::vector<int> hop_lane;                          // 0 = main stream, 1 = aux (pitch branch)
+  int vq_op = -1;                                     // index of "phone.vq" in hop_ops
+  bool any_vq = false;                                // some stream has kNN-VQ on (VQNumNeighbors > 0)
   GraphRunner graph16, graph48, graph48s;
   uint64_t launches = 0;
   uint64_t hops = 0;
@@ -117,6 +119,16 @@ void FlushPending(Engine* e) {
     UploadInts(e, &e->vq_n, n);
     B200_CHECK(cudaMemcpyAsync(e->codebook_ptrs.p, ptr.data(), ptr.size() * sizeof(float*), cudaMemcpyHostToDevice, s));
     e->vq_dirty = false;
+    // With VQ off everywhere (the reference's default, parameter_schema.cc:390-392) the VQ launch is a plain copy
+    // that the content encoder's chain kernel already made (EncoderState::head_copy): the hop graphs are captured
+    // without it, and re-captured when that changes.
+    const bool any = std::any_of(n.begin(), n.end(), [](int v) { return v > 0; });
+    if (any != e->any_vq) {
+      e->any_vq = any;
+      e->graph16.Reset();
+      e->graph48.Reset();
+      e->graph48s.Reset();
+    }
   }
   auto dedup = [](std::vector<int>* v) {
     std::sort(v->begin(), v->end());
@@ -200,6 +212,7 @@ void BuildHop(Engine* e) {
     const int C = e->dims.phone_channels;
     op.bytes = 8.0 * B * C;
     op.launch = [=](cudaStream_t s) { LaunchVq(in, out, cbs, n, C, B, s); };
+    e->vq_op = static_cast<int>(e->hop_ops.size());
     push(op, 0);
   }
   for (const Op& op : e->pitch_st.program)
@@ -224,6 +237,12 @@ void BuildHop(Engine* e) {
   for (const Op& op : e->wave_st.program) push(op, 2);  // lane 2: main stream after the join
 }
 
+// the VQ launch is redundant while no stream has VQ on and the chain kernel writes the vocoder's phone input itself
+inline bool SkipVq(const Engine* e, size_t op) {
+  return static_cast<int>(op) == e->vq_op && !e->any_vq && e->phone_st.head_dual;
+}
+inline size_t HopLaunches(const Engine* e) { return e->hop_ops.size() - (SkipVq(e, static_cast<size_t>(e->vq_op)) ? 1 : 0); }
+
 // Enqueues one model-rate hop (in16 staging already filled) with the two encoders as
 // concurrent branches.  Works both live and under stream capture.
 void EnqueueHop(Engine* e, cudaStream_t s) {
@@ -239,6 +258,7 @@ void EnqueueHop(Engine* e, cudaStream_t s) {
   for (size_t i = 0; i < e->hop_ops.size(); ++i) {
     const int lane = e->hop_lane[i];
     if (!((lane_mask >> lane) & 1)) continue;
+    if (SkipVq(e, i)) continue;
     if (lane == 2 && !joined) {
       B200_CHECK(cudaEventRecord(e->ev_join, e->aux));
       B200_CHECK(cudaStreamWaitEvent(s, e->ev_join, 0));
@@ -309,9 +329,11 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
   const int B = e->B;
   e->in16.Alloc(e->device, sizeof(float) * B * kInHop, true);
   const TcMode tc = static_cast<TcMode>(e->precision);
+  e->wave_st.cond_ready = false;
+  e->wave_st.AllocCond(e->dims, B, e->device);                 // the vocoder's input buffers exist before the encoders are built
+  e->phone_st.head_copy = e->wave_st.phone_in.as<float>();     // ... so that the content head can write its output there too
   e->phone_st.Build(&e->phone_m, B, e->device, e->in16.as<float>(), tc);
   e->pitch_st.Build(&e->pitch_m, B, e->device, e->in16.as<float>(), tc);
-  e->wave_st.cond_ready = false;
   // one hop = one graph: the vocoder's last kernel advances all three hop counters (no advance launches)
   e->wave_st.fold_frames[0] = e->phone_st.arena.frame();
   e->wave_st.fold_frames[1] = e->pitch_st.arena.frame();
@@ -354,7 +376,7 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
 void RunHop16(Engine* e, bool allow_graph) {
   FlushPending(e);
   e->graph16.Run(e->stream, [&](cudaStream_t s) { EnqueueHop(e, s); }, allow_graph && GraphsEnabled());
-  e->launches += e->hop_ops.size();
+  e->launches += HopLaunches(e);
   ++e->hops;
 }
 
@@ -370,7 +392,7 @@ void RunHop48(Engine* e, bool allow_graph) {
       },
       allow_graph && GraphsEnabled());
   e->hostrate.HopDone();
-  e->launches += e->hop_ops.size() + HostRateState::kKernelsPerHop;
+  e->launches += HopLaunches(e) + HostRateState::kKernelsPerHop;
   ++e->hops;
 }
 
@@ -395,7 +417,7 @@ void RunHop48Split(Engine* e, float* out_host, size_t bytes) {
   // (with a pageable destination this copy blocks the host; the hop is already running by then)
   B200_CHECK(cudaMemcpyAsync(out_host, e->hostrate.out48(), bytes, cudaMemcpyDeviceToHost, e->side));
   e->hostrate.HopDone();
-  e->launches += e->hop_ops.size() + HostRateState::kKernelsPerHop + 1;
+  e->launches += HopLaunches(e) + HostRateState::kKernelsPerHop + 1;
   ++e->hops;
 }
 
@@ -705,7 +727,7 @@ int BeatriceB200_ProfileHop(BeatriceB200_Engine* e, const float* in_dev, float* 
   // so that a traced kernel prints a cold and a warm (instruction cache, L2) timeline
   const char* rep = std::getenv("BEATRICE_B200_REPEAT_OP");
   for (size_t i = 0; i < n; ++i) {
-    e->hop_ops[i].launch(s);  // serialised on the main stream: each kernel timed alone
+    if (!SkipVq(e, i)) e->hop_ops[i].launch(s);  // serialised on the main stream: each kernel timed alone
     if (rep && rep[0] && e->hop_ops[i].name.find(rep) != std::string::npos) e->hop_ops[i].launch(s);
     B200_CHECK(cudaEventRecord(ev[i + 1], s));
   }

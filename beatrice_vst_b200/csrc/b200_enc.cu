@@ -353,9 +353,11 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
 #pragma unroll
           for (int i = 0; i < 4; ++i) xbuf[(cg * 4 + i) * kRs + s] = v4[i];
         }
-        if (kind == 2 && rank < owners && valid)
-          *reinterpret_cast<float4*>(p.head_out + static_cast<size_t>(b) * p.head_n + rank * kCs + cg * 4) =
-              make_float4(yo[0], yo[1], yo[2], yo[3]);
+        if (kind == 2 && rank < owners && valid) {
+          const size_t o = static_cast<size_t>(b) * p.head_n + rank * kCs + cg * 4;
+          *reinterpret_cast<float4*>(p.head_out + o) = make_float4(yo[0], yo[1], yo[2], yo[3]);
+          if (p.head_out2) *reinterpret_cast<float4*>(p.head_out2 + o) = make_float4(yo[0], yo[1], yo[2], yo[3]);
+        }
       }
       // (every thread re-reads only its own xbuf entries at the top of the next block: no barrier needed here)
       B200_ETR(r, 6);

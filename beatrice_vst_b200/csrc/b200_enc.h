@@ -41,6 +41,7 @@ struct ResStackParams {
   const uint16_t* fin_h;  // kind 1: input rows, bf16 hi / lo planes [B][2][C]
   const uint16_t* fin_l;
   float* head_out;      // kind 2: [B][head_n] fp32
+  float* head_out2;     // optional second copy of the head output (the consumer's input buffer), or nullptr
   int head_n;           // 128 or 256
   const uint16_t* w;    // PackChainWeights image
   const float* bias;    // [n_blk][C]

@@ -808,6 +808,8 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
       rp.xl_out = arena.ring(ring_xh).lo;
     } else {
       rp.head_out = head_out.as<float>();
+      rp.head_out2 = head_copy;
+      head_dual = head_copy != nullptr;
       rp.head_n = m->head_out;
     }
     rp.w = m->rs_w.as<uint16_t>();

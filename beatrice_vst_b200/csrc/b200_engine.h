@@ -213,6 +213,11 @@ struct EncoderState {
   DeviceBuffer descs;     // ConvDesc table
   DeviceBuffer in_stage;  // [B][160]
   DeviceBuffer head_out;  // [B][head_out]
+  // batched engine: where the head output is ALSO written when the head is the last block of the fused chain
+  // (the vocoder's phone input: with kNN-VQ off for every stream the VQ launch, a copy then, is skipped).
+  // Set before Build; head_dual: Build took the offer.
+  float* head_copy = nullptr;
+  bool head_dual = false;
   std::vector<Op> program;
   DeviceBuffer rs_hist, rs_blocks;   // fused residual stack: conv-input histories + their per-stream reset table
   int n_rs_blocks = 0;

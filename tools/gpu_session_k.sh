@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 L=gpurun_out/k.log
 : > $L
-run() { echo "== $*" >> $L; ( timeout 200 env "$@" ) 2>&1 | grep '^{' | cut -c1-900 >> $L; echo "rc=$?" >> $L; }
-run BEATRICE_B200_PRECISION=bf16x3 python tools/config_bench.py latency 3000
-run python tools/config_bench.py sweep 1000 128
+run() { echo "== $*" >> $L; ( timeout 300 env "$@" ) 2>&1 | cut -c1-1500 >> $L; echo "rc=$?" >> $L; }
+(timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -6) >> $L
+run python bench.py --steps 400 --warmup 30 --no-cpu-baseline
 cat $L
