@@ -225,14 +225,12 @@ void BuildHop(Engine* e) {
     const int *lo = e->min_q.as<int>(), *hi = e->max_q.as<int>();
     int* q = e->q_raw.as<int>();
     float* feat = e->wave_st.feat_in.as<float>();
-    op.launch = [=](cudaStream_t s) { LaunchPitchArgmax(head, bins, lo, hi, q, feat, B, s); };
-    push(op, 1);
-    Op ot;
-    ot.name = "pitch.transform";
+    // arg-max over [min, max] and the call site's fp64 pitch transform (processor_core_2.cc:190-252) in one launch
+    op.name = "pitch.argmax+transform";
     const PitchParams* pp = e->pitch_params.as<PitchParams>();
     int* q_used = e->wave_st.q_in.as<int>();
-    ot.launch = [=](cudaStream_t s) { LaunchPitchTransform(q, pp, bins, q_used, B, s); };
-    push(ot, 1);
+    op.launch = [=](cudaStream_t s) { LaunchPitchArgmax(head, bins, lo, hi, q, feat, B, s, pp, q_used); };
+    push(op, 1);
   }
   for (const Op& op : e->wave_st.program) push(op, 2);  // lane 2: main stream after the join
 }

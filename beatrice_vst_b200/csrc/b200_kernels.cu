@@ -521,9 +521,43 @@ __global__ void advance_kernel(int* frame) {
   *frame = NextFrame(*frame);
 }
 
+// reference src/common/processor_core_2.cc:190-252, evaluated in fp64 with explicit
+// round-to-nearest mul/add so that no FMA contraction changes a rounding the CPU makes.
+__device__ int PitchTransformOne(int q_raw, const PitchParams& p, int bins) {
+  constexpr double kBps = 96.0 / 12.0;  // BEATRICE_PITCH_BINS_PER_OCTAVE / 12
+  const double q = static_cast<double>(q_raw);
+  double tmp = __dadd_rn(__dadd_rn(p.average_source_pitch,
+                                   __dmul_rn(__dadd_rn(q, -p.average_source_pitch), p.intonation_intensity)),
+                         __dmul_rn(kBps, p.pitch_shift));
+  if (p.pitch_correction != 0.0) {
+    if (p.pitch_correction_type == 0) {
+      const double nearest = __dmul_rn(__dadd_rn(floor(tmp / kBps), 0.5), kBps);
+      const double nd = __dmul_rn(__dadd_rn(tmp, -nearest), 2.0 / kBps);
+      if (fabs(nd) < 1e-4) {
+        tmp = nearest;
+      } else {
+        tmp = __dadd_rn(nearest, __dmul_rn(__dmul_rn(nd, pow(fabs(nd), -p.pitch_correction)), kBps / 2.0));
+      }
+    } else if (p.pitch_correction_type == 1) {
+      const double nearest = __dmul_rn(round(tmp / kBps), kBps);
+      const double nd = __dmul_rn(__dadd_rn(tmp, -nearest), 2.0 / kBps);
+      if (p.pitch_correction > 1 - 1e-4) {
+        tmp = nearest;
+      } else if (nd >= 0.0) {
+        tmp = __dadd_rn(nearest, __dmul_rn(pow(nd, 1.0 / (1.0 - p.pitch_correction)), kBps / 2.0));
+      } else {
+        tmp = __dadd_rn(nearest, -__dmul_rn(pow(-nd, 1.0 / (1.0 - p.pitch_correction)), kBps / 2.0));
+      }
+    }
+  }
+  const double r = round(tmp);
+  int qi = (r < 1.0) ? 1 : ((r > static_cast<double>(bins - 1)) ? bins - 1 : static_cast<int>(r));
+  return qi;
+}
+
 __global__ void pitch_argmax_kernel(const float* __restrict__ head, int bins, const int* __restrict__ min_q,
                                     const int* __restrict__ max_q, int* __restrict__ q, float* __restrict__ feat,
-                                    int B) {
+                                    int B, const PitchParams* __restrict__ params, int* __restrict__ q_used) {
   PdlWait();
   PdlLaunchDependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -551,48 +585,21 @@ __global__ void pitch_argmax_kernel(const float* __restrict__ head, int bins, co
       besti = oi;
     }
   }
-  if (lane == 0) q[warp] = (besti == INT_MAX) ? lo : besti;
+  if (lane == 0) {
+    const int qr = (besti == INT_MAX) ? lo : besti;
+    q[warp] = qr;
+    if (params) q_used[warp] = PitchTransformOne(qr, params[warp], bins);   // batched engine: the call site's transform, same launch
+  }
   if (lane < kPitchFeatures) feat[warp * kPitchFeatures + lane] = h[bins + lane];
 }
 
-// reference src/common/processor_core_2.cc:190-252, evaluated in fp64 with explicit
-// round-to-nearest mul/add so that no FMA contraction changes a rounding the CPU makes.
 __global__ void pitch_transform_kernel(const int* __restrict__ q_in, const PitchParams* __restrict__ params,
                                        int bins, int* __restrict__ q_out, int B) {
   PdlWait();
   PdlLaunchDependents();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const PitchParams p = params[b];
-  constexpr double kBps = 96.0 / 12.0;  // BEATRICE_PITCH_BINS_PER_OCTAVE / 12
-  const double q = static_cast<double>(q_in[b]);
-  double tmp = __dadd_rn(__dadd_rn(p.average_source_pitch,
-                                   __dmul_rn(__dadd_rn(q, -p.average_source_pitch), p.intonation_intensity)),
-                         __dmul_rn(kBps, p.pitch_shift));
-  if (p.pitch_correction != 0.0) {
-    if (p.pitch_correction_type == 0) {
-      const double nearest = __dmul_rn(__dadd_rn(floor(tmp / kBps), 0.5), kBps);
-      const double nd = __dmul_rn(__dadd_rn(tmp, -nearest), 2.0 / kBps);
-      if (fabs(nd) < 1e-4) {
-        tmp = nearest;
-      } else {
-        tmp = __dadd_rn(nearest, __dmul_rn(__dmul_rn(nd, pow(fabs(nd), -p.pitch_correction)), kBps / 2.0));
-      }
-    } else if (p.pitch_correction_type == 1) {
-      const double nearest = __dmul_rn(round(tmp / kBps), kBps);
-      const double nd = __dmul_rn(__dadd_rn(tmp, -nearest), 2.0 / kBps);
-      if (p.pitch_correction > 1 - 1e-4) {
-        tmp = nearest;
-      } else if (nd >= 0.0) {
-        tmp = __dadd_rn(nearest, __dmul_rn(pow(nd, 1.0 / (1.0 - p.pitch_correction)), kBps / 2.0));
-      } else {
-        tmp = __dadd_rn(nearest, -__dmul_rn(pow(-nd, 1.0 / (1.0 - p.pitch_correction)), kBps / 2.0));
-      }
-    }
-  }
-  const double r = round(tmp);
-  int qi = (r < 1.0) ? 1 : ((r > static_cast<double>(bins - 1)) ? bins - 1 : static_cast<int>(r));
-  q_out[b] = qi;
+  q_out[b] = PitchTransformOne(q_in[b], params[b], bins);
 }
 
 // hidden[b][c] = be[c] + phone[b].We[:,c] + pitch_emb[q[b]][c] + feat[b].Wf[:,c] (+ spk + formant)
@@ -873,8 +880,9 @@ void LaunchAdvance(int* d_frame, cudaStream_t s) {
 }
 
 void LaunchPitchArgmax(const float* head, int bins, const int* min_q, const int* max_q, int* q, float* feat, int B,
-                       cudaStream_t s) {
-  LaunchPdl(pitch_argmax_kernel, dim3((B * 32 + 127) / 128), dim3(128), 0, s, 1, head, bins, min_q, max_q, q, feat, B);
+                       cudaStream_t s, const PitchParams* params, int* q_used) {
+  LaunchPdl(pitch_argmax_kernel, dim3((B * 32 + 127) / 128), dim3(128), 0, s, 1, head, bins, min_q, max_q, q, feat, B, params,
+            q_used);
   B200_CHECK(cudaGetLastError());
 }
 

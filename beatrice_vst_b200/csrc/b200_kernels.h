@@ -113,8 +113,9 @@ void LaunchIngest(const float* staging, float* ring, int slots, int T, int C, in
                   cudaStream_t s);
 void LaunchAdvance(int* d_frame, cudaStream_t s);
 // head [B][bins+4] -> q [B] (arg-max over [min_q[b], max_q[b]]), feat [B][4]
+// params / q_used non-null: also applies the call site's pitch transform (PitchParams per stream) in the same launch
 void LaunchPitchArgmax(const float* head, int bins, const int* min_q, const int* max_q, int* q, float* feat,
-                       int B, cudaStream_t s);
+                       int B, cudaStream_t s, const PitchParams* params = nullptr, int* q_used = nullptr);
 // reference call-site transform, fp64 (processor_core_2.cc:190-252)
 void LaunchPitchTransform(const int* q_in, const PitchParams* params, int bins, int* q_out, int B,
                           cudaStream_t s);
