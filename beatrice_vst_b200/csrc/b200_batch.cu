@@ -125,6 +125,7 @@ void FlushPending(Engine* e) {
     const bool any = std::any_of(n.begin(), n.end(), [](int v) { return v > 0; });
     if (any != e->any_vq) {
       e->any_vq = any;
+      B200_CHECK(cudaStreamSynchronize(e->stream));   // rare (a parameter change): no hop graph is in flight when they are dropped
       e->graph16.Reset();
       e->graph48.Reset();
       e->graph48s.Reset();
