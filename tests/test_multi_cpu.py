@@ -61,3 +61,32 @@ def test_broadcast_and_sharded_streams_world2(model_dir, oracle, tmp_path):
         _, _, _, w = st.run(signals.voice_like(160 * 3, 16000.0, seed=s))
         st.close()
         assert np.array_equal(np.load(tmp_path / f"w{s}.npy"), w)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_reference_arm_under_torchrun_world2():
+    """`bench.py --impl reference` as the driver launches it for N = 2: rank 0 alone times the CPU arm (the
+    reference call site over the oracle) and prints the one JSON line, the other rank leaves without work."""
+    import json
+    import subprocess
+
+    import callsite
+    if not callsite.available("oracle"):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "1", "--warmup", "0"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, lines                       # exactly one rank speaks
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["higher_is_better"] is True
+    assert d["metric"].startswith("voice frames/s") and d["unit"] == "frames/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
