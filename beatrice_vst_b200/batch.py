@@ -18,6 +18,10 @@ _vp = C.c_void_p
 BATCH_SYMBOLS = {
     "BeatriceB200_DeviceCount": (C.c_int, []),
     "BeatriceB200_Version": (C.c_char_p, []),
+    "BeatriceB200_SetDefaultPrecision": (None, [C.c_int]),
+    "BeatriceB200_LastError": (C.c_int, []),
+    "BeatriceB200_LastErrorString": (C.c_char_p, []),
+    "BeatriceB200_ClearError": (None, []),
     "BeatriceB200_CreateEngine": (_vp, [C.c_int, C.c_int, C.c_int]),
     "BeatriceB200_DestroyEngine": (None, [_vp]),
     "BeatriceB200_LoadModel": (C.c_int, [_vp, C.c_char_p]),
@@ -50,6 +54,7 @@ BATCH_SYMBOLS = {
     "BeatriceB200_CopyToHost": (None, [_vp, _vp, _vp, C.c_size_t]),
     "BeatriceB200_Stream": (_vp, [_vp]),
     "BeatriceB200_GetLastIntermediates": (C.c_int, [_vp, _f32p, _i32p, _i32p, _f32p]),
+    "BeatriceB200_TransformPitchBins": (C.c_int, [_vp, _i32p, _i32p]),
     "BeatriceB200_ResidentBytes": (C.c_size_t, [_vp]),
     "BeatriceB200_KernelLaunchCount": (C.c_uint64, [_vp]),
     "BeatriceB200_ProfileHop": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
@@ -73,10 +78,25 @@ def device_count(lib: BeatriceLib) -> int:
     return bind(lib).BeatriceB200_DeviceCount()
 
 
+def set_default_precision(lib: BeatriceLib, precision: int) -> None:
+    """Precision of beatrice.h contexts built from now on (0 f32, 1 bf16, 2 bf16x3, -1 default)."""
+    bind(lib).BeatriceB200_SetDefaultPrecision(precision)
+
+
+def last_error(lib: BeatriceLib):
+    """(code, text) of the latched library failure; (0, "") when none."""
+    dll = bind(lib)
+    return dll.BeatriceB200_LastError(), (dll.BeatriceB200_LastErrorString() or b"").decode()
+
+
+def clear_error(lib: BeatriceLib) -> None:
+    bind(lib).BeatriceB200_ClearError()
+
+
 class Engine:
     """n_streams voice streams on one GPU."""
 
-    def __init__(self, lib: BeatriceLib, n_streams: int, device: int = 0, precision: int = 0):
+    def __init__(self, lib: BeatriceLib, n_streams: int, device: int = 0, precision: int = 2):
         self.dll = bind(lib)
         self.n = n_streams
         self.h = self.dll.BeatriceB200_CreateEngine(device, n_streams, precision)
@@ -181,6 +201,16 @@ class Engine:
             self.h, phone.ctypes.data_as(_f32p), q_raw.ctypes.data_as(_i32p), q_used.ctypes.data_as(_i32p),
             feat.ctypes.data_as(_f32p))
         return phone, q_raw, q_used, feat
+
+    def transform_pitch_bins(self, bins_raw: np.ndarray) -> np.ndarray:
+        """The call-site pitch transform with every stream's current parameters (device kernel)."""
+        q = np.ascontiguousarray(bins_raw, np.int32)
+        assert q.shape == (self.n,)
+        out = np.empty(self.n, np.int32)
+        rc = self.dll.BeatriceB200_TransformPitchBins(self.h, q.ctypes.data_as(_i32p), out.ctypes.data_as(_i32p))
+        if rc != 0:
+            raise RuntimeError(f"BeatriceB200_TransformPitchBins -> {rc}")
+        return out
 
     def resident_bytes(self) -> int:
         return int(self.dll.BeatriceB200_ResidentBytes(self.h))

@@ -90,8 +90,32 @@ void UploadInts(Engine* e, DeviceBuffer* dst, const std::vector<int>& v) {
   B200_CHECK(cudaMemcpyAsync(dst->p, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
 }
 
+// One step of the key-value schedule: every stream (of `only`, when given) that still has blocks to apply gets its
+// next one (SetKeyValueSpeakerEmbedding(block), processor_core_2.h:161-169).
+void StepKv(Engine* e, const std::vector<char>* only) {
+  cudaStream_t s = e->stream;
+  for (int blk = 0; blk < kNBlocks; ++blk) {
+    std::vector<int> streams, spk;
+    for (int b = 0; b < e->B; ++b)
+      if (e->sp[b].kv_set_count == blk && (!only || (*only)[b])) {
+        streams.push_back(b);
+        spk.push_back(e->sp[b].speaker);
+      }
+    if (streams.empty()) continue;
+    UploadInts(e, &e->idx_a, spk);
+    UploadInts(e, &e->idx_b, streams);
+    LaunchKvFilm(e->kv.as<float>(), e->idx_a.as<int>(), static_cast<size_t>(kKvLength) * kKvChannels,
+                 e->setter_m.query[blk], e->setter_m.film_w[blk], e->setter_m.film_b[blk], kStageC[blk],
+                 e->wave_st.film[blk].as<float>(), e->idx_b.as<int>(), static_cast<int>(streams.size()), s);
+    ++e->launches;
+    for (int b : streams) e->sp[b].kv_set_count = -(blk + 1);  // mark, bumped below
+  }
+  for (int b = 0; b < e->B; ++b)
+    if (e->sp[b].kv_set_count < 0) e->sp[b].kv_set_count = -e->sp[b].kv_set_count;
+}
+
 // Applies everything the setters queued; runs on e->stream before the hop (outside the graph).
-void FlushPending(Engine* e) {
+void FlushPending(Engine* e, const std::vector<char>* kv_only = nullptr) {
   cudaStream_t s = e->stream;
   if (e->pitch_dirty) {
     B200_CHECK(cudaMemcpyAsync(e->pitch_params.p, e->pp.data(), e->pp.size() * sizeof(PitchParams),
@@ -164,30 +188,15 @@ void FlushPending(Engine* e) {
     e->pending_formant.clear();
   }
   // key-value speaker embedding: one block per stream per hop until all four are applied
-  for (int blk = 0; blk < kNBlocks; ++blk) {
-    std::vector<int> streams, spk;
-    for (int b = 0; b < e->B; ++b)
-      if (e->sp[b].kv_set_count == blk) {
-        streams.push_back(b);
-        spk.push_back(e->sp[b].speaker);
-      }
-    if (streams.empty()) continue;
-    UploadInts(e, &e->idx_a, spk);
-    UploadInts(e, &e->idx_b, streams);
-    LaunchKvFilm(e->kv.as<float>(), e->idx_a.as<int>(), static_cast<size_t>(kKvLength) * kKvChannels,
-                 e->setter_m.query[blk], e->setter_m.film_w[blk], e->setter_m.film_b[blk], kStageC[blk],
-                 e->wave_st.film[blk].as<float>(), e->idx_b.as<int>(), static_cast<int>(streams.size()), s);
-    ++e->launches;
-    for (int b : streams) e->sp[b].kv_set_count = -(blk + 1);  // mark, bumped below
-  }
-  for (int b = 0; b < e->B; ++b)
-    if (e->sp[b].kv_set_count < 0) e->sp[b].kv_set_count = -e->sp[b].kv_set_count;
+  StepKv(e, kv_only);
 }
 
-// Applies all remaining key-value blocks of `b` now (LoadModel / ResetContext do
-// `while (SetKeyValueSpeakerEmbedding());`, processor_core_2.cc:270, :414).
-void FlushAllKv(Engine* e) {
-  for (int round = 0; round < kNBlocks; ++round) FlushPending(e);
+// Applies all remaining key-value blocks of the streams in `only` now (LoadModel / ResetContext do
+// `while (SetKeyValueSpeakerEmbedding());`, processor_core_2.cc:270, :414) together with their queued speaker /
+// formant projections.  Streams outside `only` keep their one-block-per-hop schedule (processor_core_2.h:161-169).
+void FlushAllKv(Engine* e, const std::vector<char>& only) {
+  FlushPending(e, &only);   // queued projections + the first block
+  for (int round = 1; round < kNBlocks; ++round) StepKv(e, &only);
 }
 
 void BuildHop(Engine* e) {
@@ -318,7 +327,7 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
   }
   auto up = [&](DeviceBuffer* b, const float* h, size_t count) {
     b->Alloc(e->device, count * sizeof(float), false);
-    B200_CHECK(cudaMemcpy(b->p, h, count * sizeof(float), cudaMemcpyHostToDevice));
+    UploadSync(b->p, h, count * sizeof(float));
   };
   up(&e->codebooks, h_cb.data(), h_cb.size());
   up(&e->additive, h_add.data(), h_add.size());
@@ -366,7 +375,7 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
   }
   BuildHop(e);
   e->loaded = true;
-  FlushAllKv(e);  // speaker 0 with all four key-value blocks, like LoadModel (:411-414)
+  FlushAllKv(e, std::vector<char>(B, 1));  // speaker 0 with all four key-value blocks, like LoadModel (:411-414)
   B200_CHECK(cudaStreamSynchronize(e->stream));
   e->hops = 0;
   return 0;
@@ -430,10 +439,12 @@ const char* BeatriceB200_Version(void) { return "beatrice-b200 0.1 (spec M0, sm_
 BeatriceB200_Engine* BeatriceB200_CreateEngine(int device, int n_streams, int precision) {
   if (n_streams <= 0 || device < 0 || device >= UsableDeviceCount()) return nullptr;
   if (precision < BEATRICE_B200_PRECISION_F32 || precision > BEATRICE_B200_PRECISION_BF16X3) return nullptr;
+  if (Failed()) return nullptr;
   auto* e = new Engine();
   e->device = device;
   e->B = n_streams;
   e->precision = precision;
+  try {
   B200_CHECK(cudaSetDevice(device));
   if (std::getenv("BEATRICE_B200_MRF_TRACE")) {   // developer traces print one line per CTA: room for all of them
     cudaDeviceSetLimit(cudaLimitPrintfFifoSize, 64u << 20);
@@ -444,6 +455,10 @@ BeatriceB200_Engine* BeatriceB200_CreateEngine(int device, int n_streams, int pr
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_side, cudaEventDisableTiming));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  } catch (const Failure&) {
+    delete e;
+    return nullptr;
+  }
   return e;
 }
 
@@ -468,11 +483,17 @@ void BeatriceB200_DestroyEngine(BeatriceB200_Engine* e) {
 }
 
 int BeatriceB200_LoadModelFromMemory(BeatriceB200_Engine* e, const void* const images[5], const size_t sizes[5]) {
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(if (e) e->loaded = false; rc__ = BEATRICE_B200_ERR_DEVICE, rc__ = [&]() -> int {
   if (!e || !images || !sizes) return BEATRICE_B200_ERR_BAD_ARGUMENT;
   return LoadImages(e, images, sizes);
+  }(););
+  return rc__;
 }
 
 int BeatriceB200_LoadModel(BeatriceB200_Engine* e, const char* utf8_model_dir) {
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(if (e) e->loaded = false; rc__ = BEATRICE_B200_ERR_DEVICE, rc__ = [&]() -> int {
   if (!e || !utf8_model_dir) return BEATRICE_B200_ERR_BAD_ARGUMENT;
   static const char* kNames[5] = {"phone_extractor.bin", "pitch_estimator.bin", "waveform_generator.bin",
                                   "embedding_setter.bin", "speaker_embeddings.bin"};
@@ -486,6 +507,8 @@ int BeatriceB200_LoadModel(BeatriceB200_Engine* e, const char* utf8_model_dir) {
     sizes[i] = bytes[i].size();
   }
   return LoadImages(e, images, sizes);
+  }(););
+  return rc__;
 }
 
 int BeatriceB200_NumSpeakers(const BeatriceB200_Engine* e) { return e ? e->n_speakers : 0; }
@@ -578,6 +601,8 @@ int BeatriceB200_SetOutputGain(BeatriceB200_Engine* e, int stream, double db) {
 // Like ResetContext: only the model contexts are re-created; the resampler / FIFO / gain state of
 // AnyFreqInOut persists (processor_core_2.cc:258-266 touches the four library contexts only).
 int BeatriceB200_ResetStream(BeatriceB200_Engine* e, int stream) {
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(rc__ = BEATRICE_B200_ERR_DEVICE, rc__ = [&]() -> int {
   B200_SETTER_PROLOGUE();
   B200_CHECK(cudaSetDevice(e->device));
   B200_CHECK(cudaStreamSynchronize(e->stream));
@@ -586,6 +611,7 @@ int BeatriceB200_ResetStream(BeatriceB200_Engine* e, int stream) {
     e->pitch_st.ZeroAll(e->stream);
     e->wave_st.ZeroAll(e->stream);
   }
+  std::vector<char> only(e->B, 0);
   ForStreams(e, stream, [&](int b) {
     if (stream >= 0) {
       e->phone_st.ZeroStream(b, e->stream);
@@ -595,13 +621,20 @@ int BeatriceB200_ResetStream(BeatriceB200_Engine* e, int stream) {
     e->sp[b].kv_set_count = 0;
     e->pending_speaker.push_back(b);
     e->pending_formant.push_back(b);
+    only[b] = 1;
   });
-  FlushAllKv(e);  // ResetContext re-applies the speaker with all four blocks at once (:269-270)
+  // ResetContext re-applies the speaker with all four blocks at once (:269-270) -- for the streams being reset only;
+  // any other stream that is part-way through its own four-hop schedule keeps it
+  FlushAllKv(e, only);
   B200_CHECK(cudaStreamSynchronize(e->stream));
   return 0;
+  }(););
+  return rc__;
 }
 
 int BeatriceB200_ProcessFramesDevice(BeatriceB200_Engine* e, const float* in_dev, float* out_dev) {
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(rc__ = BEATRICE_B200_ERR_DEVICE, rc__ = [&]() -> int {
   if (!e || !in_dev || !out_dev) return BEATRICE_B200_ERR_BAD_ARGUMENT;
   if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
   B200_CHECK(cudaSetDevice(e->device));
@@ -610,9 +643,13 @@ int BeatriceB200_ProcessFramesDevice(BeatriceB200_Engine* e, const float* in_dev
   RunHop16(e, true);
   B200_CHECK(cudaMemcpyAsync(out_dev, e->wave_st.out.p, nout, cudaMemcpyDeviceToDevice, e->stream));
   return 0;
+  }(););
+  return rc__;
 }
 
 int BeatriceB200_ProcessFrames(BeatriceB200_Engine* e, const float* in_host, float* out_host) {
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(if (e && out_host) std::memset(out_host, 0, sizeof(float) * e->B * kOutHop); rc__ = BEATRICE_B200_ERR_DEVICE, rc__ = [&]() -> int {
   if (!e || !in_host || !out_host) return BEATRICE_B200_ERR_BAD_ARGUMENT;
   if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
   B200_CHECK(cudaSetDevice(e->device));
@@ -622,9 +659,13 @@ int BeatriceB200_ProcessFrames(BeatriceB200_Engine* e, const float* in_host, flo
   B200_CHECK(cudaMemcpyAsync(out_host, e->wave_st.out.p, nout, cudaMemcpyDeviceToHost, e->stream));
   B200_CHECK(cudaStreamSynchronize(e->stream));
   return 0;
+  }(););
+  return rc__;
 }
 
 int BeatriceB200_Process48kDevice(BeatriceB200_Engine* e, const float* in_dev, float* out_dev) {
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(rc__ = BEATRICE_B200_ERR_DEVICE, rc__ = [&]() -> int {
   if (!e || !in_dev || !out_dev) return BEATRICE_B200_ERR_BAD_ARGUMENT;
   if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
   B200_CHECK(cudaSetDevice(e->device));
@@ -633,9 +674,13 @@ int BeatriceB200_Process48kDevice(BeatriceB200_Engine* e, const float* in_dev, f
   RunHop48(e, true);
   B200_CHECK(cudaMemcpyAsync(out_dev, e->hostrate.out48(), n, cudaMemcpyDeviceToDevice, e->stream));
   return 0;
+  }(););
+  return rc__;
 }
 
 int BeatriceB200_Process48k(BeatriceB200_Engine* e, const float* in_host, float* out_host) {
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(if (e && out_host) std::memset(out_host, 0, sizeof(float) * e->B * kHostHop48k); rc__ = BEATRICE_B200_ERR_DEVICE, rc__ = [&]() -> int {
   if (!e || !in_host || !out_host) return BEATRICE_B200_ERR_BAD_ARGUMENT;
   if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
   B200_CHECK(cudaSetDevice(e->device));
@@ -645,17 +690,24 @@ int BeatriceB200_Process48k(BeatriceB200_Engine* e, const float* in_host, float*
   B200_CHECK(cudaStreamSynchronize(e->side));
   B200_CHECK(cudaStreamSynchronize(e->stream));
   return 0;
+  }(););
+  return rc__;
 }
 
 void BeatriceB200_Synchronize(BeatriceB200_Engine* e) {
+  B200_GUARDED((void)0, {
   if (!e) return;
   B200_CHECK(cudaSetDevice(e->device));
   B200_CHECK(cudaStreamSynchronize(e->stream));
+  });
 }
 
 void* BeatriceB200_AllocPinned(size_t bytes) {
   void* p = nullptr;
-  B200_CHECK(cudaMallocHost(&p, bytes ? bytes : 16));
+  if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
   return p;
 }
 void BeatriceB200_FreePinned(void* p) {
@@ -663,9 +715,11 @@ void BeatriceB200_FreePinned(void* p) {
 }
 void* BeatriceB200_AllocDevice(BeatriceB200_Engine* e, size_t bytes) {
   if (!e) return nullptr;
-  B200_CHECK(cudaSetDevice(e->device));
   void* p = nullptr;
-  B200_CHECK(cudaMalloc(&p, bytes ? bytes : 16));
+  if (cudaSetDevice(e->device) != cudaSuccess || cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
   return p;
 }
 void BeatriceB200_FreeDevice(BeatriceB200_Engine* e, void* p) {
@@ -674,19 +728,25 @@ void BeatriceB200_FreeDevice(BeatriceB200_Engine* e, void* p) {
   cudaFree(p);
 }
 void BeatriceB200_CopyToDevice(BeatriceB200_Engine* e, void* dst_dev, const void* src_host, size_t bytes) {
+  B200_GUARDED((void)0, {
   B200_CHECK(cudaSetDevice(e->device));
   B200_CHECK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, e->stream));
   B200_CHECK(cudaStreamSynchronize(e->stream));
+  });
 }
 void BeatriceB200_CopyToHost(BeatriceB200_Engine* e, void* dst_host, const void* src_dev, size_t bytes) {
+  B200_GUARDED(if (dst_host) std::memset(dst_host, 0, bytes), {
   B200_CHECK(cudaSetDevice(e->device));
   B200_CHECK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, e->stream));
   B200_CHECK(cudaStreamSynchronize(e->stream));
+  });
 }
 void* BeatriceB200_Stream(BeatriceB200_Engine* e) { return e ? static_cast<void*>(e->stream) : nullptr; }
 
 int BeatriceB200_GetLastIntermediates(BeatriceB200_Engine* e, float* phone, int* bin_raw, int* bin_used,
                                       float* feature4) {
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(rc__ = BEATRICE_B200_ERR_DEVICE, rc__ = [&]() -> int {
   if (!e) return BEATRICE_B200_ERR_BAD_ARGUMENT;
   if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
   B200_CHECK(cudaSetDevice(e->device));
@@ -698,6 +758,33 @@ int BeatriceB200_GetLastIntermediates(BeatriceB200_Engine* e, float* phone, int*
   if (bin_used) B200_CHECK(cudaMemcpy(bin_used, e->wave_st.q_in.p, sizeof(int) * B, cudaMemcpyDeviceToHost));
   if (feature4) B200_CHECK(cudaMemcpy(feature4, e->wave_st.feat_in.p, sizeof(float) * B * kPitchFeatures, cudaMemcpyDeviceToHost));
   return 0;
+  }(););
+  return rc__;
+}
+
+// Test / diagnostic entry: the call-site pitch transform (processor_core_2.cc:190-252) exactly as the hop graph
+// applies it -- every stream's CURRENT pitch parameters (as clamped by the setters above) on the device -- to
+// caller-supplied raw bins.  tests/ sweep it exhaustively against the reference's own compiled call site.
+int BeatriceB200_TransformPitchBins(BeatriceB200_Engine* e, const int* bins_raw_host, int* bins_out_host) {
+  if (!e || !bins_raw_host || !bins_out_host) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(rc__ = BEATRICE_B200_ERR_DEVICE, {
+    B200_CHECK(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    if (e->pitch_dirty) {
+      B200_CHECK(cudaMemcpyAsync(e->pitch_params.p, e->pp.data(), e->pp.size() * sizeof(PitchParams), cudaMemcpyHostToDevice, s));
+      e->pitch_dirty = false;
+    }
+    // idx_a / idx_b ([B] ints) are free between hops: stream order protects them
+    B200_CHECK(cudaMemcpyAsync(e->idx_a.p, bins_raw_host, sizeof(int) * e->B, cudaMemcpyHostToDevice, s));
+    LaunchPitchTransform(e->idx_a.as<int>(), e->pitch_params.as<PitchParams>(), e->dims.pitch_bins, e->idx_b.as<int>(), e->B, s);
+    ++e->launches;
+    B200_CHECK(cudaMemcpyAsync(bins_out_host, e->idx_b.p, sizeof(int) * e->B, cudaMemcpyDeviceToHost, s));
+    B200_CHECK(cudaStreamSynchronize(s));
+    rc__ = 0;
+  });
+  return rc__;
 }
 
 size_t BeatriceB200_ResidentBytes(const BeatriceB200_Engine* e) {
@@ -711,6 +798,8 @@ uint64_t BeatriceB200_KernelLaunchCount(const BeatriceB200_Engine* e) { return e
 
 int BeatriceB200_ProfileHop(BeatriceB200_Engine* e, const float* in_dev, float* out_dev,
                             BeatriceB200_KernelRecord* records, int capacity) {
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(rc__ = BEATRICE_B200_ERR_DEVICE, rc__ = [&]() -> int {
   if (!e || !in_dev || !out_dev) return BEATRICE_B200_ERR_BAD_ARGUMENT;
   if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
   B200_CHECK(cudaSetDevice(e->device));
@@ -748,6 +837,8 @@ int BeatriceB200_ProfileHop(BeatriceB200_Engine* e, const float* in_dev, float* 
   }
   for (auto& x : ev) cudaEventDestroy(x);
   return static_cast<int>(n);
+  }(););
+  return rc__;
 }
 
 }  // extern "C"

@@ -134,7 +134,7 @@ uint64_t Checksum(const float* p, size_t n) {
 // ---------------------------------------------------------------------------------------
 // per-frame entry points
 // ---------------------------------------------------------------------------------------
-void ExtractPhone(const PhoneExtractorObj* pe, const float* in, float* out, PhoneContextObj* c) {
+void ExtractPhoneImpl(const PhoneExtractorObj* pe, const float* in, float* out, PhoneContextObj* c) {
   const int P = c->dims.phone_channels;
   if (!pe->m.loaded) {
     std::memset(out, 0, sizeof(float) * P);
@@ -196,7 +196,7 @@ void ExtractPhone(const PhoneExtractorObj* pe, const float* in, float* out, Phon
   std::memcpy(out, c->out.p, sizeof(float) * P);
 }
 
-void EstimatePitch(const PitchEstimatorObj* pi, const float* in, int* q, float* feat, PitchContextObj* c) {
+void EstimatePitchImpl(const PitchEstimatorObj* pi, const float* in, int* q, float* feat, PitchContextObj* c) {
   if (!pi->m.loaded) {
     *q = 1;
     std::memset(feat, 0, sizeof(float) * kPitchFeatures);
@@ -241,8 +241,8 @@ void EstimatePitch(const PitchEstimatorObj* pi, const float* in, int* q, float* 
   std::memcpy(feat, c->out.as<float>() + 1, sizeof(float) * kPitchFeatures);
 }
 
-void GenerateWaveform(const WaveformGeneratorObj* wg, const float* phone, const int* q, const float* feat,
-                      const float* speaker_or_null, float* out, WaveformContextObj* c) {
+void GenerateWaveformImpl(const WaveformGeneratorObj* wg, const float* phone, const int* q, const float* feat,
+                          const float* speaker_or_null, float* out, WaveformContextObj* c) {
   if (!wg->m.loaded) {
     std::memset(out, 0, sizeof(float) * kOutHop);
     return;
@@ -287,6 +287,28 @@ void GenerateWaveform(const WaveformGeneratorObj* wg, const float* phone, const 
   std::memcpy(out, c->out.p, sizeof(float) * kOutHop);
 }
 
+// The guarded forms the ABI calls: on a (latched) failure the whole output is written as silence, like the call
+// site's own guards (processor_core_2.cc:26-43) -- never an abort, never a CPU fallback.
+void ExtractPhone(const PhoneExtractorObj* pe, const float* in, float* out, PhoneContextObj* c) {
+  B200_GUARDED(c->st.model = nullptr; std::memset(out, 0, sizeof(float) * c->dims.phone_channels), ExtractPhoneImpl(pe, in, out, c););
+}
+void EstimatePitch(const PitchEstimatorObj* pi, const float* in, int* q, float* feat, PitchContextObj* c) {
+  B200_GUARDED(c->st.model = nullptr; *q = 1; std::memset(feat, 0, sizeof(float) * kPitchFeatures), EstimatePitchImpl(pi, in, q, feat, c););
+}
+void GenerateWaveform(const WaveformGeneratorObj* wg, const float* phone, const int* q, const float* feat,
+                      const float* speaker_or_null, float* out, WaveformContextObj* c) {
+  B200_GUARDED(c->st.model = nullptr; std::memset(out, 0, sizeof(float) * kOutHop), GenerateWaveformImpl(wg, phone, q, feat, speaker_or_null, out, c););
+}
+// Read*Parameters: host-side validation errors keep their Beatrice_ErrorCode (beatrice.h:30-37); a device failure
+// while uploading reads as kFileOpenError (1) -- the model is not usable, and the call site surfaces the code
+// (processor_core_2.cc:302-351)
+template <class M>
+int GuardedLoad(M* m, const char* path) {
+  int rc = 1;
+  B200_GUARDED(m->loaded = false; rc = 1, rc = m->LoadFromFile(path););
+  return rc;
+}
+
 int ReadSpeakerTable(int family, const char* path, std::vector<uint8_t>* bytes, FileImage* img) {
   if (const int e = LoadFileBytes(path, bytes)) return e;
   const FamilyDims d = kFamilies[family];
@@ -315,7 +337,7 @@ int ReadSpeakerTable(int family, const char* path, std::vector<uint8_t>* bytes, 
   }                                                                                                 \
   void PFX##_DestroyPhoneContext1(void* p) { delete static_cast<PhoneContextObj*>(p); }             \
   int PFX##_ReadPhoneExtractorParameters(void* m, const char* path) {                               \
-    return static_cast<PhoneExtractorObj*>(m)->m.LoadFromFile(path);                                \
+    return GuardedLoad(&static_cast<PhoneExtractorObj*>(m)->m, path);                                \
   }                                                                                                 \
   void PFX##_ExtractPhone1(const void* m, const float* in, float* out, void* c) {                   \
     ExtractPhone(static_cast<const PhoneExtractorObj*>(m), in, out, static_cast<PhoneContextObj*>(c)); \
@@ -335,7 +357,7 @@ int ReadSpeakerTable(int family, const char* path, std::vector<uint8_t>* bytes, 
   }                                                                                                 \
   void PFX##_DestroyPitchContext1(void* p) { delete static_cast<PitchContextObj*>(p); }             \
   int PFX##_ReadPitchEstimatorParameters(void* m, const char* path) {                               \
-    return static_cast<PitchEstimatorObj*>(m)->m.LoadFromFile(path);                                \
+    return GuardedLoad(&static_cast<PitchEstimatorObj*>(m)->m, path);                                \
   }                                                                                                 \
   void PFX##_SetMinQuantizedPitch(void* c, int v) {                                                 \
     auto* o = static_cast<PitchContextObj*>(c);                                                     \
@@ -370,7 +392,7 @@ int ReadSpeakerTable(int family, const char* path, std::vector<uint8_t>* bytes, 
   }                                                                                                 \
   void PFX##_DestroyWaveformContext1(void* p) { delete static_cast<WaveformContextObj*>(p); }       \
   int PFX##_ReadWaveformGeneratorParameters(void* m, const char* path) {                            \
-    return static_cast<WaveformGeneratorObj*>(m)->m.LoadFromFile(path);                             \
+    return GuardedLoad(&static_cast<WaveformGeneratorObj*>(m)->m, path);                             \
   }                                                                                                 \
   }
 
@@ -446,7 +468,7 @@ void Beatrice20rc0_DestroyEmbeddingSetter(void* p) { delete static_cast<Embeddin
 void* Beatrice20rc0_CreateEmbeddingContext(void) { return new EmbeddingContextObj(); }
 void Beatrice20rc0_DestroyEmbeddingContext(void* p) { delete static_cast<EmbeddingContextObj*>(p); }
 int Beatrice20rc0_ReadEmbeddingSetterParameters(void* m, const char* path) {
-  return static_cast<EmbeddingSetterObj*>(m)->m.LoadFromFile(path);
+  return GuardedLoad(&static_cast<EmbeddingSetterObj*>(m)->m, path);
 }
 
 // beatrice.h:318-322.  Only the pointer is recorded; the 256 KiB slice is uploaded lazily and
@@ -458,8 +480,9 @@ void Beatrice20rc0_SetCodebook(void* c, const float* codebook) {
   o->host_codebook = codebook;
 }
 
-static void ProjectInto(const float* W, const float* b, const float* emb, WaveformContextObj* wc, float* dst) {
+static void ProjectInto(const float* W, const float* b, const float* emb, WaveformContextObj* wc, bool formant) {
   wc->EnsureCond();
+  float* dst = formant ? wc->st.formant.as<float>() : wc->st.spk.as<float>();
   B200_CHECK(cudaSetDevice(wc->stream.device));
   cudaStream_t s = wc->stream.s;
   B200_CHECK(cudaMemcpyAsync(wc->emb_tmp.p, emb, sizeof(float) * kHidden, cudaMemcpyHostToDevice, s));
@@ -473,26 +496,29 @@ void Beatrice20rc0_SetAdditiveSpeakerEmbedding(const void* m, const float* emb, 
   const auto* es = static_cast<const EmbeddingSetterObj*>(m);
   if (!es->m.loaded) return;
   auto* wc = static_cast<WaveformContextObj*>(wc_);
-  wc->EnsureCond();
-  ProjectInto(es->m.add_w, es->m.add_b, emb, wc, wc->st.spk.as<float>());
+  B200_GUARDED((void)0, ProjectInto(es->m.add_w, es->m.add_b, emb, wc, false););
 }
 // beatrice.h:328-332
 void Beatrice20rc0_SetFormantShiftEmbedding(const void* m, const float* emb, void* /*ec*/, void* wc_) {
   const auto* es = static_cast<const EmbeddingSetterObj*>(m);
   if (!es->m.loaded) return;
   auto* wc = static_cast<WaveformContextObj*>(wc_);
-  wc->EnsureCond();
-  ProjectInto(es->m.for_w, es->m.for_b, emb, wc, wc->st.formant.as<float>());
+  B200_GUARDED((void)0, ProjectInto(es->m.for_w, es->m.for_b, emb, wc, true););
 }
 // beatrice.h:333-338
 void Beatrice20rc0_RegisterKeyValueSpeakerEmbedding(const void* /*m*/, const float* kv, void* ec_) {
   auto* ec = static_cast<EmbeddingContextObj*>(ec_);
-  const int dev = DefaultDevice();
-  const size_t bytes = sizeof(float) * kKvLength * kKvChannels;
-  if (!ec->kv.p) ec->kv.Alloc(dev, bytes, false);
-  B200_CHECK(cudaSetDevice(ec->kv.device));
-  B200_CHECK(cudaMemcpy(ec->kv.p, kv, bytes, cudaMemcpyHostToDevice));
-  ec->registered = true;
+  B200_GUARDED(ec->registered = false, {
+    const int dev = DefaultDevice();
+    const size_t bytes = sizeof(float) * kKvLength * kKvChannels;
+    if (!ec->kv.p) ec->kv.Alloc(dev, bytes, false);
+    B200_CHECK(cudaSetDevice(ec->kv.device));
+    // synchronous copy + device-wide sync: the consumer (kv_film_kernel) runs on the waveform context's non-blocking
+    // stream, which does not order against the legacy stream a pageable cudaMemcpy may still be draining on
+    B200_CHECK(cudaMemcpy(ec->kv.p, kv, bytes, cudaMemcpyHostToDevice));
+    B200_CHECK(cudaDeviceSynchronize());
+    ec->registered = true;
+  });
 }
 // beatrice.h:339-343
 void Beatrice20rc0_SetKeyValueSpeakerEmbedding(const void* m, int block, void* ec_, void* wc_) {
@@ -500,19 +526,22 @@ void Beatrice20rc0_SetKeyValueSpeakerEmbedding(const void* m, int block, void* e
   auto* ec = static_cast<EmbeddingContextObj*>(ec_);
   auto* wc = static_cast<WaveformContextObj*>(wc_);
   if (!es->m.loaded || !ec->registered || block < 0 || block >= kNBlocks) return;
-  wc->EnsureCond();
-  B200_CHECK(cudaSetDevice(wc->stream.device));
-  static const int kC[4] = {128, 64, 32, 16};
-  LaunchKvFilm(ec->kv.as<float>(), nullptr, 0, es->m.query[block], es->m.film_w[block], es->m.film_b[block],
-               kC[block], wc->st.film[block].as<float>(), nullptr, 1, wc->stream.s);
-  g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-  B200_CHECK(cudaStreamSynchronize(wc->stream.s));
+  B200_GUARDED((void)0, {
+    wc->EnsureCond();
+    B200_CHECK(cudaSetDevice(wc->stream.device));
+    static const int kC[4] = {128, 64, 32, 16};
+    LaunchKvFilm(ec->kv.as<float>(), nullptr, 0, es->m.query[block], es->m.film_w[block], es->m.film_b[block],
+                 kC[block], wc->st.film[block].as<float>(), nullptr, 1, wc->stream.s);
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    B200_CHECK(cudaStreamSynchronize(wc->stream.s));
+  });
 }
 
 // test-only tap (include/beatrice_b200.h)
 int BeatriceB200_WaveformTap(const void* wc_, int which, float* out, int capacity) {
   const auto* wc = static_cast<const WaveformContextObj*>(wc_);
-  if (!wc->st.model || wc->hops == 0) return -1;
+  if (!wc->st.model || wc->hops == 0 || Failed()) return -1;
+  try {
   B200_CHECK(cudaSetDevice(wc->stream.device));
   B200_CHECK(cudaStreamSynchronize(wc->stream.s));
   const uint64_t last = wc->hops - 1;
@@ -539,6 +568,18 @@ int BeatriceB200_WaveformTap(const void* wc_, int which, float* out, int capacit
   const int n = static_cast<int>(v.size());
   if (out && capacity >= n) std::memcpy(out, v.data(), sizeof(float) * n);
   return n;
+  } catch (const Failure&) {
+    return -1;
+  }
 }
+
+// Arithmetic of the contexts behind beatrice.h that are BUILT after this call (a context builds on its first
+// per-frame call, or when it meets a new model): BEATRICE_B200_PRECISION_* or -1 for the default.
+void BeatriceB200_SetDefaultPrecision(int precision) { SetDefaultTcMode(precision); }
+
+// sticky failure state (b200_common.h)
+int BeatriceB200_LastError(void) { return LastErrorCode(); }
+const char* BeatriceB200_LastErrorString(void) { return LastErrorText(); }
+void BeatriceB200_ClearError(void) { ClearError(); }
 
 }  // extern "C"

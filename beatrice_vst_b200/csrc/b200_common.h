@@ -6,20 +6,60 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <exception>
 
-// The per-frame ABI returns void (reference lib/beatricelib/beatrice.h:243-247, :266-271,
-// :301-307), so a CUDA failure has no error channel: fail loudly, never fall back to a CPU.
+// The per-frame ABI returns void and "must never fail visibly" (reference lib/beatricelib/beatrice.h:243-247,
+// :266-271, :301-307; the call site's own guards zero the output and return a code,
+// src/common/processor_core_2.cc:26-43).  A CUDA failure therefore never kills the host process:
+// B200_CHECK latches a sticky library-wide error (first failure wins, one line on stderr), and throws
+// b200::Failure, which every extern "C" entry point catches -- per-frame calls then write silence, loaders
+// return an error code.  While the error is latched every later per-frame call short-circuits to silence;
+// BeatriceB200_LastError / _LastErrorString / _ClearError (include/beatrice_b200.h) expose it.  There is still no
+// CPU fallback.  BEATRICE_B200_ABORT_ON_ERROR=1 restores abort() for debugging.
+namespace b200 {
+struct Failure {
+  int code;  // cudaError_t, or a negative BEATRICE_B200_ERR_* value for non-CUDA conditions
+};
+[[noreturn]] void Fail(int code, const char* what, const char* file, int line);
+bool Failed();                 // a failure is latched
+int LastErrorCode();           // 0 when none
+const char* LastErrorText();   // "" when none; stable storage
+void ClearError();
+void NoteException(const char* what) noexcept;   // latches a host-side exception (bad_alloc ...) without throwing
+}  // namespace b200
+
 #define B200_CHECK(expr)                                                                          \
   do {                                                                                            \
     cudaError_t err__ = (expr);                                                                   \
-    if (err__ != cudaSuccess) {                                                                   \
-      std::fprintf(stderr, "[libbeatrice_b200] FATAL %s:%d: %s -> %s\n", __FILE__, __LINE__, #expr, \
-                   cudaGetErrorString(err__));                                                    \
-      std::abort();                                                                               \
-    }                                                                                             \
+    if (err__ != cudaSuccess) b200::Fail(static_cast<int>(err__), #expr, __FILE__, __LINE__);     \
+  } while (0)
+
+// Body of an extern "C" entry point: runs `...` unless a failure is latched; on failure runs `on_fail`.
+#define B200_GUARDED(on_fail, ...)                 \
+  do {                                             \
+    if (b200::Failed()) {                          \
+      on_fail;                                     \
+    } else {                                       \
+      try {                                        \
+        __VA_ARGS__                                \
+      } catch (const b200::Failure&) {             \
+        on_fail;                                   \
+      } catch (const std::exception& ex__) {       \
+        b200::NoteException(ex__.what());          \
+        on_fail;                                   \
+      }                                            \
+    }                                              \
   } while (0)
 
 namespace b200 {
+
+// Load-time host -> device upload.  A cudaMemcpy from pageable memory may return once the bytes are staged, before
+// the DMA into `dst` has finished, and the kernels that read `dst` run on cudaStreamNonBlocking streams, which do not
+// order against the legacy stream the copy drains on: wait for the device before anyone can consume the data.
+inline void UploadSync(void* dst, const void* src, size_t bytes) {
+  B200_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  B200_CHECK(cudaDeviceSynchronize());
+}
 
 // Programmatic dependent launch: the kernel may begin (prologue up to its griddepcontrol.wait)
 // while the previous kernel on `s` drains.  BEATRICE_B200_NO_PDL=1 turns the attribute off.

@@ -599,16 +599,10 @@ void LaunchResStack(const ResStackParams& p, int C, cudaStream_t s) {
   // the single-inbox hand-shake (see the kernel) covers residual blocks, heads and the pre conv anywhere, the
   // front conv and the conditioning block only as the first block of a chain
   for (int r = 1; r < p.n_blk; ++r)
-    if (p.kind[r] == 1 || p.kind[r] == 4) {
-      std::fprintf(stderr, "[libbeatrice_b200] FATAL: chain block %d of kind %d must be the first of its chain\n", r, p.kind[r]);
-      std::abort();
-    }
+    if (p.kind[r] == 1 || p.kind[r] == 4) Fail(-103, "chain block of kind 1 / 4 must be the first of its chain", __FILE__, __LINE__);
   if (C == 256) LaunchResStackT<256>(p, s);
   else if (C == 128) LaunchResStackT<128>(p, s);
-  else {
-    std::fprintf(stderr, "[libbeatrice_b200] FATAL: residual-stack kernel has no C = %d form\n", C);
-    std::abort();
-  }
+  else Fail(-104, "residual-stack kernel has no form for this width", __FILE__, __LINE__);
   B200_CHECK(cudaGetLastError());
 }
 

@@ -9,6 +9,56 @@ namespace b200 {
 
 std::atomic<uint64_t> g_kernel_launches{0};
 
+// ---------------------------------------------------------------------------------------
+// sticky failure state (b200_common.h): first failure wins, later per-frame calls write silence
+// ---------------------------------------------------------------------------------------
+namespace {
+std::atomic<int> g_error_code{0};
+std::mutex g_error_mu;
+char g_error_text[512] = "";
+bool AbortOnError() {
+  static const bool on = [] {
+    const char* e = std::getenv("BEATRICE_B200_ABORT_ON_ERROR");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+void Latch(int code, const char* text) noexcept {
+  std::lock_guard<std::mutex> lock(g_error_mu);
+  if (g_error_code.load(std::memory_order_relaxed) != 0) return;
+  std::snprintf(g_error_text, sizeof(g_error_text), "%s", text);
+  std::fprintf(stderr, "[libbeatrice_b200] ERROR (latched; output is silence until cleared): %s\n", g_error_text);
+  g_error_code.store(code, std::memory_order_release);
+}
+}  // namespace
+
+void Fail(int code, const char* what, const char* file, int line) {
+  char text[480];
+  if (code > 0) {
+    std::snprintf(text, sizeof(text), "%s:%d: %s -> %s", file, line, what, cudaGetErrorString(static_cast<cudaError_t>(code)));
+    (void)cudaGetLastError();   // non-sticky CUDA errors are consumed; sticky ones keep failing and keep being caught
+  } else {
+    std::snprintf(text, sizeof(text), "%s:%d: %s", file, line, what);
+  }
+  Latch(code, text);
+  if (AbortOnError()) std::abort();
+  throw Failure{code};
+}
+bool Failed() { return g_error_code.load(std::memory_order_acquire) != 0; }
+int LastErrorCode() { return g_error_code.load(std::memory_order_acquire); }
+const char* LastErrorText() { return Failed() ? g_error_text : ""; }
+void ClearError() {
+  std::lock_guard<std::mutex> lock(g_error_mu);
+  (void)cudaGetLastError();
+  g_error_code.store(0, std::memory_order_release);
+  g_error_text[0] = 0;
+}
+void NoteException(const char* what) noexcept {
+  char text[480];
+  std::snprintf(text, sizeof(text), "host exception: %s", what ? what : "?");
+  Latch(-100, text);
+}
+
 // network spec "M0" (SURVEY.md App. B / beatrice_vst_b200/model_spec.py); the product's own
 // statement of it -- the oracle and the torch cross-check each carry an independent one.
 namespace spec {
@@ -119,29 +169,35 @@ int UsableDeviceCount() {
 int DefaultDevice() {
   static int dev = [] {
     const int n = UsableDeviceCount();
-    if (n <= 0) {
-      std::fprintf(stderr,
-                   "[libbeatrice_b200] FATAL: no usable CUDA device; this library has no CPU fallback.\n");
-      std::abort();
-    }
+    if (n <= 0) return -1;
     const char* e = std::getenv("BEATRICE_B200_DEVICE");
     int d = e ? std::atoi(e) : 0;
-    if (d < 0 || d >= n) d = 0;
+    if (d < 0 || d >= n) return -1;   // an explicit, unusable choice is an error, not a silent move to device 0
     return d;
   }();
+  // no device: latched like any other failure (silence out, error codes from the loaders) -- never a CPU fallback
+  if (dev < 0) Fail(-101, "no usable CUDA device (or BEATRICE_B200_DEVICE out of range); this library has no CPU fallback", __FILE__, __LINE__);
   return dev;
 }
 
+namespace {
+std::atomic<int> g_precision_override{-1};
+}
+void SetDefaultTcMode(int mode) { g_precision_override.store(mode >= 0 && mode <= 2 ? mode : -1, std::memory_order_relaxed); }
+
 TcMode DefaultTcMode() {
+  const int ov = g_precision_override.load(std::memory_order_relaxed);
+  if (ov >= 0) return static_cast<TcMode>(ov);
   static TcMode mode = [] {
     const char* e = std::getenv("BEATRICE_B200_PRECISION");
-    if (!e) return kTcOff;
+    // default: split-bf16 on tcgen05 -- the fastest mode inside the <= 1e-4 RMS bar; f32 (CUDA cores) is opt-in
+    if (!e) return kTcSplit;
     const std::string v(e);
     if (v == "bf16") return kTcBf16;
-    if (v == "bf16x3") return kTcSplit;
-    if (v == "f32" || v.empty()) return kTcOff;
-    std::fprintf(stderr, "[libbeatrice_b200] FATAL: BEATRICE_B200_PRECISION=%s (expected f32|bf16|bf16x3)\n", e);
-    std::abort();
+    if (v == "bf16x3" || v.empty()) return kTcSplit;
+    if (v == "f32") return kTcOff;
+    std::fprintf(stderr, "[libbeatrice_b200] warning: BEATRICE_B200_PRECISION=%s ignored (expected f32|bf16|bf16x3); using bf16x3\n", e);
+    return kTcSplit;
   }();
   return mode;
 }
@@ -168,7 +224,7 @@ void TcWeights::Pack(int device, const float* host_blob, const float* dev_blob, 
     slots.push_back({c, off, off + n});
   }
   buf.Alloc(device, all.size() * sizeof(uint16_t), false);
-  B200_CHECK(cudaMemcpy(buf.p, all.data(), all.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  UploadSync(buf.p, all.data(), all.size() * sizeof(uint16_t));
   for (const Slot& sl : slots) {
     sl.c->tc_hi = buf.as<uint16_t>() + sl.off_hi;
     sl.c->tc_lo = buf.as<uint16_t>() + sl.off_lo;
@@ -244,7 +300,7 @@ ConvW TakeConv(Cursor* c, int k, int cin, int cout) {
 }
 void Upload(DeviceBuffer* buf, int dev, const float* host, size_t n) {
   buf->Alloc(dev, n * sizeof(float), false);
-  B200_CHECK(cudaMemcpy(buf->p, host, n * sizeof(float), cudaMemcpyHostToDevice));
+  UploadSync(buf->p, host, n * sizeof(float));
 }
 }  // namespace
 
@@ -324,7 +380,7 @@ int EncoderModel::LoadFromImage(const void* data, size_t size, int on_device) {
     std::vector<uint16_t> packed(PackChainWeights(layers.data(), rs_n_blk, width, nullptr));
     PackChainWeights(layers.data(), rs_n_blk, width, packed.data());
     rs_w.Alloc(device, packed.size() * sizeof(uint16_t), false);
-    B200_CHECK(cudaMemcpy(rs_w.p, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    UploadSync(rs_w.p, packed.data(), packed.size() * sizeof(uint16_t));
     Upload(&rs_par, device, par.data(), par.size());
     rs_bias = rs_par.as<float>();
     rs_gamma = rs_bias + static_cast<size_t>(rs_n_blk) * width;
@@ -401,7 +457,7 @@ int WaveModel::LoadFromImage(const void* data, size_t size, int on_device) {
       std::vector<uint16_t> packed(PackChainWeights(&layer, 1, kHidden, nullptr));
       PackChainWeights(&layer, 1, kHidden, packed.data());
       pre_w.Alloc(device, packed.size() * sizeof(uint16_t), false);
-      B200_CHECK(cudaMemcpy(pre_w.p, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      UploadSync(pre_w.p, packed.data(), packed.size() * sizeof(uint16_t));
       std::vector<float> par(static_cast<size_t>(3) * kHidden, 0.0f);   // bias | gamma (unused) | beta (unused)
       std::memcpy(par.data(), c.HostAt(pre.b), sizeof(float) * kHidden);
       Upload(&pre_par, device, par.data(), par.size());
@@ -414,7 +470,7 @@ int WaveModel::LoadFromImage(const void* data, size_t size, int on_device) {
         std::vector<uint16_t> packed2(PackChainWeights(layers, 2, kHidden, nullptr));
         PackChainWeights(layers, 2, kHidden, packed2.data());
         cond_pre_w.Alloc(device, packed2.size() * sizeof(uint16_t), false);
-        B200_CHECK(cudaMemcpy(cond_pre_w.p, packed2.data(), packed2.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        UploadSync(cond_pre_w.p, packed2.data(), packed2.size() * sizeof(uint16_t));
         std::vector<float> par2(static_cast<size_t>(3) * 2 * kHidden, 0.0f);   // bias[2][C] | gamma[2][C] | beta[2][C]
         std::memcpy(par2.data(), c.HostAt(embed.b), sizeof(float) * kHidden);
         std::memcpy(par2.data() + kHidden, c.HostAt(pre.b), sizeof(float) * kHidden);
@@ -460,7 +516,7 @@ int WaveModel::LoadFromImage(const void* data, size_t size, int on_device) {
     for (int sp = 0; sp < 2; ++sp) {
       mrf_w[sp].Alloc(device, packed[sp].size() * sizeof(uint16_t), false);
       if (!packed[sp].empty())
-        B200_CHECK(cudaMemcpy(mrf_w[sp].p, packed[sp].data(), packed[sp].size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        UploadSync(mrf_w[sp].p, packed[sp].data(), packed[sp].size() * sizeof(uint16_t));
     }
     for (int s = 0; s < 4; ++s)
       for (int ki = 0; ki < 3; ++ki) {
@@ -512,10 +568,7 @@ int SetterModel::LoadFromFile(const char* path, int on_device) {
 // ---------------------------------------------------------------------------------------
 static int SlotsFor(int history_rows, int T) {
   const int slots = history_rows > 0 ? (history_rows + T - 1) / T + 1 : 1;
-  if (slots > 16) {
-    std::fprintf(stderr, "[libbeatrice_b200] FATAL: ring needs %d slots (> 16)\n", slots);
-    std::abort();
-  }
+  if (slots > 16) Fail(-102, "ring needs more than 16 slots", __FILE__, __LINE__);
   return slots;
 }
 int StateArena::Plan(int history_rows, int T, int C) {
@@ -755,7 +808,7 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
   const int head_idx = db.Add(hd);
 
   descs.Alloc(device, sizeof(ConvDesc) * db.host.size(), false);
-  B200_CHECK(cudaMemcpy(descs.p, db.host.data(), sizeof(ConvDesc) * db.host.size(), cudaMemcpyHostToDevice));
+  UploadSync(descs.p, db.host.data(), sizeof(ConvDesc) * db.host.size());
   const ConvDesc* dd = descs.as<ConvDesc>();
   const int* frame = arena.frame();
   const int Bn = B;
@@ -796,7 +849,7 @@ void EncoderState::Build(const EncoderModel* m, int B_, int device_, const float
     ResStackHistBlocks(m->width, m->n_res, m->dil, B, rs_hist.as<uint16_t>(), &blocks);
     n_rs_blocks = static_cast<int>(blocks.size());
     rs_blocks.Alloc(device, sizeof(MrfHistBlock) * blocks.size(), false);
-    B200_CHECK(cudaMemcpy(rs_blocks.p, blocks.data(), sizeof(MrfHistBlock) * blocks.size(), cudaMemcpyHostToDevice));
+    UploadSync(rs_blocks.p, blocks.data(), sizeof(MrfHistBlock) * blocks.size());
     ResStackParams rp;
     std::memset(&rp, 0, sizeof(rp));
     const Ring& fin = arena.ring(ring_in[5]);           // front layer 5 reads the hop's two rows of layer 4's output
@@ -1032,7 +1085,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
     n_mrf_blocks = static_cast<int>(blocks.size());
     mrf_blocks.Alloc(device, sizeof(MrfHistBlock) * std::max<size_t>(blocks.size(), 1), true);
     if (!blocks.empty())
-      B200_CHECK(cudaMemcpy(mrf_blocks.p, blocks.data(), sizeof(MrfHistBlock) * blocks.size(), cudaMemcpyHostToDevice));
+      UploadSync(mrf_blocks.p, blocks.data(), sizeof(MrfHistBlock) * blocks.size());
   }
 
   DescBuilder db;
@@ -1094,7 +1147,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
   const int post_idx = db.Add(pd);
 
   descs.Alloc(device, sizeof(ConvDesc) * db.host.size(), false);
-  B200_CHECK(cudaMemcpy(descs.p, db.host.data(), sizeof(ConvDesc) * db.host.size(), cudaMemcpyHostToDevice));
+  UploadSync(descs.p, db.host.data(), sizeof(ConvDesc) * db.host.size());
   const ConvDesc* dd = descs.as<ConvDesc>();
   const int* frame = arena.frame();
   const int Bn = B;
@@ -1139,7 +1192,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
     ResStackHistBlocks(kHidden, 1, &d3, B, pre_hist.as<uint16_t>(), &blocks);
     n_pre_blocks = static_cast<int>(blocks.size());
     pre_blocks.Alloc(device, sizeof(MrfHistBlock) * blocks.size(), false);
-    B200_CHECK(cudaMemcpy(pre_blocks.p, blocks.data(), sizeof(MrfHistBlock) * blocks.size(), cudaMemcpyHostToDevice));
+    UploadSync(pre_blocks.p, blocks.data(), sizeof(MrfHistBlock) * blocks.size());
     ResStackParams rp;
     std::memset(&rp, 0, sizeof(rp));
     rp.x_in = arena.ring(ring_hidden).base;             // [B][256]: the hop's conditioning row (one slot)
@@ -1310,7 +1363,14 @@ void GraphRunner::Run(cudaStream_t s, const std::function<void(cudaStream_t)>& b
   if (!exec_) {
     cudaGraph_t graph = nullptr;
     B200_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    body(s);
+    try {
+      body(s);
+    } catch (...) {   // leave capture mode before the failure travels up to the ABI boundary
+      cudaStreamEndCapture(s, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      (void)cudaGetLastError();
+      throw;
+    }
     B200_CHECK(cudaStreamEndCapture(s, &graph));
     B200_CHECK(cudaGraphInstantiate(&exec_, graph, 0));
     B200_CHECK(cudaGraphDestroy(graph));

@@ -76,7 +76,8 @@ struct ConvW {
 // Precision of the conv GEMMs: fp32 CUDA cores (parity path), bf16 tcgen05, or split-bf16
 // tcgen05 (hi/lo decomposition, three MMAs, near-fp32 accuracy).
 enum TcMode : int { kTcOff = 0, kTcBf16 = 1, kTcSplit = 2 };
-TcMode DefaultTcMode();  // env BEATRICE_B200_PRECISION = f32 | bf16 | bf16x3 (default f32)
+TcMode DefaultTcMode();  // BeatriceB200_SetDefaultPrecision, else env BEATRICE_B200_PRECISION = f32 | bf16 | bf16x3 (default bf16x3)
+void SetDefaultTcMode(int mode);  // 0..2, anything else: back to the environment / built-in default
 
 // bf16 re-packing of a set of conv weights, resident in HBM next to the fp32 blob.
 struct TcWeights {

@@ -77,15 +77,21 @@ __global__ void __launch_bounds__(kHop) hostrate_out_kernel(const float* __restr
   __shared__ float z[kZHist + kOutHop];
   __shared__ double amp[kHop];
   __shared__ float c[kTaps];
+  __shared__ int frame_s;
   const int b = blockIdx.x, tid = threadIdx.x;
-  const int frame = frame_value >= 0 ? frame_value : *frame_ptr;
+  // ONE read of the hop counter per block, published through shared memory: the last block to arrive below
+  // advances the counter, and no thread of any block may look at it after that
+  if (tid == 0) frame_s = frame_value >= 0 ? frame_value : *frame_ptr;
+  __syncthreads();
+  const int frame = frame_s;
   const int cur = frame % 3, p1 = (frame + 2) % 3, p2 = (frame + 1) % 3;
   float* ring_b = o_ring + static_cast<long long>(b) * 3 * kOutHop;
   if (store) {
     PdlWait();   // o24 is the previous kernel's output (no-op unless launched with the PDL attribute)
     if (tid < kOutHop) ring_b[cur * kOutHop + tid] = o24[b * kOutHop + tid];  // becomes hop c+1's input
     if (tid == 0 && atomicAdd(done, 1) == static_cast<int>(gridDim.x) - 1) {
-      // every block read the counter on entry; the last one out advances it (wrap: see advance_kernel)
+      // every block's thread 0 read the counter before arriving here (and its other threads use frame_s); the last
+      // one to arrive advances it (wrap: see advance_kernel)
       *done = 0;
       *frame_ptr = (frame + 1 >= 738017280) ? 0 : frame + 1;
     }
@@ -155,7 +161,7 @@ void HostRateState::Init(int device, int B) {
     table[kTaps + i] = static_cast<float>(cutoff_up * sinc_up * window);
   }
   coef_.Alloc(device, sizeof(table), false);
-  B200_CHECK(cudaMemcpy(coef_.p, table, sizeof(table), cudaMemcpyHostToDevice));
+  UploadSync(coef_.p, table, sizeof(table));
   gin_.assign(B, HostGain());
   gout_.assign(B, HostGain());
   hseg_in_.assign(B, GainSeg{1.0, 1.0, 1.0, 0, 0});

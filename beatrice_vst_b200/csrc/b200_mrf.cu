@@ -579,8 +579,7 @@ void LaunchMrfStage(const MrfStageParams& p, int C, bool split, cudaStream_t s) 
     B200_MRF_CASE(64);
     B200_MRF_CASE(128);
     default:
-      std::fprintf(stderr, "[libbeatrice_b200] FATAL: fused MRF kernel has no C = %d form\n", C);
-      std::abort();
+      Fail(-105, "fused MRF kernel has no form for this width", __FILE__, __LINE__);
   }
 #undef B200_MRF_CASE
   B200_CHECK(cudaGetLastError());

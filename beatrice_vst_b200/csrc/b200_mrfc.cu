@@ -561,8 +561,7 @@ void LaunchMrfStageCluster(const MrfStageParams& p, int C, int NC, bool split, c
   B200_MRFC_CASE(64, 2)
   B200_MRFC_CASE(64, 4)
 #undef B200_MRFC_CASE
-  std::fprintf(stderr, "[libbeatrice_b200] FATAL: cluster MRF kernel has no C = %d / NC = %d form\n", C, NC);
-  std::abort();
+  Fail(-106, "cluster MRF kernel has no form for this width / cluster size", __FILE__, __LINE__);
 }
 
 }  // namespace b200

@@ -1,11 +1,11 @@
 """ctypes bindings for the beatricelib C ABI (reference ``lib/beatricelib/beatrice.h``).
 
-The same binding class drives both the CUDA product library
-(``csrc/libbeatrice_b200.so``) and -- in tests, ``smoke()`` and the bench's CPU
-baseline only -- the CPU oracle, because both export the identical ABI.
+Binds the CUDA product library (``csrc/libbeatrice_b200.so``).  The class is ABI-generic, which is why the
+test infrastructure (``oracle/loader.py``) can reuse it for the CPU oracle -- nothing in this package loads
+or knows about the oracle.
 
-There is no CPU fallback: :func:`load_product` raises if the CUDA library is
-missing, and the library's own calls abort loudly when no GPU is usable.
+There is no CPU fallback: :func:`load_product` raises if the CUDA library is missing; with no usable GPU the
+library latches an error (``BeatriceB200_LastError``), reports it on stderr and writes silence.
 """
 from __future__ import annotations
 
@@ -17,7 +17,6 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
 PRODUCT_SO = os.path.join(_HERE, "csrc", "libbeatrice_b200.so")
-ORACLE_SO = os.path.join(REPO_ROOT, "oracle", "libbeatrice_oracle.so")
 
 IN_HOP = 160
 OUT_HOP = 240
@@ -114,11 +113,6 @@ class BeatriceLib:
 
 def load_product() -> BeatriceLib:
     return BeatriceLib(PRODUCT_SO)
-
-
-def load_oracle() -> BeatriceLib:
-    """Test infrastructure only (tests/, smoke(), bench cpu_baseline)."""
-    return BeatriceLib(ORACLE_SO)
 
 
 class SingleStream:

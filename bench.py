@@ -155,7 +155,8 @@ def cpu_reference_run(model_toml: str, threads: int, frames_per_thread: int, war
         return r["frames_per_s"], "reference src/common call site (ProcessorCore2::Process) + CPU oracle of spec M0"
     # fallback when oracle/_ref was not built: the oracle's ABI alone, one Python thread per stream
     from beatrice_vst_b200 import lib as blib
-    L = blib.load_oracle()
+    import loader as oracle_loader   # oracle/loader.py
+    L = oracle_loader.load_oracle()
     md = os.path.dirname(model_toml)
     t0 = time.time()
     s = blib.SingleStream(L, md)
@@ -169,7 +170,8 @@ def parity_sample(product, model_dir, prec):
     from beatrice_vst_b200 import batch as bbatch
     from beatrice_vst_b200 import lib as blib
     from beatrice_vst_b200 import signals
-    oracle = blib.load_oracle()
+    import loader as oracle_loader
+    oracle = oracle_loader.load_oracle()
     n, hops = 2, 20
     xs = signals.batch_16k(n, hops, seed0=77)
     eng = bbatch.Engine(product, n, precision=prec)

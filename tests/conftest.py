@@ -15,6 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 from beatrice_vst_b200 import lib as blib  # noqa: E402
 from beatrice_vst_b200 import model_spec  # noqa: E402
+import loader as oracle_loader  # noqa: E402  (oracle/loader.py: test infrastructure)
 
 
 def pytest_configure(config):
@@ -23,7 +24,7 @@ def pytest_configure(config):
 
 def _ensure_built():
     import __graft_entry__ as g
-    if not (os.path.exists(blib.PRODUCT_SO) and os.path.exists(blib.ORACLE_SO)):
+    if not (os.path.exists(blib.PRODUCT_SO) and os.path.exists(oracle_loader.ORACLE_SO)):
         g.build()
 
 
@@ -46,7 +47,7 @@ def model_dir(model_dirs):
 @pytest.fixture(scope="session")
 def oracle():
     _ensure_built()
-    return blib.load_oracle()
+    return oracle_loader.load_oracle()
 
 
 @pytest.fixture(scope="session")

@@ -30,7 +30,8 @@ from beatrice_vst_b200 import lib, model_spec, signals  # noqa: E402
 
 
 def main():
-    oracle = lib.load_oracle()
+    import loader as oracle_loader
+    oracle = oracle_loader.load_oracle()
     with tempfile.TemporaryDirectory() as d:
         for fam in (0, 2):
             md = os.path.join(d, f"f{fam}")

@@ -38,7 +38,9 @@ def _worker(rank, world, port, model_dir, out_dir):
     with tempfile.TemporaryDirectory() as d:
         for name, im in zip(bdist.MODEL_FILES, images):
             im.tofile(os.path.join(d, name))
-        oracle = blib.load_oracle()
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import loader as oracle_loader
+        oracle = oracle_loader.load_oracle()
         first, count = bdist.shard_streams(4, world, rank)
         for s in range(first, first + count):
             st = blib.SingleStream(oracle, d, speaker=s % 8)

@@ -10,7 +10,7 @@ import pytest
 from beatrice_vst_b200 import batch as bbatch
 from beatrice_vst_b200 import lib as blib
 from beatrice_vst_b200 import model_spec, signals
-from conftest import ROOT, rms
+from conftest import ROOT, oracle_loader, rms
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -72,7 +72,7 @@ def test_spec_flops_match_survey():
 # both libraries: ABI export + reader error codes (host logic only, no GPU needed)
 # ---------------------------------------------------------------------------------------
 def _libs():
-    return [("oracle", blib.ORACLE_SO), ("product", blib.PRODUCT_SO)]
+    return [("oracle", oracle_loader.ORACLE_SO), ("product", blib.PRODUCT_SO)]
 
 
 @pytest.mark.parametrize("name,path", _libs())

@@ -20,7 +20,9 @@ def rms(a, b):
 
 
 def main():
-    product, oracle = blib.load_product(), blib.load_oracle()
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import loader as oracle_loader
+    product, oracle = blib.load_product(), oracle_loader.load_oracle()
     print("devices:", bbatch.device_count(product))
     with tempfile.TemporaryDirectory() as d:
         model_spec.write_model_dir(d, 8, 2, 0)

@@ -31,7 +31,9 @@ def main():
     prec = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 5
     hops = int(sys.argv[3]) if len(sys.argv) > 3 else 6
-    product, oracle = blib.load_product(), blib.load_oracle()
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import loader as oracle_loader
+    product, oracle = blib.load_product(), oracle_loader.load_oracle()
     with tempfile.TemporaryDirectory() as d:
         model_spec.write_model_dir(d, 8, 2, 0)
         xs = signals.batch_16k(n, hops, seed0=300)
