@@ -55,6 +55,7 @@ BATCH_SYMBOLS = {
     "BeatriceB200_Stream": (_vp, [_vp]),
     "BeatriceB200_GetLastIntermediates": (C.c_int, [_vp, _f32p, _i32p, _i32p, _f32p]),
     "BeatriceB200_TransformPitchBins": (C.c_int, [_vp, _i32p, _i32p]),
+    "BeatriceB200_AdapterOnly48k": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "BeatriceB200_ResidentBytes": (C.c_size_t, [_vp]),
     "BeatriceB200_KernelLaunchCount": (C.c_uint64, [_vp]),
     "BeatriceB200_ProfileHop": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
@@ -211,6 +212,19 @@ class Engine:
         if rc != 0:
             raise RuntimeError(f"BeatriceB200_TransformPitchBins -> {rc}")
         return out
+
+    def adapter_only_48k(self, x48: np.ndarray, model24: np.ndarray):
+        """One hop of the device-side 48 kHz adapter with the model replaced by ``model24``; returns (x16, out48)."""
+        x48 = np.ascontiguousarray(x48, np.float32)
+        model24 = np.ascontiguousarray(model24, np.float32)
+        assert x48.shape == (self.n, 480) and model24.shape == (self.n, 240)
+        x16 = np.empty((self.n, 160), np.float32)
+        out = np.empty((self.n, 480), np.float32)
+        rc = self.dll.BeatriceB200_AdapterOnly48k(self.h, x48.ctypes.data, model24.ctypes.data, x16.ctypes.data,
+                                                  out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"BeatriceB200_AdapterOnly48k -> {rc}")
+        return x16, out
 
     def resident_bytes(self) -> int:
         return int(self.dll.BeatriceB200_ResidentBytes(self.h))

@@ -787,6 +787,36 @@ int BeatriceB200_TransformPitchBins(BeatriceB200_Engine* e, const int* bins_raw_
   return rc__;
 }
 
+// Test / diagnostic entry: ONE 48 kHz hop of the device-side host-rate adapter alone (gain.h:41-71,
+// resample.h:401-438) with the model call replaced by caller-supplied 24 kHz frames: in48 [B][480] ->
+// x16_out [B][160] (what the model would be fed), model24 [B][240] (what it is pretended to return) ->
+// out48 [B][480].  The engine's adapter state (gain slews, FIR histories, block FIFO, hop counter) advances exactly
+// as in BeatriceB200_Process48k; the model state is untouched.  tests/ compare this bit-for-bit with
+// oracle/hostrate_ref.py, which is pinned bit-for-bit to the reference's own compiled code.
+int BeatriceB200_AdapterOnly48k(BeatriceB200_Engine* e, const float* in48_host, const float* model24_host,
+                                float* x16_out_host, float* out48_host) {
+  if (!e || !in48_host || !model24_host || !x16_out_host || !out48_host) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(rc__ = BEATRICE_B200_ERR_DEVICE, {
+    B200_CHECK(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    const size_t n48 = sizeof(float) * e->B * kHostHop48k;
+    B200_CHECK(cudaMemcpyAsync(e->hostrate.in48(), in48_host, n48, cudaMemcpyHostToDevice, s));
+    e->hostrate.PrepareHop(s);
+    e->hostrate.EnqueueIn(e->in16.as<float>(), s);
+    B200_CHECK(cudaMemcpyAsync(x16_out_host, e->in16.p, sizeof(float) * e->B * kInHop, cudaMemcpyDeviceToHost, s));
+    B200_CHECK(cudaMemcpyAsync(e->wave_st.out.p, model24_host, sizeof(float) * e->B * kOutHop, cudaMemcpyHostToDevice, s));
+    e->hostrate.EnqueueOut(e->wave_st.out.as<float>(), s);
+    e->hostrate.HopDone();
+    e->launches += HostRateState::kKernelsPerHop;
+    B200_CHECK(cudaMemcpyAsync(out48_host, e->hostrate.out48(), n48, cudaMemcpyDeviceToHost, s));
+    B200_CHECK(cudaStreamSynchronize(s));
+    rc__ = 0;
+  });
+  return rc__;
+}
+
 size_t BeatriceB200_ResidentBytes(const BeatriceB200_Engine* e) {
   if (!e || !e->loaded) return 0;
   return e->phone_st.arena.bytes() + e->pitch_st.arena.bytes() + e->wave_st.arena.bytes() + e->phone_m.blob.bytes +

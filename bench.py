@@ -100,6 +100,27 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     self.reasons.add(name)
 
+    def sample_now(self):
+        """One synchronous sample (region start / mid / end), so that a short region never ends up with none."""
+        if not self.nvml:
+            return
+        nv, h = self.nvml
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            r = int(get_reasons(h))
+            for n, a, b in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                            ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                            ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                            ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap")):
+                m = getattr(nv, a, None) or getattr(nv, b, 0)
+                if m and (r & m):
+                    self.reasons.add(n)
+        except Exception:
+            pass
+
     def __enter__(self):
         try:
             import pynvml as nv
@@ -142,7 +163,8 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)) if self.mx else None,
                 "reasons": sorted(self.reasons), "samples": len(self.sm),
-                "how": "NVML every 5 ms during the device-timed region" if self.nvml else "nvidia-smi -lms 20"}
+                "how": ("NVML every 5 ms from a thread during the device-timed region + synchronous samples at its start, "
+                        "at the end of enqueueing and at its end") if self.nvml else "nvidia-smi -lms 20"}
 
 
 def cpu_reference_run(model_toml: str, threads: int, frames_per_thread: int, warmup: int):
@@ -165,27 +187,33 @@ def cpu_reference_run(model_toml: str, threads: int, frames_per_thread: int, war
     return frames_per_thread / (time.time() - t0), "CPU oracle of spec M0 through the beatrice.h ABI, 1 thread"
 
 
-def parity_sample(product, model_dir, prec):
-    """RMS of the engine's 24 kHz output against the CPU oracle (checker) on 2 streams x 20 hops."""
-    from beatrice_vst_b200 import batch as bbatch
-    from beatrice_vst_b200 import lib as blib
-    from beatrice_vst_b200 import signals
-    import loader as oracle_loader
-    oracle = oracle_loader.load_oracle()
-    n, hops = 2, 20
-    xs = signals.batch_16k(n, hops, seed0=77)
-    eng = bbatch.Engine(product, n, precision=prec)
-    eng.load(model_dir)
-    got = np.stack([eng.process_frames(xs[h]).copy() for h in range(hops)], axis=1)
-    eng.close()
-    err = 0.0
-    for s in range(n):
-        o = blib.SingleStream(oracle, model_dir)
-        o.set_pitch_range(1, 383)
-        _, _, _, w = o.run(xs[:, s, :].reshape(-1))
-        o.close()
-        err = max(err, float(np.sqrt(np.mean((got[s] - w) ** 2))))
-    return err
+PARITY_STREAMS = [0, 5, 6, 15, 16, 127, 128, 240, 251, 252, 255]   # first / last members of the 16 / 6 / 3-stream kernel groups
+PARITY_TAIL_HOPS = 20
+
+
+def bench_engine_parity(model_toml, histories, got_tail, speakers):
+    """Parity of the TIMED engine itself (checker only; runs after every timed region): for each sampled stream the
+    reference call site (oracle/_ref, ProcessorCore2::Process) over the CPU oracle is fed that stream's complete
+    input history since model load -- warm-up + timed hops of both timed loops + PARITY_TAIL_HOPS more -- and its
+    last PARITY_TAIL_HOPS output blocks are compared with what the 256-stream engine returned for them."""
+    import callsite
+    from concurrent.futures import ThreadPoolExecutor
+    if not callsite.available("oracle"):
+        return None
+
+    def one(i):
+        y, info = callsite.run("oracle", model_toml, histories[i].reshape(-1), events=[(0, "voice", speakers[i])])
+        if info.get("load") != 0:
+            raise RuntimeError(f"reference call site failed to load the model: {info}")
+        tail = y[-PARITY_TAIL_HOPS * 480:]
+        return float(np.sqrt(np.mean((tail.astype(np.float64) - got_tail[i].reshape(-1).astype(np.float64)) ** 2))), \
+            float(tail.std())
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(histories), os.cpu_count() or 1))) as pool:
+        res = list(pool.map(one, range(len(histories))))
+    return {"rms_worst": max(r[0] for r in res), "signal_rms_min": min(r[1] for r in res), "streams": len(res),
+            "hops_of_history": int(histories[0].shape[0]), "hops_compared": PARITY_TAIL_HOPS,
+            "against": "reference call site (ProcessorCore2::Process, oracle/_ref) + CPU oracle, same per-stream input history"}
 
 
 def run_reference_arm(args, rank, world):
@@ -267,9 +295,8 @@ def main():
     if rc != 0:
         raise SystemExit(f"LoadModelFromMemory -> {rc}")
     first, count = bdist.shard_streams(B * world, world, rank)
-    for s in range(B):                      # config 2: per-stream speaker, default parameters otherwise
-        eng.set("TargetSpeaker", (first + s) % eng.n_speakers, s)
-    eng.reset_stream(-1)
+    for s in range(B):                      # config 2: per-stream speaker, default parameters otherwise; the
+        eng.set("TargetSpeaker", (first + s) % eng.n_speakers, s)   # key-value blocks follow over the first four hops, like the call site
 
     # ---- synthetic input: a bank of distinct hops resident in HBM (larger than L2) ----
     bank_hops = N_INPUT_HOPS
@@ -280,9 +307,13 @@ def main():
     d_bank = eng.dev_alloc("bank", bank_hops * hop_floats)
     d_out = eng.dev_alloc("out", hop_floats)
     rng = np.random.default_rng(first)
+    psel = [p for p in PARITY_STREAMS if p < B] if rank == 0 else []
+    bank_sel = np.empty((bank_hops, len(psel), 480), np.float32)    # host copy of the sampled streams' bank rows
     for h in range(bank_hops):
         x = base[h % 64] * np.float32(0.9 + 0.2 * rng.random())
+        bank_sel[h] = x[psel]
         eng.dll.BeatriceB200_CopyToDevice(eng.h, d_bank + h * hop_floats * 4, x.ctypes.data, x.nbytes)
+    fed = []   # per executed hop: the sampled streams' input rows, in order (parity check after the timed regions)
     stream = torch.cuda.ExternalStream(eng.cuda_stream, device=torch.device("cuda", local_rank))
 
     def barrier():
@@ -297,15 +328,19 @@ def main():
     for i in range(args.warmup):
         hop_device(i)
     eng.synchronize()
+    fed += [bank_sel[i % bank_hops] for i in range(args.warmup + args.steps)]
     launches0 = eng.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     with ClockSampler(local_rank) as clk:
+        clk.sample_now()
         ev0.record(stream)
         for i in range(args.steps):
             hop_device(args.warmup + i)
         ev1.record(stream)
+        clk.sample_now()      # the queue is full here: the GPU is mid-region
         eng.synchronize()
+        clk.sample_now()
     barrier()
     launches = eng.kernel_launches() - launches0
     ms = ev0.elapsed_time(ev1)
@@ -321,6 +356,7 @@ def main():
     h_out = eng.pinned("out", (B, 480))
     for i in range(3):
         eng.process_48k(h_in[i], h_out)
+    fed += [base[i][psel] for i in range(3)] + [base[i % 64][psel] for i in range(args.steps)]
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -349,6 +385,14 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- parity of THIS engine (untimed): a few more hops whose output blocks are kept for the sampled streams ----
+    got_tail = np.empty((len(psel), PARITY_TAIL_HOPS, 480), np.float32)
+    for i in range(PARITY_TAIL_HOPS):
+        eng.process_48k(h_in[i % 64], h_out)
+        fed.append(base[i % 64][psel])
+        got_tail[:, i, :] = h_out[psel]
+    histories = np.stack(fed, axis=1)            # [sampled][hops][480]
+
     # ---- roofline of the dominant kernel family (vocoder MRF Conv1d), timed live per launch ----
     peaks = _peaks()
     d_in16 = eng.dev_alloc("in16", B * 160)
@@ -365,34 +409,41 @@ def main():
     tot_ms = sum(r["ms"] for r in recs)
     achieved = mrf_flops / (mrf_ms * 1e-3) / 1e12 if mrf_ms > 0 else 0.0
     # DRAM traffic of the same launches from the committed ncu --set full capture (profiles/), per launch
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_mrf_traffic.json")
-    if args.precision == "bf16x3" and os.path.exists(tpath):
-        try:
-            # per stage launch, like `achieved` (stage 0 is a pair of kernels launched and timed as one step)
-            traffic = float(json.load(open(tpath))["per_hop_MB"]) * 1e6 / max(len(mrf), 1)
-        except (ValueError, KeyError):
-            traffic = None
+    traffic, traffic_source = None, None
+    for name in ("r2_mrf_traffic.json", "r1_mrf_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if args.precision == "bf16x3" and os.path.exists(tpath):
+            try:
+                # per stage launch, like `achieved` (stage 0 is a pair of kernels launched and timed as one step)
+                traffic = float(json.load(open(tpath))["per_hop_MB"]) * 1e6 / max(len(mrf), 1)
+                traffic_source = f"NOT measured by this run: committed ncu --set full capture profiles/{name} (dram read + write of the MRF launches of one hop / launches)"
+                break
+            except (ValueError, KeyError):
+                traffic = None
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["tflops"], "traffic": traffic,
+        "frac": achieved / peaks["tflops"], "traffic": traffic, "traffic_source": traffic_source,
         "kernel": ("conv_gemm_kernel (CUDA cores)" if args.precision == "f32" else
                    "mrf_cluster_kernel<128,4> + mrf_branch_kernel<64|32|16> (tcgen05/TMEM/TMA, six convs of a branch per CTA)")
                   + ", vocoder MRF dilated Conv1d stage", "launches_per_step": len(mrf),
         "launch_note": "one launch per vocoder stage; stage 0 is two kernels (cluster k=11/7 + single-CTA k=3) issued as a PDL pair and timed as one",
         "algorithmic_flops_per_step": mrf_flops, "avg_launch_us": 1e3 * mrf_ms / max(len(mrf), 1),
-        "share_of_step": mrf_ms / tot_ms if tot_ms > 0 else None, "peak_source": peaks["source"] + " bf16 sustained",
+        "share_of_step": mrf_ms / (ms / args.steps), "share_note": "MRF launch time (serialised, event-timed) / the timed hop",
+        "share_of_serialised_ops": mrf_ms / tot_ms if tot_ms > 0 else None, "peak_source": peaks["source"] + " bf16 sustained",
         "timing": "CUDA events around every launch of one hop on the engine's stream (BeatriceB200_ProfileHop), median of 4 hops; "
                   "each bracket carries ~4 us of event overhead, so frac is a lower bound",
         "mma_work_factor": 3.0 if args.precision == "bf16x3" else 1.0,
+        "frac_issued": (3.0 if args.precision == "bf16x3" else 1.0) * achieved / peaks["tflops"],
+        "frac_issued_note": "tensor-pipe work actually issued (split-bf16 = 3 bf16 products per algorithmic one) / peak",
     }
     resident = eng.resident_bytes()
     eng.close()
 
     cpu = None
-    rms_check = None
+    parity = None
     if not args.no_cpu_baseline:
-        rms_check = parity_sample(product, tmp.name, prec)
+        speakers = [(first + p) % 8 for p in psel]
+        parity = bench_engine_parity(os.path.join(tmp.name, "model.toml"), histories, got_tail, speakers)
         cores = os.cpu_count() or 1
         frames = 300
         t0 = time.time()
@@ -405,7 +456,7 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"f32": "f32", "bf16": "bf16 (tcgen05, fp32 accumulate; encoders split-bf16)",
                   "bf16x3": "bf16x3 (split-bf16 tcgen05 operands, fp32 accumulate)"}[args.precision],
-        "data": "synthetic", "rms_vs_cpu_oracle": rms_check,
+        "data": "synthetic", "rms_vs_cpu_oracle": parity["rms_worst"] if parity else None, "parity": parity,
         "config": {"workload": WORKLOAD, "streams_per_gpu": B, "precision": args.precision, "model": "spec M0 (seeded synthetic weights, 8 speakers)",
                    "parallelism": f"{world} x independent stream shards, no per-hop collective; weights broadcast once over NCCL",
                    "l2": f"inputs cycle through {bank_hops} distinct device-resident hops "

@@ -1,0 +1,242 @@
+"""GPU parity of the configuration bench.py reports (VERDICT r1 "next round" items 1 and 6): the batched engine at its
+default precision (split-bf16 on tcgen05), 256 streams, through BeatriceB200_Process48k and ..._Process48kDevice,
+against the reference's own call site (oracle/_ref, compiled from the reference) over the CPU oracle; BASELINE.json
+config 1 at its stated length through the reference call site linked against the CUDA library; the call-site pitch
+transform swept exhaustively against the reference's compiled code; the device-side 48 kHz adapter isolated and
+compared bit for bit.
+
+Nothing here reads /root/reference: the call site is the prebuilt oracle/_ref binaries."""
+import os
+import subprocess
+import tempfile
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+import callsite
+import hostrate_ref
+from beatrice_vst_b200 import batch as bbatch
+from beatrice_vst_b200 import signals
+from conftest import ROOT, rms
+
+pytestmark = pytest.mark.gpu
+TOL_WAVE = 1e-4     # north_star: <= 1e-4 RMS vs the CPU reference
+SWEEP = os.path.join(ROOT, "oracle", "_ref", "pitch_sweep")
+
+
+# ---------------------------------------------------------------------------------------
+# the benchmarked configuration itself
+# ---------------------------------------------------------------------------------------
+def _stream_plan(sid, hops, change_every=100):
+    """Config 5's per-stream sweep: speaker id % 8, pitch shift -12 .. +12 st, formant
+    ((id % 9) - 4) / 2, kNN-VQ on for every fourth stream, pitch correction on some; every `change_every` hops the
+    stream moves to the next speaker (set-speaker + the 4-hop key-value schedule under load)."""
+    ev = [(0, "voice", sid % 8), (0, "pitch_shift", float((sid % 25) - 12)), (0, "formant_shift", ((sid % 9) - 4) / 2.0)]
+    if sid % 4 == 3:
+        ev.append((0, "vq_num_neighbors", 4))
+    if sid % 5 == 1:
+        ev += [(0, "pitch_correction", 0.4), (0, "pitch_correction_type", sid % 2)]
+    for h in range(change_every, hops, change_every):
+        ev.append((h, "voice", (sid + h // change_every) % 8))
+    return ev
+
+
+_SETTER = dict(input_gain="InputGain", output_gain="OutputGain", pitch_shift="PitchShift", voice="TargetSpeaker",
+               pitch_correction="PitchCorrection", formant_shift="FormantShift", vq_num_neighbors="VQNumNeighbors",
+               pitch_correction_type="PitchCorrectionType", intonation_intensity="IntonationIntensity",
+               min_source_pitch="MinSourcePitch", max_source_pitch="MaxSourcePitch",
+               average_source_pitch="AverageSourcePitch")
+_INT = ("voice", "vq_num_neighbors", "pitch_correction_type")
+
+
+def _apply(eng, plan, h, s):
+    for (b, name, v) in plan:
+        if b == h:
+            assert eng.set(_SETTER[name], int(v) if name in _INT else float(v), s) == 0
+
+
+@pytest.mark.skipif(not callsite.available("oracle"), reason="oracle/_ref not built")
+def test_256_streams_48k_default_precision_matches_reference_callsite(product, model_dir):
+    """bench.py's workload: 256 streams, default precision (bf16x3), both 48 kHz entries.  Sampled streams cover
+    the first / last member of every stream group the fused vocoder kernels form (16 / 6 / 3 / 1 streams per CTA
+    or cluster; 256 = 42 * 6 + 4 leaves the last group of 6 partial)."""
+    n, hops = 256, 210
+    sampled = [0, 5, 6, 15, 16, 17, 127, 128, 239, 240, 251, 252, 255]
+    x = signals.batch_48k(n, hops, seed0=4000)                     # [hops][n][480]
+    plans = [_stream_plan(s, hops) for s in range(n)]
+    host = bbatch.Engine(product, n)                                # default precision
+    dev = bbatch.Engine(product, n, precision=2)
+    assert host.load(model_dir) == 0 and dev.load(model_dir) == 0
+    d_in, d_out = dev.dev_alloc("in48", n * 480), dev.dev_alloc("out48", n * 480)
+    got = np.empty((len(sampled), hops, 480), np.float32)
+    for h in range(hops):
+        for s in range(n):
+            _apply(host, plans[s], h, s)
+            _apply(dev, plans[s], h, s)
+        y = host.process_48k(x[h])
+        dev.to_device(d_in, x[h])
+        assert dev.process_48k_device(d_in, d_out) == 0
+        dev.synchronize()
+        y2 = dev.to_host(d_out, (n, 480))
+        assert np.array_equal(y, y2), h                             # the two entries are the same arithmetic
+        got[:, h, :] = y[sampled]
+    launches = host.kernel_launches()
+    host.close()
+    dev.close()
+    assert launches > 0
+
+    toml = os.path.join(model_dir, "model.toml")
+
+    def ref(i):
+        s = sampled[i]
+        y, info = callsite.run("oracle", toml, x[:, s, :].reshape(-1), events=plans[s])
+        assert info["load"] == 0 and info["last"] == 0
+        return y
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as pool:
+        refs = list(pool.map(ref, range(len(sampled))))
+    worst, worst_tail = 0.0, 0.0
+    for i, s in enumerate(sampled):
+        e = rms(got[i].reshape(-1), refs[i])
+        tail = rms(got[i, -20:].reshape(-1), refs[i][-20 * 480:])
+        assert refs[i].std() > 0.01
+        assert e <= TOL_WAVE and tail <= TOL_WAVE, (s, e, tail)
+        worst, worst_tail = max(worst, e), max(worst_tail, tail)
+    print(f"[headline] 256 streams x {hops} hops, bf16x3: worst RMS vs reference call site {worst:.3e} "
+          f"(last 20 hops {worst_tail:.3e})")
+
+
+@pytest.mark.skipif(not (callsite.available("oracle") and callsite.available("b200")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("block", [480, 333])
+def test_config1_1000_hops_through_reference_callsite(model_dir, block):
+    """BASELINE.json config 1 as SURVEY.md 8(d) states it: one 48 kHz stream, 1000 frames (480 000 samples), the
+    config-1 signal, through the reference's unmodified ProcessorCore2::Process linked against (i) the CPU oracle
+    and (ii) the CUDA library at its default (tensor-core) precision; RMS over all samples, and over the last 100
+    hops alone (long-run drift of the recurrent conv histories)."""
+    x = signals.voice_like(480 * 1000, 48000.0, seed=1)
+    toml = os.path.join(model_dir, "model.toml")
+    old = os.environ.get("BEATRICE_B200_PRECISION")
+    os.environ["BEATRICE_B200_PRECISION"] = "bf16x3"
+    try:
+        with ThreadPoolExecutor(max_workers=2) as pool:
+            fa = pool.submit(callsite.run, "b200", toml, x, 48000.0, block)
+            fb = pool.submit(callsite.run, "oracle", toml, x, 48000.0, block)
+            (ya, ia), (yb, ib) = fa.result(), fb.result()
+    finally:
+        if old is None:
+            del os.environ["BEATRICE_B200_PRECISION"]
+        else:
+            os.environ["BEATRICE_B200_PRECISION"] = old
+    assert ia == ib == {"load": 0, "last": 0, "version": 2}
+    assert len(ya) == len(yb) == 480000 and yb.std() > 0.01
+    e_all, e_tail = rms(ya, yb), rms(ya[-48000:], yb[-48000:])
+    print(f"[config 1] block {block}: RMS over 480000 samples {e_all:.3e}, last 100 hops {e_tail:.3e}")
+    assert e_all <= TOL_WAVE and e_tail <= TOL_WAVE, (e_all, e_tail)
+
+
+# ---------------------------------------------------------------------------------------
+# integer parity: the call-site pitch transform, exhaustively
+# ---------------------------------------------------------------------------------------
+def _sweep_rows():
+    rows = []
+    for avg in (36.7, 52.0, 64.5):
+        for inten in (0.0, 0.35, 1.0, 1.5, 3.0):
+            for shift in (-24.0, -12.0, -5.5, -0.01, 0.0, 0.37, 7.0, 12.0, 24.0):
+                for corr in (0.0, 1e-3, 0.1, 0.25, 0.5, 0.75, 0.9, 0.99, 0.9999, 0.99995, 1.0):
+                    for typ in (0, 1):
+                        rows.append((avg, inten, shift, corr, typ))
+    rng = np.random.default_rng(7)
+    for _ in range(600):
+        rows.append((rng.uniform(0, 128), rng.uniform(0, 2.5), rng.uniform(-24, 24), rng.uniform(0, 1),
+                     int(rng.integers(0, 2))))
+    return np.asarray(rows, np.float64)
+
+
+def _reference_bins(rows, toml):
+    """[rows][447] bins the reference's compiled Process1 hands to GenerateWaveform1 for raw bins 1 .. 447."""
+    workers = max(1, min(16, os.cpu_count() or 2))
+    chunks = np.array_split(rows, workers)
+
+    def run(chunk):
+        with tempfile.TemporaryDirectory() as d:
+            fp, fo = os.path.join(d, "p.f64"), os.path.join(d, "o.i32")
+            np.ascontiguousarray(chunk, "<f8").tofile(fp)
+            p = subprocess.run([SWEEP, toml, fp, fo], capture_output=True, text=True, timeout=1200)
+            assert p.returncode == 0, (p.returncode, p.stderr[-500:])
+            return np.fromfile(fo, "<i4").reshape(len(chunk), 447)
+
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        return np.concatenate(list(pool.map(run, chunks)))
+
+
+@pytest.mark.skipif(not os.path.exists(SWEEP), reason="oracle/_ref/pitch_sweep not built")
+def test_pitch_transform_bit_exact_over_parameter_grid(product, model_dir):
+    """processor_core_2.cc:190-252 on the device == the reference's compiled code for EVERY raw bin 1 .. 447 over a
+    dense grid of (average source pitch, intonation, shift, correction in [0, 1], type 0 / 1) plus random
+    parameter sets: integer work, so equality, not a tolerance."""
+    rows = _sweep_rows()
+    want = _reference_bins(rows, os.path.join(model_dir, "model.toml"))
+    eng = bbatch.Engine(product, 447)
+    assert eng.load(model_dir) == 0
+    raw = np.arange(1, 448, dtype=np.int32)
+    bad = []
+    for r, (avg, inten, shift, corr, typ) in enumerate(rows):
+        assert eng.set("AverageSourcePitch", float(avg)) == 0
+        assert eng.set("IntonationIntensity", float(inten)) == 0
+        assert eng.set("PitchShift", float(shift)) == 0
+        assert eng.set("PitchCorrection", float(corr)) == 0
+        assert eng.set("PitchCorrectionType", int(typ)) == 0
+        got = eng.transform_pitch_bins(raw)
+        if not np.array_equal(got, want[r]):
+            q = int(np.flatnonzero(got != want[r])[0])
+            bad.append((tuple(rows[r]), q + 1, int(got[q]), int(want[r][q])))
+    eng.close()
+    print(f"[pitch sweep] {len(rows)} parameter sets x 447 bins compared")
+    assert not bad, bad[:10]
+
+
+# ---------------------------------------------------------------------------------------
+# bit-exact claims, isolated: the device-side 48 kHz adapter without the model
+# ---------------------------------------------------------------------------------------
+def test_device_adapter_alone_is_bit_exact(product, model_dir):
+    """hostrate_in / hostrate_out kernels (gain + decimating FIR at samples 3i+2, block FIFO, zero-stuffed
+    interpolating FIR + gain) against oracle/hostrate_ref.py -- itself pinned bit for bit to the reference's
+    gain.h / resample.h -- with the model replaced by fixed pseudo-random frames: array_equal on both the 16 kHz
+    frames the model would see and the 48 kHz blocks handed back, through rising and falling slews of both gains."""
+    n, hops = 3, 36
+    x = signals.batch_48k(n, hops, seed0=60)
+    rng = np.random.default_rng(3)
+    model24 = (0.4 * rng.standard_normal((hops, n, 240))).astype(np.float32)
+    gains = {0: [(0, True, -6.0), (9, False, 3.0), (20, True, 2.5), (28, False, -12.0)],
+             1: [(5, False, -3.0), (6, True, 6.0)],
+             2: []}
+    eng = bbatch.Engine(product, n)
+    assert eng.load(model_dir) == 0
+    got16 = np.empty((hops, n, 160), np.float32)
+    got48 = np.empty((hops, n, 480), np.float32)
+    for h in range(hops):
+        for s in range(n):
+            for (at, is_in, db) in gains[s]:
+                if at == h:
+                    assert eng.set("InputGain" if is_in else "OutputGain", db, s) == 0
+        got16[h], got48[h] = eng.adapter_only_48k(x[h], model24[h])
+    eng.close()
+    for s in range(n):
+        seen = []
+        frames = iter(model24[:, s, :])
+
+        def model(x16, seen=seen, frames=frames):
+            seen.append(np.array(x16, np.float32))
+            return next(frames)
+
+        hr = hostrate_ref.HostRateRef(model)
+        want48 = []
+        for h in range(hops):
+            for (at, is_in, db) in gains[s]:
+                if at == h:
+                    (hr.gain_in if is_in else hr.gain_out).target_db = db
+            want48.append(hr.process(x[h, s]))
+        assert np.array_equal(got16[:, s, :], np.stack(seen)), s
+        assert np.array_equal(got48[:, s, :], np.stack(want48)), s
+    assert got48[-1].std() > 0.01

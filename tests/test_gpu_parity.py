@@ -24,6 +24,15 @@ TOL_WAVE = 1e-4     # north_star: <= 1e-4 RMS (fp32)
 TOL_FEAT = 2e-5
 
 
+@pytest.fixture(params=[2, 0], ids=["bf16x3", "f32"])
+def abi_precision(request, product):
+    """Arithmetic of the per-stream contexts behind beatrice.h: the default (split-bf16 on tcgen05) and the opt-in
+    fp32 CUDA-core mode.  Contexts build on their first per-frame call, so the switch is set around the test."""
+    bbatch.set_default_precision(product, request.param)
+    yield request.param
+    bbatch.set_default_precision(product, -1)
+
+
 def _pair(product, oracle, model_dir, family=2, **kw):
     a = blib.SingleStream(product, model_dir, family=family, **kw)
     b = blib.SingleStream(oracle, model_dir, family=family, **kw)
@@ -37,7 +46,7 @@ def test_native_library_is_the_one_loaded(product):
 
 
 @pytest.mark.parametrize("family", [2, 0, 1])
-def test_single_stream_abi_matches_oracle(product, oracle, model_dirs, family):
+def test_single_stream_abi_matches_oracle(product, oracle, model_dirs, family, abi_precision):
     x = signals.voice_like(160 * 40, 16000.0, seed=21)
     a, b = _pair(product, oracle, model_dirs[family], family, speaker=3, formant_index=6)
     a.set_pitch_range(1, 383)
@@ -53,7 +62,7 @@ def test_single_stream_abi_matches_oracle(product, oracle, model_dirs, family):
 
 
 @pytest.mark.parametrize("family", [0, 2])
-def test_single_stream_abi_matches_golden(product, model_dirs, family):
+def test_single_stream_abi_matches_golden(product, model_dirs, family, abi_precision):
     g = np.load(os.path.join(GOLDEN, f"m0_family{family}.npz"))
     s = blib.SingleStream(product, model_dirs[family], family=family, speaker=1, formant_index=5)
     s.set_pitch_range(1, 383)
@@ -71,8 +80,10 @@ def test_single_stream_abi_matches_golden(product, model_dirs, family):
 
 
 def test_vocoder_stage_taps_match_oracle(product, oracle, model_dir):
-    """Per-stage activations of the vocoder (hidden, pre, 4 stage outputs)."""
+    """Per-stage activations of the vocoder (hidden, pre, 4 stage outputs); fp32 mode, where every intermediate
+    lives in an fp32 ring (the tensor-core modes keep hidden / pre inside the fused chain kernel)."""
     x = signals.voice_like(160 * 6, 16000.0, seed=4)
+    bbatch.set_default_precision(product, 0)
     a, b = _pair(product, oracle, model_dir)
     a.run(x)
     b.run(x)
@@ -87,9 +98,10 @@ def test_vocoder_stage_taps_match_oracle(product, oracle, model_dir):
         assert rms(ta, tb) / scale <= 2e-5, (which, rms(ta, tb), scale)
     a.close()
     b.close()
+    bbatch.set_default_precision(product, -1)
 
 
-def test_vq_speaker_switch_and_formant(product, oracle, model_dir):
+def test_vq_speaker_switch_and_formant(product, oracle, model_dir, abi_precision):
     """kNN-VQ on/off, set-speaker with the key-value blocks one per hop, formant change."""
     x = signals.voice_like(160 * 30, 16000.0, seed=8).reshape(30, 160)
     a, b = _pair(product, oracle, model_dir)
@@ -177,10 +189,11 @@ def _oracle_stream(oracle, model_dir, x, speaker=0, formant_index=4, vq=0, shift
     return np.stack(out), qs
 
 
-def test_batched_frames_match_oracle_per_stream(product, oracle, model_dir):
+@pytest.mark.parametrize("engine_precision", [2, 0], ids=["bf16x3", "f32"])
+def test_batched_frames_match_oracle_per_stream(product, oracle, model_dir, engine_precision):
     n, hops = 6, 12
     xs = signals.batch_16k(n, hops, seed0=100)
-    eng = bbatch.Engine(product, n)
+    eng = bbatch.Engine(product, n, precision=engine_precision)
     assert eng.load(model_dir) == 0 and eng.n_speakers == 8
     spk = [0, 3, 7, 1, 2, 5]
     shift = [0.0, 12.0, -12.0, 3.0, 0.0, 24.0]
@@ -215,8 +228,9 @@ def test_batched_rejects_bad_arguments(product, model_dir):
     eng.close()
 
 
+@pytest.mark.parametrize("engine_precision", [2, 0], ids=["bf16x3", "f32"])
 @pytest.mark.skipif(not callsite.available("oracle"), reason="oracle/_ref not built")
-def test_batched_48k_matches_reference_callsite(product, model_dir):
+def test_batched_48k_matches_reference_callsite(product, model_dir, engine_precision):
     """Process48k == ProcessorCore2::Process at 48 kHz / 480-sample blocks, per stream, incl.
     gain slews, pitch shift, correction and a speaker change (4-hop key-value schedule)."""
     n, hops = 3, 24
@@ -231,7 +245,7 @@ def test_batched_48k_matches_reference_callsite(product, model_dir):
                   pitch_correction="PitchCorrection", formant_shift="FormantShift", vq_num_neighbors="VQNumNeighbors",
                   pitch_correction_type="PitchCorrectionType", intonation_intensity="IntonationIntensity",
                   min_source_pitch="MinSourcePitch", max_source_pitch="MaxSourcePitch")
-    eng = bbatch.Engine(product, n)
+    eng = bbatch.Engine(product, n, precision=engine_precision)
     assert eng.load(model_dir) == 0
     out = np.empty((n, hops, 480), np.float32)
     for h in range(hops):
@@ -299,8 +313,8 @@ def test_batched_48k_matches_committed_callsite_golden(product, model_dir):
 
 @pytest.mark.skipif(not (callsite.available("oracle") and callsite.available("b200")), reason="oracle/_ref not built")
 def test_dropin_through_reference_callsite(model_dir):
-    """The reference's unmodified ProcessorProxy/ProcessorCore2 linked against the CUDA library
-    produces the same audio as the same call site linked against the CPU oracle."""
+    """The reference's unmodified ProcessorProxy/ProcessorCore2 linked against the CUDA library (its default
+    arithmetic: split-bf16 on tcgen05) produces the same audio as the same call site linked against the CPU oracle."""
     x = signals.voice_like(480 * 40, 48000.0, seed=77)
     events = [(-1, "pitch_shift", -5.0), (6, "voice", 2), (11, "vq_num_neighbors", 4), (20, "reset", 1),
               (25, "formant_shift", 2.0)]
