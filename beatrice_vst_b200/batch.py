@@ -46,6 +46,9 @@ BATCH_SYMBOLS = {
     "BeatriceB200_Process48k": (C.c_int, [_vp, _vp, _vp]),
     "BeatriceB200_Process48kDevice": (C.c_int, [_vp, _vp, _vp]),
     "BeatriceB200_Synchronize": (None, [_vp]),
+    "BeatriceB200_SetPipelineDepth": (C.c_int, [_vp, C.c_int]),
+    "BeatriceB200_PipelineDepth": (C.c_int, [_vp]),
+    "BeatriceB200_DrainPipeline": (C.c_int, [_vp, _vp, _vp]),
     "BeatriceB200_AllocPinned": (_vp, [C.c_size_t]),
     "BeatriceB200_FreePinned": (None, [_vp]),
     "BeatriceB200_AllocDevice": (_vp, [_vp, C.c_size_t]),
@@ -184,6 +187,19 @@ class Engine:
 
     def process_48k_device(self, in_dev, out_dev) -> int:
         return self.dll.BeatriceB200_Process48kDevice(self.h, in_dev, out_dev)
+
+    def set_pipeline_depth(self, depth: int) -> int:
+        """1: a call returns the hop it was given; 2: vocoder of the previous hop || encoders of this one."""
+        return self.dll.BeatriceB200_SetPipelineDepth(self.h, depth)
+
+    def drain(self, model_rate: bool = False) -> np.ndarray:
+        """Depth 2: the blocks of the hop still in flight ([n,480] @48 kHz, or [n,240] @24 kHz)."""
+        out = np.empty((self.n, 240 if model_rate else 480), np.float32)
+        rc = self.dll.BeatriceB200_DrainPipeline(self.h, out.ctypes.data if model_rate else None,
+                                                 None if model_rate else out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"BeatriceB200_DrainPipeline -> {rc}")
+        return out
 
     def synchronize(self):
         self.dll.BeatriceB200_Synchronize(self.h)

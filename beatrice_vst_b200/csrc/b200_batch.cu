@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -38,9 +39,17 @@ int NoteToBin(double note, int bins) {  // processor_core_2.cc:561-583
 
 struct BeatriceB200_Engine {
   int device = 0, B = 0, precision = 0;
-  cudaStream_t stream = nullptr, aux = nullptr;
+  cudaStream_t stream = nullptr, aux = nullptr, aux2 = nullptr;
   cudaStream_t side = nullptr;                        // host-buffer path: early output block + its D2H copy
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_side = nullptr;
+  cudaEvent_t ev_join2 = nullptr, ev_cond = nullptr;  // pipelined hop: pitch-lane join, "vocoder has read the hand-off"
+  // Pipeline depth 2 (BeatriceB200_SetPipelineDepth): a call runs the vocoder of the PREVIOUS hop side by side with
+  // the two encoders of the hop it is given; outputs are those of depth 1, one call later.  `primed`: the hand-off
+  // buffers (phone / pitch bin / features) hold a hop the vocoder has not consumed yet.
+  int pipeline = 1;
+  bool primed = false;
+  DeviceBuffer zero24;                                // [B][240] zeros: the model output "before the first hop"
+  std::vector<std::function<void()>> after_hop;       // vocoder-side actions deferred behind the next hop (depth 2)
   bool loaded = false;
   FamilyDims dims = kFamilies[2];
 
@@ -65,6 +74,7 @@ struct BeatriceB200_Engine {
   int vq_op = -1;                                     // index of "phone.vq" in hop_ops
   bool any_vq = false;                                // some stream has kNN-VQ on (VQNumNeighbors > 0)
   GraphRunner graph16, graph48, graph48s;
+  GraphRunner graph16p, graph48p, graph48sp;          // depth-2 forms of the same three entries
   uint64_t launches = 0;
   uint64_t hops = 0;
 
@@ -114,8 +124,20 @@ void StepKv(Engine* e, const std::vector<char>* only) {
     if (e->sp[b].kv_set_count < 0) e->sp[b].kv_set_count = -e->sp[b].kv_set_count;
 }
 
-// Applies everything the setters queued; runs on e->stream before the hop (outside the graph).
-void FlushPending(Engine* e, const std::vector<char>* kv_only = nullptr) {
+void ResetGraphs(Engine* e) {
+  e->graph16.Reset();
+  e->graph48.Reset();
+  e->graph48s.Reset();
+  e->graph16p.Reset();
+  e->graph48p.Reset();
+  e->graph48sp.Reset();
+}
+
+// Applies what the setters queued; runs on e->stream around the hop (outside the graph).  Two halves: what the
+// ENCODER lanes consume (pitch parameters, pitch range, kNN-VQ) and what the VOCODER consumes (speaker / formant
+// projections, the key-value schedule).  At pipeline depth 1 both run before the hop; at depth 2 the vocoder half
+// runs AFTER the call's graph is enqueued, because that graph still vocodes the previous hop (see RunHop*).
+void FlushEncoderSide(Engine* e) {
   cudaStream_t s = e->stream;
   if (e->pitch_dirty) {
     B200_CHECK(cudaMemcpyAsync(e->pitch_params.p, e->pp.data(), e->pp.size() * sizeof(PitchParams),
@@ -150,11 +172,13 @@ void FlushPending(Engine* e, const std::vector<char>* kv_only = nullptr) {
     if (any != e->any_vq) {
       e->any_vq = any;
       B200_CHECK(cudaStreamSynchronize(e->stream));   // rare (a parameter change): no hop graph is in flight when they are dropped
-      e->graph16.Reset();
-      e->graph48.Reset();
-      e->graph48s.Reset();
+      ResetGraphs(e);
     }
   }
+}
+
+void FlushVocoderSide(Engine* e, const std::vector<char>* kv_only = nullptr) {
+  cudaStream_t s = e->stream;
   auto dedup = [](std::vector<int>* v) {
     std::sort(v->begin(), v->end());
     v->erase(std::unique(v->begin(), v->end()), v->end());
@@ -189,6 +213,11 @@ void FlushPending(Engine* e, const std::vector<char>* kv_only = nullptr) {
   }
   // key-value speaker embedding: one block per stream per hop until all four are applied
   StepKv(e, kv_only);
+}
+
+void FlushPending(Engine* e, const std::vector<char>* kv_only = nullptr) {
+  FlushEncoderSide(e);
+  FlushVocoderSide(e, kv_only);
 }
 
 // Applies all remaining key-value blocks of the streams in `only` now (LoadModel / ResetContext do
@@ -280,6 +309,82 @@ void EnqueueHop(Engine* e, cudaStream_t s) {
   }
 }
 
+// Depth-2 form of the hop: the vocoder of the PREVIOUS hop (main stream; its inputs are the hand-off buffers the
+// encoders filled one call ago) side by side with the content encoder (aux) and the pitch estimator (aux2) of THIS
+// hop.  The encoder lanes (<= 96 CTAs, ~90 us) depend only on their own state, so they fill the SMs the vocoder's
+// latency-bound stages leave idle, and the steady-state period is the vocoder alone.
+//   * the kernels that overwrite the hand-off buffers (the content chain / VQ, the pitch arg-max) wait until the
+//     vocoder's conditioning kernel -- its only reader of them, the first kernel of its lane -- has finished;
+//   * the post conv, last kernel of the vocoder, advances all three hop counters (AdvanceFold), so it waits for
+//     both encoder lanes;
+//   * with_vocoder == false (first call after load / reset-all: nothing to vocode yet): encoders only, their
+//     counters advanced by two single-thread launches.
+void EnqueueHopPipelined(Engine* e, cudaStream_t s, bool with_vocoder) {
+  B200_CHECK(cudaEventRecord(e->ev_fork, s));
+  B200_CHECK(cudaStreamWaitEvent(e->aux, e->ev_fork, 0));
+  B200_CHECK(cudaStreamWaitEvent(e->aux2, e->ev_fork, 0));
+  auto starts = [](const std::string& n, const char* p) { return n.compare(0, std::strlen(p), p) == 0; };
+  size_t first_wave = e->hop_ops.size(), post = e->hop_ops.size();
+  for (size_t i = 0; i < e->hop_ops.size(); ++i)
+    if (e->hop_lane[i] == 2) {
+      if (first_wave == e->hop_ops.size()) first_wave = i;
+      if (e->hop_ops[i].name == "wave.post") post = i;
+    }
+  // vocoder, up to and including its conditioning (the reader of the hand-off buffers)
+  size_t w = first_wave;
+  if (with_vocoder) {
+    for (; w < post; ++w) {
+      e->hop_ops[w].launch(s);
+      if (starts(e->hop_ops[w].name, "wave.cond")) {
+        ++w;
+        break;
+      }
+    }
+    B200_CHECK(cudaEventRecord(e->ev_cond, s));
+  }
+  // encoders of this hop
+  bool waited[2] = {false, false};
+  for (size_t i = 0; i < first_wave; ++i) {
+    const int lane = e->hop_lane[i];
+    if (SkipVq(e, i)) continue;
+    cudaStream_t ls = lane == 0 ? e->aux : e->aux2;
+    const std::string& n = e->hop_ops[i].name;
+    const bool writer = lane == 0 ? (n == "phone.chain" || n == "phone.head" || n == "phone.vq") : starts(n, "pitch.argmax");
+    if (with_vocoder && writer && !waited[lane]) {
+      B200_CHECK(cudaStreamWaitEvent(ls, e->ev_cond, 0));
+      waited[lane] = true;
+    }
+    e->hop_ops[i].launch(ls);
+  }
+  B200_CHECK(cudaEventRecord(e->ev_join, e->aux));
+  B200_CHECK(cudaEventRecord(e->ev_join2, e->aux2));
+  if (with_vocoder) {
+    for (; w < post; ++w) e->hop_ops[w].launch(s);
+    B200_CHECK(cudaStreamWaitEvent(s, e->ev_join, 0));
+    B200_CHECK(cudaStreamWaitEvent(s, e->ev_join2, 0));
+    for (; w < e->hop_ops.size(); ++w) e->hop_ops[w].launch(s);   // post conv (+ nothing else: the advance is folded)
+  } else {
+    B200_CHECK(cudaStreamWaitEvent(s, e->ev_join, 0));
+    B200_CHECK(cudaStreamWaitEvent(s, e->ev_join2, 0));
+    LaunchAdvance(e->phone_st.arena.frame(), s);
+    LaunchAdvance(e->pitch_st.arena.frame(), s);
+  }
+}
+inline size_t PipelinedLaunches(const Engine* e, bool with_vocoder) {
+  if (with_vocoder) return HopLaunches(e);
+  size_t n = 2;
+  for (size_t i = 0; i < e->hop_ops.size(); ++i)
+    if (e->hop_lane[i] != 2 && !SkipVq(e, i)) ++n;
+  return n;
+}
+// after the call's graph is enqueued (depth 2): what the NEXT vocoder run must see
+void AfterPipelinedHop(Engine* e) {
+  FlushVocoderSide(e);
+  for (auto& f : e->after_hop) f();
+  e->after_hop.clear();
+  e->primed = true;
+}
+
 void EnsurePinned(Engine* e) {
   const size_t need = sizeof(float) * e->B * kHostHop48k;
   if (e->pin_bytes >= need) return;
@@ -294,9 +399,9 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
   B200_CHECK(cudaSetDevice(e->device));
   B200_CHECK(cudaStreamSynchronize(e->stream));
   e->loaded = false;
-  e->graph16.Reset();
-  e->graph48.Reset();
-  e->graph48s.Reset();
+  ResetGraphs(e);
+  e->primed = false;
+  e->after_hop.clear();
   e->phone_m.dims = e->pitch_m.dims = e->wave_m.dims = e->setter_m.dims = e->dims;
   e->pitch_m.is_pitch = true;
   if (const int err = e->phone_m.LoadFromImage(images[0], sizes[0], e->device)) return err;
@@ -355,6 +460,7 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
   e->idx_a.Alloc(e->device, sizeof(int) * B, true);
   e->idx_b.Alloc(e->device, sizeof(int) * B, true);
   e->hostrate.Init(e->device, B);
+  e->zero24.Alloc(e->device, sizeof(float) * B * kOutHop, true);
 
   e->sp.assign(B, StreamParams());
   PitchParams def;
@@ -382,6 +488,17 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
 }
 
 void RunHop16(Engine* e, bool allow_graph) {
+  if (e->pipeline == 2) {
+    FlushEncoderSide(e);
+    const bool voc = e->primed;
+    if (!voc) B200_CHECK(cudaMemsetAsync(e->wave_st.out.p, 0, e->wave_st.out.bytes, e->stream));   // "output of the hop before the first"
+    (voc ? e->graph16p : e->graph16).Run(e->stream, [&](cudaStream_t s) { EnqueueHopPipelined(e, s, voc); },
+                                         voc && allow_graph && GraphsEnabled());
+    e->launches += PipelinedLaunches(e, voc);
+    AfterPipelinedHop(e);
+    ++e->hops;
+    return;
+  }
   FlushPending(e);
   e->graph16.Run(e->stream, [&](cudaStream_t s) { EnqueueHop(e, s); }, allow_graph && GraphsEnabled());
   e->launches += HopLaunches(e);
@@ -389,6 +506,25 @@ void RunHop16(Engine* e, bool allow_graph) {
 }
 
 void RunHop48(Engine* e, bool allow_graph) {
+  if (e->pipeline == 2) {
+    FlushEncoderSide(e);
+    e->hostrate.PrepareHop(e->stream, /*out_lag=*/true);
+    const bool voc = e->primed;
+    const float* o24 = voc ? e->wave_st.out.as<float>() : e->zero24.as<float>();
+    (voc ? e->graph48p : e->graph48).Run(
+        e->stream,
+        [&](cudaStream_t s) {
+          e->hostrate.EnqueueIn(e->in16.as<float>(), s);
+          EnqueueHopPipelined(e, s, voc);
+          e->hostrate.EnqueueOut(o24, s);
+        },
+        voc && allow_graph && GraphsEnabled());
+    e->hostrate.HopDone();
+    e->launches += PipelinedLaunches(e, voc) + HostRateState::kKernelsPerHop;
+    AfterPipelinedHop(e);
+    ++e->hops;
+    return;
+  }
   FlushPending(e);
   e->hostrate.PrepareHop(e->stream);
   e->graph48.Run(
@@ -408,24 +544,39 @@ void RunHop48(Engine* e, bool allow_graph) {
 // two previous hops (the adapter's block FIFO), so it is computed and copied to the host on a side stream
 // WHILE this hop's model call runs; the hop graph itself only stores its model output for the next call.
 void RunHop48Split(Engine* e, float* out_host, size_t bytes) {
-  FlushPending(e);
-  e->hostrate.PrepareHop(e->stream);
+  const bool pipe = e->pipeline == 2, voc = e->primed;
+  if (pipe) FlushEncoderSide(e);
+  else FlushPending(e);
+  e->hostrate.PrepareHop(e->stream, /*out_lag=*/pipe);
   B200_CHECK(cudaEventRecord(e->ev_side, e->stream));          // gain segments uploaded, previous hop complete
   // the hop graph goes out first: the host work below then overlaps the input copy and the first kernels
-  e->graph48s.Run(
-      e->stream,
-      [&](cudaStream_t s) {
-        e->hostrate.EnqueueIn(e->in16.as<float>(), s);
-        EnqueueHop(e, s);
-        e->hostrate.EnqueueStore(e->wave_st.out.as<float>(), s);
-      },
-      GraphsEnabled());
+  if (pipe) {
+    const float* o24 = voc ? e->wave_st.out.as<float>() : e->zero24.as<float>();
+    (voc ? e->graph48sp : e->graph48s).Run(
+        e->stream,
+        [&](cudaStream_t s) {
+          e->hostrate.EnqueueIn(e->in16.as<float>(), s);
+          EnqueueHopPipelined(e, s, voc);
+          e->hostrate.EnqueueStore(o24, s);
+        },
+        voc && GraphsEnabled());
+  } else {
+    e->graph48s.Run(
+        e->stream,
+        [&](cudaStream_t s) {
+          e->hostrate.EnqueueIn(e->in16.as<float>(), s);
+          EnqueueHop(e, s);
+          e->hostrate.EnqueueStore(e->wave_st.out.as<float>(), s);
+        },
+        GraphsEnabled());
+  }
   B200_CHECK(cudaStreamWaitEvent(e->side, e->ev_side, 0));
   e->hostrate.EnqueueOutEarly(e->side);
   // (with a pageable destination this copy blocks the host; the hop is already running by then)
   B200_CHECK(cudaMemcpyAsync(out_host, e->hostrate.out48(), bytes, cudaMemcpyDeviceToHost, e->side));
   e->hostrate.HopDone();
-  e->launches += HopLaunches(e) + HostRateState::kKernelsPerHop + 1;
+  e->launches += (pipe ? PipelinedLaunches(e, voc) : HopLaunches(e)) + HostRateState::kKernelsPerHop + 1;
+  if (pipe) AfterPipelinedHop(e);
   ++e->hops;
 }
 
@@ -449,8 +600,14 @@ BeatriceB200_Engine* BeatriceB200_CreateEngine(int device, int n_streams, int pr
   if (std::getenv("BEATRICE_B200_MRF_TRACE")) {   // developer traces print one line per CTA: room for all of them
     cudaDeviceSetLimit(cudaLimitPrintfFifoSize, 64u << 20);
   }
-  B200_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  B200_CHECK(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
+  // the main stream carries the vocoder, the critical path of a hop: highest priority, the encoder lanes lowest
+  int prio_lo = 0, prio_hi = 0;
+  B200_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  B200_CHECK(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_hi));
+  B200_CHECK(cudaStreamCreateWithPriority(&e->aux, cudaStreamNonBlocking, prio_lo));
+  B200_CHECK(cudaStreamCreateWithPriority(&e->aux2, cudaStreamNonBlocking, prio_lo));
+  B200_CHECK(cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming));
+  B200_CHECK(cudaEventCreateWithFlags(&e->ev_cond, cudaEventDisableTiming));
   B200_CHECK(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_side, cudaEventDisableTiming));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
@@ -467,9 +624,8 @@ void BeatriceB200_DestroyEngine(BeatriceB200_Engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   cudaStreamSynchronize(e->aux);
-  e->graph16.Reset();
-  e->graph48.Reset();
-  e->graph48s.Reset();
+  if (e->aux2) cudaStreamSynchronize(e->aux2);
+  ResetGraphs(e);
   if (e->pin_in) cudaFreeHost(e->pin_in);
   if (e->pin_out) cudaFreeHost(e->pin_out);
   cudaStreamSynchronize(e->side);
@@ -479,6 +635,9 @@ void BeatriceB200_DestroyEngine(BeatriceB200_Engine* e) {
   cudaEventDestroy(e->ev_join);
   cudaStreamDestroy(e->stream);
   cudaStreamDestroy(e->aux);
+  if (e->aux2) cudaStreamDestroy(e->aux2);
+  if (e->ev_join2) cudaEventDestroy(e->ev_join2);
+  if (e->ev_cond) cudaEventDestroy(e->ev_cond);
   delete e;
 }
 
@@ -510,6 +669,20 @@ int BeatriceB200_LoadModel(BeatriceB200_Engine* e, const char* utf8_model_dir) {
   }(););
   return rc__;
 }
+
+// Pipeline depth of the throughput entries (see EnqueueHopPipelined).  Depth 1 (default): a call returns the hop
+// it was given -- the reference's latency.  Depth 2: a call returns what depth 1 returns ONE CALL EARLIER (the first
+// call returns the silence "before the first hop"); every output sample is bit-identical, 10 ms later.  Allowed
+// while no hop is in flight (right after load, ResetStream(-1) or a drain).
+int BeatriceB200_SetPipelineDepth(BeatriceB200_Engine* e, int depth) {
+  if (!e || depth < 1 || depth > 2) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
+  if (e->primed) return BEATRICE_B200_ERR_BAD_ARGUMENT;   // drain first
+  if (depth == 2 && !e->wave_st.advance_folded) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  e->pipeline = depth;
+  return 0;
+}
+int BeatriceB200_PipelineDepth(const BeatriceB200_Engine* e) { return e ? e->pipeline : 0; }
 
 int BeatriceB200_NumSpeakers(const BeatriceB200_Engine* e) { return e ? e->n_speakers : 0; }
 int BeatriceB200_NumStreams(const BeatriceB200_Engine* e) { return e ? e->B : 0; }
@@ -606,10 +779,29 @@ int BeatriceB200_ResetStream(BeatriceB200_Engine* e, int stream) {
   B200_SETTER_PROLOGUE();
   B200_CHECK(cudaSetDevice(e->device));
   B200_CHECK(cudaStreamSynchronize(e->stream));
+  if (e->pipeline == 2 && e->primed && stream >= 0) {
+    // Depth 2, one stream: its encoders restart now; its vocoder still owes the hop taken before the reset, so the
+    // vocoder half (state, conditioning, all four key-value blocks) is re-created right behind the next hop.
+    e->phone_st.ZeroStream(stream, e->stream);
+    e->pitch_st.ZeroStream(stream, e->stream);
+    e->after_hop.push_back([e, stream] {
+      e->wave_st.ZeroStream(stream, e->stream);
+      e->sp[stream].kv_set_count = 0;
+      e->pending_speaker.push_back(stream);
+      e->pending_formant.push_back(stream);
+      std::vector<char> only(e->B, 0);
+      only[stream] = 1;
+      FlushVocoderSide(e, &only);
+      for (int round = 1; round < kNBlocks; ++round) StepKv(e, &only);
+    });
+    return 0;
+  }
   if (stream < 0) {   // every stream: three memsets instead of O(streams x rings) of them
     e->phone_st.ZeroAll(e->stream);
     e->pitch_st.ZeroAll(e->stream);
     e->wave_st.ZeroAll(e->stream);
+    e->primed = false;       // depth 2: the hop in flight is dropped with everything else
+    e->after_hop.clear();
   }
   std::vector<char> only(e->B, 0);
   ForStreams(e, stream, [&](int b) {
@@ -691,6 +883,53 @@ int BeatriceB200_Process48k(BeatriceB200_Engine* e, const float* in_host, float*
   B200_CHECK(cudaStreamSynchronize(e->stream));
   return 0;
   }(););
+  return rc__;
+}
+
+// Depth 2 only: vocodes the hop still in flight without taking a new one and returns its blocks -- what the next
+// Process call would have returned -- leaving the pipeline empty (depth may then be changed; processing may simply
+// continue).  frames24_host [n][240] and / or block48_host [n][480] may be null; the 48 kHz adapter advances only
+// when block48_host is given (pair it with the 48 kHz entries, frames24_host with the model-rate ones).
+int BeatriceB200_DrainPipeline(BeatriceB200_Engine* e, float* frames24_host, float* block48_host) {
+  if (!e) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(rc__ = BEATRICE_B200_ERR_DEVICE, {
+    B200_CHECK(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    const bool voc = e->pipeline == 2 && e->primed;
+    if (voc) {
+      for (size_t i = 0; i < e->hop_ops.size(); ++i)
+        if (e->hop_lane[i] == 2) {
+          if (e->hop_ops[i].name == "wave.post") e->wave_st.post_own_advance(s);
+          else e->hop_ops[i].launch(s);
+          ++e->launches;
+        }
+    } else {
+      B200_CHECK(cudaMemsetAsync(e->wave_st.out.p, 0, e->wave_st.out.bytes, s));
+    }
+    if (frames24_host)
+      B200_CHECK(cudaMemcpyAsync(frames24_host, e->wave_st.out.p, sizeof(float) * e->B * kOutHop, cudaMemcpyDeviceToHost, s));
+    if (block48_host) {
+      // the adapter's input side takes a hop of silence here (there is no input); its gain / FIR state is the only
+      // thing a later call could notice, exactly as after 10 ms of silence on the host side
+      B200_CHECK(cudaMemsetAsync(e->hostrate.in48(), 0, sizeof(float) * e->B * kHostHop48k, s));
+      e->hostrate.PrepareHop(s, /*out_lag=*/e->pipeline == 2);
+      e->hostrate.EnqueueIn(e->in16.as<float>(), s);
+      e->hostrate.EnqueueOut(e->wave_st.out.as<float>(), s);
+      e->hostrate.HopDone();
+      e->launches += HostRateState::kKernelsPerHop;
+      B200_CHECK(cudaMemcpyAsync(block48_host, e->hostrate.out48(), sizeof(float) * e->B * kHostHop48k, cudaMemcpyDeviceToHost, s));
+    }
+    B200_CHECK(cudaStreamSynchronize(s));
+    if (voc) {
+      FlushVocoderSide(e);
+      for (auto& f : e->after_hop) f();
+      e->after_hop.clear();
+    }
+    e->primed = false;
+    rc__ = 0;
+  });
   return rc__;
 }
 
@@ -832,6 +1071,7 @@ int BeatriceB200_ProfileHop(BeatriceB200_Engine* e, const float* in_dev, float* 
   B200_GUARDED(rc__ = BEATRICE_B200_ERR_DEVICE, rc__ = [&]() -> int {
   if (!e || !in_dev || !out_dev) return BEATRICE_B200_ERR_BAD_ARGUMENT;
   if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
+  if (e->primed) return BEATRICE_B200_ERR_BAD_ARGUMENT;   // a serial, un-graphed hop: drain the pipeline first
   B200_CHECK(cudaSetDevice(e->device));
   cudaStream_t s = e->stream;
   const size_t nin = sizeof(float) * e->B * kInHop, nout = sizeof(float) * e->B * kOutHop;

@@ -1325,6 +1325,10 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
     }
     op.launch = [=](cudaStream_t s) { LaunchPostConv(dp, h, Bn, frame, fold, s); };
     program.push_back(op);
+    // the same launch advancing this state's counter only: a pipeline drain vocodes a hop the encoders took earlier
+    AdvanceFold own = fold;
+    own.frames[1] = own.frames[2] = nullptr;
+    post_own_advance = [=](cudaStream_t s) { LaunchPostConv(dp, h, Bn, frame, own, s); };
   }
   if (!advance_folded) {
     int* f = arena.frame();

@@ -252,6 +252,7 @@ struct WaveState {
   int* fold_frames[2] = {nullptr, nullptr};
   bool advance_folded = false;
   DeviceBuffer fold_done;
+  std::function<void(cudaStream_t)> post_own_advance;   // "wave.post" advancing only this state's hop counter
   // fused MRF stages: conv-input histories (bf16, stream-group layout) + reset table
   DeviceBuffer mrf_hist, mrf_blocks;
   int n_mrf_blocks = 0;

@@ -168,6 +168,7 @@ void HostRateState::Init(int device, int B) {
   hseg_out_ = hseg_in_;
   up_in_.clear();
   up_out_.clear();
+  lag_out_.clear();
   uploaded_ = false;
 }
 
@@ -182,7 +183,7 @@ void HostRateState::ResetStream(int b, cudaStream_t s) {
   B200_CHECK(cudaMemsetAsync(o_ring_.as<float>() + static_cast<size_t>(b) * 3 * kOutHop, 0, sizeof(float) * 3 * kOutHop, s));
 }
 
-void HostRateState::PrepareHop(cudaStream_t s) {
+void HostRateState::PrepareHop(cudaStream_t s, bool out_lag) {
   // Gain::Process (gain.h:41-71) on the host for the scalar state; the device replays the
   // same recurrence per sample.
   auto step = [](HostGain* g, GainSeg* seg) {
@@ -214,9 +215,15 @@ void HostRateState::PrepareHop(cudaStream_t s) {
     g->settled = (std::memcmp(&new_db, &g->current_db, sizeof(double)) == 0);
     g->current_db = new_db;
   };
+  std::vector<GainSeg> prev_out;
+  if (out_lag) prev_out = lag_out_.empty() ? std::vector<GainSeg>(B_, GainSeg{1.0, 1.0, 1.0, 0, 0}) : lag_out_;
   for (int b = 0; b < B_; ++b) {
     step(&gin_[b], &hseg_in_[b]);
     step(&gout_[b], &hseg_out_[b]);
+  }
+  if (out_lag) {
+    lag_out_ = hseg_out_;       // this call's segment: applied by the next call
+    hseg_out_.swap(prev_out);   // uploaded now: the previous call's
   }
   const size_t bytes = sizeof(GainSeg) * B_;
   if (!uploaded_ || std::memcmp(up_in_.data(), hseg_in_.data(), bytes) != 0) {
@@ -228,6 +235,7 @@ void HostRateState::PrepareHop(cudaStream_t s) {
     up_out_ = hseg_out_;
   }
   uploaded_ = true;
+  if (out_lag) hseg_out_ = lag_out_;   // the host-side recurrence continues from the un-lagged state
 }
 
 void HostRateState::EnqueueIn(float* x16, cudaStream_t s) {

@@ -39,7 +39,9 @@ class HostRateState {
   void ResetStream(int b, cudaStream_t s);
   // host side of one hop: advances the per-stream gain state like Gain::Process does and
   // uploads the segments if they changed.  Call before EnqueueIn, outside graph capture.
-  void PrepareHop(cudaStream_t s);
+  // out_lag (pipeline depth 2 of the engine): the block handed back by this call is the one depth 1 hands back one
+  // call earlier, so the OUTPUT gain segment uploaded is the one computed for the previous call.
+  void PrepareHop(cudaStream_t s, bool out_lag = false);
   // in48 (device, [B][480]) -> x16 (device, [B][160]); graph-capturable
   void EnqueueIn(float* x16, cudaStream_t s);
   // model output o24 (device, [B][240]) -> out48 (device, [B][480]); graph-capturable
@@ -63,7 +65,7 @@ class HostRateState {
   DeviceBuffer in48_, out48_, g_ring_, o_ring_, frame_, done_, coef_, seg_in_, seg_out_;
   int host_frame_ = 0;
   std::vector<HostGain> gin_, gout_;
-  std::vector<GainSeg> hseg_in_, hseg_out_, up_in_, up_out_;
+  std::vector<GainSeg> hseg_in_, hseg_out_, up_in_, up_out_, lag_out_;
   bool uploaded_ = false;
 };
 

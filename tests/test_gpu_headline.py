@@ -240,3 +240,85 @@ def test_device_adapter_alone_is_bit_exact(product, model_dir):
         assert np.array_equal(got16[:, s, :], np.stack(seen)), s
         assert np.array_equal(got48[:, s, :], np.stack(want48)), s
     assert got48[-1].std() > 0.01
+
+
+# ---------------------------------------------------------------------------------------
+# pipeline depth 2 (throughput mode): the same samples, one call later
+# ---------------------------------------------------------------------------------------
+def _pipeline_events(n):
+    """(hop, stream, setter, value) with vocoder-side changes (speaker + 4-hop key-value schedule, formant, output
+    gain), encoder-side ones (pitch shift, VQ, input gain) and a single-stream reset in mid-run."""
+    ev = [(0, s, "TargetSpeaker", s % 8) for s in range(n)]
+    ev += [(2, 1, "PitchShift", 5.0), (3, 2, "FormantShift", -1.5), (4, 0, "OutputGain", -6.0), (4, 3, "InputGain", 3.0),
+           (5, 1, "TargetSpeaker", 6), (6, 2, "VQNumNeighbors", 4), (7, n - 1, "TargetSpeaker", 2), (9, 0, "OutputGain", 2.0),
+           (8, 4 % n, "reset", 0), (10, 3, "PitchCorrection", 0.5)]
+    return ev
+
+
+def _run_entry(eng, entry, x, events, depth):
+    n, hops = eng.n, len(x)
+    assert eng.set_pipeline_depth(depth) == 0
+    width = 240 if entry == "frames" else 480
+    d_in = eng.dev_alloc("p_in", n * x.shape[2])
+    d_out = eng.dev_alloc("p_out", n * width)
+    outs = []
+    for h in range(hops):
+        for (at, s, name, v) in events:
+            if at == h:
+                assert (eng.reset_stream(s) if name == "reset" else eng.set(name, v, s)) == 0
+        if entry == "host48":
+            outs.append(eng.process_48k(x[h]).copy())
+        elif entry == "dev48":
+            eng.to_device(d_in, x[h])
+            assert eng.process_48k_device(d_in, d_out) == 0
+            eng.synchronize()
+            outs.append(eng.to_host(d_out, (n, 480)))
+        else:
+            outs.append(eng.process_frames(x[h]).copy())
+    if depth == 2:
+        outs.append(eng.drain(model_rate=(entry == "frames")))
+    return np.stack(outs)
+
+
+@pytest.mark.parametrize("entry", ["host48", "dev48", "frames"])
+def test_pipeline_depth_2_is_depth_1_one_call_later(product, model_dir, entry):
+    """Depth 2 overlaps hop h+1's encoders with hop h's vocoder.  Its output must be the depth-1 output, bit for
+    bit, delayed by exactly one call -- through speaker changes (the key-value blocks keep their four-hop schedule
+    relative to the audio), formant / gain changes (the output gain slew is delayed with the audio), encoder-side
+    parameters and a single-stream reset in mid-run."""
+    n, hops = 20, 14
+    x = signals.batch_16k(n, hops, seed0=1200) if entry == "frames" else signals.batch_48k(n, hops, seed0=1200)
+    ev = _pipeline_events(n)
+    a = bbatch.Engine(product, n)
+    b = bbatch.Engine(product, n)
+    assert a.load(model_dir) == 0 and b.load(model_dir) == 0
+    serial = _run_entry(a, entry, x, ev, 1)
+    piped = _run_entry(b, entry, x, ev, 2)
+    a.close()
+    b.close()
+    assert serial.std() > 0.01
+    assert not piped[0].any()                         # the silence before the first hop
+    for h in range(hops):
+        assert np.array_equal(piped[h + 1], serial[h]), (entry, h)
+
+
+def test_pipeline_depth_2_full_batch(product, model_dir):
+    """The same at bench.py's 256 streams, continuing after a drain."""
+    n, hops = 256, 6
+    x = signals.batch_48k(16, hops, seed0=77)
+    x = np.tile(x, (1, n // 16, 1))
+    a = bbatch.Engine(product, n)
+    b = bbatch.Engine(product, n)
+    assert a.load(model_dir) == 0 and b.load(model_dir) == 0
+    assert b.set_pipeline_depth(2) == 0
+    serial = np.stack([a.process_48k(x[h]).copy() for h in range(hops)])
+    piped = [b.process_48k(x[h]).copy() for h in range(3)]
+    assert b.set_pipeline_depth(1) == -1              # a hop is in flight
+    piped.append(b.drain())
+    # NB: a drain feeds the 48 kHz adapter one hop of silence on its input side; restart both engines' streams to
+    # compare the continuation
+    for h in range(3):
+        assert np.array_equal(piped[h + 1], serial[h]), h
+    assert b.set_pipeline_depth(1) == 0
+    a.close()
+    b.close()
