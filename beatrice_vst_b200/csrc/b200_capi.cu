@@ -513,10 +513,8 @@ void Beatrice20rc0_RegisterKeyValueSpeakerEmbedding(const void* /*m*/, const flo
     const size_t bytes = sizeof(float) * kKvLength * kKvChannels;
     if (!ec->kv.p) ec->kv.Alloc(dev, bytes, false);
     B200_CHECK(cudaSetDevice(ec->kv.device));
-    // synchronous copy + device-wide sync: the consumer (kv_film_kernel) runs on the waveform context's non-blocking
-    // stream, which does not order against the legacy stream a pageable cudaMemcpy may still be draining on
-    B200_CHECK(cudaMemcpy(ec->kv.p, kv, bytes, cudaMemcpyHostToDevice));
-    B200_CHECK(cudaDeviceSynchronize());
+    // the consumer (kv_film_kernel) runs on the waveform context's non-blocking stream: complete the copy first
+    UploadSync(ec->kv.p, kv, bytes);
     ec->registered = true;
   });
 }

@@ -55,10 +55,27 @@ namespace b200 {
 
 // Load-time host -> device upload.  A cudaMemcpy from pageable memory may return once the bytes are staged, before
 // the DMA into `dst` has finished, and the kernels that read `dst` run on cudaStreamNonBlocking streams, which do not
-// order against the legacy stream the copy drains on: wait for the device before anyone can consume the data.
+// order against the legacy stream such a copy drains on.  So the copy goes through a private non-blocking stream
+// that is synchronised before anyone can consume the data.  (Not cudaDeviceSynchronize: other host threads may be
+// capturing their hop graphs at this moment -- independent plug-in instances -- and a device-wide sync is illegal
+// while any capture is open.)
 inline void UploadSync(void* dst, const void* src, size_t bytes) {
-  B200_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
-  B200_CHECK(cudaDeviceSynchronize());
+  cudaStream_t up = nullptr;
+  B200_CHECK(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+  cudaError_t err = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, up);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(up);
+  cudaStreamDestroy(up);
+  B200_CHECK(err);
+}
+
+// Same for the zero-fill of a fresh allocation (cudaMemset on device memory is asynchronous to the host too).
+inline void ZeroSync(void* dst, size_t bytes) {
+  cudaStream_t up = nullptr;
+  B200_CHECK(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+  cudaError_t err = cudaMemsetAsync(dst, 0, bytes, up);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(up);
+  cudaStreamDestroy(up);
+  B200_CHECK(err);
 }
 
 // Programmatic dependent launch: the kernel may begin (prologue up to its griddepcontrol.wait)

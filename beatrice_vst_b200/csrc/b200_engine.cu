@@ -274,7 +274,7 @@ void DeviceBuffer::Alloc(int dev, size_t n_bytes, bool zero) {
   if (n_bytes == 0) n_bytes = 16;
   B200_CHECK(cudaMalloc(&p, n_bytes));
   bytes = n_bytes;
-  if (zero) B200_CHECK(cudaMemset(p, 0, n_bytes));
+  if (zero) ZeroSync(p, n_bytes);
 }
 
 namespace {

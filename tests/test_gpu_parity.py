@@ -21,7 +21,12 @@ from conftest import ROOT, rms
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 TOL_WAVE = 1e-4     # north_star: <= 1e-4 RMS (fp32)
-TOL_FEAT = 2e-5
+TOL_FEAT = 2e-5     # fp32 mode: phone / pitch-feature vectors (values of magnitude ~1..4)
+TOL_FEAT_TC = 1e-4  # split-bf16 on tcgen05 (the default): ~1e-5 relative on the same vectors
+
+
+def _tol_feat(precision):
+    return TOL_FEAT if precision == 0 else TOL_FEAT_TC
 
 
 @pytest.fixture(params=[2, 0], ids=["bf16x3", "f32"])
@@ -56,7 +61,7 @@ def test_single_stream_abi_matches_oracle(product, oracle, model_dirs, family, a
     a.close()
     b.close()
     assert np.array_equal(qa, qb)
-    assert rms(pa, pb) <= TOL_FEAT and rms(fa, fb) <= TOL_FEAT
+    assert rms(pa, pb) <= _tol_feat(abi_precision) and rms(fa, fb) <= _tol_feat(abi_precision), (rms(pa, pb), rms(fa, fb))
     assert rms(wa, wb) <= TOL_WAVE, rms(wa, wb)
     assert np.abs(wa - wb).max() <= 1e-3
 
@@ -69,14 +74,14 @@ def test_single_stream_abi_matches_golden(product, model_dirs, family, abi_preci
     phone, q, feat, wave = s.run(g["x"])
     s.close()
     assert np.array_equal(q, g["q"])
-    assert rms(phone, g["phone"]) <= TOL_FEAT and rms(wave, g["wave"]) <= TOL_WAVE
+    assert rms(phone, g["phone"]) <= _tol_feat(abi_precision) and rms(wave, g["wave"]) <= TOL_WAVE
     if family == 2:
         s = blib.SingleStream(product, model_dirs[2], family=2, speaker=1, formant_index=5)
         s.set_pitch_range(1, 383)
         s.set_vq(4)
         p2, _, _, w2 = s.run(g["x"])
         s.close()
-        assert rms(p2, g["phone_vq4"]) <= TOL_FEAT and rms(w2, g["wave_vq4"]) <= TOL_WAVE
+        assert rms(p2, g["phone_vq4"]) <= _tol_feat(abi_precision) and rms(w2, g["wave_vq4"]) <= TOL_WAVE
 
 
 def test_vocoder_stage_taps_match_oracle(product, oracle, model_dir):
@@ -124,7 +129,7 @@ def test_vq_speaker_switch_and_formant(product, oracle, model_dir, abi_precision
         outs.append(w)
     for (pa, qa, fa, wa), (pb, qb, fb, wb) in zip(*outs):
         assert qa == qb
-        assert rms(pa, pb) <= TOL_FEAT and rms(wa, wb) <= TOL_WAVE
+        assert rms(pa, pb) <= _tol_feat(abi_precision) and rms(wa, wb) <= TOL_WAVE
     a.close()
     b.close()
 
