@@ -313,8 +313,8 @@ void EnqueueHop(Engine* e, cudaStream_t s) {
 // encoders filled one call ago) side by side with the content encoder (aux) and the pitch estimator (aux2) of THIS
 // hop.  The encoder lanes (<= 96 CTAs, ~90 us) depend only on their own state, so they fill the SMs the vocoder's
 // latency-bound stages leave idle, and the steady-state period is the vocoder alone.
-//   * the kernels that overwrite the hand-off buffers (the content chain / VQ, the pitch arg-max) wait until the
-//     vocoder's conditioning kernel -- its only reader of them, the first kernel of its lane -- has finished;
+//   * the encoder lanes run behind a GATE kernel of the vocoder (see below); the gate is never earlier than the
+//     vocoder's conditioning kernel, the only reader of the hand-off buffers the lanes' last kernels overwrite;
 //   * the post conv, last kernel of the vocoder, advances all three hop counters (AdvanceFold), so it waits for
 //     both encoder lanes;
 //   * with_vocoder == false (first call after load / reset-all: nothing to vocode yet): encoders only, their
@@ -330,31 +330,37 @@ void EnqueueHopPipelined(Engine* e, cudaStream_t s, bool with_vocoder) {
       if (first_wave == e->hop_ops.size()) first_wave = i;
       if (e->hop_ops[i].name == "wave.post") post = i;
     }
-  // vocoder, up to and including its conditioning (the reader of the hand-off buffers)
+  // Vocoder first, up to its GATE kernel.  The encoder lanes start behind the gate (only their first kernel, a
+  // block-per-stream ingest that is gone within the vocoder's conditioning / first upsampler, runs from the fork):
+  // stage 0 of the vocoder is one wave of 4-CTA clusters and stage 1 one wave of single CTAs at one CTA per SM, so an
+  // SM held by an encoder CTA when they launch costs a whole extra wave, while behind them the stages are many
+  // short CTAs and the early-finishing k = 3 / k = 7 branches leave room.  The gate is at or after the conditioning
+  // kernel -- the only reader of the hand-off buffers the lanes' last kernels overwrite.
+  static const std::string gate_name = [] {
+    const char* ev = std::getenv("BEATRICE_B200_PIPE_GATE");   // developer: substring of the gate op's name
+    return std::string(ev && ev[0] ? ev : "wave.mrf0");
+  }();
   size_t w = first_wave;
   if (with_vocoder) {
-    for (; w < post; ++w) {
-      e->hop_ops[w].launch(s);
-      if (starts(e->hop_ops[w].name, "wave.cond")) {
-        ++w;
-        break;
-      }
-    }
+    size_t gate = post;
+    for (size_t i = first_wave; i < post; ++i)
+      if (e->hop_ops[i].name.find(gate_name) != std::string::npos) gate = i;
+    size_t cond = first_wave;
+    for (size_t i = first_wave; i < post; ++i)
+      if (starts(e->hop_ops[i].name, "wave.cond")) cond = i;
+    if (gate == post || gate < cond) gate = cond;
+    for (; w <= gate; ++w) e->hop_ops[w].launch(s);
     B200_CHECK(cudaEventRecord(e->ev_cond, s));
   }
   // encoders of this hop
-  bool waited[2] = {false, false};
+  bool first_of_lane[2] = {true, true};
   for (size_t i = 0; i < first_wave; ++i) {
     const int lane = e->hop_lane[i];
     if (SkipVq(e, i)) continue;
     cudaStream_t ls = lane == 0 ? e->aux : e->aux2;
-    const std::string& n = e->hop_ops[i].name;
-    const bool writer = lane == 0 ? (n == "phone.chain" || n == "phone.head" || n == "phone.vq") : starts(n, "pitch.argmax");
-    if (with_vocoder && writer && !waited[lane]) {
-      B200_CHECK(cudaStreamWaitEvent(ls, e->ev_cond, 0));
-      waited[lane] = true;
-    }
     e->hop_ops[i].launch(ls);
+    if (with_vocoder && first_of_lane[lane]) B200_CHECK(cudaStreamWaitEvent(ls, e->ev_cond, 0));   // everything behind the ingest waits for the gate
+    first_of_lane[lane] = false;
   }
   B200_CHECK(cudaEventRecord(e->ev_join, e->aux));
   B200_CHECK(cudaEventRecord(e->ev_join2, e->aux2));
