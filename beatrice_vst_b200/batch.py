@@ -29,6 +29,9 @@ BATCH_SYMBOLS = {
     "BeatriceB200_NumSpeakers": (C.c_int, [_vp]),
     "BeatriceB200_NumStreams": (C.c_int, [_vp]),
     "BeatriceB200_SetTargetSpeaker": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "BeatriceB200_SetSpeakerMorphingWeights": (C.c_int, [_vp, C.c_int, _f32p, C.c_int]),
+    "BeatriceB200_SeedMorphLottery": (C.c_int, [_vp, C.c_uint]),
+    "BeatriceB200_GetMorphState": (C.c_int, [_vp, C.c_int, _f32p, _f32p, _i32p]),
     "BeatriceB200_SetFormantShift": (C.c_int, [_vp, C.c_int, C.c_double]),
     "BeatriceB200_SetPitchShift": (C.c_int, [_vp, C.c_int, C.c_double]),
     "BeatriceB200_SetAverageSourcePitch": (C.c_int, [_vp, C.c_int, C.c_double]),
@@ -131,6 +134,25 @@ class Engine:
     def set(self, name: str, value, stream: int = -1) -> int:
         fn = getattr(self.dll, "BeatriceB200_Set" + name)
         return fn(self.h, stream, value)
+
+    def set_morph_weights(self, weights, stream: int = -1) -> int:
+        """ProcessorCore2::SetSpeakerMorphingWeights; select the morphing slot with set("TargetSpeaker", n_speakers)."""
+        w = np.ascontiguousarray(weights, np.float32)
+        return self.dll.BeatriceB200_SetSpeakerMorphingWeights(self.h, stream, w.ctypes.data_as(_f32p), int(w.size))
+
+    def seed_morph_lottery(self, seed: int) -> int:
+        return self.dll.BeatriceB200_SeedMorphLottery(self.h, seed)
+
+    def morph_state(self, stream: int):
+        """(additive average [256], registered key-value embedding [384,128], lottery pick) of a stream's morphing slot."""
+        add = np.empty(256, np.float32)
+        kv = np.empty((384, 128), np.float32)
+        pick = C.c_int(-1)
+        rc = self.dll.BeatriceB200_GetMorphState(self.h, stream, add.ctypes.data_as(_f32p), kv.ctypes.data_as(_f32p),
+                                                 C.byref(pick))
+        if rc != 0:
+            raise RuntimeError(f"BeatriceB200_GetMorphState -> {rc}")
+        return add, kv, pick.value
 
     def reset_stream(self, stream: int = -1) -> int:
         return self.dll.BeatriceB200_ResetStream(self.h, stream)

@@ -8,6 +8,9 @@
 #include <cmath>
 #include <cstring>
 #include <functional>
+#include <limits>
+#include <numeric>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -29,6 +32,20 @@ struct StreamParams {  // host mirror; defaults = processor_core_2.h:103-113
   double max_source_pitch = 80.875;
   int vq = 0;
   int kv_set_count = kNBlocks;  // blocks 0..3 still to apply, one per hop (processor_core_2.h:161-169)
+};
+
+// Voice morphing of one stream (processor_core_2.cc:51-177, :498-532, processor_core_2.h:138-145).
+constexpr int kMaxNSpeakers = 256;          // model_config.h:17
+constexpr int kSphAvgMaxNSpeakers = 8;      // processor_core_2.h:26
+constexpr int kSphAvgMaxNState = 4;         // processor_core_2.h:91
+constexpr float kVoiceMorphWeightThreshold = 0.01f;   // voice_morph_state.h:21
+struct MorphState {
+  std::vector<float> weights = std::vector<float>(kMaxNSpeakers, 0.0f);   // as set (speaker_morphing_weights_)
+  std::vector<float> pruned = std::vector<float>(kMaxNSpeakers, 0.0f);    // speaker_morphing_weights_pruned_
+  std::vector<int> argsort = std::vector<int>(kMaxNSpeakers, 0);          // speaker_morphing_weights_argsort_indices_
+  int counter = std::numeric_limits<int>::max();                          // speaker_morphing_state_counter_
+  bool register_pending = false;   // RegisterKeyValueSpeakerEmbedding(morph slot) queued for the next vocoder-side flush
+  int pick = 0;                    // codebook lottery result of the latest hop
 };
 
 int NoteToBin(double note, int bins) {  // processor_core_2.cc:561-583
@@ -66,6 +83,10 @@ struct BeatriceB200_Engine {
   HostRateState hostrate;  // 48 kHz adapter (gain + FIRs + FIFO), b200_hostrate.h
 
   std::vector<StreamParams> sp;
+  std::vector<MorphState> morph;
+  std::mt19937 lottery{std::random_device{}()};       // processor_core_2.h:48, :145 (one engine for all streams here)
+  DeviceBuffer kv_stage;                              // [B][384*128]: key-value averages in progress (the call site's slot n_speakers)
+  DeviceBuffer morph_jobs;                            // [2][B] MorphJob
   std::vector<PitchParams> pp;
   bool pitch_dirty = true, range_dirty = true, vq_dirty = true;
   std::vector<int> pending_speaker, pending_formant;  // stream ids whose projection must be refreshed
@@ -100,6 +121,130 @@ void UploadInts(Engine* e, DeviceBuffer* dst, const std::vector<int>& v) {
   B200_CHECK(cudaMemcpyAsync(dst->p, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
 }
 
+// Row of the additive / key-value tables a stream's conditioning is read from: its speaker, or -- in morphing mode,
+// target speaker == n_speakers (processor_core_2.cc:51) -- the stream's own slot behind the model's speakers.
+inline int TableRow(const Engine* e, int b) {
+  return e->sp[b].speaker < e->n_speakers ? e->sp[b].speaker : e->n_speakers + b;
+}
+inline bool Morphing(const Engine* e, int b) { return e->sp[b].speaker == e->n_speakers; }
+
+// ApplySpeakerMorphingWeights (processor_core_2.cc:507-532) with PrepareVoiceMorphWeights (voice_morph_state.h:87-104)
+void ApplyMorphWeights(Engine* e, int b) {
+  MorphState& m = e->morph[b];
+  const int n = e->n_speakers;
+  std::vector<float> w = m.weights;
+  const int count = std::min(n, kMaxNSpeakers);
+  for (int i = count; i < kMaxNSpeakers; ++i) w[count - 1] += w[i];
+  std::fill(w.begin() + count, w.end(), 0.0f);
+  for (int i = 0; i < count; ++i)
+    if (w[i] < kVoiceMorphWeightThreshold) w[i] = 0.0f;
+  std::iota(m.argsort.data(), m.argsort.data() + n, 0);
+  std::sort(m.argsort.data(), m.argsort.data() + n, [&w](const int a, const int c) -> bool { return w[a] > w[c]; });
+  std::fill(m.pruned.begin(), m.pruned.end(), 0.0f);
+  const int n_weights = std::min(n, kSphAvgMaxNSpeakers);
+  for (int i = 0; i < n_weights; ++i) m.pruned[m.argsort[i]] = w[m.argsort[i]];
+  m.counter = 0;
+}
+
+// SphericalAverage::SetWeights' selection (spherical_average.h:171-181): arg-sorted, cut at the first zero weight
+MorphJob MakeMorphJob(const Engine* e, int b, int item0) {
+  const MorphState& m = e->morph[b];
+  MorphJob j;
+  std::memset(&j, 0, sizeof(j));
+  const int lim = std::min(e->n_speakers, kSphAvgMaxNSpeakers);
+  int n = 0;
+  for (; n < lim; ++n) {
+    const float wv = m.pruned[m.argsort[n]];
+    if (wv == 0.0f) break;
+    j.idx[n] = m.argsort[n];
+    j.w[n] = wv;
+  }
+  j.n = n;
+  j.item0 = item0;
+  j.dst_row = b;
+  return j;
+}
+
+// The per-frame codebook lottery of morphing streams (processor_core_2.cc:93-121): encoder side.
+void MorphLottery(Engine* e) {
+  const int n = e->n_speakers;
+  for (int b = 0; b < e->B; ++b) {
+    if (!Morphing(e, b)) continue;
+    MorphState& m = e->morph[b];
+    const int n_weights = std::min(n, kSphAvgMaxNSpeakers);
+    float weight_sum = 0.0f;
+    for (int i = 0; i < n_weights; ++i) weight_sum += m.pruned[m.argsort[i]];
+    int idx = m.argsort[0];
+    if (weight_sum <= std::numeric_limits<float>::epsilon()) {
+      idx = std::uniform_int_distribution<int>(0, n - 1)(e->lottery);
+    } else {
+      float random_weight = std::uniform_real_distribution<float>(0.0f, weight_sum)(e->lottery);
+      for (int i = 0; i < n_weights; ++i) {
+        const int speaker_id = m.argsort[i];
+        random_weight -= m.pruned[speaker_id];
+        if (random_weight < 0.0f) {
+          idx = speaker_id;
+          break;
+        }
+      }
+    }
+    m.pick = idx;
+    e->vq_dirty = true;   // the stream's codebook pointer moves
+  }
+}
+
+// The vocoder-side part of the morphing block of Process1 (processor_core_2.cc:123-176), for every morphing stream:
+// frame 0 after a weight change: the additive embedding's average (then its projection, queued); frames 0..3: a
+// quarter of the key-value rows each, into the stream's staging slot; frame 4: the staging slot is registered
+// (copied to the stream's table row) and the four-hop key-value schedule restarts.
+void MorphVocoderStep(Engine* e, bool hop) {
+  cudaStream_t s = e->stream;
+  const size_t kvn = static_cast<size_t>(kKvLength) * kKvChannels;
+  std::vector<MorphJob> add_jobs, kv_jobs;
+  for (int b = 0; b < e->B; ++b) {
+    MorphState& m = e->morph[b];
+    if (m.register_pending) {   // SetTargetSpeaker(morph slot) / ResetContext: the slot as it is now (:456-462)
+      B200_CHECK(cudaMemcpyAsync(e->kv.as<float>() + kvn * (e->n_speakers + b), e->kv_stage.as<float>() + kvn * b,
+                                 kvn * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      m.register_pending = false;
+    }
+    if (!hop || !Morphing(e, b)) continue;
+    if (m.counter == 0) {
+      MorphJob j = MakeMorphJob(e, b, 0);
+      j.dst_row = e->n_speakers + b;
+      add_jobs.push_back(j);
+      e->pending_speaker.push_back(b);   // SetAdditiveSpeakerEmbedding(morph slot), :137-141
+    }
+    if (m.counter < kSphAvgMaxNState) {
+      const int start = kKvLength * m.counter / kSphAvgMaxNState;
+      kv_jobs.push_back(MakeMorphJob(e, b, start));   // dst_row = b: the staging slot
+    }
+  }
+  MorphJob* dj = e->morph_jobs.as<MorphJob>();
+  if (!add_jobs.empty()) {
+    B200_CHECK(cudaMemcpyAsync(dj, add_jobs.data(), add_jobs.size() * sizeof(MorphJob), cudaMemcpyHostToDevice, s));
+    LaunchSphAvg(kHidden, e->additive.as<float>(), kHidden, dj, static_cast<int>(add_jobs.size()), 1,
+                 e->additive.as<float>(), kHidden, s);
+    ++e->launches;
+  }
+  if (!kv_jobs.empty()) {
+    B200_CHECK(cudaMemcpyAsync(dj + e->B, kv_jobs.data(), kv_jobs.size() * sizeof(MorphJob), cudaMemcpyHostToDevice, s));
+    LaunchSphAvg(kKvChannels, e->kv.as<float>(), static_cast<long long>(kvn), dj + e->B, static_cast<int>(kv_jobs.size()),
+                 kKvLength / kSphAvgMaxNState, e->kv_stage.as<float>(), static_cast<long long>(kvn), s);
+    ++e->launches;
+  }
+  for (int b = 0; hop && b < e->B; ++b) {
+    if (!Morphing(e, b)) continue;
+    MorphState& m = e->morph[b];
+    if (m.counter == kSphAvgMaxNState) {   // :166-173
+      B200_CHECK(cudaMemcpyAsync(e->kv.as<float>() + kvn * (e->n_speakers + b), e->kv_stage.as<float>() + kvn * b,
+                                 kvn * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      e->sp[b].kv_set_count = 0;
+    }
+    if (m.counter <= kSphAvgMaxNState) ++m.counter;
+  }
+}
+
 // One step of the key-value schedule: every stream (of `only`, when given) that still has blocks to apply gets its
 // next one (SetKeyValueSpeakerEmbedding(block), processor_core_2.h:161-169).
 void StepKv(Engine* e, const std::vector<char>* only) {
@@ -109,7 +254,7 @@ void StepKv(Engine* e, const std::vector<char>* only) {
     for (int b = 0; b < e->B; ++b)
       if (e->sp[b].kv_set_count == blk && (!only || (*only)[b])) {
         streams.push_back(b);
-        spk.push_back(e->sp[b].speaker);
+        spk.push_back(TableRow(e, b));
       }
     if (streams.empty()) continue;
     UploadInts(e, &e->idx_a, spk);
@@ -137,8 +282,9 @@ void ResetGraphs(Engine* e) {
 // ENCODER lanes consume (pitch parameters, pitch range, kNN-VQ) and what the VOCODER consumes (speaker / formant
 // projections, the key-value schedule).  At pipeline depth 1 both run before the hop; at depth 2 the vocoder half
 // runs AFTER the call's graph is enqueued, because that graph still vocodes the previous hop (see RunHop*).
-void FlushEncoderSide(Engine* e) {
+void FlushEncoderSide(Engine* e, bool hop) {
   cudaStream_t s = e->stream;
+  if (hop) MorphLottery(e);   // once per frame, like Process1
   if (e->pitch_dirty) {
     B200_CHECK(cudaMemcpyAsync(e->pitch_params.p, e->pp.data(), e->pp.size() * sizeof(PitchParams),
                                cudaMemcpyHostToDevice, s));
@@ -160,7 +306,7 @@ void FlushEncoderSide(Engine* e) {
     const size_t cb = static_cast<size_t>(kCodebookSize) * e->dims.phone_channels;
     for (int b = 0; b < e->B; ++b) {
       n[b] = e->sp[b].vq;
-      ptr[b] = e->codebooks.as<float>() + cb * e->sp[b].speaker;
+      ptr[b] = e->codebooks.as<float>() + cb * (Morphing(e, b) ? e->morph[b].pick : e->sp[b].speaker);
     }
     UploadInts(e, &e->vq_n, n);
     B200_CHECK(cudaMemcpyAsync(e->codebook_ptrs.p, ptr.data(), ptr.size() * sizeof(float*), cudaMemcpyHostToDevice, s));
@@ -177,8 +323,9 @@ void FlushEncoderSide(Engine* e) {
   }
 }
 
-void FlushVocoderSide(Engine* e, const std::vector<char>* kv_only = nullptr) {
+void FlushVocoderSide(Engine* e, bool hop, const std::vector<char>* kv_only = nullptr) {
   cudaStream_t s = e->stream;
+  MorphVocoderStep(e, hop);
   auto dedup = [](std::vector<int>* v) {
     std::sort(v->begin(), v->end());
     v->erase(std::unique(v->begin(), v->end()), v->end());
@@ -186,7 +333,7 @@ void FlushVocoderSide(Engine* e, const std::vector<char>* kv_only = nullptr) {
   if (!e->pending_speaker.empty()) {  // SetAdditiveSpeakerEmbedding, processor_core_2.cc:451-455
     dedup(&e->pending_speaker);
     std::vector<int> src;
-    for (int b : e->pending_speaker) src.push_back(e->sp[b].speaker);
+    for (int b : e->pending_speaker) src.push_back(TableRow(e, b));
     const int n = static_cast<int>(src.size());
     UploadInts(e, &e->idx_a, src);
     UploadInts(e, &e->idx_b, e->pending_speaker);
@@ -215,16 +362,17 @@ void FlushVocoderSide(Engine* e, const std::vector<char>* kv_only = nullptr) {
   StepKv(e, kv_only);
 }
 
-void FlushPending(Engine* e, const std::vector<char>* kv_only = nullptr) {
-  FlushEncoderSide(e);
-  FlushVocoderSide(e, kv_only);
+// hop: the flush in front of a frame (the morphing block of Process1 runs); false: LoadModel / ResetContext
+void FlushPending(Engine* e, bool hop, const std::vector<char>* kv_only = nullptr) {
+  FlushEncoderSide(e, hop);
+  FlushVocoderSide(e, hop, kv_only);
 }
 
 // Applies all remaining key-value blocks of the streams in `only` now (LoadModel / ResetContext do
 // `while (SetKeyValueSpeakerEmbedding());`, processor_core_2.cc:270, :414) together with their queued speaker /
 // formant projections.  Streams outside `only` keep their one-block-per-hop schedule (processor_core_2.h:161-169).
 void FlushAllKv(Engine* e, const std::vector<char>& only) {
-  FlushPending(e, &only);   // queued projections + the first block
+  FlushPending(e, /*hop=*/false, &only);   // queued projections + the first block
   for (int round = 1; round < kNBlocks; ++round) StepKv(e, &only);
 }
 
@@ -385,7 +533,7 @@ inline size_t PipelinedLaunches(const Engine* e, bool with_vocoder) {
 }
 // after the call's graph is enqueued (depth 2): what the NEXT vocoder run must see
 void AfterPipelinedHop(Engine* e) {
-  FlushVocoderSide(e);
+  FlushVocoderSide(e, /*hop=*/true);
   for (auto& f : e->after_hop) f();
   e->after_hop.clear();
   e->primed = true;
@@ -436,16 +584,20 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
     std::memcpy(h_kv.data() + kvn * i, p, kvn * sizeof(float));
     p += kvn;
   }
-  auto up = [&](DeviceBuffer* b, const float* h, size_t count) {
-    b->Alloc(e->device, count * sizeof(float), false);
+  const int B = e->B;
+  // `extra` zeroed rows behind the model's speakers: one morphing slot per stream (the call site keeps one slot,
+  // index n_speakers, per instance: processor_core_2.cc:340-372)
+  auto up = [&](DeviceBuffer* b, const float* h, size_t count, size_t extra) {
+    b->Alloc(e->device, (count + extra) * sizeof(float), extra > 0);
     UploadSync(b->p, h, count * sizeof(float));
   };
-  up(&e->codebooks, h_cb.data(), h_cb.size());
-  up(&e->additive, h_add.data(), h_add.size());
-  up(&e->formant_tab, h_formant, static_cast<size_t>(kNFormant) * kHidden);
-  up(&e->kv, h_kv.data(), h_kv.size());
+  up(&e->codebooks, h_cb.data(), h_cb.size(), 0);
+  up(&e->additive, h_add.data(), h_add.size(), static_cast<size_t>(kHidden) * B);
+  up(&e->formant_tab, h_formant, static_cast<size_t>(kNFormant) * kHidden, 0);
+  up(&e->kv, h_kv.data(), h_kv.size(), kvn * B);
+  e->kv_stage.Alloc(e->device, kvn * B * sizeof(float), true);
+  e->morph_jobs.Alloc(e->device, sizeof(MorphJob) * 2 * B, true);
 
-  const int B = e->B;
   e->in16.Alloc(e->device, sizeof(float) * B * kInHop, true);
   const TcMode tc = static_cast<TcMode>(e->precision);
   e->wave_st.cond_ready = false;
@@ -469,6 +621,8 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
   e->zero24.Alloc(e->device, sizeof(float) * B * kOutHop, true);
 
   e->sp.assign(B, StreamParams());
+  e->morph.assign(B, MorphState());
+  for (int b = 0; b < B; ++b) ApplyMorphWeights(e, b);   // LoadModel ends with ApplySpeakerMorphingWeights (:417)
   PitchParams def;
   def.average_source_pitch = 52.0;
   def.intonation_intensity = 1.0;
@@ -495,7 +649,7 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
 
 void RunHop16(Engine* e, bool allow_graph) {
   if (e->pipeline == 2) {
-    FlushEncoderSide(e);
+    FlushEncoderSide(e, true);
     const bool voc = e->primed;
     if (!voc) B200_CHECK(cudaMemsetAsync(e->wave_st.out.p, 0, e->wave_st.out.bytes, e->stream));   // "output of the hop before the first"
     (voc ? e->graph16p : e->graph16).Run(e->stream, [&](cudaStream_t s) { EnqueueHopPipelined(e, s, voc); },
@@ -505,7 +659,7 @@ void RunHop16(Engine* e, bool allow_graph) {
     ++e->hops;
     return;
   }
-  FlushPending(e);
+  FlushPending(e, true);
   e->graph16.Run(e->stream, [&](cudaStream_t s) { EnqueueHop(e, s); }, allow_graph && GraphsEnabled());
   e->launches += HopLaunches(e);
   ++e->hops;
@@ -513,7 +667,7 @@ void RunHop16(Engine* e, bool allow_graph) {
 
 void RunHop48(Engine* e, bool allow_graph) {
   if (e->pipeline == 2) {
-    FlushEncoderSide(e);
+    FlushEncoderSide(e, true);
     e->hostrate.PrepareHop(e->stream, /*out_lag=*/true);
     const bool voc = e->primed;
     const float* o24 = voc ? e->wave_st.out.as<float>() : e->zero24.as<float>();
@@ -531,7 +685,7 @@ void RunHop48(Engine* e, bool allow_graph) {
     ++e->hops;
     return;
   }
-  FlushPending(e);
+  FlushPending(e, true);
   e->hostrate.PrepareHop(e->stream);
   e->graph48.Run(
       e->stream,
@@ -551,8 +705,8 @@ void RunHop48(Engine* e, bool allow_graph) {
 // WHILE this hop's model call runs; the hop graph itself only stores its model output for the next call.
 void RunHop48Split(Engine* e, float* out_host, size_t bytes) {
   const bool pipe = e->pipeline == 2, voc = e->primed;
-  if (pipe) FlushEncoderSide(e);
-  else FlushPending(e);
+  if (pipe) FlushEncoderSide(e, true);
+  else FlushPending(e, true);
   e->hostrate.PrepareHop(e->stream, /*out_lag=*/pipe);
   B200_CHECK(cudaEventRecord(e->ev_side, e->stream));          // gain segments uploaded, previous hop complete
   // the hop graph goes out first: the host work below then overlaps the input copy and the first kernels
@@ -699,16 +853,61 @@ int BeatriceB200_NumStreams(const BeatriceB200_Engine* e) { return e ? e->B : 0;
 
 int BeatriceB200_SetTargetSpeaker(BeatriceB200_Engine* e, int stream, int speaker) {
   B200_SETTER_PROLOGUE();
-  // the morph slot (id == n_speakers, processor_core_2.cc:51-177) is out of scope: SURVEY 8f-4
-  if (speaker < 0 || speaker >= e->n_speakers) return BEATRICE_B200_ERR_SPEAKER_RANGE;
+  // speaker == n_speakers is the morphing slot (processor_core_2.cc:436, :51-177)
+  if (speaker < 0 || speaker > e->n_speakers) return BEATRICE_B200_ERR_SPEAKER_RANGE;
   ForStreams(e, stream, [&](int b) {
     e->sp[b].speaker = speaker;
     e->sp[b].kv_set_count = 0;  // :464 -- blocks are applied over the next four hops
     e->pending_speaker.push_back(b);
+    // the morphing slot is registered as it is NOW, possibly part-way through its four frames of averaging (:456-462)
+    if (speaker == e->n_speakers) e->morph[b].register_pending = true;
   });
   e->vq_dirty = true;
   return 0;
 }
+// ProcessorCore2::SetSpeakerMorphingWeights (processor_core_2.cc:498-505): weights per speaker id (up to 256; the
+// call site's std::array<float, kMaxNSpeakers>, missing entries zero).  Takes effect while the stream's target
+// speaker is the morphing slot, SetTargetSpeaker(stream, NumSpeakers()).
+int BeatriceB200_SetSpeakerMorphingWeights(BeatriceB200_Engine* e, int stream, const float* weights, int n_weights) {
+  B200_SETTER_PROLOGUE();
+  if (!weights || n_weights < 0 || n_weights > kMaxNSpeakers) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  std::vector<float> w(kMaxNSpeakers, 0.0f);
+  std::copy(weights, weights + n_weights, w.begin());
+  ForStreams(e, stream, [&](int b) {
+    if (w == e->morph[b].weights) return;   // :500-502
+    e->morph[b].weights = w;
+    ApplyMorphWeights(e, b);
+  });
+  return 0;
+}
+// The reference seeds its lottery engine from std::random_device (processor_core_2.h:48); tests fix the seed.
+int BeatriceB200_SeedMorphLottery(BeatriceB200_Engine* e, unsigned seed) {
+  if (!e) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  e->lottery.seed(seed);
+  return 0;
+}
+// Test / diagnostic: a stream's morphing slot as the vocoder sees it -- the additive embedding's average [256], the
+// registered key-value embedding [384*128] -- and the speaker the latest hop's codebook lottery picked.
+int BeatriceB200_GetMorphState(BeatriceB200_Engine* e, int stream, float* additive256, float* kv, int* lottery_speaker) {
+  if (!e || stream < 0 || stream >= e->B) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(rc__ = BEATRICE_B200_ERR_DEVICE, {
+    B200_CHECK(cudaSetDevice(e->device));
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+    const size_t kvn = static_cast<size_t>(kKvLength) * kKvChannels;
+    const int row = e->n_speakers + stream;
+    if (additive256)
+      B200_CHECK(cudaMemcpyAsync(additive256, e->additive.as<float>() + static_cast<size_t>(kHidden) * row, sizeof(float) * kHidden,
+                                 cudaMemcpyDeviceToHost, e->stream));
+    if (kv) B200_CHECK(cudaMemcpyAsync(kv, e->kv.as<float>() + kvn * row, sizeof(float) * kvn, cudaMemcpyDeviceToHost, e->stream));
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+    if (lottery_speaker) *lottery_speaker = e->morph[stream].pick;
+    rc__ = 0;
+  });
+  return rc__;
+}
+
 int BeatriceB200_SetFormantShift(BeatriceB200_Engine* e, int stream, double v) {
   B200_SETTER_PROLOGUE();
   ForStreams(e, stream, [&](int b) {
@@ -795,9 +994,10 @@ int BeatriceB200_ResetStream(BeatriceB200_Engine* e, int stream) {
       e->sp[stream].kv_set_count = 0;
       e->pending_speaker.push_back(stream);
       e->pending_formant.push_back(stream);
+      if (Morphing(e, stream)) e->morph[stream].register_pending = true;
       std::vector<char> only(e->B, 0);
       only[stream] = 1;
-      FlushVocoderSide(e, &only);
+      FlushVocoderSide(e, /*hop=*/false, &only);
       for (int round = 1; round < kNBlocks; ++round) StepKv(e, &only);
     });
     return 0;
@@ -819,6 +1019,7 @@ int BeatriceB200_ResetStream(BeatriceB200_Engine* e, int stream) {
     e->sp[b].kv_set_count = 0;
     e->pending_speaker.push_back(b);
     e->pending_formant.push_back(b);
+    if (Morphing(e, b)) e->morph[b].register_pending = true;   // ResetContext -> SetTargetSpeaker(target_speaker_), :269
     only[b] = 1;
   });
   // ResetContext re-applies the speaker with all four blocks at once (:269-270) -- for the streams being reset only;
@@ -928,8 +1129,7 @@ int BeatriceB200_DrainPipeline(BeatriceB200_Engine* e, float* frames24_host, flo
       B200_CHECK(cudaMemcpyAsync(block48_host, e->hostrate.out48(), sizeof(float) * e->B * kHostHop48k, cudaMemcpyDeviceToHost, s));
     }
     B200_CHECK(cudaStreamSynchronize(s));
-    if (voc) {
-      FlushVocoderSide(e);
+    if (voc) {   // what was queued behind this hop's vocoder (single-stream resets); its own flush ran one call ago
       for (auto& f : e->after_hop) f();
       e->after_hop.clear();
     }
@@ -1066,7 +1266,7 @@ size_t BeatriceB200_ResidentBytes(const BeatriceB200_Engine* e) {
   if (!e || !e->loaded) return 0;
   return e->phone_st.arena.bytes() + e->pitch_st.arena.bytes() + e->wave_st.arena.bytes() + e->phone_m.blob.bytes +
          e->pitch_m.blob.bytes + e->wave_m.blob.bytes + e->setter_m.blob.bytes + e->codebooks.bytes +
-         e->additive.bytes + e->kv.bytes;
+         e->additive.bytes + e->kv.bytes + e->kv_stage.bytes;
 }
 
 uint64_t BeatriceB200_KernelLaunchCount(const BeatriceB200_Engine* e) { return e ? e->launches : 0; }
@@ -1082,7 +1282,7 @@ int BeatriceB200_ProfileHop(BeatriceB200_Engine* e, const float* in_dev, float* 
   cudaStream_t s = e->stream;
   const size_t nin = sizeof(float) * e->B * kInHop, nout = sizeof(float) * e->B * kOutHop;
   B200_CHECK(cudaMemcpyAsync(e->in16.p, in_dev, nin, cudaMemcpyDeviceToDevice, s));
-  FlushPending(e);
+  FlushPending(e, true);
   const size_t n = e->hop_ops.size();
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& x : ev) B200_CHECK(cudaEventCreate(&x));

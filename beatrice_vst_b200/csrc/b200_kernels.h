@@ -117,6 +117,18 @@ void LaunchAdvance(int* d_frame, cudaStream_t s);
 void LaunchPitchArgmax(const float* head, int bins, const int* min_q, const int* max_q, int* q, float* feat,
                        int B, cudaStream_t s, const PitchParams* params = nullptr, int* q_used = nullptr);
 // reference call-site transform, fp64 (processor_core_2.cc:190-252)
+// Voice morphing (b200_morph.cu): one stream's pruned, arg-sorted morphing weights (processor_core_2.cc:507-532) and
+// where its averages go.  Item i of a job averages row item0 + i of the speakers idx[0..n).
+struct MorphJob {
+  int n;          // speakers with non-zero weight, <= 8 (kSphAvgMaxNSpeakers)
+  int item0;      // first row (key-value embedding: 96 rows per frame; additive embedding: 0)
+  int dst_row;    // destination slot, in units of dst_stride
+  int pad;
+  int idx[8];     // speaker ids, by descending weight
+  float w[8];     // their weights (not normalised)
+};
+void LaunchSphAvg(int M, const float* table, long long speaker_stride, const MorphJob* d_jobs, int n_jobs,
+                  int items_per_job, float* dst, long long dst_stride, cudaStream_t s);
 void LaunchPitchTransform(const int* q_in, const PitchParams* params, int bins, int* q_out, int B,
                           cudaStream_t s);
 // conditioning: phone 1x1 + pitch embedding gather + feature projection + speaker (+ formant)

@@ -14,6 +14,7 @@
 // at load time from whichever implementation the .so was linked against (the CPU oracle
 // for libcallsite_oracle.so, the CUDA library for libcallsite_b200.so).
 
+#include <array>
 #include <chrono>
 #include <cstring>
 #include <string>
@@ -57,6 +58,13 @@ int Callsite_SetSampleRate(void* h, double sr) {
 int Callsite_GetVersion(void* h) { return static_cast<Harness*>(h)->proxy.GetCore()->GetVersion(); }
 int Callsite_ResetContext(void* h) {
   return static_cast<int>(static_cast<Harness*>(h)->proxy.GetCore()->ResetContext());
+}
+// ProcessorCore2::SetSpeakerMorphingWeights (processor_core_2.cc:498-505), the call the voice-morph parameters end in
+// (parameter_schema.cc:36-40).  weights: 256 floats (std::array<float, kMaxNSpeakers>).
+int Callsite_SetMorphWeights(void* h, const float* weights256) {
+  std::array<float, beatrice::common::kMaxNSpeakers> w{};
+  std::memcpy(w.data(), weights256, sizeof(float) * w.size());
+  return static_cast<int>(static_cast<Harness*>(h)->proxy.GetCore()->SetSpeakerMorphingWeights(w));
 }
 // In-place allowed, like Processor::process does (src/vst/processor.cc:216-217).
 int Callsite_Process(void* h, const float* in, float* out, int n) {

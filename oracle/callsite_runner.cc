@@ -6,7 +6,7 @@
 //       Feeds in.f32 through ProcessorCore::Process in `block`-sample calls (in place, like
 //       src/vst/processor.cc:216-217).  "idx:name=value" applies SetParameter before block
 //       `idx` (idx = -1: before LoadModel; names as in parameter_schema.h:44-70, see table).
-//       "idx:reset=1" calls ResetContext().  Prints one line: "error_codes: load=<e> last=<e>".
+//       "idx:reset=1" calls ResetContext().  "idx:morphw<k>=w" + "idx:morph_apply=1": voice-morphing weights.  Prints one line: "error_codes: load=<e> last=<e>".
 //   callsite_runner bench <model.toml> <signal.f32> <threads> <frames> <warmup>
 //       signal.f32 holds threads*frames*480 floats.  Prints JSON with frames/s.
 
@@ -25,6 +25,7 @@ int Callsite_SetDouble(void* h, int id, double value);
 int Callsite_GetVersion(void* h);
 int Callsite_ResetContext(void* h);
 int Callsite_Process(void* h, const float* in, float* out, int n);
+int Callsite_SetMorphWeights(void* h, const float* weights256);
 double Callsite_Bench(const char* toml_utf8, double sample_rate, int n_threads, int n_frames, int warmup,
                       const float* signal, double* seconds_out);
 }
@@ -69,8 +70,19 @@ std::vector<float> ReadF32(const char* path) {
   return v;
 }
 
+// "morphw<k>=v" stages the morphing weight of speaker k; "morph_apply=1" hands the staged array to
+// ProcessorCore2::SetSpeakerMorphingWeights.  ("voice=<n_speakers>" selects the morphing slot.)
+float g_morph_weights[256] = {};
+
 int Apply(void* h, const Event& e) {
   if (e.name == "reset") return Callsite_ResetContext(h);
+  if (e.name.rfind("morphw", 0) == 0) {
+    const int k = std::atoi(e.name.c_str() + 6);
+    if (k < 0 || k >= 256) return -1;
+    g_morph_weights[k] = static_cast<float>(e.value);
+    return 0;
+  }
+  if (e.name == "morph_apply") return Callsite_SetMorphWeights(h, g_morph_weights);
   for (const Param& p : kParams)
     if (e.name == p.name)
       return p.is_int ? Callsite_SetInt(h, p.id, static_cast<int>(e.value)) : Callsite_SetDouble(h, p.id, e.value);

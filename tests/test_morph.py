@@ -1,0 +1,183 @@
+"""Voice-morphing mode (reference src/common/processor_core_2.cc:51-177, :498-532 and
+src/common/spherical_average.h:80-444).
+
+CPU: the reference call site in morphing mode through the test harness (known answer: all weight on one speaker
+converges to that speaker).  GPU: the device-side spherical averages against the reference header compiled in
+oracle/_ref (sphavg_ref), the engine in morphing mode against the reference call site over the CPU oracle, and the
+per-hop codebook lottery distribution (the reference seeds its engine from std::random_device, so that part can
+only be checked as a distribution)."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import callsite
+from beatrice_vst_b200 import batch as bbatch
+from beatrice_vst_b200 import lib as blib
+from beatrice_vst_b200 import signals
+from conftest import ROOT, rms
+
+SPHAVG = os.path.join(ROOT, "oracle", "_ref", "sphavg_ref")
+N_SPK = 8
+
+
+def _morph_events(at, weights):
+    ev = [(at, f"morphw{k}", float(w)) for k, w in enumerate(weights)]
+    return ev + [(at, "morph_apply", 1)]
+
+
+@pytest.mark.skipif(not callsite.available("oracle"), reason="oracle/_ref not built")
+def test_callsite_morph_mode_with_all_weight_on_one_speaker_converges_to_it(model_dir):
+    """processor_core_2.cc:51-177 through the harness: target speaker = n_speakers selects the morphing slot; with
+    the whole weight on speaker 3 the averages equal speaker 3's embeddings (spherical_average.h: one point), so
+    once the five-frame schedule and the conv histories have flushed the audio is that of a plain voice = 3 run."""
+    x = signals.voice_like(480 * 60, 48000.0, seed=3)
+    toml = os.path.join(model_dir, "model.toml")
+    w = np.zeros(N_SPK)
+    w[3] = 1.0
+    y, info = callsite.run("oracle", toml, x, events=_morph_events(0, w) + [(0, "voice", N_SPK)])
+    y3, _ = callsite.run("oracle", toml, x, events=[(0, "voice", 3)])
+    assert info == {"load": 0, "last": 0, "version": 2}
+    assert rms(y[:4800], y3[:4800]) > 1e-3                    # the transition is audible ...
+    assert rms(y[-4800:], y3[-4800:]) <= 2e-6                  # ... and ends in the same voice
+
+
+def _reference_average(M, rows, table, weights256):
+    with tempfile.TemporaryDirectory() as d:
+        fp, fw, fo = (os.path.join(d, n) for n in ("p.f32", "w.f32", "o.f32"))
+        np.ascontiguousarray(table, "<f4").tofile(fp)
+        np.ascontiguousarray(weights256, "<f4").tofile(fw)
+        p = subprocess.run([SPHAVG, str(M), str(N_SPK), str(rows), fp, fw, fo], capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, (p.returncode, p.stderr[-500:])
+        return np.fromfile(fo, "<f4").reshape(rows, M)
+
+
+WEIGHT_SETS = [
+    {0: 0.6, 5: 0.4},
+    {1: 0.05, 2: 0.4, 3: 0.3, 6: 0.15, 7: 0.1},
+    {0: 0.2, 1: 0.2, 2: 0.15, 3: 0.15, 4: 0.1, 5: 0.1, 6: 0.095, 7: 0.005},   # the last one is under the 0.01 threshold
+    {4: 1.0},
+    {2: 0.5, 6: 0.5},                                                            # tie: arg-sort order matters
+]
+
+
+def _w256(ws):
+    w = np.zeros(256, np.float32)
+    for k, v in ws.items():
+        w[k] = v
+    return w
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(SPHAVG), reason="oracle/_ref/sphavg_ref not built")
+def test_device_spherical_averages_match_reference_header(product, model_dir):
+    """The morphing slot the vocoder sees -- additive average [256] and the registered key-value embedding
+    [384][128] -- after the call site's five-frame schedule, per stream, against spherical_average.h driven the
+    way Process1 drives it (<= 4 L-BFGS updates per average)."""
+    one = blib.SingleStream(product, model_dir)                 # host-side reader of the speaker tables
+    additive, kv = one.additive.copy(), one.kv.copy()
+    one.close()
+    n = len(WEIGHT_SETS)
+    eng = bbatch.Engine(product, n)
+    assert eng.load(model_dir) == 0 and eng.n_speakers == N_SPK
+    for s, ws in enumerate(WEIGHT_SETS):
+        assert eng.set_morph_weights(_w256(ws)[:N_SPK], s) == 0
+        assert eng.set("TargetSpeaker", N_SPK, s) == 0
+    x = signals.batch_16k(n, 6, seed0=11)
+    for h in range(6):
+        eng.process_frames(x[h])
+    worst_a, worst_k = 0.0, 0.0
+    for s, ws in enumerate(WEIGHT_SETS):
+        got_a, got_k, _ = eng.morph_state(s)
+        want_a = _reference_average(256, 1, additive[:, None, :], _w256(ws))[0]
+        want_k = _reference_average(128, 384, kv, _w256(ws))
+        ea = np.abs(got_a - want_a).max() / max(np.abs(want_a).max(), 1e-9)
+        ek = np.abs(got_k - want_k).max() / max(np.abs(want_k).max(), 1e-9)
+        worst_a, worst_k = max(worst_a, ea), max(worst_k, ek)
+        assert ea <= 1e-6 and ek <= 1e-6, (s, ea, ek)
+    eng.close()
+    print(f"[morph] averages vs reference header: additive {worst_a:.2e}, key-value {worst_k:.2e} (relative to max |value|)")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not callsite.available("oracle"), reason="oracle/_ref not built")
+@pytest.mark.parametrize("depth", [1, 2])
+def test_engine_morph_mode_matches_reference_callsite(product, model_dir, depth):
+    """48 kHz entry, three streams in morphing mode with different weights, a weight change in mid-run (the averages
+    are re-computed over five hops while the old ones stay in effect), a ResetContext and a return to a plain
+    speaker; kNN-VQ off (with VQ on the per-hop codebook is a lottery).  Audio <= 1e-4 RMS vs the reference call
+    site over the CPU oracle, at both pipeline depths."""
+    n, hops = 3, 34
+    x = signals.batch_48k(n, hops, seed0=2100)
+    plans = [
+        _morph_events(0, [0.6, 0, 0, 0, 0, 0.4, 0, 0]) + [(0, "voice", N_SPK)] + _morph_events(12, [0, 0.5, 0, 0.2, 0, 0, 0.3, 0]),
+        _morph_events(0, [0, 0.3, 0.3, 0, 0, 0, 0.2, 0.2]) + [(3, "voice", N_SPK), (20, "reset", 1), (27, "voice", 2)],
+        [(0, "voice", 5)] + _morph_events(6, [0.25] * 4 + [0] * 4) + [(9, "voice", N_SPK), (9, "pitch_shift", 3.0)],
+    ]
+    eng = bbatch.Engine(product, n)
+    assert eng.load(model_dir) == 0
+    assert eng.set_pipeline_depth(depth) == 0
+    outs = []
+    for h in range(hops):
+        for s in range(n):
+            staged = {}
+            for (b, name, v) in plans[s]:
+                if b != h:
+                    continue
+                if name.startswith("morphw"):
+                    staged[int(name[6:])] = v
+                elif name == "morph_apply":
+                    w = np.zeros(N_SPK, np.float32)
+                    for k, val in staged.items():
+                        w[k] = val
+                    assert eng.set_morph_weights(w, s) == 0
+                elif name == "reset":
+                    assert eng.reset_stream(s) == 0
+                elif name == "voice":
+                    assert eng.set("TargetSpeaker", int(v), s) == 0
+                elif name == "pitch_shift":
+                    assert eng.set("PitchShift", float(v), s) == 0
+        outs.append(eng.process_48k(x[h]).copy())
+    if depth == 2:
+        outs = outs[1:] + [eng.drain()]
+    eng.close()
+    got = np.stack(outs, axis=1)
+    toml = os.path.join(model_dir, "model.toml")
+    for s in range(n):
+        y, info = callsite.run("oracle", toml, x[:, s, :].reshape(-1), events=plans[s])
+        assert info["load"] == 0 and info["last"] == 0
+        e = rms(got[s].reshape(-1), y)
+        assert y.std() > 0.01 and e <= 1e-4, (s, e)
+
+
+@pytest.mark.gpu
+def test_morph_codebook_lottery_follows_the_weights(product, model_dir):
+    """processor_core_2.cc:93-121: every hop a morphing stream draws its kNN-VQ codebook among the <= 8 heaviest
+    speakers with the (pruned) weights as probabilities; all-zero weights draw uniformly.  Distributional check
+    (the reference's engine is seeded from std::random_device)."""
+    n, hops = 16, 250
+    eng = bbatch.Engine(product, n)
+    assert eng.load(model_dir) == 0
+    assert eng.seed_morph_lottery(1234) == 0
+    w = np.zeros(N_SPK, np.float32)
+    w[[1, 4, 6]] = [0.6, 0.3, 0.1]
+    for s in range(n):
+        assert eng.set_morph_weights(w if s < 8 else np.zeros(N_SPK, np.float32), s) == 0
+        assert eng.set("TargetSpeaker", N_SPK, s) == 0
+        assert eng.set("VQNumNeighbors", 4, s) == 0
+    x = signals.batch_16k(n, 4, seed0=5)
+    counts = np.zeros((2, N_SPK))
+    for h in range(hops):
+        out = eng.process_frames(x[h % 4])
+        for s in range(n):
+            counts[0 if s < 8 else 1, eng.morph_state(s)[2]] += 1
+    eng.close()
+    assert np.isfinite(out).all()
+    total = 8 * hops
+    for k, p in ((1, 0.6), (4, 0.3), (6, 0.1)):
+        sigma = np.sqrt(p * (1 - p) / total)
+        assert abs(counts[0, k] / total - p) <= 5 * sigma, (k, counts[0])
+    assert counts[0, [0, 2, 3, 5, 7]].sum() == 0
+    assert (counts[1] > total / N_SPK * 0.7).all() and (counts[1] < total / N_SPK * 1.3).all(), counts[1]
