@@ -34,9 +34,14 @@ __device__ __forceinline__ float Dot(const float (&a)[E], const float (&b)[E]) {
   for (int e = 0; e < E; ++e) s = fmaf(a[e], b[e], s);
   return WarpSum(s);
 }
-__device__ __forceinline__ float SincRef(float x) {   // spherical_average.h:307-325
+// spherical_average.h:307-325.  NB the reference writes an unqualified `abs(x)` there, which -- as the reference
+// compiles on this platform (g++ / glibc: oracle/_ref) -- binds to the C library's abs(int): the angle is TRUNCATED to
+// an integer before the threshold tests, so the series branch returns exactly 1 for every |x| < 1 and sin(x)/x is
+// used from 1 radian on.  Results must be those of the reference as built here, so the truncation is reproduced
+// (tests/test_morph.py compares with that build; a build whose <cmath> offers a global abs(float) would differ).
+__device__ __forceinline__ float SincRef(float x) {
   const float t0 = FLT_EPSILON, t1 = sqrtf(t0), t2 = sqrtf(t1);
-  const float ax = fabsf(x);
+  const float ax = fabsf(truncf(x));
   if (ax >= t2) return sinf(x) / x;
   float y = 1.0f;
   if (ax >= t0) {
