@@ -28,6 +28,8 @@ BATCH_SYMBOLS = {
     "BeatriceB200_LoadModelFromMemory": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "BeatriceB200_NumSpeakers": (C.c_int, [_vp]),
     "BeatriceB200_NumStreams": (C.c_int, [_vp]),
+    "BeatriceB200_ModelFamily": (C.c_int, [_vp]),
+    "BeatriceB200_PhoneChannels": (C.c_int, [_vp]),
     "BeatriceB200_SetTargetSpeaker": (C.c_int, [_vp, C.c_int, C.c_int]),
     "BeatriceB200_SetSpeakerMorphingWeights": (C.c_int, [_vp, C.c_int, _f32p, C.c_int]),
     "BeatriceB200_SeedMorphLottery": (C.c_int, [_vp, C.c_uint]),
@@ -125,6 +127,10 @@ class Engine:
         ptrs = (_vp * 5)(*[b.ctypes.data for b in bufs])
         sizes = (C.c_size_t * 5)(*[b.size for b in bufs])
         return self.dll.BeatriceB200_LoadModelFromMemory(self.h, ptrs, sizes)
+
+    @property
+    def family(self) -> int:
+        return self.dll.BeatriceB200_ModelFamily(self.h)
 
     @property
     def n_speakers(self) -> int:
@@ -232,7 +238,7 @@ class Engine:
 
     # ---- introspection ----
     def last_intermediates(self):
-        phone = np.empty((self.n, 128), np.float32)
+        phone = np.empty((self.n, self.dll.BeatriceB200_PhoneChannels(self.h)), np.float32)
         q_raw = np.empty(self.n, np.int32)
         q_used = np.empty(self.n, np.int32)
         feat = np.empty((self.n, 4), np.float32)

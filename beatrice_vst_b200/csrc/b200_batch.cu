@@ -85,6 +85,7 @@ struct BeatriceB200_Engine {
   std::vector<StreamParams> sp;
   std::vector<MorphState> morph;
   std::mt19937 lottery{std::random_device{}()};       // processor_core_2.h:48, :145 (one engine for all streams here)
+  std::vector<float> h_additive, h_formant;           // 20a2 / 20b1: the speaker vector is formed on the host (processor_core_0.cc:128-142)
   DeviceBuffer kv_stage;                              // [B][384*128]: key-value averages in progress (the call site's slot n_speakers)
   DeviceBuffer morph_jobs;                            // [2][B] MorphJob
   std::vector<PitchParams> pp;
@@ -249,6 +250,7 @@ void MorphVocoderStep(Engine* e, bool hop) {
 // next one (SetKeyValueSpeakerEmbedding(block), processor_core_2.h:161-169).
 void StepKv(Engine* e, const std::vector<char>* only) {
   cudaStream_t s = e->stream;
+  if (!e->dims.has_setter) return;   // 20a2 / 20b1 have no key-value embedding
   for (int blk = 0; blk < kNBlocks; ++blk) {
     std::vector<int> streams, spk;
     for (int b = 0; b < e->B; ++b)
@@ -284,7 +286,7 @@ void ResetGraphs(Engine* e) {
 // runs AFTER the call's graph is enqueued, because that graph still vocodes the previous hop (see RunHop*).
 void FlushEncoderSide(Engine* e, bool hop) {
   cudaStream_t s = e->stream;
-  if (hop) MorphLottery(e);   // once per frame, like Process1
+  if (hop && e->dims.has_setter) MorphLottery(e);   // once per frame, like Process1
   if (e->pitch_dirty) {
     B200_CHECK(cudaMemcpyAsync(e->pitch_params.p, e->pp.data(), e->pp.size() * sizeof(PitchParams),
                                cudaMemcpyHostToDevice, s));
@@ -306,7 +308,8 @@ void FlushEncoderSide(Engine* e, bool hop) {
     const size_t cb = static_cast<size_t>(kCodebookSize) * e->dims.phone_channels;
     for (int b = 0; b < e->B; ++b) {
       n[b] = e->sp[b].vq;
-      ptr[b] = e->codebooks.as<float>() + cb * (Morphing(e, b) ? e->morph[b].pick : e->sp[b].speaker);
+      ptr[b] = e->dims.has_setter ? e->codebooks.as<float>() + cb * (Morphing(e, b) ? e->morph[b].pick : e->sp[b].speaker) : nullptr;
+      if (!e->dims.has_setter) n[b] = 0;   // no codebook VQ in the legacy families
     }
     UploadInts(e, &e->vq_n, n);
     B200_CHECK(cudaMemcpyAsync(e->codebook_ptrs.p, ptr.data(), ptr.size() * sizeof(float*), cudaMemcpyHostToDevice, s));
@@ -325,6 +328,28 @@ void FlushEncoderSide(Engine* e, bool hop) {
 
 void FlushVocoderSide(Engine* e, bool hop, const std::vector<char>* kv_only = nullptr) {
   cudaStream_t s = e->stream;
+  if (!e->dims.has_setter) {
+    // 20a2 / 20b1 (processor_core_0.cc:128-142): speaker vector = speaker_embeddings[target] + formant_shift_embeddings[
+    // round(formant_shift * 2 + 4)], formed here on the host for the streams whose target / formant changed
+    std::vector<int> todo = e->pending_speaker;
+    todo.insert(todo.end(), e->pending_formant.begin(), e->pending_formant.end());
+    std::sort(todo.begin(), todo.end());
+    todo.erase(std::unique(todo.begin(), todo.end()), todo.end());
+    float vec[kHidden];
+    for (int b : todo) {
+      const double f = std::min(std::max(e->sp[b].formant_shift, -2.0), 2.0);
+      const int fi = static_cast<int>(std::round(f * 2.0 + 4.0));
+      const float* a = e->h_additive.data() + static_cast<size_t>(kHidden) * e->sp[b].speaker;
+      const float* fm = e->h_formant.data() + static_cast<size_t>(kHidden) * fi;
+      for (int i = 0; i < kHidden; ++i) vec[i] = a[i] + fm[i];
+      B200_CHECK(cudaMemcpyAsync(e->wave_st.spk.as<float>() + static_cast<size_t>(kHidden) * b, vec, sizeof(vec), cudaMemcpyHostToDevice, s));
+    }
+    e->pending_speaker.clear();
+    e->pending_formant.clear();
+    (void)hop;
+    (void)kv_only;
+    return;
+  }
   MorphVocoderStep(e, hop);
   auto dedup = [](std::vector<int>* v) {
     std::sort(v->begin(), v->end());
@@ -556,48 +581,77 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
   ResetGraphs(e);
   e->primed = false;
   e->after_hop.clear();
+  // the model family is the files' (header word 1: 0 = 2.0.0-alpha.2, 1 = 2.0.0-beta.1, 2 = 2.0.0-rc.0); for the two
+  // legacy families image 3 is formant_shift_embeddings.bin (there is no embedding setter: processor_core_0.cc:206-213)
+  if (!images[0] || sizes[0] < 16) return 2;
+  uint32_t hdr[4];
+  std::memcpy(hdr, images[0], 16);
+  if (hdr[0] != kFileMagic) return 4;
+  if (hdr[1] > 2) return 4;
+  e->dims = kFamilies[hdr[1]];
+  const bool rc0 = e->dims.has_setter;
   e->phone_m.dims = e->pitch_m.dims = e->wave_m.dims = e->setter_m.dims = e->dims;
   e->pitch_m.is_pitch = true;
   if (const int err = e->phone_m.LoadFromImage(images[0], sizes[0], e->device)) return err;
   if (const int err = e->pitch_m.LoadFromImage(images[1], sizes[1], e->device)) return err;
   if (const int err = e->wave_m.LoadFromImage(images[2], sizes[2], e->device)) return err;
-  if (const int err = e->setter_m.LoadFromImage(images[3], sizes[3], e->device)) return err;
-  FileImage img;
+  const int B = e->B;
   const FamilyDims d = e->dims;
-  if (const int err = ParseFileImage(images[4], sizes[4], d.family, kKindSpeakers, kKindSpeakers,
-                                     [&](uint32_t n) { return static_cast<long long>(SpeakerPayloadFloats(d, n)); }, &img))
-    return err;
-  const int n = static_cast<int>(img.count);
-  if (n <= 0) return 4;
-  e->n_speakers = n;
   const size_t cb = static_cast<size_t>(kCodebookSize) * d.phone_channels;
   const size_t kvn = static_cast<size_t>(kKvLength) * kKvChannels;
-  std::vector<float> h_cb(cb * n), h_add(static_cast<size_t>(kHidden) * n), h_kv(kvn * n);
-  const float* p = img.payload;
-  const float* h_formant = p;
-  p += kNFormant * kHidden;
-  for (int i = 0; i < n; ++i) {
-    std::memcpy(h_cb.data() + cb * i, p, cb * sizeof(float));
-    p += cb;
-    std::memcpy(h_add.data() + static_cast<size_t>(kHidden) * i, p, kHidden * sizeof(float));
-    p += kHidden;
-    std::memcpy(h_kv.data() + kvn * i, p, kvn * sizeof(float));
-    p += kvn;
-  }
-  const int B = e->B;
   // `extra` zeroed rows behind the model's speakers: one morphing slot per stream (the call site keeps one slot,
   // index n_speakers, per instance: processor_core_2.cc:340-372)
   auto up = [&](DeviceBuffer* b, const float* h, size_t count, size_t extra) {
     b->Alloc(e->device, (count + extra) * sizeof(float), extra > 0);
     UploadSync(b->p, h, count * sizeof(float));
   };
-  up(&e->codebooks, h_cb.data(), h_cb.size(), 0);
-  up(&e->additive, h_add.data(), h_add.size(), static_cast<size_t>(kHidden) * B);
-  up(&e->formant_tab, h_formant, static_cast<size_t>(kNFormant) * kHidden, 0);
-  up(&e->kv, h_kv.data(), h_kv.size(), kvn * B);
-  e->kv_stage.Alloc(e->device, kvn * B * sizeof(float), true);
-  e->morph_jobs.Alloc(e->device, sizeof(MorphJob) * 2 * B, true);
-
+  FileImage img;
+  if (rc0) {
+    if (const int err = e->setter_m.LoadFromImage(images[3], sizes[3], e->device)) return err;
+    if (const int err = ParseFileImage(images[4], sizes[4], d.family, kKindSpeakers, kKindSpeakers,
+                                       [&](uint32_t n) { return static_cast<long long>(SpeakerPayloadFloats(d, n)); }, &img))
+      return err;
+    const int n = static_cast<int>(img.count);
+    if (n <= 0) return 4;
+    e->n_speakers = n;
+    std::vector<float> h_cb(cb * n), h_add(static_cast<size_t>(kHidden) * n), h_kv(kvn * n);
+    const float* p = img.payload;
+    const float* h_formant = p;
+    p += kNFormant * kHidden;
+    for (int i = 0; i < n; ++i) {
+      std::memcpy(h_cb.data() + cb * i, p, cb * sizeof(float));
+      p += cb;
+      std::memcpy(h_add.data() + static_cast<size_t>(kHidden) * i, p, kHidden * sizeof(float));
+      p += kHidden;
+      std::memcpy(h_kv.data() + kvn * i, p, kvn * sizeof(float));
+      p += kvn;
+    }
+    up(&e->codebooks, h_cb.data(), h_cb.size(), 0);
+    up(&e->additive, h_add.data(), h_add.size(), static_cast<size_t>(kHidden) * B);
+    up(&e->formant_tab, h_formant, static_cast<size_t>(kNFormant) * kHidden, 0);
+    up(&e->kv, h_kv.data(), h_kv.size(), kvn * B);
+    e->kv_stage.Alloc(e->device, kvn * B * sizeof(float), true);
+    e->morph_jobs.Alloc(e->device, sizeof(MorphJob) * 2 * B, true);
+  } else {
+    // 20a2 / 20b1: ReadSpeakerEmbeddings twice -- the speakers' table [n][256] and the nine formant embeddings
+    // (processor_core_0.cc:196-213); the vector handed to GenerateWaveform1 is their sum, per call (:128-142)
+    FileImage fimg;
+    if (const int err = ParseFileImage(images[3], sizes[3], d.family, kKindFormant, kKindFormant,
+                                       [&](uint32_t n) { return n == static_cast<uint32_t>(kNFormant) ? static_cast<long long>(kNFormant) * kHidden : -1LL; },
+                                       &fimg))
+      return err;
+    if (const int err = ParseFileImage(images[4], sizes[4], d.family, kKindSpeakers, kKindSpeakers,
+                                       [&](uint32_t n) { return static_cast<long long>(SpeakerPayloadFloats(d, n)); }, &img))
+      return err;
+    const int n = static_cast<int>(img.count);
+    if (n <= 0) return 4;
+    e->n_speakers = n;
+    e->h_additive.assign(img.payload, img.payload + static_cast<size_t>(n) * kHidden);
+    e->h_formant.assign(fimg.payload, fimg.payload + static_cast<size_t>(kNFormant) * kHidden);
+    e->codebooks.Free();
+    e->kv.Free();
+    e->kv_stage.Free();
+  }
   e->in16.Alloc(e->device, sizeof(float) * B * kInHop, true);
   const TcMode tc = static_cast<TcMode>(e->precision);
   e->wave_st.cond_ready = false;
@@ -622,7 +676,8 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
 
   e->sp.assign(B, StreamParams());
   e->morph.assign(B, MorphState());
-  for (int b = 0; b < B; ++b) ApplyMorphWeights(e, b);   // LoadModel ends with ApplySpeakerMorphingWeights (:417)
+  if (rc0)
+    for (int b = 0; b < B; ++b) ApplyMorphWeights(e, b);   // LoadModel ends with ApplySpeakerMorphingWeights (:417)
   PitchParams def;
   def.average_source_pitch = 52.0;
   def.intonation_intensity = 1.0;
@@ -814,12 +869,17 @@ int BeatriceB200_LoadModel(BeatriceB200_Engine* e, const char* utf8_model_dir) {
   int rc__ = BEATRICE_B200_ERR_DEVICE;
   B200_GUARDED(if (e) e->loaded = false; rc__ = BEATRICE_B200_ERR_DEVICE, rc__ = [&]() -> int {
   if (!e || !utf8_model_dir) return BEATRICE_B200_ERR_BAD_ARGUMENT;
-  static const char* kNames[5] = {"phone_extractor.bin", "pitch_estimator.bin", "waveform_generator.bin",
-                                  "embedding_setter.bin", "speaker_embeddings.bin"};
+  const char* kNames[5] = {"phone_extractor.bin", "pitch_estimator.bin", "waveform_generator.bin",
+                           "embedding_setter.bin", "speaker_embeddings.bin"};
   std::vector<uint8_t> bytes[5];
   const void* images[5];
   size_t sizes[5];
   for (int i = 0; i < 5; ++i) {
+    if (i == 3 && bytes[0].size() >= 16) {   // legacy families (header word 1 < 2): the formant table instead of a setter
+      uint32_t hdr[4];
+      std::memcpy(hdr, bytes[0].data(), 16);
+      if (hdr[0] == kFileMagic && hdr[1] < 2) kNames[3] = "formant_shift_embeddings.bin";
+    }
     const std::string path = std::string(utf8_model_dir) + "/" + kNames[i];
     if (const int err = LoadFileBytes(path.c_str(), &bytes[i])) return err;
     images[i] = bytes[i].data();
@@ -845,6 +905,8 @@ int BeatriceB200_SetPipelineDepth(BeatriceB200_Engine* e, int depth) {
 int BeatriceB200_PipelineDepth(const BeatriceB200_Engine* e) { return e ? e->pipeline : 0; }
 
 int BeatriceB200_NumSpeakers(const BeatriceB200_Engine* e) { return e ? e->n_speakers : 0; }
+int BeatriceB200_ModelFamily(const BeatriceB200_Engine* e) { return e && e->loaded ? e->dims.family : -1; }
+int BeatriceB200_PhoneChannels(const BeatriceB200_Engine* e) { return e && e->loaded ? e->dims.phone_channels : 0; }
 int BeatriceB200_NumStreams(const BeatriceB200_Engine* e) { return e ? e->B : 0; }
 
 #define B200_SETTER_PROLOGUE()                                         \
@@ -854,7 +916,8 @@ int BeatriceB200_NumStreams(const BeatriceB200_Engine* e) { return e ? e->B : 0;
 int BeatriceB200_SetTargetSpeaker(BeatriceB200_Engine* e, int stream, int speaker) {
   B200_SETTER_PROLOGUE();
   // speaker == n_speakers is the morphing slot (processor_core_2.cc:436, :51-177)
-  if (speaker < 0 || speaker > e->n_speakers) return BEATRICE_B200_ERR_SPEAKER_RANGE;
+  // (the legacy families' morphing, one average of the speaker vector -- processor_core_0.cc:121-127 -- is not offered)
+  if (speaker < 0 || speaker > e->n_speakers || (speaker == e->n_speakers && !e->dims.has_setter)) return BEATRICE_B200_ERR_SPEAKER_RANGE;
   ForStreams(e, stream, [&](int b) {
     e->sp[b].speaker = speaker;
     e->sp[b].kv_set_count = 0;  // :464 -- blocks are applied over the next four hops
@@ -870,7 +933,7 @@ int BeatriceB200_SetTargetSpeaker(BeatriceB200_Engine* e, int stream, int speake
 // speaker is the morphing slot, SetTargetSpeaker(stream, NumSpeakers()).
 int BeatriceB200_SetSpeakerMorphingWeights(BeatriceB200_Engine* e, int stream, const float* weights, int n_weights) {
   B200_SETTER_PROLOGUE();
-  if (!weights || n_weights < 0 || n_weights > kMaxNSpeakers) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  if (!weights || n_weights < 0 || n_weights > kMaxNSpeakers || !e->dims.has_setter) return BEATRICE_B200_ERR_BAD_ARGUMENT;
   std::vector<float> w(kMaxNSpeakers, 0.0f);
   std::copy(weights, weights + n_weights, w.begin());
   ForStreams(e, stream, [&](int b) {
@@ -891,6 +954,7 @@ int BeatriceB200_SeedMorphLottery(BeatriceB200_Engine* e, unsigned seed) {
 int BeatriceB200_GetMorphState(BeatriceB200_Engine* e, int stream, float* additive256, float* kv, int* lottery_speaker) {
   if (!e || stream < 0 || stream >= e->B) return BEATRICE_B200_ERR_BAD_ARGUMENT;
   if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
+  if (!e->dims.has_setter) return BEATRICE_B200_ERR_BAD_ARGUMENT;
   int rc__ = BEATRICE_B200_ERR_DEVICE;
   B200_GUARDED(rc__ = BEATRICE_B200_ERR_DEVICE, {
     B200_CHECK(cudaSetDevice(e->device));

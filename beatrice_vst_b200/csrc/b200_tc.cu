@@ -681,8 +681,11 @@ void LaunchConvGemmTc(const ConvDesc* d_descs, const ConvDesc& h0, int nz, int B
     // a gathered chunk (fp32 rings of three branches, summed and rounded in registers) costs ~2.7 us per CTA,
     // a cp.async chunk ~0.6 us: gathered launches split down to one chunk per CTA
     const int min_chunks = gather ? 1 : 2;
+    // One wave only.  A B200 has 148 SMs in GPCs of 16-20: clusters of 2 pack all of them, clusters of 4 strand
+    // 16 SMs (B300_MICROARCH.md, "CTAS_ACTIVE = {1: 148, 2: 148, 4: 132}") -- this 132 is that number, not an SM count.
+    auto one_wave = [](int cluster) { return cluster >= 4 ? 132 : 148; };
     for (int cand : {4, 2}) {
-      if (n_chunks >= min_chunks * cand && (bn / cand) % 16 == 0 && m_tiles * n_tiles * cand <= 132) {
+      if (n_chunks >= min_chunks * cand && (bn / cand) % 16 == 0 && m_tiles * n_tiles * cand <= one_wave(cand)) {
         ks = cand;
         break;
       }

@@ -269,6 +269,55 @@ def test_batched_48k_matches_reference_callsite(product, model_dir, engine_preci
         assert e <= TOL_WAVE, (s, e)
 
 
+@pytest.mark.parametrize("family", [0, 1])
+@pytest.mark.skipif(not callsite.available("oracle"), reason="oracle/_ref not built")
+def test_batched_48k_legacy_families_match_reference_callsite(product, model_dirs, family):
+    """The batched engine for the 2.0.0-alpha.2 / -beta.1 model families (256 phone channels, 384 pitch bins, the
+    speaker vector = speaker embedding + formant embedding formed per call, no embedding setter / VQ / key-value
+    path) against ProcessorCore0 / ProcessorCore1 (reference src/common/processor_core_{0,1}.cc:24-142) over the
+    CPU oracle: speaker and formant changes, pitch shift / correction, gains; both pipeline depths."""
+    n, hops = 4, 22
+    x = signals.batch_48k(n, hops, seed0=640 + family)
+    plans = [
+        [(0, "voice", 3), (0, "pitch_shift", 5.0), (6, "formant_shift", 1.5), (11, "voice", 6)],
+        [(0, "voice", 1), (0, "input_gain", -4.0), (4, "pitch_correction", 0.6), (9, "output_gain", 3.0)],
+        [(0, "formant_shift", -2.0), (7, "reset", 1), (12, "voice", 7), (12, "pitch_shift", -7.0)],
+        [(3, "pitch_correction_type", 1), (3, "pitch_correction", 0.35), (8, "intonation_intensity", 1.4)],
+    ]
+    setter = dict(input_gain="InputGain", output_gain="OutputGain", pitch_shift="PitchShift", voice="TargetSpeaker",
+                  pitch_correction="PitchCorrection", formant_shift="FormantShift", pitch_correction_type="PitchCorrectionType",
+                  intonation_intensity="IntonationIntensity")
+    toml = os.path.join(model_dirs[family], "model.toml")
+    refs = []
+    for s in range(n):
+        y, info = callsite.run("oracle", toml, x[:, s, :].reshape(-1), events=plans[s])
+        assert info == {"load": 0, "last": 0, "version": family}
+        refs.append(y)
+    for depth in (1, 2):
+        eng = bbatch.Engine(product, n)
+        assert eng.load(model_dirs[family]) == 0 and eng.family == family and eng.n_speakers == 8
+        assert eng.set("TargetSpeaker", 8, 0) == 7            # no morphing slot in the legacy engine
+        assert eng.set_pipeline_depth(depth) == 0
+        outs = []
+        for h in range(hops):
+            for s in range(n):
+                for (b, name, v) in plans[s]:
+                    if b != h:
+                        continue
+                    if name == "reset":
+                        assert eng.reset_stream(s) == 0
+                    else:
+                        assert eng.set(setter[name], int(v) if name in ("voice", "pitch_correction_type") else float(v), s) == 0
+            outs.append(eng.process_48k(x[h]).copy())
+        if depth == 2:
+            outs = outs[1:] + [eng.drain()]
+        eng.close()
+        got = np.stack(outs, axis=1)
+        for s in range(n):
+            e = rms(got[s].reshape(-1), refs[s])
+            assert refs[s].std() > 0.01 and e <= TOL_WAVE, (family, depth, s, e)
+
+
 def test_48k_host_and_device_entries_interleave(product, model_dir):
     """The host-buffer entry computes the block it hands back on a side stream, with the hop index mirrored on
     the host; the device-buffer entry does it inside the hop graph with the device counter.  Alternating the
