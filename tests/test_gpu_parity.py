@@ -225,7 +225,8 @@ def test_batched_rejects_bad_arguments(product, model_dir):
     eng = bbatch.Engine(product, 2)
     assert eng.set("PitchShift", 1.0, 0) == 9            # kModelNotLoaded before LoadModel
     assert eng.load(model_dir) == 0
-    assert eng.set("TargetSpeaker", 8, 0) == 7           # morph slot / out of range -> kSpeakerIDOutOfRange
+    assert eng.set("TargetSpeaker", 8, 0) == 0           # n_speakers = the morphing slot (processor_core_2.cc:436)
+    assert eng.set("TargetSpeaker", 9, 0) == 7           # beyond it -> kSpeakerIDOutOfRange
     assert eng.set("TargetSpeaker", -1, 0) == 7
     assert eng.set("PitchCorrectionType", 2, 0) == 8     # kInvalidPitchCorrectionType
     assert eng.set("PitchShift", 1.0, 5) == -1           # no such stream
