@@ -60,6 +60,7 @@ struct BeatriceB200_Engine {
   cudaStream_t side = nullptr;                        // host-buffer path: early output block + its D2H copy
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_side = nullptr;
   cudaEvent_t ev_join2 = nullptr, ev_cond = nullptr;  // pipelined hop: pitch-lane join, "vocoder has read the hand-off"
+  cudaEvent_t ev_ingest = nullptr;                    // pipelined hop: the adapter's input half is done (head of the encoder lanes)
   // Pipeline depth 2 (BeatriceB200_SetPipelineDepth): a call runs the vocoder of the PREVIOUS hop side by side with
   // the two encoders of the hop it is given; outputs are those of depth 1, one call later.  `primed`: the hand-off
   // buffers (phone / pitch bin / features) hold a hop the vocoder has not consumed yet.
@@ -492,10 +493,18 @@ void EnqueueHop(Engine* e, cudaStream_t s) {
 //     both encoder lanes;
 //   * with_vocoder == false (first call after load / reset-all: nothing to vocode yet): encoders only, their
 //     counters advanced by two single-thread launches.
-void EnqueueHopPipelined(Engine* e, cudaStream_t s, bool with_vocoder) {
+//   * `ingest` (the 48 kHz adapter's input half, which fills the encoders' staging buffer) runs at the head of the
+//     encoder lanes, not in front of the vocoder, which does not depend on it.
+void EnqueueHopPipelined(Engine* e, cudaStream_t s, bool with_vocoder, const std::function<void(cudaStream_t)>& ingest = nullptr) {
   B200_CHECK(cudaEventRecord(e->ev_fork, s));
   B200_CHECK(cudaStreamWaitEvent(e->aux, e->ev_fork, 0));
-  B200_CHECK(cudaStreamWaitEvent(e->aux2, e->ev_fork, 0));
+  if (ingest) {
+    ingest(e->aux);
+    B200_CHECK(cudaEventRecord(e->ev_ingest, e->aux));
+    B200_CHECK(cudaStreamWaitEvent(e->aux2, e->ev_ingest, 0));
+  } else {
+    B200_CHECK(cudaStreamWaitEvent(e->aux2, e->ev_fork, 0));
+  }
   auto starts = [](const std::string& n, const char* p) { return n.compare(0, std::strlen(p), p) == 0; };
   size_t first_wave = e->hop_ops.size(), post = e->hop_ops.size();
   for (size_t i = 0; i < e->hop_ops.size(); ++i)
@@ -729,8 +738,7 @@ void RunHop48(Engine* e, bool allow_graph) {
     (voc ? e->graph48p : e->graph48).Run(
         e->stream,
         [&](cudaStream_t s) {
-          e->hostrate.EnqueueIn(e->in16.as<float>(), s);
-          EnqueueHopPipelined(e, s, voc);
+          EnqueueHopPipelined(e, s, voc, [&](cudaStream_t ls) { e->hostrate.EnqueueIn(e->in16.as<float>(), ls); });
           e->hostrate.EnqueueOut(o24, s);
         },
         voc && allow_graph && GraphsEnabled());
@@ -770,8 +778,7 @@ void RunHop48Split(Engine* e, float* out_host, size_t bytes) {
     (voc ? e->graph48sp : e->graph48s).Run(
         e->stream,
         [&](cudaStream_t s) {
-          e->hostrate.EnqueueIn(e->in16.as<float>(), s);
-          EnqueueHopPipelined(e, s, voc);
+          EnqueueHopPipelined(e, s, voc, [&](cudaStream_t ls) { e->hostrate.EnqueueIn(e->in16.as<float>(), ls); });
           e->hostrate.EnqueueStore(o24, s);
         },
         voc && GraphsEnabled());
@@ -823,6 +830,7 @@ BeatriceB200_Engine* BeatriceB200_CreateEngine(int device, int n_streams, int pr
   B200_CHECK(cudaStreamCreateWithPriority(&e->aux2, cudaStreamNonBlocking, prio_lo));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_cond, cudaEventDisableTiming));
+  B200_CHECK(cudaEventCreateWithFlags(&e->ev_ingest, cudaEventDisableTiming));
   B200_CHECK(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_side, cudaEventDisableTiming));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
@@ -853,6 +861,7 @@ void BeatriceB200_DestroyEngine(BeatriceB200_Engine* e) {
   if (e->aux2) cudaStreamDestroy(e->aux2);
   if (e->ev_join2) cudaEventDestroy(e->ev_join2);
   if (e->ev_cond) cudaEventDestroy(e->ev_cond);
+  if (e->ev_ingest) cudaEventDestroy(e->ev_ingest);
   delete e;
 }
 
