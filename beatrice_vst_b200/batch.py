@@ -53,6 +53,7 @@ BATCH_SYMBOLS = {
     "BeatriceB200_Synchronize": (None, [_vp]),
     "BeatriceB200_SetPipelineDepth": (C.c_int, [_vp, C.c_int]),
     "BeatriceB200_PipelineDepth": (C.c_int, [_vp]),
+    "BeatriceB200_SetPipelinePlan": (C.c_int, [_vp, C.c_char_p]),
     "BeatriceB200_DrainPipeline": (C.c_int, [_vp, _vp, _vp]),
     "BeatriceB200_AllocPinned": (_vp, [C.c_size_t]),
     "BeatriceB200_FreePinned": (None, [_vp]),
@@ -219,6 +220,9 @@ class Engine:
     def set_pipeline_depth(self, depth: int) -> int:
         """1: a call returns the hop it was given; 2: vocoder of the previous hop || encoders of this one."""
         return self.dll.BeatriceB200_SetPipelineDepth(self.h, depth)
+
+    def set_pipeline_plan(self, plan: str) -> int:
+        return self.dll.BeatriceB200_SetPipelinePlan(self.h, plan.encode("utf-8"))
 
     def drain(self, model_rate: bool = False) -> np.ndarray:
         """Depth 2: the blocks of the hop still in flight ([n,480] @48 kHz, or [n,240] @24 kHz)."""

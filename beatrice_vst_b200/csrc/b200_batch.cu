@@ -60,7 +60,9 @@ struct BeatriceB200_Engine {
   cudaStream_t side = nullptr;                        // host-buffer path: early output block + its D2H copy
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_side = nullptr;
   cudaEvent_t ev_join2 = nullptr, ev_cond = nullptr;  // pipelined hop: pitch-lane join, "vocoder has read the hand-off"
-  cudaEvent_t ev_ingest = nullptr;                    // pipelined hop: the adapter's input half is done (head of the encoder lanes)
+  std::string pipe_plan;                              // BeatriceB200_SetPipelinePlan (tuning aid); empty: the built-in plan
+  static constexpr size_t kMaxGates = 24;
+  cudaEvent_t ev_gate[kMaxGates] = {};                // pipelined hop: "this vocoder kernel has finished" (PipelinePlan)
   // Pipeline depth 2 (BeatriceB200_SetPipelineDepth): a call runs the vocoder of the PREVIOUS hop side by side with
   // the two encoders of the hop it is given; outputs are those of depth 1, one call later.  `primed`: the hand-off
   // buffers (phone / pitch bin / features) hold a hop the vocoder has not consumed yet.
@@ -485,75 +487,138 @@ void EnqueueHop(Engine* e, cudaStream_t s) {
 
 // Depth-2 form of the hop: the vocoder of the PREVIOUS hop (main stream; its inputs are the hand-off buffers the
 // encoders filled one call ago) side by side with the content encoder (aux) and the pitch estimator (aux2) of THIS
-// hop.  The encoder lanes (<= 96 CTAs, ~90 us) depend only on their own state, so they fill the SMs the vocoder's
-// latency-bound stages leave idle, and the steady-state period is the vocoder alone.
-//   * the encoder lanes run behind a GATE kernel of the vocoder (see below); the gate is never earlier than the
-//     vocoder's conditioning kernel, the only reader of the hand-off buffers the lanes' last kernels overwrite;
+// hop.  The encoder lanes depend only on their own state, so they fill the SMs the vocoder's latency-bound stages
+// leave idle, and the steady-state period approaches the vocoder alone.
+//   * Every encoder kernel runs behind a GATE kernel of the vocoder (PipelinePlan below).  Where the gates sit decides
+//     how much the lanes hurt the vocoder: its stages are single waves of CTAs that need most of an SM each (stage 0:
+//     4-CTA clusters; stages 0-1: one CTA per SM), so an SM held by an encoder CTA when a stage launches costs that
+//     stage an extra partial wave.  The lanes' first kernel (a block-per-stream ingest) runs from the fork; nothing
+//     else is gated earlier than the vocoder's conditioning kernel -- the only reader of the hand-off buffers the
+//     lanes' last kernels overwrite.
 //   * the post conv, last kernel of the vocoder, advances all three hop counters (AdvanceFold), so it waits for
 //     both encoder lanes;
 //   * with_vocoder == false (first call after load / reset-all: nothing to vocode yet): encoders only, their
 //     counters advanced by two single-thread launches.
-//   * `ingest` (the 48 kHz adapter's input half, which fills the encoders' staging buffer) runs at the head of the
-//     encoder lanes, not in front of the vocoder, which does not depend on it.
-void EnqueueHopPipelined(Engine* e, cudaStream_t s, bool with_vocoder, const std::function<void(cudaStream_t)>& ingest = nullptr) {
+// Gate of every lane op, as an index into hop_ops (-1: the fork).  Default plan, found with tools/pipe_plan_search.py
+// (B200, 256 streams, bench.py: 0.312 ms serial -> 0.287 every lane kernel from the fork -> 0.268 everything behind
+// stage 0 -> 0.263 with the content lane's first GEMM layer right behind the conditioning kernel and its cluster chain
+// kernel behind the stage-2 upsampler); BeatriceB200_SetPipelinePlan / BEATRICE_B200_PIPE_PLAN="<lane op substring>=
+// <vocoder op substring>,..." override entries.
+std::vector<int> PipelinePlan(const Engine* e, size_t first_wave, size_t post) {
+  auto find_wave = [&](const std::string& sub) {
+    for (size_t i = first_wave; i < post; ++i)
+      if (e->hop_ops[i].name.find(sub) != std::string::npos) return static_cast<int>(i);
+    return -2;
+  };
+  int cond = static_cast<int>(first_wave);
+  for (size_t i = first_wave; i < post; ++i)
+    if (e->hop_ops[i].name.compare(0, 9, "wave.cond") == 0) cond = static_cast<int>(i);
+  const int g_default = std::max(find_wave("wave.mrf0"), cond), g_chain = std::max(find_wave("wave.ups2"), g_default);
+  std::vector<std::pair<std::string, std::string>> overrides;
+  const char* ev = std::getenv("BEATRICE_B200_PIPE_PLAN");
+  if (!e->pipe_plan.empty() || ev) {
+    std::string t(!e->pipe_plan.empty() ? e->pipe_plan.c_str() : ev);
+    size_t pos = 0;
+    while (pos < t.size()) {
+      const size_t comma = t.find(',', pos), end = comma == std::string::npos ? t.size() : comma;
+      const std::string item = t.substr(pos, end - pos);
+      const size_t eq = item.find('=');
+      if (eq != std::string::npos) overrides.emplace_back(item.substr(0, eq), item.substr(eq + 1));
+      pos = end + 1;
+    }
+  }
+  std::vector<int> gate(first_wave, -1);
+  int last[2] = {-1, -1};
+  bool first_of_lane[2] = {true, true};
+  for (size_t i = 0; i < first_wave; ++i) {
+    const int lane = e->hop_lane[i];
+    const std::string& n = e->hop_ops[i].name;
+    int g = first_of_lane[lane] ? -1 : g_default;
+    if (n == "phone.fe1") g = cond;            // one early layer of the longer lane fits beside the vocoder's small first kernels
+    if (n == "phone.chain") g = g_chain;       // the longest SM holder (64 CTAs x ~40 us) starts when stage 2 has its SMs
+    for (const auto& ov : overrides)
+      if (n.find(ov.first) != std::string::npos) {
+        const int v = ov.second == "fork" ? -1 : find_wave(ov.second);
+        if (v != -2) g = v;
+      }
+    if (!first_of_lane[lane]) g = std::max(g, cond);   // hand-off safety
+    g = std::max(g, last[lane]);                       // monotone along a lane
+    gate[i] = g;
+    last[lane] = g;
+    first_of_lane[lane] = false;
+  }
+  return gate;
+}
+
+void EnqueueHopPipelined(Engine* e, cudaStream_t s, bool with_vocoder) {
   B200_CHECK(cudaEventRecord(e->ev_fork, s));
   B200_CHECK(cudaStreamWaitEvent(e->aux, e->ev_fork, 0));
-  if (ingest) {
-    ingest(e->aux);
-    B200_CHECK(cudaEventRecord(e->ev_ingest, e->aux));
-    B200_CHECK(cudaStreamWaitEvent(e->aux2, e->ev_ingest, 0));
-  } else {
-    B200_CHECK(cudaStreamWaitEvent(e->aux2, e->ev_fork, 0));
-  }
-  auto starts = [](const std::string& n, const char* p) { return n.compare(0, std::strlen(p), p) == 0; };
+  B200_CHECK(cudaStreamWaitEvent(e->aux2, e->ev_fork, 0));
   size_t first_wave = e->hop_ops.size(), post = e->hop_ops.size();
   for (size_t i = 0; i < e->hop_ops.size(); ++i)
     if (e->hop_lane[i] == 2) {
       if (first_wave == e->hop_ops.size()) first_wave = i;
       if (e->hop_ops[i].name == "wave.post") post = i;
     }
-  // Vocoder first, up to its GATE kernel.  The encoder lanes start behind the gate (only their first kernel, a
-  // block-per-stream ingest that is gone within the vocoder's conditioning / first upsampler, runs from the fork):
-  // stage 0 of the vocoder is one wave of 4-CTA clusters and stage 1 one wave of single CTAs at one CTA per SM, so an
-  // SM held by an encoder CTA when they launch costs a whole extra wave, while behind them the stages are many
-  // short CTAs and the early-finishing k = 3 / k = 7 branches leave room.  The gate is at or after the conditioning
-  // kernel -- the only reader of the hand-off buffers the lanes' last kernels overwrite.
-  static const std::string gate_name = [] {
-    const char* ev = std::getenv("BEATRICE_B200_PIPE_GATE");   // developer: substring of the gate op's name
-    return std::string(ev && ev[0] ? ev : "wave.mrf0");
-  }();
+  const std::vector<int> gate = PipelinePlan(e, first_wave, post);
+  static const int lane_pdl = [] { const char* ev = std::getenv("BEATRICE_B200_PIPE_LANE_PDL"); return ev ? std::atoi(ev) : -1; }();
+  static const int voc_pdl = [] { const char* ev = std::getenv("BEATRICE_B200_PIPE_VOC_PDL"); return ev ? std::atoi(ev) : -1; }();
+  size_t next_op = 0;               // lane ops are issued in program order (content lane first, then pitch)
+  std::vector<char> done(first_wave, 0);
+  int waited[2] = {-1, -1};
+  auto issue_lanes = [&](int v) {   // every not-yet-issued lane op whose gate has been enqueued
+    (void)next_op;
+    for (size_t i = 0; i < first_wave; ++i) {
+      if (done[i] || SkipVq(e, i)) continue;
+      if (with_vocoder && gate[i] > v) continue;
+      const int lane = e->hop_lane[i];
+      cudaStream_t ls = lane == 0 ? e->aux : e->aux2;
+      if (with_vocoder && gate[i] >= 0 && waited[lane] != gate[i]) {
+        B200_CHECK(cudaStreamWaitEvent(ls, e->ev_gate[gate[i] - first_wave], 0));
+        waited[lane] = gate[i];
+      }
+      {
+        PdlScope scope(lane_pdl);
+        e->hop_ops[i].launch(ls);
+      }
+      done[i] = 1;
+    }
+  };
+  issue_lanes(-1);
   size_t w = first_wave;
   if (with_vocoder) {
-    size_t gate = post;
-    for (size_t i = first_wave; i < post; ++i)
-      if (e->hop_ops[i].name.find(gate_name) != std::string::npos) gate = i;
-    size_t cond = first_wave;
-    for (size_t i = first_wave; i < post; ++i)
-      if (starts(e->hop_ops[i].name, "wave.cond")) cond = i;
-    if (gate == post || gate < cond) gate = cond;
-    for (; w <= gate; ++w) e->hop_ops[w].launch(s);
-    B200_CHECK(cudaEventRecord(e->ev_cond, s));
+    // Capture order: the vocoder's kernels up to the LAST gate first (an event behind every gate), then the lanes, then
+    // the rest of the vocoder.  The dependency graph is the same as with the lanes interleaved where their gates
+    // are, but the instantiated graph submits ready kernels in capture order, and the vocoder must win those ties.
+    int last_gate = -1;
+    for (size_t i = 0; i < first_wave; ++i) last_gate = std::max(last_gate, gate[i]);
+    static const bool interleave = [] { const char* ev = std::getenv("BEATRICE_B200_PIPE_INTERLEAVE"); return ev && ev[0] == '1'; }();
+    for (; w < post && static_cast<int>(w) <= last_gate; ++w) {
+      {
+        PdlScope scope(voc_pdl);
+        e->hop_ops[w].launch(s);
+      }
+      bool needed = false;
+      for (size_t i = 0; i < first_wave; ++i) needed = needed || (!done[i] && gate[i] == static_cast<int>(w));
+      if (needed && w - first_wave < Engine::kMaxGates) {
+        B200_CHECK(cudaEventRecord(e->ev_gate[w - first_wave], s));
+        if (interleave) issue_lanes(static_cast<int>(w));
+      }
+    }
+    issue_lanes(last_gate);
+    for (; w < post; ++w) {
+      PdlScope scope(voc_pdl);
+      e->hop_ops[w].launch(s);
+    }
   }
-  // encoders of this hop
-  bool first_of_lane[2] = {true, true};
-  for (size_t i = 0; i < first_wave; ++i) {
-    const int lane = e->hop_lane[i];
-    if (SkipVq(e, i)) continue;
-    cudaStream_t ls = lane == 0 ? e->aux : e->aux2;
-    e->hop_ops[i].launch(ls);
-    if (with_vocoder && first_of_lane[lane]) B200_CHECK(cudaStreamWaitEvent(ls, e->ev_cond, 0));   // everything behind the ingest waits for the gate
-    first_of_lane[lane] = false;
-  }
+  issue_lanes(static_cast<int>(e->hop_ops.size()));   // whatever is left (none with a well-formed plan)
   B200_CHECK(cudaEventRecord(e->ev_join, e->aux));
   B200_CHECK(cudaEventRecord(e->ev_join2, e->aux2));
+  B200_CHECK(cudaStreamWaitEvent(s, e->ev_join, 0));
+  B200_CHECK(cudaStreamWaitEvent(s, e->ev_join2, 0));
   if (with_vocoder) {
-    for (; w < post; ++w) e->hop_ops[w].launch(s);
-    B200_CHECK(cudaStreamWaitEvent(s, e->ev_join, 0));
-    B200_CHECK(cudaStreamWaitEvent(s, e->ev_join2, 0));
     for (; w < e->hop_ops.size(); ++w) e->hop_ops[w].launch(s);   // post conv (+ nothing else: the advance is folded)
   } else {
-    B200_CHECK(cudaStreamWaitEvent(s, e->ev_join, 0));
-    B200_CHECK(cudaStreamWaitEvent(s, e->ev_join2, 0));
     LaunchAdvance(e->phone_st.arena.frame(), s);
     LaunchAdvance(e->pitch_st.arena.frame(), s);
   }
@@ -738,7 +803,8 @@ void RunHop48(Engine* e, bool allow_graph) {
     (voc ? e->graph48p : e->graph48).Run(
         e->stream,
         [&](cudaStream_t s) {
-          EnqueueHopPipelined(e, s, voc, [&](cudaStream_t ls) { e->hostrate.EnqueueIn(e->in16.as<float>(), ls); });
+          e->hostrate.EnqueueIn(e->in16.as<float>(), s);
+          EnqueueHopPipelined(e, s, voc);
           e->hostrate.EnqueueOut(o24, s);
         },
         voc && allow_graph && GraphsEnabled());
@@ -778,7 +844,8 @@ void RunHop48Split(Engine* e, float* out_host, size_t bytes) {
     (voc ? e->graph48sp : e->graph48s).Run(
         e->stream,
         [&](cudaStream_t s) {
-          EnqueueHopPipelined(e, s, voc, [&](cudaStream_t ls) { e->hostrate.EnqueueIn(e->in16.as<float>(), ls); });
+          e->hostrate.EnqueueIn(e->in16.as<float>(), s);
+          EnqueueHopPipelined(e, s, voc);
           e->hostrate.EnqueueStore(o24, s);
         },
         voc && GraphsEnabled());
@@ -819,6 +886,7 @@ BeatriceB200_Engine* BeatriceB200_CreateEngine(int device, int n_streams, int pr
   e->precision = precision;
   try {
   B200_CHECK(cudaSetDevice(device));
+  InstallSpinDebug(device);
   if (std::getenv("BEATRICE_B200_MRF_TRACE")) {   // developer traces print one line per CTA: room for all of them
     cudaDeviceSetLimit(cudaLimitPrintfFifoSize, 64u << 20);
   }
@@ -830,7 +898,7 @@ BeatriceB200_Engine* BeatriceB200_CreateEngine(int device, int n_streams, int pr
   B200_CHECK(cudaStreamCreateWithPriority(&e->aux2, cudaStreamNonBlocking, prio_lo));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_cond, cudaEventDisableTiming));
-  B200_CHECK(cudaEventCreateWithFlags(&e->ev_ingest, cudaEventDisableTiming));
+  for (auto& g : e->ev_gate) B200_CHECK(cudaEventCreateWithFlags(&g, cudaEventDisableTiming));
   B200_CHECK(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_side, cudaEventDisableTiming));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
@@ -861,7 +929,8 @@ void BeatriceB200_DestroyEngine(BeatriceB200_Engine* e) {
   if (e->aux2) cudaStreamDestroy(e->aux2);
   if (e->ev_join2) cudaEventDestroy(e->ev_join2);
   if (e->ev_cond) cudaEventDestroy(e->ev_cond);
-  if (e->ev_ingest) cudaEventDestroy(e->ev_ingest);
+  for (auto& g : e->ev_gate)
+    if (g) cudaEventDestroy(g);
   delete e;
 }
 
@@ -912,6 +981,20 @@ int BeatriceB200_SetPipelineDepth(BeatriceB200_Engine* e, int depth) {
   return 0;
 }
 int BeatriceB200_PipelineDepth(const BeatriceB200_Engine* e) { return e ? e->pipeline : 0; }
+// Tuning aid: where the encoder kernels of a depth-2 hop are gated ("<encoder op substring>=<vocoder op substring>,
+// ...", see PipelinePlan; "" restores the built-in plan).  The depth-2 graphs are re-captured.
+int BeatriceB200_SetPipelinePlan(BeatriceB200_Engine* e, const char* plan) {
+  if (!e) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(rc__ = BEATRICE_B200_ERR_DEVICE, {
+    B200_CHECK(cudaSetDevice(e->device));
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+    e->pipe_plan = plan ? plan : "";
+    ResetGraphs(e);
+    rc__ = 0;
+  });
+  return rc__;
+}
 
 int BeatriceB200_NumSpeakers(const BeatriceB200_Engine* e) { return e ? e->n_speakers : 0; }
 int BeatriceB200_ModelFamily(const BeatriceB200_Engine* e) { return e && e->loaded ? e->dims.family : -1; }

@@ -48,6 +48,7 @@ struct StreamOwner {
     if (s) return;
     device = dev;
     B200_CHECK(cudaSetDevice(dev));
+    InstallSpinDebug(dev);
     B200_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   }
   ~StreamOwner() {

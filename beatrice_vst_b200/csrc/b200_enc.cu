@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
         const int buf = r & 1, H = blk_hist(r);
         const uint32_t gp = smem_base + L::kGp + buf * L::kGpBuf;
         MbarWait(bar_hist + 8 * buf, (r >> 1) & 1);
-        SpinUntil(in_cnt, static_cast<uint32_t>((kWorkers / 32) * (r + 1)));   // the new row of block r is in the panels
+        SpinUntil(in_cnt, static_cast<uint32_t>((kWorkers / 32) * (r + 1)), 300000u + 492u);   // the new row of block r is in the panels
         __threadfence_block();
         FenceProxyAsync();
         if (H > 0) {
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
           BulkCommit();
           BulkWaitRead0();
         }
-        SpinUntil(acc_cnt, static_cast<uint32_t>(r + 1));   // block r's MMAs are done reading the buffer
+        SpinUntil(acc_cnt, static_cast<uint32_t>(r + 1), 300000u + 505u);   // block r's MMAs are done reading the buffer
         if (r + 2 < p.n_blk) load_hist(r + 2);
         MbarArrive(bar_free + 8 * buf);
       }
@@ -605,5 +605,7 @@ void LaunchResStack(const ResStackParams& p, int C, cudaStream_t s) {
   else Fail(-104, "residual-stack kernel has no form for this width", __FILE__, __LINE__);
   B200_CHECK(cudaGetLastError());
 }
+
+void SetSpinDebugEnc(unsigned long long* dev_ptr) { SetSpinDebugPtr(dev_ptr); }
 
 }  // namespace b200

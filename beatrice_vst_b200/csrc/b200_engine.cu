@@ -32,6 +32,48 @@ void Latch(int code, const char* text) noexcept {
 }
 }  // namespace
 
+// Dead-lock records of the tensor-core kernels (b200_tc_common.cuh, SpinTimeout): a small mapped pinned buffer per
+// process, its device address installed in every translation unit that polls.
+void SetSpinDebugMrf(unsigned long long*);
+void SetSpinDebugMrfc(unsigned long long*);
+void SetSpinDebugEnc(unsigned long long*);
+namespace {
+unsigned long long* g_spin_host = nullptr;
+std::mutex g_spin_mu;
+bool g_spin_installed[64] = {};
+}  // namespace
+void InstallSpinDebug(int device) {
+  std::lock_guard<std::mutex> lock(g_spin_mu);
+  if (device < 0 || device >= 64 || g_spin_installed[device]) return;
+  if (!g_spin_host) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&g_spin_host), 4096, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+      (void)cudaGetLastError();
+      g_spin_host = nullptr;
+      return;
+    }
+    std::memset(g_spin_host, 0, 4096);
+  }
+  unsigned long long* dev = nullptr;
+  if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev), g_spin_host, 0) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return;
+  }
+  SetSpinDebugMrf(dev);
+  SetSpinDebugMrfc(dev);
+  SetSpinDebugEnc(dev);
+  (void)cudaGetLastError();
+  g_spin_installed[device] = true;
+}
+static void PrintSpinRecords() {
+  if (!g_spin_host || g_spin_host[0] == 0) return;
+  const unsigned long long n = g_spin_host[0] < 60 ? g_spin_host[0] : 60;
+  for (unsigned long long i = 0; i < n; ++i) {
+    const unsigned long long* r = g_spin_host + 8 + i * 8;
+    std::fprintf(stderr, "[libbeatrice_b200]   stalled wait: site %llu (file id * 1000 + line) block (%llu,%llu) have/parity %llu want/info %llu sm %llu thread %llu\n",
+                 r[0], r[1] & 0xffffffffull, r[1] >> 32, r[2] & 0xffffffffull, r[2] >> 32, r[3], r[4]);
+  }
+}
+
 void Fail(int code, const char* what, const char* file, int line) {
   char text[480];
   if (code > 0) {
@@ -41,6 +83,7 @@ void Fail(int code, const char* what, const char* file, int line) {
     std::snprintf(text, sizeof(text), "%s:%d: %s", file, line, what);
   }
   Latch(code, text);
+  PrintSpinRecords();
   if (AbortOnError()) std::abort();
   throw Failure{code};
 }

@@ -43,6 +43,7 @@ int ParseFileImage(const void* data, size_t size, int family, uint32_t kind_a, u
 // ---------------------------------------------------------------------------------------
 // device plumbing
 // ---------------------------------------------------------------------------------------
+void InstallSpinDebug(int device);  // dead-lock records of the polling kernels become visible to Fail()
 int UsableDeviceCount();           // never aborts
 int DefaultDevice();               // env BEATRICE_B200_DEVICE or 0; aborts when no GPU is usable
 bool GraphsEnabled();              // env BEATRICE_B200_NO_GRAPH=1 disables CUDA graphs

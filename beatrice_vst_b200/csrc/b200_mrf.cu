@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
         const uint32_t bbase = buf ? y_base : x_base, pstride = buf ? y_pstride : x_pstride, plane = buf ? y_plane : x_plane;
         // input of conv i complete: history landed + every new row written by the epilogue warps
         MbarWait(bar_hist + 8 * buf, (i >> 1) & 1);
-        SpinUntil(in_cnt, static_cast<uint32_t>(kEpiWarps * (i + 1)));
+        SpinUntil(in_cnt, static_cast<uint32_t>(kEpiWarps * (i + 1)), 100000u + 433u);
         __threadfence_block();
         FenceProxyAsync();
         {
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
         }
         B200_TR(i, 8);
         // conv i's MMAs done reading the buffer
-        SpinUntil(acc_cnt, static_cast<uint32_t>(i + 1));
+        SpinUntil(acc_cnt, static_cast<uint32_t>(i + 1), 100000u + 448u);
         if (i + 2 < 6) load_hist(i + 2);
         MbarArrive(bar_free + 8 * buf);
         B200_TR(i, 9);
@@ -590,5 +590,7 @@ void LaunchMrfZeroStream(const MrfHistBlock* d_blocks, int n_blocks, int b, cuda
   mrf_zero_stream_kernel<<<n_blocks, 128, 0, s>>>(d_blocks, b);
   B200_CHECK(cudaGetLastError());
 }
+
+void SetSpinDebugMrf(unsigned long long* dev_ptr) { SetSpinDebugPtr(dev_ptr); }
 
 }  // namespace b200

@@ -207,9 +207,9 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
       const uint32_t d_pstride = is_c1 ? y_pstride : x_pstride, d_plane = is_c1 ? y_plane : x_plane;
       const int d_hmax = is_c1 ? HY : HX;
       const float* bias = bias_s + i * Cs;
-      if (i >= 1 && !last) MbarWait(bar_free + 8 * ((i + 1) & 1), ((i - 1) >> 1) & 1);
+      if (i >= 1 && !last) MbarWaitDbg(bar_free + 8 * ((i + 1) & 1), ((i - 1) >> 1) & 1, 200000u + 210u, static_cast<uint32_t>(i));
       // the peers have consumed what this warp pushed for conv i-1
-      if (i >= 1) MbarWaitCluster(bar_box_free + 8 * q4, (i - 1) & 1);
+      if (i >= 1) MbarWaitClusterDbg(bar_box_free + 8 * q4, (i - 1) & 1, 200000u + 212u, static_cast<uint32_t>(i));
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
         const int r = m * 128 + rtid;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         const int b = group * S + s;
         const bool exists = r < rows_valid;
         const bool valid = exists && b < p.B;
-        MbarWait(bar_acc + 8 * m, i & 1);
+        MbarWaitDbg(bar_acc + 8 * m, i & 1, 200000u + 220u, static_cast<uint32_t>(i));
         TcFenceAfter();
         if (tid == 0 && m == 0) B200_TR(i, 0);
         if (m == MT - 1 && tid == 0) atomicAdd(const_cast<uint32_t*>(acc_cnt), 1u);   // conv i's MMAs have all retired
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         }
         if (tid == 0 && m == 0) B200_TR(i, 1);
         // ---- pull half: own columns + the peers' partials, summed in rank order ----
-        MbarWait(bar_box_full + 8 * q4, (i * MT + m) & 1);
+        MbarWaitDbg(bar_box_full + 8 * q4, (i * MT + m) & 1, 200000u + 252u, static_cast<uint32_t>(i));
         if (tid == 0 && m == 0) B200_TR(i, 2);
         const uint32_t xcol = t_lane + x_col0 + m * Cs;
         const uint32_t srow = d_base + static_cast<uint32_t>(d_hmax * S + r) * 16;
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         const uint32_t a_tmpl_lo = static_cast<uint32_t>(a_tmpl), a_hi32 = static_cast<uint32_t>(a_tmpl >> 32);
         const uint32_t tap_step = static_cast<uint32_t>(dil * S);
         const uint32_t plane16 = plane >> 4, group_step = (2 * pstride) >> 4;
-        MbarWait(bar_hist + 8 * buf, (i >> 1) & 1);
+        MbarWaitDbg(bar_hist + 8 * buf, (i >> 1) & 1, 200000u + 354u, static_cast<uint32_t>(i));
         if (lane == 0) B200_TR(i, 4);
 #pragma unroll 1
         for (int m = 0; m < MT; ++m) {
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
           uint32_t a_group = a_tmpl_lo + ((bbase >> 4) & 0x3FFFu) + static_cast<uint32_t>((hmax - (k - 1) * dil) * S + 128 * m);
 #pragma unroll 1
           for (int g = 0; g < Gs; ++g) {
-            MbarWait(bar_in + 8 * (m * Gs + g), i & 1);
+            MbarWaitDbg(bar_in + 8 * (m * Gs + g), i & 1, 200000u + 363u, static_cast<uint32_t>(i));
             TcFenceAfter();
             if (m == 0 && g == 0) if (lane == 0) B200_TR(i, 5);
             if (m == 0 && g == Gs - 1) if (lane == 0) B200_TR(i, 6);
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
 #pragma unroll 1
             for (int j = 0; j < k; ++j) {
               if (within == 0) {
-                MbarWait(bar_w_full + 8 * stage, wphase);
+                MbarWaitDbg(bar_w_full + 8 * stage, wphase, 200000u + 371u, static_cast<uint32_t>(i));
                 TcFenceAfter();
               }
               MmaW2(dcol, a_lo, a_hi32, w_lo, w_hi32, idesc, acc);
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
 #pragma unroll 1
           for (int c = 0; c < chunks; ++c) {
             const uint32_t stage = cc % kNst, round = cc / kNst;
-            if (round > 0) MbarWait(bar_w_empty + 8 * stage, (round - 1) & 1);
+            if (round > 0) MbarWaitDbg(bar_w_empty + 8 * stage, (round - 1) & 1, 200000u + 419u, round);
             const int n = min(NK, ksteps - c * NK);
             const uint32_t bytes = n * kKstepBytes;
             MbarExpectTx(bar_w_full + 8 * stage, bytes);
@@ -454,8 +454,8 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         const int hmax = buf ? HY : HX;
         const uint32_t bbase = buf ? y_base : x_base, pstride = buf ? y_pstride : x_pstride, plane = buf ? y_plane : x_plane;
         // input of conv i complete: history landed + every new row written by the epilogue warps
-        MbarWait(bar_hist + 8 * buf, (i >> 1) & 1);
-        SpinUntil(in_cnt, static_cast<uint32_t>(kEpiWarps * (i + 1)));
+        MbarWaitDbg(bar_hist + 8 * buf, (i >> 1) & 1, 200000u + 457u, static_cast<uint32_t>(i));
+        SpinUntil(in_cnt, static_cast<uint32_t>(kEpiWarps * (i + 1)), 200000u + 458u);
         __threadfence_block();
         FenceProxyAsync();
         {
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         }
         B200_TR(i, 8);
         // conv i's MMAs done reading the buffer
-        SpinUntil(acc_cnt, static_cast<uint32_t>(i + 1));
+        SpinUntil(acc_cnt, static_cast<uint32_t>(i + 1), 200000u + 473u);
         if (i + 2 < 6) load_hist(i + 2);
         MbarArrive(bar_free + 8 * buf);
         B200_TR(i, 9);
@@ -563,5 +563,7 @@ void LaunchMrfStageCluster(const MrfStageParams& p, int C, int NC, bool split, c
 #undef B200_MRFC_CASE
   Fail(-106, "cluster MRF kernel has no form for this width / cluster size", __FILE__, __LINE__);
 }
+
+void SetSpinDebugMrfc(unsigned long long* dev_ptr) { SetSpinDebugPtr(dev_ptr); }
 
 }  // namespace b200

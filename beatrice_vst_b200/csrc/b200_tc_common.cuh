@@ -156,10 +156,101 @@ __device__ __forceinline__ void BulkWait0() { asm volatile("cp.async.bulk.wait_g
 __device__ __forceinline__ void SmemAddRelease(volatile uint32_t* cnt) {
   asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(SmemAddr(const_cast<uint32_t*>(cnt))) : "memory");
 }
-__device__ __forceinline__ void SpinUntil(volatile uint32_t* cnt, uint32_t target) {
+// A wait that exceeds ~2^28 polls (seconds) means the kernel is dead-locked: rather than hang the host forever the
+// thread leaves a record of WHERE in host-visible memory (SetSpinDebug: a mapped pinned buffer the library prints when
+// it latches the resulting launch failure) and traps.  One copy of the pointer per translation unit.
+__device__ unsigned long long* g_spin_dbg = nullptr;
+inline void SetSpinDebugPtr(unsigned long long* dev_ptr) { cudaMemcpyToSymbol(g_spin_dbg, &dev_ptr, sizeof(dev_ptr)); }
+__device__ __noinline__ void SpinRecord(uint32_t site, uint32_t have, uint32_t want) {
+  unsigned long long* d = g_spin_dbg;
+  if (d != nullptr) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned long long slot = atomicAdd(d, 1ull);
+    if (slot < 60) {
+      unsigned long long* r = d + 8 + slot * 8;
+      r[0] = site;
+      r[1] = (static_cast<unsigned long long>(blockIdx.y) << 32) | blockIdx.x;
+      r[2] = (static_cast<unsigned long long>(want) << 32) | have;
+      r[3] = smid;
+      r[4] = threadIdx.x;
+    }
+    __threadfence_system();
+  }
+}
+// mbarrier waits with a watchdog (globaltimer): after ~1 s without completion the waiter leaves a record (site, CTA,
+// the conv index / parity it waits for) and KEEPS waiting, so that every party of a dead-lock reports before the
+// first polling thread traps.  try_wait suspends the thread in hardware, the extra compare is off the critical path.
+__device__ __forceinline__ void MbarWaitDbg(uint32_t bar, uint32_t parity, uint32_t site, uint32_t info) {
+  unsigned long long t0 = 0;
+  bool reported = false;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0) t0 = now;
+    if (!reported && now - t0 > 1000000000ull) {
+      SpinRecord(site, parity, info);
+      reported = true;
+    }
+  }
+}
+__device__ __forceinline__ void MbarWaitClusterDbg(uint32_t bar, uint32_t parity, uint32_t site, uint32_t info) {
+  unsigned long long t0 = 0;
+  bool reported = false;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P2;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P2, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P2;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0) t0 = now;
+    if (!reported && now - t0 > 1000000000ull) {
+      SpinRecord(site, parity, info);
+      reported = true;
+    }
+  }
+}
+__device__ __noinline__ void SpinTimeout(uint32_t site, uint32_t have, uint32_t want) {
+  unsigned long long* d = g_spin_dbg;
+  if (d != nullptr) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned long long slot = atomicAdd(d, 1ull);
+    if (slot < 60) {
+      unsigned long long* r = d + 8 + slot * 8;
+      r[0] = site;
+      r[1] = (static_cast<unsigned long long>(blockIdx.y) << 32) | blockIdx.x;
+      r[2] = (static_cast<unsigned long long>(want) << 32) | have;
+      r[3] = smid;
+      r[4] = threadIdx.x;
+    }
+    __threadfence_system();
+  }
+  __trap();
+}
+__device__ __forceinline__ void SpinUntil(volatile uint32_t* cnt, uint32_t target, uint32_t site = 0) {
   uint32_t spins = 0;
   while (*cnt < target) {
-    if (++spins > (1u << 28)) __trap();
+    if (++spins > (1u << 28)) SpinTimeout(site, *cnt, target);
   }
 }
 __device__ __forceinline__ int ConvDil(int i) { return (i & 1) ? 1 : (i == 0 ? 1 : (i == 2 ? 3 : 5)); }
