@@ -137,6 +137,14 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
     const int q4 = warp & 3, whalf = warp >> 2, rtid = tid & 127;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
     const uint32_t x_col0 = 2 * MT * C;   // fp32 residual stream of the own channel slice
+    // A lane quarter whose 32 rows lie entirely past the group's rows (S * T = 80 at stage 0: quarter 3 is empty) has
+    // nothing to push or pull.  It must then stay OUT of the box_free / box_full hand-shake altogether: with no data
+    // dependency on its peers nothing stops them from running a whole conv ahead, and a second round of box_free
+    // arrivals landing before such a warp has observed the first one flips the barrier's parity back under it --
+    // the wait then never returns (seen as a stall of the whole cluster about once per 3e4 hops under
+    // tools/pipe_stress.py; the watchdog records pointed at exactly these warps).  Every CTA of a cluster has the
+    // same rows, so the decision is the same in all of them and the barrier counts of the active quarters hold.
+    const bool q_active = rows_valid > q4 * 32;
     // Everything up to here (barriers, TMEM, bias, and in the other warps the weight ring and the
     // history loads) touches nothing the preceding kernel -- the upsampler that writes u -- produces.
     PdlWait();
@@ -209,7 +217,8 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
       const float* bias = bias_s + i * Cs;
       if (i >= 1 && !last) MbarWaitDbg(bar_free + 8 * ((i + 1) & 1), ((i - 1) >> 1) & 1, 200000u + 210u, static_cast<uint32_t>(i));
       // the peers have consumed what this warp pushed for conv i-1
-      if (i >= 1) MbarWaitClusterDbg(bar_box_free + 8 * q4, (i - 1) & 1, 200000u + 212u, static_cast<uint32_t>(i));
+      // (only quarters that own rows take part in the exchange -- see q_active)
+      if (i >= 1 && q_active) MbarWaitClusterDbg(bar_box_free + 8 * q4, (i - 1) & 1, 200000u + 212u, static_cast<uint32_t>(i));
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
         const int r = m * 128 + rtid;
@@ -226,10 +235,10 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         //      mbarrier counts the bytes (st.async complete_tx), so no fence and no arrive is needed ----
         {
           const int w_rows = min(max(rows_valid - (m * 128 + q4 * 32), 0), 32);   // rows of this lane quarter in tile m
-          if (lane == 0 && whalf == 0) MbarExpectTx(bar_box_full + 8 * q4, static_cast<uint32_t>(NC - 1) * w_rows * Cs * 4);
+          if (lane == 0 && whalf == 0 && q_active) MbarExpectTx(bar_box_full + 8 * q4, static_cast<uint32_t>(NC - 1) * w_rows * Cs * 4);
         }
 #pragma unroll 1
-        for (int q = 1; q < NC; ++q) {
+        for (int q = 1; q < NC && q_active; ++q) {
           const int pr = (rank + q) % NC;
           const int slot = rank < pr ? rank : rank - 1;
           const uint32_t dst = MapToCta(box_base + slot * box_slot + static_cast<uint32_t>(exists ? r : 0) * kBoxRow, pr);
@@ -249,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         }
         if (tid == 0 && m == 0) B200_TR(i, 1);
         // ---- pull half: own columns + the peers' partials, summed in rank order ----
-        MbarWaitDbg(bar_box_full + 8 * q4, (i * MT + m) & 1, 200000u + 252u, static_cast<uint32_t>(i));
+        if (q_active) MbarWaitDbg(bar_box_full + 8 * q4, (i * MT + m) & 1, 200000u + 252u, static_cast<uint32_t>(i));
         if (tid == 0 && m == 0) B200_TR(i, 2);
         const uint32_t xcol = t_lane + x_col0 + m * Cs;
         const uint32_t srow = d_base + static_cast<uint32_t>(d_hmax * S + r) * 16;
@@ -326,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
       if (!last) {
         // this warp's inbox rows are consumed: the peers may push conv i+1
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && q_active) {
           for (int q = 1; q < NC; ++q) MbarArriveCluster(MapToCta(bar_box_free + 8 * q4, (rank + q) % NC));
         }
         __syncwarp();

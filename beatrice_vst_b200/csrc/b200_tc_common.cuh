@@ -200,7 +200,7 @@ __device__ __forceinline__ void MbarWaitDbg(uint32_t bar, uint32_t parity, uint3
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
     if (t0 == 0) t0 = now;
     if (!reported && now - t0 > 1000000000ull) {
-      SpinRecord(site, parity, info);
+      if ((threadIdx.x & 31) == 0) SpinRecord(site, parity, info);   // one record per warp
       reported = true;
     }
   }
@@ -224,7 +224,7 @@ __device__ __forceinline__ void MbarWaitClusterDbg(uint32_t bar, uint32_t parity
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
     if (t0 == 0) t0 = now;
     if (!reported && now - t0 > 1000000000ull) {
-      SpinRecord(site, parity, info);
+      if ((threadIdx.x & 31) == 0) SpinRecord(site, parity, info);   // one record per warp
       reported = true;
     }
   }
