@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
       const uint32_t d_pstride = is_c1 ? y_pstride : x_pstride, d_plane = is_c1 ? y_plane : x_plane;
       const int d_hmax = is_c1 ? HY : HX;
       const float* bias = bias_s + i * Cs;
-      if (i >= 1 && !last) MbarWaitDbg(bar_free + 8 * ((i + 1) & 1), ((i - 1) >> 1) & 1, 200000u + 210u, static_cast<uint32_t>(i));
+      if (i >= 1 && !last) MbarWait(bar_free + 8 * ((i + 1) & 1), ((i - 1) >> 1) & 1);
       // the peers have consumed what this warp pushed for conv i-1
       // (only quarters that own rows take part in the exchange -- see q_active)
       if (i >= 1 && q_active) MbarWaitClusterDbg(bar_box_free + 8 * q4, (i - 1) & 1, 200000u + 212u, static_cast<uint32_t>(i));
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         const int b = group * S + s;
         const bool exists = r < rows_valid;
         const bool valid = exists && b < p.B;
-        MbarWaitDbg(bar_acc + 8 * m, i & 1, 200000u + 220u, static_cast<uint32_t>(i));
+        MbarWait(bar_acc + 8 * m, i & 1);
         TcFenceAfter();
         if (tid == 0 && m == 0) B200_TR(i, 0);
         if (m == MT - 1 && tid == 0) atomicAdd(const_cast<uint32_t*>(acc_cnt), 1u);   // conv i's MMAs have all retired
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         const uint32_t a_tmpl_lo = static_cast<uint32_t>(a_tmpl), a_hi32 = static_cast<uint32_t>(a_tmpl >> 32);
         const uint32_t tap_step = static_cast<uint32_t>(dil * S);
         const uint32_t plane16 = plane >> 4, group_step = (2 * pstride) >> 4;
-        MbarWaitDbg(bar_hist + 8 * buf, (i >> 1) & 1, 200000u + 354u, static_cast<uint32_t>(i));
+        MbarWait(bar_hist + 8 * buf, (i >> 1) & 1);
         if (lane == 0) B200_TR(i, 4);
 #pragma unroll 1
         for (int m = 0; m < MT; ++m) {
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
           uint32_t a_group = a_tmpl_lo + ((bbase >> 4) & 0x3FFFu) + static_cast<uint32_t>((hmax - (k - 1) * dil) * S + 128 * m);
 #pragma unroll 1
           for (int g = 0; g < Gs; ++g) {
-            MbarWaitDbg(bar_in + 8 * (m * Gs + g), i & 1, 200000u + 363u, static_cast<uint32_t>(i));
+            MbarWait(bar_in + 8 * (m * Gs + g), i & 1);
             TcFenceAfter();
             if (m == 0 && g == 0) if (lane == 0) B200_TR(i, 5);
             if (m == 0 && g == Gs - 1) if (lane == 0) B200_TR(i, 6);
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
 #pragma unroll 1
             for (int j = 0; j < k; ++j) {
               if (within == 0) {
-                MbarWaitDbg(bar_w_full + 8 * stage, wphase, 200000u + 371u, static_cast<uint32_t>(i));
+                MbarWait(bar_w_full + 8 * stage, wphase);
                 TcFenceAfter();
               }
               MmaW2(dcol, a_lo, a_hi32, w_lo, w_hi32, idesc, acc);
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
 #pragma unroll 1
           for (int c = 0; c < chunks; ++c) {
             const uint32_t stage = cc % kNst, round = cc / kNst;
-            if (round > 0) MbarWaitDbg(bar_w_empty + 8 * stage, (round - 1) & 1, 200000u + 419u, round);
+            if (round > 0) MbarWait(bar_w_empty + 8 * stage, (round - 1) & 1);
             const int n = min(NK, ksteps - c * NK);
             const uint32_t bytes = n * kKstepBytes;
             MbarExpectTx(bar_w_full + 8 * stage, bytes);
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
         const int hmax = buf ? HY : HX;
         const uint32_t bbase = buf ? y_base : x_base, pstride = buf ? y_pstride : x_pstride, plane = buf ? y_plane : x_plane;
         // input of conv i complete: history landed + every new row written by the epilogue warps
-        MbarWaitDbg(bar_hist + 8 * buf, (i >> 1) & 1, 200000u + 457u, static_cast<uint32_t>(i));
+        MbarWait(bar_hist + 8 * buf, (i >> 1) & 1);
         SpinUntil(in_cnt, static_cast<uint32_t>(kEpiWarps * (i + 1)), 200000u + 458u);
         __threadfence_block();
         FenceProxyAsync();
