@@ -59,7 +59,7 @@ struct BeatriceB200_Engine {
   cudaStream_t stream = nullptr, aux = nullptr, aux2 = nullptr;
   cudaStream_t side = nullptr;                        // host-buffer path: early output block + its D2H copy
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_side = nullptr;
-  cudaEvent_t ev_join2 = nullptr, ev_cond = nullptr;  // pipelined hop: pitch-lane join, "vocoder has read the hand-off"
+  cudaEvent_t ev_join2 = nullptr;                     // pipelined hop: pitch-lane join
   std::string pipe_plan;                              // BeatriceB200_SetPipelinePlan (tuning aid); empty: the built-in plan
   static constexpr size_t kMaxGates = 24;
   cudaEvent_t ev_gate[kMaxGates] = {};                // pipelined hop: "this vocoder kernel has finished" (PipelinePlan)
@@ -561,13 +561,9 @@ void EnqueueHopPipelined(Engine* e, cudaStream_t s, bool with_vocoder) {
       if (e->hop_ops[i].name == "wave.post") post = i;
     }
   const std::vector<int> gate = PipelinePlan(e, first_wave, post);
-  static const int lane_pdl = [] { const char* ev = std::getenv("BEATRICE_B200_PIPE_LANE_PDL"); return ev ? std::atoi(ev) : -1; }();
-  static const int voc_pdl = [] { const char* ev = std::getenv("BEATRICE_B200_PIPE_VOC_PDL"); return ev ? std::atoi(ev) : -1; }();
-  size_t next_op = 0;               // lane ops are issued in program order (content lane first, then pitch)
   std::vector<char> done(first_wave, 0);
   int waited[2] = {-1, -1};
   auto issue_lanes = [&](int v) {   // every not-yet-issued lane op whose gate has been enqueued
-    (void)next_op;
     for (size_t i = 0; i < first_wave; ++i) {
       if (done[i] || SkipVq(e, i)) continue;
       if (with_vocoder && gate[i] > v) continue;
@@ -577,10 +573,7 @@ void EnqueueHopPipelined(Engine* e, cudaStream_t s, bool with_vocoder) {
         B200_CHECK(cudaStreamWaitEvent(ls, e->ev_gate[gate[i] - first_wave], 0));
         waited[lane] = gate[i];
       }
-      {
-        PdlScope scope(lane_pdl);
-        e->hop_ops[i].launch(ls);
-      }
+      e->hop_ops[i].launch(ls);
       done[i] = 1;
     }
   };
@@ -588,28 +581,17 @@ void EnqueueHopPipelined(Engine* e, cudaStream_t s, bool with_vocoder) {
   size_t w = first_wave;
   if (with_vocoder) {
     // Capture order: the vocoder's kernels up to the LAST gate first (an event behind every gate), then the lanes, then
-    // the rest of the vocoder.  The dependency graph is the same as with the lanes interleaved where their gates
-    // are, but the instantiated graph submits ready kernels in capture order, and the vocoder must win those ties.
+    // the rest of the vocoder (interleaving the lanes where their gates are measured the same).
     int last_gate = -1;
     for (size_t i = 0; i < first_wave; ++i) last_gate = std::max(last_gate, gate[i]);
-    static const bool interleave = [] { const char* ev = std::getenv("BEATRICE_B200_PIPE_INTERLEAVE"); return ev && ev[0] == '1'; }();
     for (; w < post && static_cast<int>(w) <= last_gate; ++w) {
-      {
-        PdlScope scope(voc_pdl);
-        e->hop_ops[w].launch(s);
-      }
+      e->hop_ops[w].launch(s);
       bool needed = false;
       for (size_t i = 0; i < first_wave; ++i) needed = needed || (!done[i] && gate[i] == static_cast<int>(w));
-      if (needed && w - first_wave < Engine::kMaxGates) {
-        B200_CHECK(cudaEventRecord(e->ev_gate[w - first_wave], s));
-        if (interleave) issue_lanes(static_cast<int>(w));
-      }
+      if (needed && w - first_wave < Engine::kMaxGates) B200_CHECK(cudaEventRecord(e->ev_gate[w - first_wave], s));
     }
     issue_lanes(last_gate);
-    for (; w < post; ++w) {
-      PdlScope scope(voc_pdl);
-      e->hop_ops[w].launch(s);
-    }
+    for (; w < post; ++w) e->hop_ops[w].launch(s);
   }
   issue_lanes(static_cast<int>(e->hop_ops.size()));   // whatever is left (none with a well-formed plan)
   B200_CHECK(cudaEventRecord(e->ev_join, e->aux));
@@ -897,7 +879,6 @@ BeatriceB200_Engine* BeatriceB200_CreateEngine(int device, int n_streams, int pr
   B200_CHECK(cudaStreamCreateWithPriority(&e->aux, cudaStreamNonBlocking, prio_lo));
   B200_CHECK(cudaStreamCreateWithPriority(&e->aux2, cudaStreamNonBlocking, prio_lo));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming));
-  B200_CHECK(cudaEventCreateWithFlags(&e->ev_cond, cudaEventDisableTiming));
   for (auto& g : e->ev_gate) B200_CHECK(cudaEventCreateWithFlags(&g, cudaEventDisableTiming));
   B200_CHECK(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
   B200_CHECK(cudaEventCreateWithFlags(&e->ev_side, cudaEventDisableTiming));
@@ -928,7 +909,6 @@ void BeatriceB200_DestroyEngine(BeatriceB200_Engine* e) {
   cudaStreamDestroy(e->aux);
   if (e->aux2) cudaStreamDestroy(e->aux2);
   if (e->ev_join2) cudaEventDestroy(e->ev_join2);
-  if (e->ev_cond) cudaEventDestroy(e->ev_cond);
   for (auto& g : e->ev_gate)
     if (g) cudaEventDestroy(g);
   delete e;

@@ -80,22 +80,12 @@ inline void ZeroSync(void* dst, size_t bytes) {
 
 // Programmatic dependent launch: the kernel may begin (prologue up to its griddepcontrol.wait)
 // while the previous kernel on `s` drains.  BEATRICE_B200_NO_PDL=1 turns the attribute off.
-// (PdlScope: a launch site can switch the attribute off for the launches it encloses on this thread.)
-inline int& PdlOverride() {
-  static thread_local int v = -1;   // -1: no override, 0: off, 1: on
-  return v;
-}
-struct PdlScope {
-  int saved;
-  explicit PdlScope(int v) : saved(PdlOverride()) { PdlOverride() = v; }
-  ~PdlScope() { PdlOverride() = saved; }
-};
 inline bool PdlEnabled() {
   static const bool on = [] {
     const char* e = std::getenv("BEATRICE_B200_NO_PDL");
     return !(e && e[0] == '1');
   }();
-  return PdlOverride() >= 0 ? (PdlOverride() != 0 && on) : on;
+  return on;
 }
 template <typename... KArgs, typename... Args>
 inline void LaunchPdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x,

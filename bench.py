@@ -428,7 +428,7 @@ def main():
     achieved = mrf_flops / (mrf_ms * 1e-3) / 1e12 if mrf_ms > 0 else 0.0
     # DRAM traffic of the same launches from the committed ncu --set full capture (profiles/), per launch
     traffic, traffic_source = None, None
-    for name in ("r2_mrf_traffic.json", "r1_mrf_traffic.json"):
+    for name in ("r2_mrf_traffic.json",):
         tpath = os.path.join(ROOT, "profiles", name)
         if args.precision == "bf16x3" and os.path.exists(tpath):
             try:
