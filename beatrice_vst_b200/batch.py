@@ -54,6 +54,7 @@ BATCH_SYMBOLS = {
     "BeatriceB200_SetPipelineDepth": (C.c_int, [_vp, C.c_int]),
     "BeatriceB200_PipelineDepth": (C.c_int, [_vp]),
     "BeatriceB200_SetPipelinePlan": (C.c_int, [_vp, C.c_char_p]),
+    "BeatriceB200_SetUpsamplerForm": (C.c_int, [_vp, C.c_int]),
     "BeatriceB200_DrainPipeline": (C.c_int, [_vp, _vp, _vp]),
     "BeatriceB200_AllocPinned": (_vp, [C.c_size_t]),
     "BeatriceB200_FreePinned": (None, [_vp]),
@@ -223,6 +224,10 @@ class Engine:
 
     def set_pipeline_plan(self, plan: str) -> int:
         return self.dll.BeatriceB200_SetPipelinePlan(self.h, plan.encode("utf-8"))
+
+    def set_upsampler_form(self, form: int) -> int:
+        """1 = in the fused MRF kernels' prologue, 0 = own launches, -1 = by pipeline depth (default)."""
+        return self.dll.BeatriceB200_SetUpsamplerForm(self.h, form)
 
     def drain(self, model_rate: bool = False) -> np.ndarray:
         """Depth 2: the blocks of the hop still in flight ([n,480] @48 kHz, or [n,240] @24 kHz)."""

@@ -100,6 +100,7 @@ struct BeatriceB200_Engine {
   bool any_vq = false;                                // some stream has kNN-VQ on (VQNumNeighbors > 0)
   GraphRunner graph16, graph48, graph48s;
   GraphRunner graph16p, graph48p, graph48sp;          // depth-2 forms of the same three entries
+  int ups_form = -1;                                  // BeatriceB200_SetUpsamplerForm
   uint64_t launches = 0;
   uint64_t hops = 0;
 
@@ -408,9 +409,24 @@ void BuildHop(Engine* e) {
   e->hop_ops.clear();
   e->hop_lane.clear();
   const int B = e->B;
+  // developer ablation: BEATRICE_B200_SKIP_OPS="wave.ups1,wave.mrf2" drops the launches of the named ops from the hop
+  // (timing only -- the marginal cost of an op inside the hop graph; the audio is meaningless)
+  static const std::string skip_ops = [] {
+    const char* ev = std::getenv("BEATRICE_B200_SKIP_OPS");
+    return std::string(ev ? ev : "");
+  }();
   auto push = [&](const Op& op, int lane) {
     e->hop_ops.push_back(op);
     e->hop_lane.push_back(lane);
+    if (!skip_ops.empty()) {
+      size_t pos = 0;
+      while (pos < skip_ops.size()) {
+        const size_t comma = skip_ops.find(',', pos), end = comma == std::string::npos ? skip_ops.size() : comma;
+        const std::string item = skip_ops.substr(pos, end - pos);
+        if (!item.empty() && op.name.find(item) != std::string::npos) e->hop_ops.back().launch = [](cudaStream_t) {};
+        pos = end + 1;
+      }
+    }
   };
   // with the advance folded into the post conv the encoders' own advance launches are dropped
   auto is_advance = [](const Op& op) { return op.name.size() > 8 && op.name.compare(op.name.size() - 8, 8, ".advance") == 0; };
@@ -454,7 +470,21 @@ void BuildHop(Engine* e) {
 inline bool SkipVq(const Engine* e, size_t op) {
   return static_cast<int>(op) == e->vq_op && !e->any_vq && e->phone_st.head_dual;
 }
-inline size_t HopLaunches(const Engine* e) { return e->hop_ops.size() - (SkipVq(e, static_cast<size_t>(e->vq_op)) ? 1 : 0); }
+inline size_t HopLaunches(const Engine* e) {
+  const WaveState& w = e->wave_st;
+  return e->hop_ops.size() - (SkipVq(e, static_cast<size_t>(e->vq_op)) ? 1 : 0) -
+         ((w.ups_in_prologue && *w.ups_in_prologue) ? static_cast<size_t>(w.n_fusable_ups) : 0);
+}
+// Where the upsamplers of the fused stages run (WaveState::ups_in_prologue): inside the MRF kernels on the latency path,
+// as launches of their own at pipeline depth 2.  Read when a hop is enqueued, so set in front of every enqueue / capture.
+inline void SelectUpsForm(Engine* e) {
+  static const int env_form = [] {
+    const char* ev = std::getenv("BEATRICE_B200_UPS_IN_PROLOGUE");   // developer override: 0 / 1 for both depths
+    return ev ? std::atoi(ev) : -1;
+  }();
+  const int forced = e->ups_form >= 0 ? e->ups_form : env_form;   // BeatriceB200_SetUpsamplerForm, else the environment
+  if (e->wave_st.ups_in_prologue) *e->wave_st.ups_in_prologue = forced >= 0 ? forced != 0 : e->pipeline != 2;
+}
 
 // Enqueues one model-rate hop (in16 staging already filled) with the two encoders as
 // concurrent branches.  Works both live and under stream capture.
@@ -513,7 +543,9 @@ std::vector<int> PipelinePlan(const Engine* e, size_t first_wave, size_t post) {
   int cond = static_cast<int>(first_wave);
   for (size_t i = first_wave; i < post; ++i)
     if (e->hop_ops[i].name.compare(0, 9, "wave.cond") == 0) cond = static_cast<int>(i);
-  const int g_default = std::max(find_wave("wave.mrf0"), cond), g_chain = std::max(find_wave("wave.ups2"), g_default);
+  // (the stage-2 upsampler may be fused into the stage's MRF launch: the same point in time is then the end of stage 1)
+  const int g_ups2 = find_wave("wave.ups2") >= 0 ? find_wave("wave.ups2") : find_wave("wave.mrf1");
+  const int g_default = std::max(find_wave("wave.mrf0"), cond), g_chain = std::max(g_ups2, g_default);
   std::vector<std::pair<std::string, std::string>> overrides;
   const char* ev = std::getenv("BEATRICE_B200_PIPE_PLAN");
   if (!e->pipe_plan.empty() || ev) {
@@ -759,6 +791,7 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
 }
 
 void RunHop16(Engine* e, bool allow_graph) {
+  SelectUpsForm(e);
   if (e->pipeline == 2) {
     FlushEncoderSide(e, true);
     const bool voc = e->primed;
@@ -777,6 +810,7 @@ void RunHop16(Engine* e, bool allow_graph) {
 }
 
 void RunHop48(Engine* e, bool allow_graph) {
+  SelectUpsForm(e);
   if (e->pipeline == 2) {
     FlushEncoderSide(e, true);
     e->hostrate.PrepareHop(e->stream, /*out_lag=*/true);
@@ -815,6 +849,7 @@ void RunHop48(Engine* e, bool allow_graph) {
 // two previous hops (the adapter's block FIFO), so it is computed and copied to the host on a side stream
 // WHILE this hop's model call runs; the hop graph itself only stores its model output for the next call.
 void RunHop48Split(Engine* e, float* out_host, size_t bytes) {
+  SelectUpsForm(e);
   const bool pipe = e->pipeline == 2, voc = e->primed;
   if (pipe) FlushEncoderSide(e, true);
   else FlushPending(e, true);
@@ -971,6 +1006,19 @@ int BeatriceB200_SetPipelinePlan(BeatriceB200_Engine* e, const char* plan) {
     B200_CHECK(cudaStreamSynchronize(e->stream));
     e->pipe_plan = plan ? plan : "";
     ResetGraphs(e);
+    rc__ = 0;
+  });
+  return rc__;
+}
+
+int BeatriceB200_SetUpsamplerForm(BeatriceB200_Engine* e, int form) {
+  if (!e || form < -1 || form > 1) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(rc__ = BEATRICE_B200_ERR_DEVICE, {
+    B200_CHECK(cudaSetDevice(e->device));
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+    e->ups_form = form;
+    ResetGraphs(e);   // the form is read when a hop is captured
     rc__ = 0;
   });
   return rc__;
@@ -1241,6 +1289,7 @@ int BeatriceB200_DrainPipeline(BeatriceB200_Engine* e, float* frames24_host, flo
     B200_CHECK(cudaSetDevice(e->device));
     cudaStream_t s = e->stream;
     const bool voc = e->pipeline == 2 && e->primed;
+    SelectUpsForm(e);
     if (voc) {
       for (size_t i = 0; i < e->hop_ops.size(); ++i)
         if (e->hop_lane[i] == 2) {
@@ -1419,6 +1468,7 @@ int BeatriceB200_ProfileHop(BeatriceB200_Engine* e, const float* in_dev, float* 
   const size_t nin = sizeof(float) * e->B * kInHop, nout = sizeof(float) * e->B * kOutHop;
   B200_CHECK(cudaMemcpyAsync(e->in16.p, in_dev, nin, cudaMemcpyDeviceToDevice, s));
   FlushPending(e, true);
+  SelectUpsForm(e);
   const size_t n = e->hop_ops.size();
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& x : ev) B200_CHECK(cudaEventCreate(&x));

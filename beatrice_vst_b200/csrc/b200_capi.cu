@@ -282,7 +282,7 @@ void GenerateWaveformImpl(const WaveformGeneratorObj* wg, const float* phone, co
         B200_CHECK(cudaMemcpyAsync(c->out.p, c->st.out.p, sizeof(float) * kOutHop, cudaMemcpyDeviceToHost, st));
       },
       GraphsEnabled());
-  g_kernel_launches.fetch_add(c->st.program.size(), std::memory_order_relaxed);
+  g_kernel_launches.fetch_add(static_cast<size_t>(c->st.LaunchesPerHop()), std::memory_order_relaxed);
   B200_CHECK(cudaStreamSynchronize(s));
   ++c->hops;
   std::memcpy(out, c->out.p, sizeof(float) * kOutHop);

@@ -465,6 +465,7 @@ int WaveModel::LoadFromImage(const void* data, size_t size, int on_device) {
     u.w = c.Take(2u * cin * r * co);
     const float* b_dev = c.Take(co);
     const float* b_host = c.HostAt(b_dev);
+    ups_bias_raw[s] = b_dev;
     rep_off[s] = rep.size();
     for (int p = 0; p < r; ++p) rep.insert(rep.end(), b_host, b_host + co);
     ups[s] = u;
@@ -553,6 +554,25 @@ int WaveModel::LoadFromImage(const void* data, size_t size, int on_device) {
           PackMrfWeights(wsrc, spec::kMrfK[ki], co, sp == 1, concat, packed[sp].data() + off);
           w_off[sp][s][ki] = off;
         }
+      }
+    }
+    {
+      // upsamplers of stages 1..3 as images for the fused kernel's prologue
+      std::vector<uint16_t> img;
+      size_t off[4] = {};
+      for (int s = 1; s < 4; ++s) {
+        const int co = spec::kStageCh[s + 1], r = spec::kRates[s];
+        ups_img_ptr[s] = nullptr;
+        if (!have[s] || spec::kStageCh[s] != 2 * co) continue;
+        off[s] = (img.size() + 127) / 128 * 128;
+        img.resize(off[s] + PackMrfUpsWeights(c.HostAt(ups[s].w), co, r, nullptr));
+        PackMrfUpsWeights(c.HostAt(ups[s].w), co, r, img.data() + off[s]);
+      }
+      if (!img.empty()) {
+        ups_img.Alloc(device, img.size() * sizeof(uint16_t), false);
+        UploadSync(ups_img.p, img.data(), img.size() * sizeof(uint16_t));
+        for (int s = 1; s < 4; ++s)
+          if (have[s] && spec::kStageCh[s] == 2 * spec::kStageCh[s + 1]) ups_img_ptr[s] = ups_img.as<uint16_t>() + off[s];
       }
     }
     Upload(&mrf_bias, device, bias_all.data(), bias_all.size());
@@ -1001,6 +1021,101 @@ void WaveState::AllocCond(const FamilyDims& dims, int B_, int device_) {
   cond_ready = true;
 }
 
+namespace {
+
+// How the three MRF branches of a stage map to launches and CTAs of the single-CTA kernel (b200_mrf.cu).
+// Text form: launches separated by '/', CTA classes (blockIdx.y) of a launch by '|', the branches ONE CTA runs one
+// after the other by ',', each branch named by its kernel size; "@KB" after a launch = request at least that much
+// dynamic shared memory (fewer CTAs per SM / none of another launch beside them).  Every branch exactly once.
+//   "11|7|3"        one launch, three CTA classes (round 1)
+//   "11|7,3"        one launch, two classes of 11 and 10 taps per conv
+//   "11@128/7|3"    a PDL pair: k = 11 alone on its SMs, k = 7 and k = 3 sharing the others
+struct MrfLaunchPlan {
+  int n_launch = 0;
+  struct L {
+    int n_y = 0, ylen[3] = {0, 0, 0}, yseq[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, smem_kb = 0;
+  } l[3];
+};
+
+bool ParseMrfPlan(const std::string& text, MrfLaunchPlan* out) {
+  MrfLaunchPlan pl;
+  int seen = 0;
+  size_t i = 0;
+  pl.n_launch = 1;
+  pl.l[0].n_y = 1;
+  auto cur = [&]() -> MrfLaunchPlan::L& { return pl.l[pl.n_launch - 1]; };
+  while (i < text.size()) {
+    const char ch = text[i];
+    if (ch >= '0' && ch <= '9') {
+      int v = 0;
+      while (i < text.size() && text[i] >= '0' && text[i] <= '9') v = v * 10 + (text[i++] - '0');
+      const int ki = v == 3 ? 0 : (v == 7 ? 1 : (v == 11 ? 2 : -1));
+      MrfLaunchPlan::L& L = cur();
+      if (ki < 0 || (seen >> ki) & 1 || L.ylen[L.n_y - 1] >= 3) return false;
+      seen |= 1 << ki;
+      L.yseq[L.n_y - 1][L.ylen[L.n_y - 1]++] = ki;
+      continue;
+    }
+    if (ch == ',') {
+      ++i;
+    } else if (ch == '|') {
+      if (cur().ylen[cur().n_y - 1] == 0 || cur().n_y >= 3) return false;
+      ++cur().n_y;
+      ++i;
+    } else if (ch == '@') {
+      int v = 0;
+      ++i;
+      while (i < text.size() && text[i] >= '0' && text[i] <= '9') v = v * 10 + (text[i++] - '0');
+      cur().smem_kb = v;
+    } else if (ch == '/') {
+      if (cur().ylen[cur().n_y - 1] == 0 || pl.n_launch >= 3) return false;
+      ++pl.n_launch;
+      cur().n_y = 1;
+      ++i;
+    } else {
+      return false;
+    }
+  }
+  if (seen != 7 || cur().ylen[cur().n_y - 1] == 0) return false;
+  *out = pl;
+  return true;
+}
+
+// default plans (measured on B200 at 256 streams) and the developer override
+// BEATRICE_B200_MRF_PLAN="<C=64 plan>;<C=32 plan>;<C=16 plan>" (an empty field keeps the default)
+MrfLaunchPlan MrfPlanFor(int c) {
+  // (measured at 256 streams: "11|7,3" costs 2-10 us per stage -- a chain of twelve convs is longer than the k = 11 chain of
+  //  six, per-conv hand-off latency and not the tap count bounds these CTAs -- and "11@128/7|3" 11 us at stage 2: the k = 7 / k = 3
+  //  CTAs then queue for the SMs the k = 11 CTAs leave; the three-class single launch stays the default everywhere)
+  std::string text = "11|7|3";
+  (void)c;
+  if (const char* ev = std::getenv("BEATRICE_B200_MRF_PLAN")) {
+    std::string all(ev), field;
+    const int want = c >= 64 ? 0 : (c == 32 ? 1 : 2);
+    int idx = 0;
+    size_t start = 0;
+    for (;;) {
+      const size_t semi = all.find(';', start);
+      if (idx == want) {
+        field = all.substr(start, semi == std::string::npos ? std::string::npos : semi - start);
+        break;
+      }
+      if (semi == std::string::npos) break;
+      start = semi + 1;
+      ++idx;
+    }
+    if (!field.empty()) text = field;
+  }
+  MrfLaunchPlan pl;
+  if (!ParseMrfPlan(text, &pl)) {
+    std::fprintf(stderr, "[beatrice-b200] malformed MRF plan '%s' ignored\n", text.c_str());
+    ParseMrfPlan("11|7|3", &pl);
+  }
+  return pl;
+}
+
+}  // namespace
+
 void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
   AllocCond(m->dims, B_, device_);
   B = B_;
@@ -1009,6 +1124,8 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
   model_generation = m->generation;
   program.clear();
   arena.Clear();
+  if (!ups_in_prologue) ups_in_prologue = std::make_shared<bool>(true);
+  n_fusable_ups = 0;
   B200_CHECK(cudaSetDevice(device));
   const bool rc0 = m->dims.has_setter;
   const bool tcm = tc != kTcOff;
@@ -1288,8 +1405,24 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
     add_gemm("wave.pre", pre_idx, 1, false);
   }
   int t_stage = 1;
+  // developer switch: BEATRICE_B200_FUSE_UPS=0 keeps every upsampler a launch of its own
+  static const bool fuse_ups_enabled = [] {
+    const char* ev = std::getenv("BEATRICE_B200_FUSE_UPS");
+    return !(ev && ev[0] == '0');
+  }();
   for (int s = 0; s < 4; ++s) {
+    // stages 1..3 on the single-CTA fused kernel compute their upsampler in the kernel's prologue (MrfUpsDesc)
+    const bool ups_fused = fuse_ups_enabled && s >= 1 && fused[s] && fused_nc[s] == 1 && with_lo && m->ups_img_ptr[s] != nullptr &&
+                           MrfUpsFusable(spec::kStageCh[s + 1], t_stage * spec::kRates[s], fused_S[s], spec::kRates[s], with_lo);
     add_gemm("wave.ups" + std::to_string(s), ups_idx[s], 1, false);
+    if (ups_fused) {   // launches only while the prologue form is switched off (see WaveState::ups_in_prologue)
+      const std::function<void(cudaStream_t)> plain = program.back().launch;
+      const std::shared_ptr<bool> in_prologue = ups_in_prologue;
+      program.back().launch = [=](cudaStream_t st) {
+        if (!*in_prologue) plain(st);
+      };
+      ++n_fusable_ups;
+    }
     t_stage *= spec::kRates[s];
     if (fused[s]) {
       const int c = spec::kStageCh[s + 1];
@@ -1314,6 +1447,15 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
       mp.B = B;
       mp.n_groups = fused_groups[s];
       mp.frame = frame;
+      MrfUpsDesc ups_desc;
+      std::memset(&ups_desc, 0, sizeof(ups_desc));
+      if (ups_fused) {
+        ups_desc.w = m->ups_img_ptr[s];
+        ups_desc.bias = m->ups_bias_raw[s];
+        for (int ki = 0; ki < 3; ++ki) ups_desc.x[ki] = arena.ring(ring_stage_out[s - 1][ki]).base;
+        ups_desc.x_slots = arena.ring(ring_stage_out[s - 1][0]).slots;
+        ups_desc.r = spec::kRates[s];
+      }
       mp.n_branches = 3;
       // CTA scheduling order of the branches.  Where the stage fits in one wave: longest chain (k = 11) first.
       // Stage 3 (768 short CTAs for 592 slots): k = 11, then k = 3, then k = 7 -- the CTAs that have to wait
@@ -1327,6 +1469,7 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
       op.name = "wave.mrf" + std::to_string(s) + ".fused";
       op.flops = 2.0 * c * c * t_stage * B * 6.0 * (3 + 7 + 11);
       op.bytes = 2.0 * 6 * 21 * c * c + 4.0 * B * t_stage * c * 4;
+
       op.is_mrf = true;
       const int nc = fused_nc[s];
       if (nc > 1) {
@@ -1334,13 +1477,51 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
         mc.n_branches = 2;      // blockIdx.y = 0 -> k = 11, 1 -> k = 7
         m3.n_branches = 1;      // k = 3 on the single-CTA kernel ...
         m3.y2br[0] = 0;
+        MrfOneBranchPerCta(&m3);
         m3.pdl_mode = 1;        // ... as the second launch of the pair (see MrfStageParams::pdl_mode)
         op.launch = [=](cudaStream_t st) {
           LaunchMrfStageCluster(mc, c, nc, with_lo, st);
           LaunchMrfStage(m3, c, with_lo, st);
         };
       } else {
-        op.launch = [=](cudaStream_t st) { LaunchMrfStage(mp, c, with_lo, st); };
+        // launches / CTA classes of the stage (MrfLaunchPlan): every launch after the first is the "second launch of
+        // a pair" with respect to the one before it, so the last one completing implies the stage is complete
+        MrfLaunchPlan plan = MrfPlanFor(c);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+          bool ok = true;
+          for (int li = 0; li < plan.n_launch; ++li) {
+            int kmax = 3, nbm = 1;
+            for (int y = 0; y < plan.l[li].n_y; ++y) {
+              nbm = std::max(nbm, plan.l[li].ylen[y]);
+              for (int bi = 0; bi < plan.l[li].ylen[y]; ++bi) kmax = std::max(kmax, spec::kMrfK[plan.l[li].yseq[y][bi]]);
+            }
+            ok = ok && MrfFusedSupported(c, t_stage, fused_S[s], with_lo, kmax, nbm, ups_fused);
+          }
+          if (ok) break;
+          ParseMrfPlan("11|7|3", &plan);
+        }
+        std::vector<MrfStageParams> launches;
+        for (int li = 0; li < plan.n_launch; ++li) {
+          MrfStageParams ml = mp;
+          const MrfLaunchPlan::L& L = plan.l[li];
+          ml.n_branches = L.n_y;
+          ml.nb_max = 1;
+          for (int y = 0; y < 3; ++y) {
+            ml.ylen[y] = y < L.n_y ? L.ylen[y] : 0;
+            ml.nb_max = std::max(ml.nb_max, ml.ylen[y]);
+            for (int bi = 0; bi < 3; ++bi) ml.yseq[y][bi] = L.yseq[y][bi];
+            ml.y2br[y] = L.yseq[y][0];
+          }
+          ml.smem_min = L.smem_kb * 1024;
+          ml.pdl_mode = li == 0 ? 0 : 1;
+          launches.push_back(ml);
+        }
+        std::vector<MrfStageParams> launches_ups = launches;   // the same launches with the upsampler in their prologue
+        for (MrfStageParams& ml : launches_ups) ml.ups = ups_desc;
+        const std::shared_ptr<bool> in_prologue = ups_in_prologue;
+        op.launch = [=](cudaStream_t st) {
+          for (const MrfStageParams& ml : (ups_fused && *in_prologue) ? launches_ups : launches) LaunchMrfStage(ml, c, with_lo, st);
+        };
       }
       program.push_back(op);
       continue;

@@ -145,6 +145,10 @@ struct WaveModel {
   bool cond_chain_ok = false;
   const uint16_t* mrf_w_ptr[2][4][3] = {};
   const float* mrf_bias_ptr[4][3] = {};
+  // upsampler images for the fused kernel's prologue (MrfUpsDesc, split precision) and the un-replicated biases
+  DeviceBuffer ups_img;
+  const uint16_t* ups_img_ptr[4] = {};
+  const float* ups_bias_raw[4] = {};
   int LoadFromImage(const void* data, size_t size, int on_device = -1);
   int LoadFromFile(const char* utf8_path, int on_device = -1);
 };
@@ -246,6 +250,13 @@ struct WaveState {
   DeviceBuffer film[4];   // [B][2*C_s] rc0 only (zero = identity)
   DeviceBuffer out;       // [B][240]
   std::vector<Op> program;
+  // Upsamplers of the stages whose fused MRF kernel can compute them in its prologue (MrfUpsDesc).  The choice is made
+  // when a hop is ENQUEUED (read by the ops' launchers, i.e. at graph capture): in the prologue for the latency path
+  // (one launch and one kernel boundary less per stage on the hop's critical path), as launches of their own at pipeline
+  // depth 2, where the hop is bound by SM time and the prologue form computes every upsampler once per branch CTA.
+  std::shared_ptr<bool> ups_in_prologue;
+  int n_fusable_ups = 0;   // "wave.ups*" ops that launch nothing while *ups_in_prologue
+  int LaunchesPerHop() const { return static_cast<int>(program.size()) - ((ups_in_prologue && *ups_in_prologue) ? n_fusable_ups : 0); }
   int ring_hidden = -1, ring_pre = -1, ring_stage_out[4][3];
   bool cond_ready = false;
   // batched engine: the post conv, last kernel of a hop, advances this state's hop counter and the two encoders'

@@ -280,18 +280,25 @@ def _run_entry(eng, entry, x, events, depth):
     return np.stack(outs)
 
 
+@pytest.mark.parametrize("form", [0, 1, -1])
 @pytest.mark.parametrize("entry", ["host48", "dev48", "frames"])
-def test_pipeline_depth_2_is_depth_1_one_call_later(product, model_dir, entry):
+def test_pipeline_depth_2_is_depth_1_one_call_later(product, model_dir, entry, form):
     """Depth 2 overlaps hop h+1's encoders with hop h's vocoder.  Its output must be the depth-1 output, bit for
     bit, delayed by exactly one call -- through speaker changes (the key-value blocks keep their four-hop schedule
     relative to the audio), formant / gain changes (the output gain slew is delayed with the audio), encoder-side
-    parameters and a single-stream reset in mid-run."""
+    parameters and a single-stream reset in mid-run.
+
+    `form` = where the upsamplers of stages 1-3 run (BeatriceB200_SetUpsamplerForm): with the same form at both
+    depths (0: own launches, 1: the fused MRF kernels' prologue) the samples are bit-identical; the default (-1) runs
+    them in the prologue at depth 1 and as launches at depth 2, which sums the same products in a different order --
+    then the two depths agree to fp32 rounding (measured 3e-7 RMS, asserted 2e-6), still one call apart."""
     n, hops = 20, 14
     x = signals.batch_16k(n, hops, seed0=1200) if entry == "frames" else signals.batch_48k(n, hops, seed0=1200)
     ev = _pipeline_events(n)
     a = bbatch.Engine(product, n)
     b = bbatch.Engine(product, n)
     assert a.load(model_dir) == 0 and b.load(model_dir) == 0
+    assert a.set_upsampler_form(form) == 0 and b.set_upsampler_form(form) == 0
     serial = _run_entry(a, entry, x, ev, 1)
     piped = _run_entry(b, entry, x, ev, 2)
     a.close()
@@ -299,7 +306,10 @@ def test_pipeline_depth_2_is_depth_1_one_call_later(product, model_dir, entry):
     assert serial.std() > 0.01
     assert not piped[0].any()                         # the silence before the first hop
     for h in range(hops):
-        assert np.array_equal(piped[h + 1], serial[h]), (entry, h)
+        if form >= 0:
+            assert np.array_equal(piped[h + 1], serial[h]), (entry, h)
+        else:
+            assert rms(piped[h + 1], serial[h]) <= 2e-6, (entry, h, rms(piped[h + 1], serial[h]))
 
 
 def test_pipeline_depth_2_full_batch(product, model_dir):
@@ -310,6 +320,7 @@ def test_pipeline_depth_2_full_batch(product, model_dir):
     a = bbatch.Engine(product, n)
     b = bbatch.Engine(product, n)
     assert a.load(model_dir) == 0 and b.load(model_dir) == 0
+    assert a.set_upsampler_form(0) == 0 and b.set_upsampler_form(0) == 0   # the same upsampler form at both depths
     assert b.set_pipeline_depth(2) == 0
     serial = np.stack([a.process_48k(x[h]).copy() for h in range(hops)])
     piped = [b.process_48k(x[h]).copy() for h in range(3)]
