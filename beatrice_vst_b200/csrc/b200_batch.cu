@@ -472,18 +472,18 @@ inline bool SkipVq(const Engine* e, size_t op) {
 }
 inline size_t HopLaunches(const Engine* e) {
   const WaveState& w = e->wave_st;
-  return e->hop_ops.size() - (SkipVq(e, static_cast<size_t>(e->vq_op)) ? 1 : 0) -
-         ((w.ups_in_prologue && *w.ups_in_prologue) ? static_cast<size_t>(w.n_fusable_ups) : 0);
+  return e->hop_ops.size() - (SkipVq(e, static_cast<size_t>(e->vq_op)) ? 1 : 0) - (w.program.size() - static_cast<size_t>(w.LaunchesPerHop()));
 }
 // Where the upsamplers of the fused stages run (WaveState::ups_in_prologue): inside the MRF kernels on the latency path,
 // as launches of their own at pipeline depth 2.  Read when a hop is enqueued, so set in front of every enqueue / capture.
 inline void SelectUpsForm(Engine* e) {
-  static const int env_form = [] {
-    const char* ev = std::getenv("BEATRICE_B200_UPS_IN_PROLOGUE");   // developer override: 0 / 1 for both depths
-    return ev ? std::atoi(ev) : -1;
+  static const int env_d2 = [] {
+    const char* ev = std::getenv("BEATRICE_B200_UPS_MASK_D2");   // developer override: stage bit mask used at depth 2
+    return ev ? std::atoi(ev) : 0;
   }();
-  const int forced = e->ups_form >= 0 ? e->ups_form : env_form;   // BeatriceB200_SetUpsamplerForm, else the environment
-  if (e->wave_st.ups_in_prologue) *e->wave_st.ups_in_prologue = forced >= 0 ? forced != 0 : e->pipeline != 2;
+  if (!e->wave_st.ups_in_prologue) return;
+  if (e->ups_form >= 0) *e->wave_st.ups_in_prologue = e->ups_form ? 0xE : 0;   // BeatriceB200_SetUpsamplerForm
+  else *e->wave_st.ups_in_prologue = e->pipeline != 2 ? 0xE : env_d2;
 }
 
 // Enqueues one model-rate hop (in16 staging already filled) with the two encoders as

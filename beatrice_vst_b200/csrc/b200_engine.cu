@@ -1124,8 +1124,8 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
   model_generation = m->generation;
   program.clear();
   arena.Clear();
-  if (!ups_in_prologue) ups_in_prologue = std::make_shared<bool>(true);
-  n_fusable_ups = 0;
+  if (!ups_in_prologue) ups_in_prologue = std::make_shared<int>(0xE);
+  fusable_ups_mask = 0;
   B200_CHECK(cudaSetDevice(device));
   const bool rc0 = m->dims.has_setter;
   const bool tcm = tc != kTcOff;
@@ -1417,11 +1417,11 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
     add_gemm("wave.ups" + std::to_string(s), ups_idx[s], 1, false);
     if (ups_fused) {   // launches only while the prologue form is switched off (see WaveState::ups_in_prologue)
       const std::function<void(cudaStream_t)> plain = program.back().launch;
-      const std::shared_ptr<bool> in_prologue = ups_in_prologue;
+      const std::shared_ptr<int> in_prologue = ups_in_prologue;
       program.back().launch = [=](cudaStream_t st) {
-        if (!*in_prologue) plain(st);
+        if (!((*in_prologue >> s) & 1)) plain(st);
       };
-      ++n_fusable_ups;
+      fusable_ups_mask |= 1 << s;
     }
     t_stage *= spec::kRates[s];
     if (fused[s]) {
@@ -1518,9 +1518,9 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
         }
         std::vector<MrfStageParams> launches_ups = launches;   // the same launches with the upsampler in their prologue
         for (MrfStageParams& ml : launches_ups) ml.ups = ups_desc;
-        const std::shared_ptr<bool> in_prologue = ups_in_prologue;
+        const std::shared_ptr<int> in_prologue = ups_in_prologue;
         op.launch = [=](cudaStream_t st) {
-          for (const MrfStageParams& ml : (ups_fused && *in_prologue) ? launches_ups : launches) LaunchMrfStage(ml, c, with_lo, st);
+          for (const MrfStageParams& ml : (ups_fused && ((*in_prologue >> s) & 1)) ? launches_ups : launches) LaunchMrfStage(ml, c, with_lo, st);
         };
       }
       program.push_back(op);

@@ -254,9 +254,12 @@ struct WaveState {
   // when a hop is ENQUEUED (read by the ops' launchers, i.e. at graph capture): in the prologue for the latency path
   // (one launch and one kernel boundary less per stage on the hop's critical path), as launches of their own at pipeline
   // depth 2, where the hop is bound by SM time and the prologue form computes every upsampler once per branch CTA.
-  std::shared_ptr<bool> ups_in_prologue;
-  int n_fusable_ups = 0;   // "wave.ups*" ops that launch nothing while *ups_in_prologue
-  int LaunchesPerHop() const { return static_cast<int>(program.size()) - ((ups_in_prologue && *ups_in_prologue) ? n_fusable_ups : 0); }
+  std::shared_ptr<int> ups_in_prologue;   // bit s: stage s's upsampler runs in the prologue of its MRF kernel
+  int fusable_ups_mask = 0;               // stages that have the prologue form ("wave.ups<s>" launches nothing while selected)
+  int LaunchesPerHop() const {
+    const int m = ups_in_prologue ? (*ups_in_prologue & fusable_ups_mask) : 0;
+    return static_cast<int>(program.size()) - ((m >> 1) & 1) - ((m >> 2) & 1) - ((m >> 3) & 1);
+  }
   int ring_hidden = -1, ring_pre = -1, ring_stage_out[4][3];
   bool cond_ready = false;
   // batched engine: the post conv, last kernel of a hop, advances this state's hop counter and the two encoders'

@@ -58,7 +58,8 @@ struct MrfCfg {
   static constexpr int kNk = NkFor(C);                    // K steps per weight chunk
 };
 
-template <int C, bool kSplit>
+// kUps: the stage's upsampler runs in the prologue (MrfUpsDesc); a template parameter so that the plain form carries none of it
+template <int C, bool kSplit, bool kUps>
 __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)) mrf_branch_kernel(const __grid_constant__ MrfStageParams p) {
   constexpr int kEpiWarps = EpiWarpsFor(C), kThreads = ThreadsFor(C);
   constexpr int kWarpMma = kEpiWarps, kWarpW = kEpiWarps + 1, kWarpH = kEpiWarps + 2;
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
   float* bias_s = reinterpret_cast<float*>(smem + 8 * 40 + 16);          // [branch of this CTA][6][C], then the upsampler's [C]
   float* bias_u = bias_s + p.nb_max * 6 * C;
   float* film_s = bias_u + C;                                            // [S][2C] gamma | beta of the group's streams (fused upsampler)
-  const uint32_t x_off = (8 * 40 + 16 + ((p.nb_max * 6 + 1) * C + (p.ups.w != nullptr ? p.S * 2 * C : 0)) * 4 + 127) / 128 * 128;
+  const uint32_t x_off = (8 * 40 + 16 + ((p.nb_max * 6 + 1) * C + (kUps ? p.S * 2 * C : 0)) * 4 + 127) / 128 * 128;
   const uint32_t x_pstride = static_cast<uint32_t>(RX) * 16, y_pstride = static_cast<uint32_t>(RY) * 16;
   const uint32_t x_plane = PAN * x_pstride, y_plane = PAN * y_pstride;
   const uint32_t y_off = x_off + P * x_plane;
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
     const float* bsrc = p.br[p.yseq[blockIdx.y][bi]].bias;
     for (int i = tid; i < 6 * C; i += kThreads) bias_s[bi * 6 * C + i] = __ldg(bsrc + i);
   }
-  if (p.ups.w != nullptr) {
+  if (kUps) {
     for (int i = tid; i < C; i += kThreads) bias_u[i] = __ldg(p.ups.bias + i);
     // FiLM parameters are written by the setters, outside and in front of the hop graph: readable before the dependency wait
     for (int i = tid; i < p.S * 2 * C; i += kThreads) {
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
 
   const int rows_valid = S * T;
   // ---- fused upsampler (MrfUpsDesc) ----
-  const bool fuse_ups = p.ups.w != nullptr;
+  constexpr bool fuse_ups = kUps;
   constexpr int GU = (2 * C) / 16;                     // 16-channel groups of the upsampler's input
   const int r_up = fuse_ups ? p.ups.r : 1, Tin = T / r_up;
   const int rows_in = S * (Tin + 1);                   // one row of history per stream in front (time-major, like X)
@@ -718,16 +719,16 @@ __global__ void mrf_zero_stream_kernel(const MrfHistBlock* __restrict__ blocks, 
   for (int i = threadIdx.x; i < n; i += blockDim.x) base[static_cast<size_t>(i) * hb.S + s] = make_uint4(0, 0, 0, 0);
 }
 
-template <int C, bool kSplit>
+template <int C, bool kSplit, bool kUps>
 void LaunchMrfT(const MrfStageParams& p, size_t smem, cudaStream_t s) {
   static bool attr_set[64] = {};
   int dev = 0;
   B200_CHECK(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    B200_CHECK(cudaFuncSetAttribute(mrf_branch_kernel<C, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(mrf_branch_kernel<C, kSplit, kUps>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev & 63] = true;
   }
-  LaunchPdl(mrf_branch_kernel<C, kSplit>, dim3(p.n_groups, p.n_branches, 1), dim3(ThreadsFor(C), 1, 1), smem, s, 1, p);
+  LaunchPdl(mrf_branch_kernel<C, kSplit, kUps>, dim3(p.n_groups, p.n_branches, 1), dim3(ThreadsFor(C), 1, 1), smem, s, 1, p);
 }
 
 
@@ -841,16 +842,22 @@ void LaunchMrfStage(const MrfStageParams& p, int C, bool split, cudaStream_t s) 
     for (int bi = 0; bi < p.ylen[y]; ++bi) kmax = std::max(kmax, p.br[p.yseq[y][bi]].k);
   }
   const size_t smem = std::min<size_t>(std::max<size_t>(MrfSmemBytes(C, p.T, p.S, split, kmax, p.nb_max, p.ups.w != nullptr), static_cast<size_t>(p.smem_min)), 227 * 1024);
+  const bool ups = p.ups.w != nullptr;
+  if (ups && (!split || C > 64)) Fail(-108, "the fused MRF kernel computes the upsampler only in split precision at C <= 64", __FILE__, __LINE__);
 #define B200_MRF_CASE(CC)                                  \
   case CC:                                                 \
-    if (split) LaunchMrfT<CC, true>(p, smem, s);           \
-    else LaunchMrfT<CC, false>(p, smem, s);                \
+    if (split && ups) LaunchMrfT<CC, true, true>(p, smem, s);   \
+    else if (split) LaunchMrfT<CC, true, false>(p, smem, s);    \
+    else LaunchMrfT<CC, false, false>(p, smem, s);         \
     break
   switch (C) {
     B200_MRF_CASE(16);
     B200_MRF_CASE(32);
     B200_MRF_CASE(64);
-    B200_MRF_CASE(128);
+    case 128:
+      if (split) LaunchMrfT<128, true, false>(p, smem, s);
+      else LaunchMrfT<128, false, false>(p, smem, s);
+      break;
     default:
       Fail(-105, "fused MRF kernel has no form for this width", __FILE__, __LINE__);
   }
