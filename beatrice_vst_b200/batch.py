@@ -55,6 +55,9 @@ BATCH_SYMBOLS = {
     "BeatriceB200_PipelineDepth": (C.c_int, [_vp]),
     "BeatriceB200_SetPipelinePlan": (C.c_int, [_vp, C.c_char_p]),
     "BeatriceB200_SetUpsamplerForm": (C.c_int, [_vp, C.c_int]),
+    "BeatriceB200_SetHostSampleRate": (C.c_int, [_vp, C.c_double]),
+    "BeatriceB200_ProcessAnyRate": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "BeatriceB200_SetEchoModel": (C.c_int, [_vp, C.c_int]),
     "BeatriceB200_DrainPipeline": (C.c_int, [_vp, _vp, _vp]),
     "BeatriceB200_AllocPinned": (_vp, [C.c_size_t]),
     "BeatriceB200_FreePinned": (None, [_vp]),
@@ -224,6 +227,23 @@ class Engine:
 
     def set_pipeline_plan(self, plan: str) -> int:
         return self.dll.BeatriceB200_SetPipelinePlan(self.h, plan.encode("utf-8"))
+
+    def set_host_sample_rate(self, rate: float) -> int:
+        """ProcessorCore2::SetSampleRate for :meth:`process_any_rate`."""
+        return self.dll.BeatriceB200_SetHostSampleRate(self.h, float(rate))
+
+    def process_any_rate(self, x: np.ndarray) -> np.ndarray:
+        """x [n][m] at the host rate -> [n][m] (ProcessorCore2::Process per stream, any block size m)."""
+        x = np.ascontiguousarray(x, np.float32)
+        assert x.ndim == 2 and x.shape[0] == self.n
+        out = np.empty_like(x)
+        rc = self.dll.BeatriceB200_ProcessAnyRate(self.h, x.ctypes.data, out.ctypes.data, x.shape[1])
+        if rc != 0:
+            raise RuntimeError(f"BeatriceB200_ProcessAnyRate -> {rc}")
+        return out
+
+    def set_echo_model(self, on: bool) -> int:
+        return self.dll.BeatriceB200_SetEchoModel(self.h, 1 if on else 0)
 
     def set_upsampler_form(self, form: int) -> int:
         """1 = in the fused MRF kernels' prologue, 0 = own launches, -1 = by pipeline depth (default)."""

@@ -17,6 +17,7 @@
 #include "../../include/beatrice_b200.h"
 #include "b200_common.h"
 #include "b200_engine.h"
+#include "b200_anyrate.h"
 #include "b200_hostrate.h"
 #include "b200_kernels.h"
 
@@ -84,6 +85,9 @@ struct BeatriceB200_Engine {
   WaveState wave_st;
   DeviceBuffer q_raw, min_q, max_q, vq_n, codebook_ptrs, pitch_params, idx_a, idx_b;
   HostRateState hostrate;  // 48 kHz adapter (gain + FIRs + FIFO), b200_hostrate.h
+  AnyRateState anyrate;    // any host rate / block size (b200_anyrate.h), set up by BeatriceB200_SetHostSampleRate
+  bool anyrate_ready = false;
+  bool echo_model = false; // test hook of the any-rate entry: the model hop is replaced by an echo (BeatriceB200_SetEchoModel)
 
   std::vector<StreamParams> sp;
   std::vector<MorphState> morph;
@@ -1151,12 +1155,18 @@ int BeatriceB200_SetVQNumNeighbors(BeatriceB200_Engine* e, int stream, int n) {
 }
 int BeatriceB200_SetInputGain(BeatriceB200_Engine* e, int stream, double db) {
   B200_SETTER_PROLOGUE();
-  ForStreams(e, stream, [&](int b) { e->hostrate.SetTargetGain(b, true, db); });
+  ForStreams(e, stream, [&](int b) {
+    e->hostrate.SetTargetGain(b, true, db);
+    if (e->anyrate_ready) e->anyrate.SetTargetGain(b, true, db);
+  });
   return 0;
 }
 int BeatriceB200_SetOutputGain(BeatriceB200_Engine* e, int stream, double db) {
   B200_SETTER_PROLOGUE();
-  ForStreams(e, stream, [&](int b) { e->hostrate.SetTargetGain(b, false, db); });
+  ForStreams(e, stream, [&](int b) {
+    e->hostrate.SetTargetGain(b, false, db);
+    if (e->anyrate_ready) e->anyrate.SetTargetGain(b, false, db);
+  });
   return 0;
 }
 
@@ -1275,6 +1285,58 @@ int BeatriceB200_Process48k(BeatriceB200_Engine* e, const float* in_host, float*
   return 0;
   }(););
   return rc__;
+}
+
+// ProcessorCore2::SetSampleRate (processor_core_2.cc:421-429) for the any-rate entry below: a new rate re-creates the
+// resampler (AnyFreqInOut::SetSampleRate, resample.h:425-431), the same rate is a no-op.  The gain targets set so far
+// are NOT carried into the new adapter (the reference keeps its Gain::Context; set the gains after the rate).
+int BeatriceB200_SetHostSampleRate(BeatriceB200_Engine* e, double sample_rate) {
+  if (!e) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(rc__ = BEATRICE_B200_ERR_DEVICE, rc__ = [&]() -> int {
+    if (e->anyrate_ready && e->anyrate.sample_rate() == sample_rate) return 0;
+    B200_CHECK(cudaSetDevice(e->device));
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+    e->anyrate_ready = e->anyrate.Init(e->device, e->B, sample_rate);
+    return e->anyrate_ready ? 0 : BEATRICE_B200_ERR_BAD_ARGUMENT;   // the reference's resampler would not be ready either
+  }(););
+  return rc__;
+}
+
+// ProcessorCore2::Process (processor_core_2.cc:24-48) for every stream at the host rate set above: m samples in, m
+// samples out per stream ([n][m], host memory), any 1 <= m <= 4096 and any sequence of block sizes; the model runs
+// whenever the 48 kHz block FIFO fills (zero, one or several hops per call).  Pipeline depth 1 only.
+int BeatriceB200_ProcessAnyRate(BeatriceB200_Engine* e, const float* in_host, float* out_host, int m) {
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(if (e && out_host && m > 0) std::memset(out_host, 0, sizeof(float) * e->B * m); rc__ = BEATRICE_B200_ERR_DEVICE, rc__ = [&]() -> int {
+  if (!e || !in_host || !out_host || m < 1 || m > AnyRateState::kMaxBlock) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  auto silence = [&](int code) {   // fill_zero(), processor_core_2.cc:26-43
+    std::memset(out_host, 0, sizeof(float) * e->B * m);
+    return code;
+  };
+  if (!e->loaded) return silence(BEATRICE_B200_ERR_NOT_LOADED);
+  if (!e->anyrate_ready || e->pipeline != 1) return silence(BEATRICE_B200_ERR_BAD_ARGUMENT);
+  B200_CHECK(cudaSetDevice(e->device));
+  e->anyrate.Process(in_host, out_host, m, e->in16.as<float>(), e->wave_st.out.as<float>(),
+                     [&] {
+                       if (e->echo_model) {
+                         LaunchEchoModel(e->in16.as<float>(), e->wave_st.out.as<float>(), e->B, e->stream);
+                         ++e->launches;
+                       } else {
+                         RunHop16(e, true);
+                       }
+                     },
+                     e->stream, &e->launches);
+  return 0;
+  }(););
+  return rc__;
+}
+// Test hook for the entry above: the model hop becomes o24[i] = x16[i] (i < 160), 0 above -- with the same stand-in
+// behind the reference call site (oracle/stub_beatricelib.cc, echo mode) the adapter is compared bit for bit.
+int BeatriceB200_SetEchoModel(BeatriceB200_Engine* e, int on) {
+  if (!e) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  e->echo_model = on != 0;
+  return 0;
 }
 
 // Depth 2 only: vocodes the hop still in flight without taking a new one and returns its blocks -- what the next

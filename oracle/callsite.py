@@ -38,19 +38,22 @@ def available(which: str) -> bool:
 
 
 def run(which: str, toml_path, x: np.ndarray, sample_rate: float = 48000.0, block: int = 480,
-        events=(), timeout: float = 600.0):
+        events=(), timeout: float = 600.0, echo: bool = False):
     """Feeds ``x`` through ProcessorCore::Process in ``block``-sample calls.
 
     ``events``: iterable of ``(block_index, name, value)``; ``block_index`` -1 applies the
     parameter before LoadModel, ``name="reset"`` calls ResetContext().  ``toml_path=None``
     leaves the proxy unloaded.  Returns ``(y, info)`` with info = dict(load, last, version).
+    ``which="stub"`` with ``echo=True``: the call site over ``oracle/stub_beatricelib.cc`` whose "model" returns its
+    160 input samples followed by 80 zeros -- bit-exact known answers for the host-rate adapter at any rate / block.
     """
     with tempfile.TemporaryDirectory() as d:
         fin, fout = os.path.join(d, "in.f32"), os.path.join(d, "out.f32")
         np.ascontiguousarray(x, "<f4").tofile(fin)
         cmd = [exe_path(which), "run", toml_path or "-", fin, fout, repr(float(sample_rate)), str(int(block))]
         cmd += [f"{int(b)}:{n}={float(v)!r}" for b, n, v in events]
-        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        env = dict(os.environ, STUB_ECHO="1" if echo else "0")
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
         if p.returncode != 0:
             raise RuntimeError(f"callsite_runner failed ({p.returncode}): {p.stderr[-2000:]}")
         y = np.fromfile(fout, "<f4")

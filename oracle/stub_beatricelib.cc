@@ -8,6 +8,11 @@
 //   ReadSpeakerEmbeddings fills the caller's tables with a fixed pseudo-random pattern (the call site normalises
 //   them for its spherical averages; zeros would divide by zero).
 //
+//   Echo mode (environment STUB_ECHO=1, used by _ref/callsite_runner_stub): GenerateWaveform1 returns the 160 input
+//   samples ExtractPhone1 was last given, followed by 80 zeros -- a "model" whose output is a known function of its
+//   input, so that the call site's host-rate adapter (gain, resampler, block FIFO: gain.h, resample.h) can be compared
+//   BIT FOR BIT with the device adapter of the product driven by the same stand-in (BeatriceB200_SetEchoModel).
+//
 // All 77 symbols of beatrice.h exist so that ProcessorProxy (cores 0, 1, 2) links.  C linkage: only names matter.
 #include <cstdint>
 #include <cstdlib>
@@ -16,6 +21,18 @@
 namespace {
 int g_next_q = 1, g_last_q = -1;
 long g_wave_calls = 0;
+float g_last_in[160] = {};
+bool Echo() {
+  static const bool on = [] {
+    const char* ev = std::getenv("STUB_ECHO");
+    return ev && ev[0] == '1';
+  }();
+  return on;
+}
+void Wave(float* out) {
+  std::memset(out, 0, sizeof(float) * 240);
+  if (Echo()) std::memcpy(out, g_last_in, sizeof(g_last_in));
+}
 constexpr int kSpeakers = 2;
 void Fill(float* p, size_t n, uint32_t seed) {
   uint32_t s = seed * 2654435761u + 12345u;
@@ -37,7 +54,10 @@ long Stub_WaveformCalls(void) { return g_wave_calls; }
   void* P##_CreatePhoneContext1(void) { return std::calloc(1, 8); }                                 \
   void P##_DestroyPhoneContext1(void* p) { std::free(p); }                                          \
   int P##_ReadPhoneExtractorParameters(void*, const char*) { return 0; }                            \
-  void P##_ExtractPhone1(const void*, const float*, float* out, void*) { std::memset(out, 0, sizeof(float) * PHONE); } \
+  void P##_ExtractPhone1(const void*, const float* in, float* out, void*) {                         \
+    std::memcpy(g_last_in, in, sizeof(g_last_in));                                                  \
+    std::memset(out, 0, sizeof(float) * PHONE);                                                     \
+  }                                                                                                 \
   void* P##_CreatePitchEstimator(void) { return std::calloc(1, 8); }                                \
   void P##_DestroyPitchEstimator(void* p) { std::free(p); }                                         \
   void* P##_CreatePitchContext1(void) { return std::calloc(1, 8); }                                 \
@@ -72,7 +92,7 @@ STUB_COMMON(Beatrice20rc0, 128)
                              float* out, void*) {                                                   \
     g_last_q = *q;                                                                                  \
     ++g_wave_calls;                                                                                 \
-    std::memset(out, 0, sizeof(float) * 240);                                                       \
+    Wave(out);                                                                                      \
   }
 STUB_LEGACY(Beatrice20a2)
 STUB_LEGACY(Beatrice20b1)
@@ -88,7 +108,7 @@ int Beatrice20rc0_ReadSpeakerEmbeddings(const char*, float* codebooks, float* ad
 void Beatrice20rc0_GenerateWaveform1(const void*, const float*, const int* q, const float*, float* out, void*) {
   g_last_q = *q;
   ++g_wave_calls;
-  std::memset(out, 0, sizeof(float) * 240);
+  Wave(out);
 }
 void* Beatrice20rc0_CreateEmbeddingSetter(void) { return std::calloc(1, 8); }
 void Beatrice20rc0_DestroyEmbeddingSetter(void* p) { std::free(p); }

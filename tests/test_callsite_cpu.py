@@ -175,3 +175,25 @@ def test_committed_callsite_golden_is_reproduced(model_dir):
     y, info = callsite.run("oracle", _toml(model_dir), g["x"], events=events)
     assert info["load"] == 0
     assert np.array_equal(y, g["y"])
+
+
+@pytest.mark.skipif(not callsite.available("stub"), reason="oracle/_ref/callsite_runner_stub not built")
+def test_stub_echo_runner_agrees_with_the_numpy_adapter(model_dir):
+    """The reference call site over the stub library in echo mode (the known-answer source of tests/test_gpu_anyrate.py)
+    at 48 kHz / 480 equals the numpy restatement of the adapter around the same echo "model", bit for bit; and at another
+    host rate it is a different, non-trivial signal of the block size's length."""
+    x = signals.batch_48k(1, 12, seed0=5)[:, 0, :].reshape(-1)
+    toml = os.path.join(model_dir, "model.toml")
+    y, info = callsite.run("stub", toml, x, 48000.0, 480, echo=True)
+    assert info["load"] == 0 and info["last"] == 0
+
+    def echo(x16):
+        out = np.zeros(240, np.float32)
+        out[:160] = x16
+        return out
+
+    hr = hostrate_ref.HostRateRef(echo)
+    want = np.concatenate([hr.process(x[h * 480:(h + 1) * 480]) for h in range(12)])
+    assert np.array_equal(y, want) and y.std() > 0.01
+    y2, _ = callsite.run("stub", toml, x[:4410], 44100.0, 441, echo=True)
+    assert y2.shape == (4410,) and y2.std() > 0.01 and not np.array_equal(y2, y[:4410])
