@@ -87,9 +87,10 @@ inline bool PdlEnabled() {
   }();
   return on;
 }
+// early: allow the kernel to start before its predecessor on the stream has completed (programmatic dependent launch)
 template <typename... KArgs, typename... Args>
-inline void LaunchPdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x,
-                      Args... args) {
+inline void LaunchMaybePdl(bool early, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x,
+                           Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -97,7 +98,7 @@ inline void LaunchPdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sm
   cfg.stream = s;
   cudaLaunchAttribute at[2];
   unsigned n = 0;
-  if (PdlEnabled()) {
+  if (early && PdlEnabled()) {
     at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
@@ -112,6 +113,11 @@ inline void LaunchPdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sm
   cfg.attrs = at;
   cfg.numAttrs = n;
   B200_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+template <typename... KArgs, typename... Args>
+inline void LaunchPdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x,
+                      Args... args) {
+  LaunchMaybePdl(true, kernel, grid, block, smem, s, cluster_x, args...);
 }
 
 #ifdef __CUDACC__

@@ -1465,6 +1465,8 @@ void WaveState::Build(const WaveModel* m, int B_, int device_, TcMode tc) {
       mp.y2br[2] = c <= 16 ? 1 : 0;
       mp.pdl_mode = 0;
       if (const char* ev = std::getenv("BEATRICE_B200_MRF_TRACE")) mp.trace = std::atoi(ev);
+      // developer switch: BEATRICE_B200_MRF_LATE=<stage bit mask>
+      if (const char* ev = std::getenv("BEATRICE_B200_MRF_LATE")) mp.late_launch = (std::atoi(ev) >> s) & 1;
       Op op;
       op.name = "wave.mrf" + std::to_string(s) + ".fused";
       op.flops = 2.0 * c * c * t_stage * B * 6.0 * (3 + 7 + 11);

@@ -728,7 +728,8 @@ void LaunchMrfT(const MrfStageParams& p, size_t smem, cudaStream_t s) {
     B200_CHECK(cudaFuncSetAttribute(mrf_branch_kernel<C, kSplit, kUps>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev & 63] = true;
   }
-  LaunchPdl(mrf_branch_kernel<C, kSplit, kUps>, dim3(p.n_groups, p.n_branches, 1), dim3(ThreadsFor(C), 1, 1), smem, s, 1, p);
+  LaunchMaybePdl(!(p.late_launch && p.pdl_mode == 0), mrf_branch_kernel<C, kSplit, kUps>, dim3(p.n_groups, p.n_branches, 1),
+                 dim3(ThreadsFor(C), 1, 1), smem, s, 1, p);
 }
 
 

@@ -59,6 +59,8 @@ struct MrfStageParams {
   //    waits for the first launch at its very end, so that "this kernel complete" implies "stage complete".
   int pdl_mode;
   int trace;           // developer aid: 1 + blockIdx.x of the CTA whose timeline is printed (0 = off)
+  int late_launch;     // host only: the stage's first launch starts when its predecessor has COMPLETED (no programmatic
+                       // early launch): its CTAs then do not hold SMs while they wait for the stage input
 };
 
 // One history block, for per-stream reset: [group][planes * panels][H][S][8] bf16

@@ -525,7 +525,8 @@ void LaunchClusterT(const MrfStageParams& p, size_t smem, cudaStream_t s) {
     B200_CHECK(cudaFuncSetAttribute(mrf_cluster_kernel<C, NC, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev & 63] = true;
   }
-  LaunchPdl(mrf_cluster_kernel<C, NC, kSplit>, dim3(p.n_groups * NC, p.n_branches, 1), dim3(kThreads, 1, 1), smem, s, NC, p);
+  LaunchMaybePdl(!p.late_launch, mrf_cluster_kernel<C, NC, kSplit>, dim3(p.n_groups * NC, p.n_branches, 1), dim3(kThreads, 1, 1), smem, s,
+                 NC, p);
 }
 
 }  // namespace
