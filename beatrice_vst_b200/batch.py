@@ -55,6 +55,7 @@ BATCH_SYMBOLS = {
     "BeatriceB200_PipelineDepth": (C.c_int, [_vp]),
     "BeatriceB200_SetPipelinePlan": (C.c_int, [_vp, C.c_char_p]),
     "BeatriceB200_SetUpsamplerForm": (C.c_int, [_vp, C.c_int]),
+    "BeatriceB200_SetSkipOps": (C.c_int, [_vp, C.c_char_p]),
     "BeatriceB200_SetHostSampleRate": (C.c_int, [_vp, C.c_double]),
     "BeatriceB200_ProcessAnyRate": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "BeatriceB200_SetEchoModel": (C.c_int, [_vp, C.c_int]),
@@ -227,6 +228,10 @@ class Engine:
 
     def set_pipeline_plan(self, plan: str) -> int:
         return self.dll.BeatriceB200_SetPipelinePlan(self.h, plan.encode("utf-8"))
+
+    def set_skip_ops(self, names: str) -> int:
+        """Measurement aid: drop the hop ops whose names contain one of the comma-separated substrings ("" = none)."""
+        return self.dll.BeatriceB200_SetSkipOps(self.h, names.encode("utf-8"))
 
     def set_host_sample_rate(self, rate: float) -> int:
         """ProcessorCore2::SetSampleRate for :meth:`process_any_rate`."""

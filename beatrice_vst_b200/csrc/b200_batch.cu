@@ -105,6 +105,8 @@ struct BeatriceB200_Engine {
   GraphRunner graph16, graph48, graph48s;
   GraphRunner graph16p, graph48p, graph48sp;          // depth-2 forms of the same three entries
   int ups_form = -1;                                  // BeatriceB200_SetUpsamplerForm
+  std::string skip_ops;                               // BeatriceB200_SetSkipOps (measurement aid)
+  bool skip_ops_set = false;
   uint64_t launches = 0;
   uint64_t hops = 0;
 
@@ -413,12 +415,13 @@ void BuildHop(Engine* e) {
   e->hop_ops.clear();
   e->hop_lane.clear();
   const int B = e->B;
-  // developer ablation: BEATRICE_B200_SKIP_OPS="wave.ups1,wave.mrf2" drops the launches of the named ops from the hop
-  // (timing only -- the marginal cost of an op inside the hop graph; the audio is meaningless)
-  static const std::string skip_ops = [] {
+  // ablation (BeatriceB200_SetSkipOps / BEATRICE_B200_SKIP_OPS="wave.ups1,wave.mrf2"): the launches of the named ops are
+  // dropped from the hop -- timing only (the marginal cost of an op inside the hop graph); the audio is meaningless
+  static const std::string env_skip = [] {
     const char* ev = std::getenv("BEATRICE_B200_SKIP_OPS");
     return std::string(ev ? ev : "");
   }();
+  const std::string skip_ops = e->skip_ops_set ? e->skip_ops : env_skip;
   auto push = [&](const Op& op, int lane) {
     e->hop_ops.push_back(op);
     e->hop_lane.push_back(lane);
@@ -1009,6 +1012,25 @@ int BeatriceB200_SetPipelinePlan(BeatriceB200_Engine* e, const char* plan) {
     B200_CHECK(cudaSetDevice(e->device));
     B200_CHECK(cudaStreamSynchronize(e->stream));
     e->pipe_plan = plan ? plan : "";
+    ResetGraphs(e);
+    rc__ = 0;
+  });
+  return rc__;
+}
+
+// Measurement aid: drops the launches of every hop op whose name contains one of the comma-separated substrings (names as
+// BeatriceB200_ProfileHop reports them); "" restores the full hop.  The audio is meaningless while ops are skipped: this
+// exists to time the hop WITHOUT an op, i.e. the op's marginal cost inside the hop graph (bench.py: roofline.in_graph).
+int BeatriceB200_SetSkipOps(BeatriceB200_Engine* e, const char* names) {
+  if (!e) return BEATRICE_B200_ERR_BAD_ARGUMENT;
+  if (!e->loaded) return BEATRICE_B200_ERR_NOT_LOADED;
+  int rc__ = BEATRICE_B200_ERR_DEVICE;
+  B200_GUARDED(rc__ = BEATRICE_B200_ERR_DEVICE, {
+    B200_CHECK(cudaSetDevice(e->device));
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+    e->skip_ops = names ? names : "";
+    e->skip_ops_set = true;
+    BuildHop(e);
     ResetGraphs(e);
     rc__ = 0;
   });

@@ -454,6 +454,38 @@ def main():
         "frac_issued": (3.0 if args.precision == "bf16x3" else 1.0) * achieved / peaks["tflops"],
         "frac_issued_note": "tensor-pipe work actually issued (split-bf16 = 3 bf16 products per algorithmic one) / peak",
     }
+    # ---- what the MRF launches cost INSIDE the hop graph: the same device-resident loop with their launches dropped
+    #      (BeatriceB200_SetSkipOps).  The per-launch times above are taken with an event bracket around every launch, i.e.
+    #      serialised and without the programmatic overlap of a kernel's prologue with its predecessor; this is the other view:
+    #      how much shorter the hop gets without the MRF stages.  Last thing done with the engine (the audio is meaningless
+    #      while ops are skipped). ----
+    def loop_ms(steps):
+        for i in range(10):
+            hop_device(i)
+        eng.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for i in range(steps):
+            hop_device(10 + i)
+        b.record(stream)
+        eng.synchronize()
+        return a.elapsed_time(b) / steps
+
+    if mrf_flops > 0 and world == 1:
+        q_steps = max(20, min(args.steps, 200))
+        hop_full = loop_ms(q_steps)
+        if eng.set_skip_ops("wave.mrf") == 0:
+            hop_wo = loop_ms(q_steps)
+            eng.set_skip_ops("")
+            marginal = hop_full - hop_wo
+            if marginal > 0:
+                ach = mrf_flops / (marginal * 1e-3) / 1e12
+                roofline["in_graph"] = {
+                    "hop_ms": hop_full, "hop_ms_without_mrf_launches": hop_wo, "mrf_marginal_ms": marginal,
+                    "achieved": ach, "frac": ach / peaks["tflops"], "pipeline_depth": depth,
+                    "note": "marginal cost of the MRF launches inside the hop graph (hop time minus hop time with their launches "
+                            "dropped, same loop, same engine); context for `frac`, which divides by event-bracketed launch times",
+                }
     resident = eng.resident_bytes()
     eng.close()
 
@@ -480,6 +512,9 @@ def main():
                    "pipeline_note": "depth 2: a call runs the vocoder of the previous hop side by side with the encoders of the hop it is given; "
                                     "all work of a hop is done every step, output samples are bit-identical to depth 1 and arrive one call (10 ms) later; "
                                     "depth 1 (a call returns its own hop) is reported as latency_mode",
+                   "upsampler_form": "by depth (BeatriceB200_SetUpsamplerForm default): stages 1-3 ConvTranspose1d as launches of their own at "
+                                     "depth 2, in the prologue of the fused MRF kernels at depth 1 (same products, different summation "
+                                     "order: the two depths agree to fp32 rounding; bit-identical with one form forced for both)",
                    "parallelism": f"{world} x independent stream shards, no per-hop collective; weights broadcast once over NCCL",
                    "l2": f"inputs cycle through {bank_hops} distinct device-resident hops "
                          f"({bank_hops * hop_floats * 4 / 1e6:.0f} MB > 126 MB L2); weights + stream state "
