@@ -2,7 +2,6 @@
 # Developer session: marginal in-graph cost of every vocoder op (hop time with the op's launches dropped).
 O=gpurun_out
 mkdir -p $O
-export BEATRICE_B200_MRF_PLAN="11|7|3;11|7|3;11|7|3"
 one() {
   BEATRICE_B200_SKIP_OPS="$1" timeout 200 python bench.py --steps 300 --warmup 30 --no-cpu-baseline 2>$O/abl.err | python -c "
 import json,sys

@@ -1,6 +1,7 @@
 """Per-op device time of one hop of the batched engine (BeatriceB200_ProfileHop: CUDA events around
 every launch, ops run serially), under whatever BEATRICE_B200_* developer overrides are set.
-   python tools/op_profile.py [precision=2] [streams=256] [repeats=8]"""
+   python tools/op_profile.py [precision=2] [streams=256] [repeats=8] [pipeline depth=1]
+(the depth selects the upsampler form: in the fused MRF kernels' prologue at depth 1, launches of their own at depth 2)"""
 import os
 import sys
 import tempfile
@@ -18,6 +19,7 @@ def main():
     prec = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+    depth = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     product = blib.load_product()
     with tempfile.TemporaryDirectory() as d:
         model_spec.write_model_dir(d, 8, 2, 0)
@@ -29,10 +31,11 @@ def main():
         for _ in range(3):
             eng.process_frames_device(d_in, d_out)
         eng.synchronize()
+        assert eng.set_pipeline_depth(depth) == 0     # after the warm-up: ProfileHop wants an empty pipeline
         allr = [eng.profile_hop(d_in, d_out) for _ in range(reps)]
         eng.close()
     tag = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("BEATRICE_B200_"))
-    print(f"[ops] precision {prec} streams {n} {tag}")
+    print(f"[ops] precision {prec} streams {n} pipeline depth {depth} {tag}")
     tot = 0.0
     for i, r in enumerate(allr[-1]):
         us = 1e3 * float(np.median([a[i]["ms"] for a in allr[1:]]))

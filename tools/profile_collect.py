@@ -64,7 +64,7 @@ def main():
     if os.path.exists(g("launches.csv")):
         sp.launches(tag, g("launches.csv"))
     traffic = {}
-    for name in ("mrf_cluster", "mrf_branch", "conv_tc", "enc_res_stack"):
+    for name in ("mrf_cluster", "mrf_branch", "mrf_branch_ups", "conv_tc", "enc_res_stack"):
         rep = g(name + ".ncu-rep")
         if os.path.exists(rep):
             sp.full(tag, rep)
@@ -85,7 +85,7 @@ def main():
                    "per_hop_MB": tot, "kernels": len(rows)}
         json.dump(traffic, open(os.path.join(P, f"{tag}_mrf_traffic.json"), "w"), indent=1)
     for n in ("bench_20.json", "bench_1000.json", "bench_reference.json", "bench_bf16.json", "bench_f32.json", "ops_bf16x3.txt",
-              "mrf_timeline.txt", "config4_latency.json", "config5_1gpu.json", "config5_8gpu.json", "bench_2gpu.json",
+              "ops_bf16x3_depth1.txt", "ablation.txt", "mrf_timeline.txt", "mrf_timeline_ups.txt", "config4_latency.json", "config5_1gpu.json", "config5_8gpu.json", "bench_2gpu.json",
               "bench_4gpu.json", "bench_8gpu.json"):
         if os.path.exists(g(n)) and os.path.getsize(g(n)) > 0:
             shutil.copy(g(n), os.path.join(P, f"{tag}_{n}"))
