@@ -40,6 +40,13 @@ CHILD = textwrap.dedent("""
         raise SystemExit("CreateEngine must fail without a device")
     except RuntimeError:
         pass
+    # the entries added later in round 2 reject a missing engine without touching the device
+    dll = bbatch.bind(product)
+    # (BAD_ARGUMENT, or DEVICE where the latched failure is looked at first)
+    assert dll.BeatriceB200_SetHostSampleRate(None, 44100.0) in (-1, -2)
+    assert dll.BeatriceB200_ProcessAnyRate(None, None, None, 16) in (-1, -2)
+    assert dll.BeatriceB200_SetUpsamplerForm(None, 1) in (-1, -2)
+    assert dll.BeatriceB200_SetSkipOps(None, b"wave.mrf") in (-1, -2)
     bbatch.clear_error(product)
     assert bbatch.last_error(product) == (0, "")
     print("child ok")
