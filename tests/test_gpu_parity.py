@@ -495,3 +495,35 @@ def test_reset_all_streams_and_cluster_determinism(product, oracle, model_dir):
     for s in (0, 15, 16, 31, 32, 39):
         ref, _ = _oracle_stream(oracle, model_dir, xs[:, s, :].reshape(-1))
         assert rms(first[s], ref) <= TOL_WAVE, (s, rms(first[s], ref))
+
+
+@pytest.mark.parametrize("form", [0, 1])
+@pytest.mark.parametrize("plan", ["11|7,3;11@128/7|3;11,7,3", "7,3|11;3|7|11;11/7/3"])
+def test_mrf_launch_plans_do_not_change_a_sample(product, model_dir, plan, form):
+    """The fused MRF stages can be cut into launches and CTA classes in other ways than the default "11|7|3" (branch
+    lists run back to back in one CTA, a stage as several launches chained as a PDL pair, a minimum shared-memory request:
+    `MrfLaunchPlan`, BEATRICE_B200_MRF_PLAN, read when an engine loads).  Which CTA runs a branch must not change its
+    arithmetic: every sample is bit-identical to the default plan, with either upsampler form (own launches / in the
+    prologue of the fused kernel, where a CTA with several branches computes the upsampler once per branch)."""
+    n, hops = 20, 6
+    xs = signals.batch_16k(n, hops, seed0=1500)
+
+    def run(env_plan):
+        old = os.environ.pop("BEATRICE_B200_MRF_PLAN", None)
+        if env_plan:
+            os.environ["BEATRICE_B200_MRF_PLAN"] = env_plan
+        try:
+            eng = bbatch.Engine(product, n, precision=2)
+            assert eng.load(model_dir) == 0
+        finally:
+            os.environ.pop("BEATRICE_B200_MRF_PLAN", None)
+            if old is not None:
+                os.environ["BEATRICE_B200_MRF_PLAN"] = old
+        assert eng.set_upsampler_form(form) == 0
+        out = np.stack([eng.process_frames(xs[h]).copy() for h in range(hops)], axis=1)
+        eng.close()
+        return out
+
+    base, other = run(None), run(plan)
+    assert base.std() > 0.01
+    assert np.array_equal(base, other)
