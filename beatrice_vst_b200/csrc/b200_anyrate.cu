@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 
+#include "b200_hostrate.h"
 #include "b200_kernels.h"
 
 namespace b200 {
@@ -157,7 +158,7 @@ size_t ResampleSmem(int H, int q, int N) { return sizeof(float) * (static_cast<s
 
 }  // namespace
 
-bool AnyRateState::Init(int device, int B, double sample_rate) {
+bool AnyRateState::Init(int device, int B, double sample_rate, const HostRateState* seed) {
   device_ = device;
   B_ = B;
   rate_ = 0.0;
@@ -207,8 +208,14 @@ bool AnyRateState::Init(int device, int B, double sample_rate) {
   fifo_.Alloc(device, sizeof(float) * B * kFifo, true);       // buffer_() value-initialised (resample.h:339)
   seg_in_.Alloc(device, sizeof(GainSegDev) * B, true);
   seg_out_.Alloc(device, sizeof(GainSegDev) * B, true);
-  gin_.assign(B, HostGain());
-  gout_.assign(B, HostGain());
+  if (static_cast<int>(gin_.size()) != B) {   // first set-up: start from the gains the engine has been given so far
+    gin_.assign(B, HostGain());
+    gout_.assign(B, HostGain());
+    for (int b = 0; seed && b < B; ++b) {
+      seed->GetGain(b, true, &gin_[b].target_db, &gin_[b].current_db);
+      seed->GetGain(b, false, &gout_[b].target_db, &gout_[b].current_db);
+    }
+  }
   hseg_in_.assign(B, Seg{1.0, 1.0, 1.0, 0, 0});
   hseg_out_ = hseg_in_;
   rate_ = sample_rate;

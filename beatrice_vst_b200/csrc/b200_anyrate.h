@@ -34,7 +34,9 @@ class AnyRateState {
  public:
   static constexpr int kMaxBlock = 4096;   // host samples per call
   // false: the reference's resampler would not be ready for this rate (resample.h:243-258)
-  bool Init(int device, int B, double sample_rate);
+  // The gain state survives a change of rate (Gain::Context is kept across SetSampleRate, processor_core_2.cc:425-428);
+  // the first Init takes it from `seed` (the engine's 48 kHz adapter, which has seen every gain setter so far).
+  bool Init(int device, int B, double sample_rate, const class HostRateState* seed);
   double sample_rate() const { return rate_; }
   void SetTargetGain(int b, bool input, double db);
   // One Process call: in_host / out_host [B][m].  run_hop(x16_dev -> o24_dev is implied by the engine): called once per

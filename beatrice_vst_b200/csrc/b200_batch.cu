@@ -1310,8 +1310,8 @@ int BeatriceB200_Process48k(BeatriceB200_Engine* e, const float* in_host, float*
 }
 
 // ProcessorCore2::SetSampleRate (processor_core_2.cc:421-429) for the any-rate entry below: a new rate re-creates the
-// resampler (AnyFreqInOut::SetSampleRate, resample.h:425-431), the same rate is a no-op.  The gain targets set so far
-// are NOT carried into the new adapter (the reference keeps its Gain::Context; set the gains after the rate).
+// resampler (AnyFreqInOut::SetSampleRate, resample.h:425-431), the same rate is a no-op; the gain state is kept, like the
+// call site's Gain::Context (the first call takes it from the 48 kHz adapter, which has seen every gain setter so far).
 int BeatriceB200_SetHostSampleRate(BeatriceB200_Engine* e, double sample_rate) {
   if (!e) return BEATRICE_B200_ERR_BAD_ARGUMENT;
   int rc__ = BEATRICE_B200_ERR_DEVICE;
@@ -1319,7 +1319,7 @@ int BeatriceB200_SetHostSampleRate(BeatriceB200_Engine* e, double sample_rate) {
     if (e->anyrate_ready && e->anyrate.sample_rate() == sample_rate) return 0;
     B200_CHECK(cudaSetDevice(e->device));
     B200_CHECK(cudaStreamSynchronize(e->stream));
-    e->anyrate_ready = e->anyrate.Init(e->device, e->B, sample_rate);
+    e->anyrate_ready = e->anyrate.Init(e->device, e->B, sample_rate, &e->hostrate);
     return e->anyrate_ready ? 0 : BEATRICE_B200_ERR_BAD_ARGUMENT;   // the reference's resampler would not be ready either
   }(););
   return rc__;

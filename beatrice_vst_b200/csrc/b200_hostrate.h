@@ -36,6 +36,12 @@ class HostRateState {
  public:
   void Init(int device, int B);
   void SetTargetGain(int b, bool input, double db);
+  // Gain::Context state of stream b (target / current gain in dB): the any-rate adapter starts from it
+  void GetGain(int b, bool input, double* target_db, double* current_db) const {
+    const HostGain& g = input ? gin_[b] : gout_[b];
+    *target_db = g.target_db;
+    *current_db = g.current_db;
+  }
   void ResetStream(int b, cudaStream_t s);
   // host side of one hop: advances the per-stream gain state like Gain::Process does and
   // uploads the segments if they changed.  Call before EnqueueIn, outside graph capture.

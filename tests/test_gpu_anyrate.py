@@ -49,8 +49,10 @@ def test_any_rate_adapter_is_bit_exact(product, model_dir, rate, block):
     # gain changes in mid-run: rising and falling slews of both gains (block index, name, dB)
     nb = (samples + block - 1) // block
     events = [(nb // 5, "input_gain", 6.0), (nb // 3, "output_gain", -9.0), (nb // 2, "input_gain", -3.0), (2 * nb // 3, "output_gain", 4.0)]
-    eng = bbatch.Engine(product, n)
+    events.insert(0, (-1, "output_gain", -4.0))      # set before the rate (and, in the reference, before LoadModel): the
+    eng = bbatch.Engine(product, n)                  # Gain::Context survives SetSampleRate, so the first block slews to it
     assert eng.load(model_dir) == 0
+    assert eng.set("OutputGain", -4.0, -1) == 0
     assert eng.set_host_sample_rate(rate) == 0
     assert eng.set_echo_model(True) == 0
     got = np.zeros_like(x)
