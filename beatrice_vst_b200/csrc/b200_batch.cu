@@ -104,6 +104,7 @@ struct BeatriceB200_Engine {
   bool any_vq = false;                                // some stream has kNN-VQ on (VQNumNeighbors > 0)
   GraphRunner graph16, graph48, graph48s;
   GraphRunner graph16p, graph48p, graph48sp;          // depth-2 forms of the same three entries
+  std::vector<int> dev_vq_n, dev_vq_idx;              // host mirror of vq_n / the codebook index behind codebook_ptrs
   int ups_form = -1;                                  // BeatriceB200_SetUpsamplerForm
   std::string skip_ops;                               // BeatriceB200_SetSkipOps (measurement aid)
   bool skip_ops_set = false;
@@ -261,24 +262,33 @@ void MorphVocoderStep(Engine* e, bool hop) {
 void StepKv(Engine* e, const std::vector<char>* only) {
   cudaStream_t s = e->stream;
   if (!e->dims.has_setter) return;   // 20a2 / 20b1 have no key-value embedding
+  // one launch for every (stream, block) due this hop, the list by value in the kernel parameters (LaunchKvFilmItems)
+  KvBlockTable tab;
   for (int blk = 0; blk < kNBlocks; ++blk) {
-    std::vector<int> streams, spk;
-    for (int b = 0; b < e->B; ++b)
-      if (e->sp[b].kv_set_count == blk && (!only || (*only)[b])) {
-        streams.push_back(b);
-        spk.push_back(TableRow(e, b));
-      }
-    if (streams.empty()) continue;
-    UploadInts(e, &e->idx_a, spk);
-    UploadInts(e, &e->idx_b, streams);
-    LaunchKvFilm(e->kv.as<float>(), e->idx_a.as<int>(), static_cast<size_t>(kKvLength) * kKvChannels,
-                 e->setter_m.query[blk], e->setter_m.film_w[blk], e->setter_m.film_b[blk], kStageC[blk],
-                 e->wave_st.film[blk].as<float>(), e->idx_b.as<int>(), static_cast<int>(streams.size()), s);
-    ++e->launches;
-    for (int b : streams) e->sp[b].kv_set_count = -(blk + 1);  // mark, bumped below
+    tab.query[blk] = e->setter_m.query[blk];
+    tab.W[blk] = e->setter_m.film_w[blk];
+    tab.bias[blk] = e->setter_m.film_b[blk];
+    tab.film[blk] = e->wave_st.film[blk].as<float>();
+    tab.C[blk] = kStageC[blk];
   }
-  for (int b = 0; b < e->B; ++b)
-    if (e->sp[b].kv_set_count < 0) e->sp[b].kv_set_count = -e->sp[b].kv_set_count;
+  SetterItems items;
+  items.n = 0;
+  auto flush = [&] {
+    if (items.n == 0) return;
+    LaunchKvFilmItems(e->kv.as<float>(), static_cast<size_t>(kKvLength) * kKvChannels, tab, items, s);
+    ++e->launches;
+    items.n = 0;
+  };
+  for (int b = 0; b < e->B; ++b) {
+    const int blk = e->sp[b].kv_set_count;
+    if (blk < 0 || blk >= kNBlocks || (only && !(*only)[b])) continue;
+    items.src[items.n] = TableRow(e, b);
+    items.dst[items.n] = b;
+    items.blk[items.n] = blk;
+    if (++items.n == kSetterItems) flush();
+    e->sp[b].kv_set_count = blk + 1;
+  }
+  flush();
 }
 
 void ResetGraphs(Engine* e) {
@@ -313,16 +323,37 @@ void FlushEncoderSide(Engine* e, bool hop) {
     e->range_dirty = false;
   }
   if (e->vq_dirty) {
-    std::vector<int> n(e->B);
-    std::vector<const float*> ptr(e->B);
+    // per stream: neighbour count and codebook (speaker, or the morphing lottery's pick); only the entries that differ from
+    // what the device holds are written, as a by-value list (a speaker change of a stream without kNN-VQ writes nothing)
+    std::vector<int> n(e->B), idx(e->B);
     const size_t cb = static_cast<size_t>(kCodebookSize) * e->dims.phone_channels;
     for (int b = 0; b < e->B; ++b) {
-      n[b] = e->sp[b].vq;
-      ptr[b] = e->dims.has_setter ? e->codebooks.as<float>() + cb * (Morphing(e, b) ? e->morph[b].pick : e->sp[b].speaker) : nullptr;
-      if (!e->dims.has_setter) n[b] = 0;   // no codebook VQ in the legacy families
+      n[b] = e->dims.has_setter ? e->sp[b].vq : 0;   // no codebook VQ in the legacy families
+      idx[b] = e->dims.has_setter ? (Morphing(e, b) ? e->morph[b].pick : e->sp[b].speaker) : -1;
     }
-    UploadInts(e, &e->vq_n, n);
-    B200_CHECK(cudaMemcpyAsync(e->codebook_ptrs.p, ptr.data(), ptr.size() * sizeof(float*), cudaMemcpyHostToDevice, s));
+    if (e->dev_vq_n.size() != static_cast<size_t>(e->B)) {   // (re)loaded: the device arrays are zero (count 0, null codebook)
+      e->dev_vq_n.assign(e->B, 0);
+      e->dev_vq_idx.assign(e->B, -1);
+    }
+    SetterItems items;
+    items.n = 0;
+    for (int b = 0; b < e->B; ++b) {
+      // the codebook of a stream with VQ off is never read: leave it alone until VQ is switched on
+      const bool differs = n[b] != e->dev_vq_n[b] || (n[b] > 0 && idx[b] != e->dev_vq_idx[b]);
+      if (differs) {
+        items.src[items.n] = idx[b];
+        items.dst[items.n] = b;
+        items.blk[items.n] = n[b];
+        e->dev_vq_n[b] = n[b];
+        e->dev_vq_idx[b] = idx[b];
+        ++items.n;
+      }
+      if (items.n == kSetterItems || (b + 1 == e->B && items.n > 0)) {
+        LaunchVqPatchItems(e->vq_n.as<int>(), e->codebook_ptrs.as<const float*>(), e->codebooks.as<float>(), cb, items, s);
+        ++e->launches;
+        items.n = 0;
+      }
+    }
     e->vq_dirty = false;
     // With VQ off everywhere (the reference's default, parameter_schema.cc:390-392) the VQ launch is a plain copy
     // that the content encoder's chain kernel already made (EncoderState::head_copy): the hop graphs are captured
@@ -367,30 +398,38 @@ void FlushVocoderSide(Engine* e, bool hop, const std::vector<char>* kv_only = nu
   };
   if (!e->pending_speaker.empty()) {  // SetAdditiveSpeakerEmbedding, processor_core_2.cc:451-455
     dedup(&e->pending_speaker);
-    std::vector<int> src;
-    for (int b : e->pending_speaker) src.push_back(TableRow(e, b));
-    const int n = static_cast<int>(src.size());
-    UploadInts(e, &e->idx_a, src);
-    UploadInts(e, &e->idx_b, e->pending_speaker);
-    LaunchProject256(e->setter_m.add_w, e->setter_m.add_b, e->additive.as<float>(), kHidden, e->idx_a.as<int>(),
-                     e->wave_st.spk.as<float>(), e->idx_b.as<int>(), n, s);
-    ++e->launches;
+    SetterItems items;
+    items.n = 0;
+    for (size_t i = 0; i < e->pending_speaker.size(); ++i) {
+      const int b = e->pending_speaker[i];
+      items.src[items.n] = TableRow(e, b);
+      items.dst[items.n] = b;
+      items.blk[items.n] = 0;
+      if (++items.n == kSetterItems || i + 1 == e->pending_speaker.size()) {
+        LaunchProject256Items(e->setter_m.add_w, e->setter_m.add_b, e->additive.as<float>(), kHidden, e->wave_st.spk.as<float>(), items, s);
+        ++e->launches;
+        items.n = 0;
+      }
+    }
     e->pending_speaker.clear();
   }
   if (!e->pending_formant.empty()) {  // SetFormantShift, processor_core_2.cc:468-481
     dedup(&e->pending_formant);
-    std::vector<int> src;
-    for (int b : e->pending_formant) {
+    SetterItems items;
+    items.n = 0;
+    for (size_t i = 0; i < e->pending_formant.size(); ++i) {
+      const int b = e->pending_formant[i];
       const double f = std::min(std::max(e->sp[b].formant_shift, -2.0), 2.0);
-      src.push_back(static_cast<int>(std::round(f * 2.0 + 4.0)));
+      items.src[items.n] = static_cast<int>(std::round(f * 2.0 + 4.0));
+      items.dst[items.n] = b;
+      items.blk[items.n] = 0;
+      if (++items.n == kSetterItems || i + 1 == e->pending_formant.size()) {
+        LaunchProject256Items(e->setter_m.for_w, e->setter_m.for_b, e->formant_tab.as<float>(), kHidden, e->wave_st.formant.as<float>(), items,
+                              s);
+        ++e->launches;
+        items.n = 0;
+      }
     }
-    const int n = static_cast<int>(src.size());
-    // idx_a / idx_b are reused: stream order guarantees the previous launch consumed them
-    UploadInts(e, &e->idx_a, src);
-    UploadInts(e, &e->idx_b, e->pending_formant);
-    LaunchProject256(e->setter_m.for_w, e->setter_m.for_b, e->formant_tab.as<float>(), kHidden, e->idx_a.as<int>(),
-                     e->wave_st.formant.as<float>(), e->idx_b.as<int>(), n, s);
-    ++e->launches;
     e->pending_formant.clear();
   }
   // key-value speaker embedding: one block per stream per hop until all four are applied
@@ -763,6 +802,8 @@ int LoadImages(Engine* e, const void* const images[5], const size_t sizes[5]) {
   e->max_q.Alloc(e->device, sizeof(int) * B, true);
   e->vq_n.Alloc(e->device, sizeof(int) * B, true);
   e->codebook_ptrs.Alloc(e->device, sizeof(float*) * B, true);
+  e->dev_vq_n.clear();      // the device arrays are zero again: FlushEncoderSide re-creates its mirror
+  e->dev_vq_idx.clear();
   e->pitch_params.Alloc(e->device, sizeof(PitchParams) * B, true);
   e->idx_a.Alloc(e->device, sizeof(int) * B, true);
   e->idx_b.Alloc(e->device, sizeof(int) * B, true);

@@ -690,12 +690,25 @@ __global__ void __launch_bounds__(kCodebookSize) vq_kernel(const float* __restri
     return;
   }
   {
-    const float* e = cb + static_cast<long long>(tid) * C;
+    // One thread per codebook row, channels accumulated in order (the oracle's arithmetic: the neighbour CHOICE must be the
+    // oracle's).  The rows come through shared memory in tiles of 16 channels so that global loads are coalesced -- a thread
+    // walking its own 512-byte row took ~50 us per hop (the content lane then outlasted the vocoder at pipeline depth 2).
+    __shared__ float tile[kCodebookSize][17];
     float nn = 0.f, dot = 0.f;
-    for (int ch = 0; ch < C; ++ch) {
-      const float ev = __ldg(e + ch);
-      nn = fmaf(ev, ev, nn);
-      dot = fmaf(ev, ph[ch], dot);
+    for (int c0 = 0; c0 < C; c0 += 16) {
+      __syncthreads();
+#pragma unroll 4
+      for (int i = tid; i < kCodebookSize * 16; i += kCodebookSize) {
+        const int r = i >> 4, c = i & 15;
+        tile[r][c] = __ldg(cb + static_cast<long long>(r) * C + c0 + c);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float ev = tile[tid][c];
+        nn = fmaf(ev, ev, nn);
+        dot = fmaf(ev, ph[c0 + c], dot);
+      }
     }
     dist[tid] = nn - 2.0f * dot;
   }
@@ -742,69 +755,143 @@ __global__ void __launch_bounds__(kCodebookSize) vq_kernel(const float* __restri
   if (tid < C) phone_out[static_cast<long long>(b) * C + tid] = acc * (1.0f / static_cast<float>(n));
 }
 
-__global__ void __launch_bounds__(256) project256_kernel(const float* __restrict__ W, const float* __restrict__ bias,
-                                                         const float* __restrict__ e, size_t e_stride,
-                                                         const int* __restrict__ e_index, float* __restrict__ out,
-                                                         const int* __restrict__ out_index) {
+__device__ __forceinline__ void Project256Body(const float* __restrict__ W, const float* __restrict__ bias,
+                                               const float* __restrict__ e, size_t e_stride, size_t src, float* __restrict__ out,
+                                               int row) {
   __shared__ float ev[kHidden];
-  const int item = blockIdx.x, o = threadIdx.x;
-  const size_t src = e_index ? static_cast<size_t>(e_index[item]) : static_cast<size_t>(item);
+  const int o = threadIdx.x;
   ev[o] = e[src * e_stride + o];
   __syncthreads();
   float acc = __ldg(bias + o);
   for (int i = 0; i < kHidden; ++i) acc = fmaf(ev[i], __ldg(W + i * kHidden + o), acc);
-  const int row = out_index ? out_index[item] : item;
   out[static_cast<long long>(row) * kHidden + o] = acc;
 }
+__global__ void __launch_bounds__(256) project256_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                         const float* __restrict__ e, size_t e_stride,
+                                                         const int* __restrict__ e_index, float* __restrict__ out,
+                                                         const int* __restrict__ out_index) {
+  const int item = blockIdx.x;
+  const size_t src = e_index ? static_cast<size_t>(e_index[item]) : static_cast<size_t>(item);
+  Project256Body(W, bias, e, e_stride, src, out, out_index ? out_index[item] : item);
+}
+__global__ void __launch_bounds__(256) project256_items_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                               const float* __restrict__ e, size_t e_stride,
+                                                               float* __restrict__ out, const __grid_constant__ SetterItems items) {
+  const int item = blockIdx.x;
+  Project256Body(W, bias, e, e_stride, static_cast<size_t>(items.src[item]), out, items.dst[item]);
+}
 
-__global__ void __launch_bounds__(kKvLength) kv_film_kernel(const float* __restrict__ kv_base,
-                                                            const int* __restrict__ kv_index, size_t kv_stride,
-                                                            const float* __restrict__ query,
-                                                            const float* __restrict__ W, const float* __restrict__ bias,
-                                                            int C, float* __restrict__ film_base,
-                                                            const int* __restrict__ out_index) {
+// One stream per block: attention pool of the stream's key-value embedding [384][128] with a learned query, then the linear
+// layer to the stage's FiLM (gamma | beta).  Runs at parameter-change rate, but a speaker change costs four of these (one per
+// vocoder stage, one per hop) in front of the hop graph, so it is laid out for latency: scores with a warp per row (coalesced
+// 512-byte rows, four rows in flight per warp), the pooled vector in three row thirds summed in a fixed order.
+__device__ __forceinline__ void KvFilmBody(const float* __restrict__ kv, const float* __restrict__ query,
+                                           const float* __restrict__ W, const float* __restrict__ bias, int C,
+                                           float* __restrict__ film_row) {
+  static_assert(kKvLength == 384 && kKvChannels == 128, "kv_film_kernel is laid out for a 384 x 128 embedding");
   __shared__ float qv[kKvChannels];
   __shared__ float p[kKvLength];
+  __shared__ float part[3][kKvChannels];
   __shared__ float pooled[kKvChannels];
   __shared__ float red[kKvLength / 32];
-  const int item = blockIdx.x, tid = threadIdx.x;
-  const float* kv = kv_base + (kv_index ? static_cast<size_t>(kv_index[item]) : 0) * kv_stride;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < kKvChannels) qv[tid] = __ldg(query + tid);
   __syncthreads();
-  float s = 0.f;
   {
-    const float* row = kv + static_cast<size_t>(tid) * kKvChannels;
-    for (int ch = 0; ch < kKvChannels; ++ch) s = fmaf(__ldg(row + ch), qv[ch], s);
-    s *= 1.0f / sqrtf(static_cast<float>(kKvChannels));
+    // scores: warp w takes rows w, w + 12, ...; a lane holds 4 consecutive channels of the row
+    const float4 q4 = *reinterpret_cast<const float4*>(qv + 4 * lane);
+    constexpr int kWarps = kKvLength / 32;
+#pragma unroll 1
+    for (int r0 = warp; r0 < kKvLength; r0 += 4 * kWarps) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * kWarps;
+        v[u] = r < kKvLength ? __ldg(reinterpret_cast<const float4*>(kv + static_cast<size_t>(r) * kKvChannels) + lane)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * kWarps;
+        float d = fmaf(v[u].x, q4.x, fmaf(v[u].y, q4.y, fmaf(v[u].z, q4.z, v[u].w * q4.w)));
+        d = WarpSum(d);
+        if (lane == 0 && r < kKvLength) p[r] = d * (1.0f / sqrtf(static_cast<float>(kKvChannels)));
+      }
+    }
   }
+  __syncthreads();
+  const float s = p[tid];
   // block max
   float m = s;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((tid & 31) == 0) red[tid >> 5] = m;
+  if (lane == 0) red[warp] = m;
   __syncthreads();
   m = red[0];
   for (int i = 1; i < kKvLength / 32; ++i) m = fmaxf(m, red[i]);
   __syncthreads();
   const float ex = expf(s - m);
   float den = WarpSum(ex);
-  if ((tid & 31) == 0) red[tid >> 5] = den;
+  if (lane == 0) red[warp] = den;
   __syncthreads();
   den = 0.f;
   for (int i = 0; i < kKvLength / 32; ++i) den += red[i];
   p[tid] = ex / den;
   __syncthreads();
-  if (tid < kKvChannels) {
-    float acc = 0.f;
-    for (int i = 0; i < kKvLength; ++i) acc = fmaf(p[i], __ldg(kv + static_cast<size_t>(i) * kKvChannels + tid), acc);
-    pooled[tid] = acc;
+  {
+    // pooled[ch] = sum_i p[i] kv[i][ch]: thread (third g, channel ch) sums 128 rows, the thirds are added in order
+    const int g = tid / kKvChannels, ch = tid - g * kKvChannels;
+    const float* col = kv + static_cast<size_t>(g) * 128 * kKvChannels + ch;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < 128; i += 4) {
+      a0 = fmaf(p[g * 128 + i], __ldg(col + static_cast<size_t>(i) * kKvChannels), a0);
+      a1 = fmaf(p[g * 128 + i + 1], __ldg(col + static_cast<size_t>(i + 1) * kKvChannels), a1);
+      a2 = fmaf(p[g * 128 + i + 2], __ldg(col + static_cast<size_t>(i + 2) * kKvChannels), a2);
+      a3 = fmaf(p[g * 128 + i + 3], __ldg(col + static_cast<size_t>(i + 3) * kKvChannels), a3);
+    }
+    part[g][ch] = (a0 + a1) + (a2 + a3);
   }
   __syncthreads();
+  if (tid < kKvChannels) pooled[tid] = (part[0][tid] + part[1][tid]) + part[2][tid];
+  __syncthreads();
   if (tid < 2 * C) {
-    float acc = __ldg(bias + tid);
-    for (int i = 0; i < kKvChannels; ++i) acc = fmaf(pooled[i], __ldg(W + i * 2 * C + tid), acc);
-    const int row = out_index ? out_index[item] : item;
-    film_base[static_cast<long long>(row) * 2 * C + tid] = acc;
+    float a0 = __ldg(bias + tid), a1 = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < kKvChannels; i += 2) {
+      a0 = fmaf(pooled[i], __ldg(W + static_cast<size_t>(i) * 2 * C + tid), a0);
+      a1 = fmaf(pooled[i + 1], __ldg(W + static_cast<size_t>(i + 1) * 2 * C + tid), a1);
+    }
+    film_row[tid] = a0 + a1;
+  }
+}
+__global__ void __launch_bounds__(kKvLength) kv_film_kernel(const float* __restrict__ kv_base,
+                                                            const int* __restrict__ kv_index, size_t kv_stride,
+                                                            const float* __restrict__ query,
+                                                            const float* __restrict__ W, const float* __restrict__ bias,
+                                                            int C, float* __restrict__ film_base,
+                                                            const int* __restrict__ out_index) {
+  const int item = blockIdx.x;
+  const float* kv = kv_base + (kv_index ? static_cast<size_t>(kv_index[item]) : 0) * kv_stride;
+  const int row = out_index ? out_index[item] : item;
+  KvFilmBody(kv, query, W, bias, C, film_base + static_cast<long long>(row) * 2 * C);
+}
+// the same for a by-value list of (key-value slot, stream, block): one launch serves every block of a hop's schedule
+__global__ void __launch_bounds__(kKvLength) kv_film_items_kernel(const float* __restrict__ kv_base, size_t kv_stride,
+                                                                  const __grid_constant__ KvBlockTable tab,
+                                                                  const __grid_constant__ SetterItems items) {
+  const int item = blockIdx.x, blk = items.blk[item];
+  const int C = tab.C[blk];
+  KvFilmBody(kv_base + static_cast<size_t>(items.src[item]) * kv_stride, tab.query[blk], tab.W[blk], tab.bias[blk], C,
+             tab.film[blk] + static_cast<long long>(items.dst[item]) * 2 * C);
+}
+__global__ void vq_patch_items_kernel(int* __restrict__ vq_n, const float** __restrict__ codebook_ptrs,
+                                      const float* __restrict__ codebooks, size_t cb_stride,
+                                      const __grid_constant__ SetterItems items) {
+  const int i = threadIdx.x;
+  if (i < items.n) {
+    vq_n[items.dst[i]] = items.blk[i];
+    codebook_ptrs[items.dst[i]] = items.src[i] >= 0 ? codebooks + cb_stride * static_cast<size_t>(items.src[i]) : nullptr;
   }
 }
 
@@ -916,6 +1003,24 @@ void LaunchKvFilm(const float* kv_base, const int* kv_index, size_t kv_stride, c
                   const float* b, int C, float* film_base, const int* out_index, int n_items, cudaStream_t s) {
   if (n_items <= 0) return;
   kv_film_kernel<<<n_items, kKvLength, 0, s>>>(kv_base, kv_index, kv_stride, query, W, b, C, film_base, out_index);
+  B200_CHECK(cudaGetLastError());
+}
+
+void LaunchProject256Items(const float* W, const float* b, const float* e, size_t e_stride, float* out, const SetterItems& items,
+                           cudaStream_t s) {
+  if (items.n <= 0) return;
+  project256_items_kernel<<<items.n, kHidden, 0, s>>>(W, b, e, e_stride, out, items);
+  B200_CHECK(cudaGetLastError());
+}
+void LaunchKvFilmItems(const float* kv_base, size_t kv_stride, const KvBlockTable& tab, const SetterItems& items, cudaStream_t s) {
+  if (items.n <= 0) return;
+  kv_film_items_kernel<<<items.n, kKvLength, 0, s>>>(kv_base, kv_stride, tab, items);
+  B200_CHECK(cudaGetLastError());
+}
+void LaunchVqPatchItems(int* vq_n, const float** codebook_ptrs, const float* codebooks, size_t cb_stride, const SetterItems& items,
+                        cudaStream_t s) {
+  if (items.n <= 0) return;
+  vq_patch_items_kernel<<<1, kSetterItems, 0, s>>>(vq_n, codebook_ptrs, codebooks, cb_stride, items);
   B200_CHECK(cudaGetLastError());
 }
 

@@ -147,6 +147,29 @@ void LaunchProject256(const float* W, const float* b, const float* e, size_t e_s
 // attention-pool kv (384 x 128) with `query`, then film = b + pooled . W  (W [128][2C])
 // item i reads kv_base + kv_index[i]*kv_stride (kv_index null -> 0) and writes film_base +
 // (out_index ? out_index[i] : i) * 2C
+// Setter launches whose (source row, destination stream[, block]) lists travel BY VALUE in the kernel parameters: a
+// parameter change touches a handful of streams, and an index upload per launch (a pageable cudaMemcpyAsync: host
+// staging + a copy operation in front of the kernel) costs more than the kernel.  Longer lists go out in chunks.
+constexpr int kSetterItems = 48;
+struct SetterItems {
+  int n;
+  int src[kSetterItems];   // row of the table read (speaker / formant index / key-value slot)
+  int dst[kSetterItems];   // stream written
+  int blk[kSetterItems];   // key-value block = vocoder stage (LaunchKvFilmItems); kNN-VQ neighbour count (LaunchVqPatchItems)
+};
+struct KvBlockTable {      // EmbeddingSetter block parameters, by value
+  const float* query[4];
+  const float* W[4];
+  const float* bias[4];
+  float* film[4];          // [B][2 C_blk]
+  int C[4];
+};
+void LaunchProject256Items(const float* W, const float* b, const float* e, size_t e_stride, float* out, const SetterItems& items,
+                           cudaStream_t s);
+void LaunchKvFilmItems(const float* kv_base, size_t kv_stride, const KvBlockTable& tab, const SetterItems& items, cudaStream_t s);
+// vq_n[dst] = blk, codebook_ptrs[dst] = blk > 0 || src >= 0 ? codebooks + cb_stride * src : nullptr
+void LaunchVqPatchItems(int* vq_n, const float** codebook_ptrs, const float* codebooks, size_t cb_stride, const SetterItems& items,
+                        cudaStream_t s);
 void LaunchKvFilm(const float* kv_base, const int* kv_index, size_t kv_stride, const float* query,
                   const float* W, const float* b, int C, float* film_base, const int* out_index, int n_items,
                   cudaStream_t s);
