@@ -33,6 +33,7 @@ struct StreamParams {  // host mirror; defaults = processor_core_2.h:103-113
   double max_source_pitch = 80.875;
   int vq = 0;
   int kv_set_count = kNBlocks;  // blocks 0..3 still to apply, one per hop (processor_core_2.h:161-169)
+  unsigned speaker_seq = 0;     // bumped by every SetTargetSpeaker: a deferred reset (depth 2) tells a later change from its own
 };
 
 // Voice morphing of one stream (processor_core_2.cc:51-177, :498-532, processor_core_2.h:138-145).
@@ -692,9 +693,13 @@ inline size_t PipelinedLaunches(const Engine* e, bool with_vocoder) {
 }
 // after the call's graph is enqueued (depth 2): what the NEXT vocoder run must see
 void AfterPipelinedHop(Engine* e) {
-  FlushVocoderSide(e, /*hop=*/true);
+  // A single-stream reset asked for in front of this call's hop comes FIRST, as at depth 1 (reset, then the hop's own
+  // flush): in morphing mode the reset registers the slot as it is NOW, and the hop's flush below averages the next
+  // quarter of the key-value rows -- in the other order the registration saw one quarter too many (found by
+  // tools/soak_diff.py: a reset one to four hops after the morphing slot was selected).
   for (auto& f : e->after_hop) f();
   e->after_hop.clear();
+  FlushVocoderSide(e, /*hop=*/true);
   e->primed = true;
 }
 
@@ -1107,6 +1112,7 @@ int BeatriceB200_SetTargetSpeaker(BeatriceB200_Engine* e, int stream, int speake
   if (speaker < 0 || speaker > e->n_speakers || (speaker == e->n_speakers && !e->dims.has_setter)) return BEATRICE_B200_ERR_SPEAKER_RANGE;
   ForStreams(e, stream, [&](int b) {
     e->sp[b].speaker = speaker;
+    ++e->sp[b].speaker_seq;
     e->sp[b].kv_set_count = 0;  // :464 -- blocks are applied over the next four hops
     e->pending_speaker.push_back(b);
     // the morphing slot is registered as it is NOW, possibly part-way through its four frames of averaging (:456-462)
@@ -1246,7 +1252,14 @@ int BeatriceB200_ResetStream(BeatriceB200_Engine* e, int stream) {
     // vocoder half (state, conditioning, all four key-value blocks) is re-created right behind the next hop.
     e->phone_st.ZeroStream(stream, e->stream);
     e->pitch_st.ZeroStream(stream, e->stream);
-    e->after_hop.push_back([e, stream] {
+    // ResetContext re-applies the speaker that is the target AT THE TIME OF THE RESET with all four blocks at once (:269-270);
+    // a SetTargetSpeaker that follows before the next hop then starts its own four-hop schedule, as at depth 1
+    const int speaker_at_reset = e->sp[stream].speaker;
+    const unsigned seq_at_reset = e->sp[stream].speaker_seq;
+    e->after_hop.push_back([e, stream, speaker_at_reset, seq_at_reset] {
+      const int speaker_now = e->sp[stream].speaker;
+      const bool changed_since = e->sp[stream].speaker_seq != seq_at_reset;
+      e->sp[stream].speaker = speaker_at_reset;
       e->wave_st.ZeroStream(stream, e->stream);
       e->sp[stream].kv_set_count = 0;
       e->pending_speaker.push_back(stream);
@@ -1256,6 +1269,12 @@ int BeatriceB200_ResetStream(BeatriceB200_Engine* e, int stream) {
       only[stream] = 1;
       FlushVocoderSide(e, /*hop=*/false, &only);
       for (int round = 1; round < kNBlocks; ++round) StepKv(e, &only);
+      if (changed_since) {   // the later SetTargetSpeaker, replayed on top of the reset
+        e->sp[stream].speaker = speaker_now;
+        e->sp[stream].kv_set_count = 0;
+        e->pending_speaker.push_back(stream);
+        if (speaker_now == e->n_speakers) e->morph[stream].register_pending = true;
+      }
     });
     return 0;
   }
