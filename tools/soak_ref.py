@@ -1,0 +1,147 @@
+"""Randomised soak against the REFERENCE: a random stream of parameter events through the batched engine (48 kHz host-buffer
+entry, pipeline depth 1 or 2) and, stream by stream, through the reference's own call site (ProcessorCore2::Process, compiled in
+oracle/_ref) over the CPU oracle -- the same events at the same blocks.  Checks the setters' SEMANTICS (clamping, the four-hop
+key-value schedule, morphing slots, resets, gain slews, pitch parameters) against the reference under sequences nobody scripted.
+kNN-VQ stays off in morphing mode (the reference seeds its codebook lottery from std::random_device).
+   python tools/soak_ref.py [hops=400] [streams=8] [seed=1] [depth=1]"""
+import os
+import sys
+import tempfile
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import callsite  # noqa: E402
+from beatrice_vst_b200 import batch as bbatch  # noqa: E402
+from beatrice_vst_b200 import lib as blib  # noqa: E402
+from beatrice_vst_b200 import model_spec, signals  # noqa: E402
+
+SETTER = dict(voice="TargetSpeaker", pitch_shift="PitchShift", formant_shift="FormantShift", input_gain="InputGain",
+              output_gain="OutputGain", vq_num_neighbors="VQNumNeighbors", pitch_correction="PitchCorrection",
+              pitch_correction_type="PitchCorrectionType", intonation_intensity="IntonationIntensity",
+              average_source_pitch="AverageSourcePitch", min_source_pitch="MinSourcePitch", max_source_pitch="MaxSourcePitch")
+
+
+def soak(hops=400, n=8, seed=1, depth=1, product=None):
+    rng = np.random.default_rng(seed)
+    product = product or blib.load_product()
+    with tempfile.TemporaryDirectory() as d:
+        model_spec.write_model_dir(d, 8, 2, 0)
+        eng = bbatch.Engine(product, n, precision=int(os.environ.get("SOAK_PRECISION", "2")))   # 0 = fp32 CUDA cores (diagnosis)
+        assert eng.load(d) == 0
+        assert eng.set_pipeline_depth(depth) == 0
+        x = signals.batch_48k(n, hops, seed0=500 + seed)        # [hops][n][480]
+        plans = [[] for _ in range(n)]                          # per stream: (block, runner name, value)
+        morphing = [False] * n
+        vq = [0] * n
+        got, q_log, f_log = [], [], []
+        for h in range(hops):
+            for _ in range(rng.poisson(0.5)):
+                s = int(rng.integers(0, n))
+                kind = int(rng.integers(0, 12))
+                ev = []
+                if kind == 0:
+                    ev = [("voice", int(rng.integers(0, 8)))]
+                    morphing[s] = False
+                elif kind == 1:
+                    ev = [("pitch_shift", float(rng.integers(-24, 25)) / 2.0)]
+                elif kind == 2:
+                    ev = [("formant_shift", float(rng.integers(-4, 5)) / 2.0)]
+                elif kind == 3:
+                    ev = [("input_gain", float(rng.integers(-12, 7)))]
+                elif kind == 4:
+                    ev = [("output_gain", float(rng.integers(-12, 7)))]
+                elif kind == 5:
+                    if not morphing[s]:
+                        vq[s] = int(rng.choice([0, 2, 4, 8]))
+                        ev = [("vq_num_neighbors", float(vq[s]))]
+                elif kind == 6:
+                    ev = [("pitch_correction", float(rng.choice([0.0, 0.3, 0.7, 1.0]))), ("pitch_correction_type", int(rng.integers(0, 2)))]
+                elif kind == 7:
+                    ev = [("reset", 1)]
+                elif kind == 8:
+                    ev = [("intonation_intensity", float(rng.choice([0.5, 1.0, 1.5]))), ("average_source_pitch", float(rng.integers(48, 66)))]
+                elif kind == 9:
+                    lo = float(rng.integers(30, 45))
+                    ev = [("min_source_pitch", lo), ("max_source_pitch", lo + float(rng.integers(20, 45)))]
+                else:
+                    w = rng.random(8).astype(np.float32)
+                    w[rng.integers(0, 8, 3)] = 0.0
+                    if vq[s]:
+                        ev.append(("vq_num_neighbors", 0.0))
+                        vq[s] = 0
+                    ev += [(f"morphw{k}", float(w[k])) for k in range(8)] + [("morph_apply", 1), ("voice", 8)]
+                    morphing[s] = True
+                    assert eng.set_morph_weights(w, s) == 0
+                for name, v in ev:
+                    plans[s].append((h, name, v))
+                    if name == "reset":
+                        assert eng.reset_stream(s) == 0
+                    elif name.startswith("morph"):
+                        pass
+                    else:
+                        arg = int(v) if name in ("voice", "vq_num_neighbors", "pitch_correction_type") else float(v)
+                        assert eng.set(SETTER[name], arg, s) == 0, (name, v)
+            got.append(eng.process_48k(x[h]).copy())
+            if depth == 1:
+                inter = eng.last_intermediates()
+                q_log.append(inter[1].copy())       # raw pitch bins of the hop (diagnosis of a mismatch)
+                f_log.append(inter[3].copy())       # the pitch head's four feature outputs
+        if depth == 2:
+            got = got[1:] + [eng.drain()]
+        got = np.stack(got, axis=1)                             # [n][hops][480]
+        eng.close()
+        toml = os.path.join(d, "model.toml")
+
+        def one(s):
+            y, info = callsite.run("oracle", toml, x[:, s, :].reshape(-1), events=plans[s])
+            assert info["load"] == 0 and info["last"] == 0, info
+            e = float(np.sqrt(np.mean((y.astype(np.float64) - got[s].reshape(-1)) ** 2)))
+            if e > 1e-4:   # where it starts, and what had been asked of the stream by then
+                per_hop = np.sqrt(np.mean((y.reshape(hops, 480).astype(np.float64) - got[s]) ** 2, axis=1))
+                first = int(np.argmax(per_hop > 1e-4))
+                print(f"  stream {s}: first hop above 1e-4: {first} ({per_hop[first]:.2e}); hops above: {int((per_hop > 1e-4).sum())}; "
+                      f"events up to it: {[p for p in plans[s] if p[0] <= first][-14:]}")
+                upto = min([p[0] for p in plans[s] if p[1] in ("input_gain", "reset")] + [hops])   # unit input gain, one context
+                if q_log and upto > first:
+                    # is it the pitch estimator's arg-max (a near-tie decided differently by fp32 and split-bf16)?  The oracle's raw
+                    # bins for the same 16 kHz frames (numpy adapter, unit gain) against the engine's
+                    import hostrate_ref
+                    import loader
+                    frames16 = []
+
+                    def model(x16):
+                        frames16.append(np.array(x16, np.float32))
+                        return np.zeros(240, np.float32)
+
+                    hr = hostrate_ref.HostRateRef(model)
+                    for h in range(upto):
+                        hr.process(x[h, s])
+                    st = blib.SingleStream(loader.load_oracle(), d)
+                    st.set_pitch_range(1, 383)     # the call site default (no min / max source pitch event for this stream assumed)
+                    _, q_or, f_or, _ = st.run(np.concatenate(frames16))
+                    f_en = np.array([f[s] for f in f_log])[:upto]
+                    ferr = np.abs(f_or[:upto] - f_en).max(axis=1)
+                    print(f"    pitch-head feature error (max of 4) per hop, hops {max(first - 12, 0)}..{first + 30}: "
+                          f"{[float(f'{v:.1e}') for v in ferr[max(first - 12, 0):first + 30]]}; median over the run {np.median(ferr):.1e}; feature magnitude {np.abs(f_or).mean():.2f}")
+                    st.close()
+                    q_en = np.array([q[s] for q in q_log])[:upto]
+                    diff = np.nonzero(q_or[:upto] != q_en)[0]
+                    print(f"    raw pitch bins differ at hops {diff[:12].tolist()} ({len(diff)} hops): oracle {q_or[diff[:6]].tolist()} engine {q_en[diff[:6]].tolist()}")
+            return e, float(y.std())
+
+        with ThreadPoolExecutor(max_workers=min(n, os.cpu_count() or 1)) as pool:
+            res = list(pool.map(one, range(n)))
+    worst = max(r[0] for r in res)
+    print(f"soak vs reference call site: {hops} hops x {n} streams, {sum(len(p) for p in plans)} events, depth {depth}: worst RMS {worst:.2e} "
+          f"(signal {min(r[1] for r in res):.3f}); per stream {[f'{r[0]:.1e}' for r in res]}")
+    return worst
+
+
+if __name__ == "__main__":
+    w = soak(int(sys.argv[1]) if len(sys.argv) > 1 else 400, int(sys.argv[2]) if len(sys.argv) > 2 else 8,
+             int(sys.argv[3]) if len(sys.argv) > 3 else 1, int(sys.argv[4]) if len(sys.argv) > 4 else 1)
+    raise SystemExit(0 if w <= 1e-4 else 1)
