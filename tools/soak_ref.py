@@ -3,7 +3,7 @@ entry, pipeline depth 1 or 2) and, stream by stream, through the reference's own
 oracle/_ref) over the CPU oracle -- the same events at the same blocks.  Checks the setters' SEMANTICS (clamping, the four-hop
 key-value schedule, morphing slots, resets, gain slews, pitch parameters) against the reference under sequences nobody scripted.
 kNN-VQ stays off in morphing mode (the reference seeds its codebook lottery from std::random_device).
-   python tools/soak_ref.py [hops=400] [streams=8] [seed=1] [depth=1]"""
+   python tools/soak_ref.py [hops=400] [streams=8] [seed=1] [depth=1] [family=2]"""
 import os
 import sys
 import tempfile
@@ -25,11 +25,11 @@ SETTER = dict(voice="TargetSpeaker", pitch_shift="PitchShift", formant_shift="Fo
               average_source_pitch="AverageSourcePitch", min_source_pitch="MinSourcePitch", max_source_pitch="MaxSourcePitch")
 
 
-def soak(hops=400, n=8, seed=1, depth=1, product=None):
+def soak(hops=400, n=8, seed=1, depth=1, product=None, family=2):
     rng = np.random.default_rng(seed)
     product = product or blib.load_product()
     with tempfile.TemporaryDirectory() as d:
-        model_spec.write_model_dir(d, 8, 2, 0)
+        model_spec.write_model_dir(d, 8, family, 0)     # family 0 / 1: ProcessorCore0 / 1 (no kNN-VQ, no morphing slot here)
         eng = bbatch.Engine(product, n, precision=int(os.environ.get("SOAK_PRECISION", "2")))   # 0 = fp32 CUDA cores (diagnosis)
         assert eng.load(d) == 0
         assert eng.set_pipeline_depth(depth) == 0
@@ -42,6 +42,8 @@ def soak(hops=400, n=8, seed=1, depth=1, product=None):
             for _ in range(rng.poisson(0.5)):
                 s = int(rng.integers(0, n))
                 kind = int(rng.integers(0, 12))
+                if family != 2 and kind in (5, 10, 11):
+                    kind = 0
                 ev = []
                 if kind == 0:
                     ev = [("voice", int(rng.integers(0, 8)))]
@@ -143,5 +145,6 @@ def soak(hops=400, n=8, seed=1, depth=1, product=None):
 
 if __name__ == "__main__":
     w = soak(int(sys.argv[1]) if len(sys.argv) > 1 else 400, int(sys.argv[2]) if len(sys.argv) > 2 else 8,
-             int(sys.argv[3]) if len(sys.argv) > 3 else 1, int(sys.argv[4]) if len(sys.argv) > 4 else 1)
+             int(sys.argv[3]) if len(sys.argv) > 3 else 1, int(sys.argv[4]) if len(sys.argv) > 4 else 1,
+             family=int(sys.argv[5]) if len(sys.argv) > 5 else 2)
     raise SystemExit(0 if w <= 1e-4 else 1)
