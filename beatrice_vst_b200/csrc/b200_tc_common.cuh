@@ -256,8 +256,7 @@ __device__ __forceinline__ void SpinUntil(volatile uint32_t* cnt, uint32_t targe
 __device__ __forceinline__ int ConvDil(int i) { return (i & 1) ? 1 : (i == 0 ? 1 : (i == 2 ? 3 : 5)); }
 // sum of the dilations of convs 0..i-1 (1,1,3,1,5,1)
 __device__ __forceinline__ int DilPrefix(int i) {
-  const int pre[7] = {0, 1, 2, 5, 6, 11, 12};
-  return pre[i];
+  return static_cast<int>((0xCB65210u >> (4 * i)) & 0xFu);   // {0, 1, 2, 5, 6, 11, 12} as nibbles: no local-memory table
 }
 
 
