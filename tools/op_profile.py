@@ -15,6 +15,18 @@ from beatrice_vst_b200 import lib as blib  # noqa: E402
 from beatrice_vst_b200 import model_spec, signals  # noqa: E402
 
 
+def _peaks():
+    import json
+    try:
+        m = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(m["bf16_tflops_sustained"]), float(m["hbm_gbs"])
+    except (OSError, KeyError, ValueError):
+        return 1357.1, 6539.2
+
+
+PEAK_TF, PEAK_GBS = _peaks()
+
+
 def main():
     prec = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
@@ -41,7 +53,10 @@ def main():
         us = 1e3 * float(np.median([a[i]["ms"] for a in allr[1:]]))
         tot += us
         tf = r["flops"] / (us * 1e-6) / 1e12 if us > 0 else 0.0
-        print(f"[ops] {r['name']:<28s} {us:8.1f} us  {r['flops'] / 1e9:7.3f} GFLOP  {tf:7.1f} TF/s")
+        gbs = r["bytes"] / (us * 1e-6) / 1e9 if us > 0 else 0.0
+        # algorithmic work of the op (weights + activations in and out, once) against the two measured ceilings
+        print(f"[ops] {r['name']:<28s} {us:8.1f} us  {r['flops'] / 1e9:7.3f} GFLOP  {tf:7.1f} TF/s ({100 * tf / PEAK_TF:4.1f} %)  "
+              f"{r['bytes'] / 1e6:7.2f} MB  {gbs:7.1f} GB/s ({100 * gbs / PEAK_GBS:4.1f} %)")
     print(f"[ops] serial sum {tot:.1f} us")
 
 
