@@ -1362,7 +1362,9 @@ int BeatriceB200_Process48k(BeatriceB200_Engine* e, const float* in_host, float*
   const size_t n = sizeof(float) * e->B * kHostHop48k;
   B200_CHECK(cudaMemcpyAsync(e->hostrate.in48(), in_host, n, cudaMemcpyHostToDevice, e->stream));
   RunHop48Split(e, out_host, n);
-  B200_CHECK(cudaStreamSynchronize(e->side));
+  // one host wait for both streams: the main stream joins the side stream (early output block + its copy to the host)
+  B200_CHECK(cudaEventRecord(e->ev_side, e->side));
+  B200_CHECK(cudaStreamWaitEvent(e->stream, e->ev_side, 0));
   B200_CHECK(cudaStreamSynchronize(e->stream));
   return 0;
   }(););
