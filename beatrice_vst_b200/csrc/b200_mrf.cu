@@ -395,17 +395,25 @@ __global__ void __launch_bounds__(ThreadsFor(C), C <= 16 ? 4 : (C <= 32 ? 2 : 1)
         for (int g = 0; g < G; ++g) {
           if (kEpiWarps == 8 && ((m * G + g) & 1) != whalf) continue;   // the partner warp's item
           uint32_t raw[16];
-          TmemLd16(tcol + 16 * g, raw);
           float v[16];
+          if (kSplit) {   // accumulator columns [0,C) + the x_hi*W_lo half in [C,2C): both loads in flight, one wait
+            uint32_t raw2[16];
+            TmemLd16x2(tcol + 16 * g, raw, tcol + C + 16 * g, raw2);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]);
-          if (kSplit) {   // + the x_hi*W_lo half
-            TmemLd16(tcol + C + 16 * g, raw);
+            for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]) + __uint_as_float(raw2[e]);
+          } else {
+            TmemLd16(tcol + 16 * g, raw);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] += __uint_as_float(raw[e]);
+            for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]);
           }
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] += bias[16 * g + e];
+          for (int q = 0; q < 4; ++q) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias + 16 * g + 4 * q);
+            v[4 * q] += b4.x;
+            v[4 * q + 1] += b4.y;
+            v[4 * q + 2] += b4.z;
+            v[4 * q + 3] += b4.w;
+          }
           if (!is_c1) {
             if (!last) {
 #pragma unroll

@@ -267,8 +267,10 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
 #pragma unroll 1
         for (int g = 0; g < Gs; ++g) {
           if (((m * Gs + g) & 1) != whalf) continue;
-          uint32_t raw[16];
-          TmemLd16(dcol + rank * Cs + 16 * g, raw);
+          uint32_t raw[16], xr[16];
+          // own partial columns and (c2) the fp32 residual slice: both loads in flight, one wait
+          if (!is_c1) TmemLd16x2(dcol + rank * Cs + 16 * g, raw, xcol + 16 * g, xr);
+          else TmemLd16(dcol + rank * Cs + 16 * g, raw);
           float v[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] = 0.0f;
@@ -288,10 +290,14 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
             }
           }
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] += bias[16 * g + e];
+          for (int q = 0; q < 4; ++q) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias + 16 * g + 4 * q);
+            v[4 * q] += b4.x;
+            v[4 * q + 1] += b4.y;
+            v[4 * q + 2] += b4.z;
+            v[4 * q + 3] += b4.w;
+          }
           if (!is_c1) {
-            uint32_t xr[16];
-            TmemLd16(xcol + 16 * g, xr);
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] += __uint_as_float(xr[e]);
             if (!last) {

@@ -135,6 +135,21 @@ __device__ __forceinline__ void TmemLd16(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// two 16-column loads in flight, one wait
+__device__ __forceinline__ void TmemLd16x2(uint32_t taddr0, uint32_t* r0, uint32_t taddr1, uint32_t* r1) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]), "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]), "=r"(r0[8]),
+        "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11]), "=r"(r0[12]), "=r"(r0[13]), "=r"(r0[14]), "=r"(r0[15])
+      : "r"(taddr0));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]),
+        "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]), "=r"(r1[15])
+      : "r"(taddr1));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void TmemSt16(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
@@ -328,17 +343,22 @@ __device__ __forceinline__ float ActTc(float v, int act) {
 }
 
 // 8 fp32 -> 8 bf16 (round to nearest even) packed in a uint4; optionally the bf16 of the residual.
+// two fp32 -> packed bf16x2 (round to nearest even), one cvt.rn.bf16x2.f32: `a` in the low half
+__device__ __forceinline__ uint32_t CvtBf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 template <bool kSplit>
 __device__ __forceinline__ void Pack8(const float* v, uint4* hi, uint4* lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 a = __float2bfloat16_rn(v[2 * i]), b = __float2bfloat16_rn(v[2 * i + 1]);
-    h[i] = static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
-    if (kSplit) {
-      const __nv_bfloat16 ra = __float2bfloat16_rn(v[2 * i] - __bfloat162float(a));
-      const __nv_bfloat16 rb = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(b));
-      l[i] = static_cast<uint32_t>(__bfloat16_as_ushort(ra)) | (static_cast<uint32_t>(__bfloat16_as_ushort(rb)) << 16);
+    h[i] = CvtBf16x2(v[2 * i], v[2 * i + 1]);
+    if (kSplit) {   // the bf16 of what the first rounding left: a bf16 is the upper half of its fp32
+      const float ra = v[2 * i] - __uint_as_float(h[i] << 16);
+      const float rb = v[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
+      l[i] = CvtBf16x2(ra, rb);
     }
   }
   *hi = make_uint4(h[0], h[1], h[2], h[3]);
