@@ -254,14 +254,10 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
           g[0] = xv[0]; g[1] = xv[1]; g[2] = xv[2]; g[3] = xv[3];
         }
         if (!valid) g[0] = g[1] = g[2] = g[3] = 0.0f;
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(g[0]), h1 = __float2bfloat16_rn(g[1]), h2 = __float2bfloat16_rn(g[2]),
-                            h3 = __float2bfloat16_rn(g[3]);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(g[0] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(g[1] - __bfloat162float(h1)),
-                            l2 = __float2bfloat16_rn(g[2] - __bfloat162float(h2)), l3 = __float2bfloat16_rn(g[3] - __bfloat162float(h3));
-        const uint32_t hi0 = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-        const uint32_t hi1 = static_cast<uint32_t>(__bfloat16_as_ushort(h2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h3)) << 16);
-        const uint32_t lo0 = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
-        const uint32_t lo1 = static_cast<uint32_t>(__bfloat16_as_ushort(l2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l3)) << 16);
+        // packed conversions (cvt.rn.bf16x2.f32); the residual against the bf16 read back as the upper half of an fp32
+        const uint32_t hi0 = CvtBf16x2(g[0], g[1]), hi1 = CvtBf16x2(g[2], g[3]);
+        const uint32_t lo0 = CvtBf16x2(g[0] - __uint_as_float(hi0 << 16), g[1] - __uint_as_float(hi0 & 0xffff0000u));
+        const uint32_t lo1 = CvtBf16x2(g[2] - __uint_as_float(hi1 << 16), g[3] - __uint_as_float(hi1 & 0xffff0000u));
         // channel lc = 4 cg + i -> panel cg / 2, byte (cg & 1) * 8 inside the 16-byte row entry; row = newest time step
         const uint32_t dst = gp + (cg >> 1) * L::kGpPanel + static_cast<uint32_t>(kHmax * kRs + s) * 16 + (cg & 1) * 8;
         asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(dst), "r"(hi0), "r"(hi1) : "memory");
@@ -383,17 +379,13 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_res_stack_kernel(const __g
         for (int i = 0; i < 4; ++i) xo[i] = xo[i] > 0.0f ? xo[i] : 0.1f * xo[i];
       }
       if (p.xh_out) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(xo[0]), h1 = __float2bfloat16_rn(xo[1]), h2 = __float2bfloat16_rn(xo[2]),
-                            h3 = __float2bfloat16_rn(xo[3]);
         uint2 hv, lv;
-        hv.x = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-        hv.y = static_cast<uint32_t>(__bfloat16_as_ushort(h2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h3)) << 16);
+        hv.x = CvtBf16x2(xo[0], xo[1]);
+        hv.y = CvtBf16x2(xo[2], xo[3]);
         *reinterpret_cast<uint2*>(p.xh_out + o) = hv;
         if (p.xl_out) {
-          const __nv_bfloat16 l0 = __float2bfloat16_rn(xo[0] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(xo[1] - __bfloat162float(h1)),
-                              l2 = __float2bfloat16_rn(xo[2] - __bfloat162float(h2)), l3 = __float2bfloat16_rn(xo[3] - __bfloat162float(h3));
-          lv.x = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
-          lv.y = static_cast<uint32_t>(__bfloat16_as_ushort(l2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l3)) << 16);
+          lv.x = CvtBf16x2(xo[0] - __uint_as_float(hv.x << 16), xo[1] - __uint_as_float(hv.x & 0xffff0000u));
+          lv.y = CvtBf16x2(xo[2] - __uint_as_float(hv.y << 16), xo[3] - __uint_as_float(hv.y & 0xffff0000u));
           *reinterpret_cast<uint2*>(p.xl_out + o) = lv;
         }
       }
