@@ -237,22 +237,41 @@ __global__ void __launch_bounds__(kThreads, 1) mrf_cluster_kernel(const __grid_c
           const int w_rows = min(max(rows_valid - (m * 128 + q4 * 32), 0), 32);   // rows of this lane quarter in tile m
           if (lane == 0 && whalf == 0 && q_active) MbarExpectTx(bar_box_full + 8 * q4, static_cast<uint32_t>(NC - 1) * w_rows * Cs * 4);
         }
+        // this warp's (peer, 16-column group) items are those of its parity; two at a time, so that two TMEM loads are in
+        // flight under one wait and eight remote stores follow back to back
+        if (q_active) {
+          constexpr int kItems = (NC - 1) * Gs;
+          auto target = [&](int it, uint32_t* dst, uint32_t* rbar, uint32_t* tcol) {
+            const int q = 1 + it / Gs, h = it - (q - 1) * Gs;
+            const int pr = (rank + q) % NC;
+            const int slot = rank < pr ? rank : rank - 1;
+            *dst = MapToCta(box_base + slot * box_slot + static_cast<uint32_t>(exists ? r : 0) * kBoxRow, pr) + 64 * h;
+            *rbar = MapToCta(bar_box_full + 8 * q4, pr);
+            *tcol = dcol + pr * Cs + 16 * h;
+          };
 #pragma unroll 1
-        for (int q = 1; q < NC && q_active; ++q) {
-          const int pr = (rank + q) % NC;
-          const int slot = rank < pr ? rank : rank - 1;
-          const uint32_t dst = MapToCta(box_base + slot * box_slot + static_cast<uint32_t>(exists ? r : 0) * kBoxRow, pr);
-          const uint32_t rbar = MapToCta(bar_box_full + 8 * q4, pr);
-#pragma unroll 1
-          for (int h = 0; h < Gs; ++h) {
-            if ((((q - 1) * Gs + h) & 1) != whalf) continue;
-            uint32_t raw[16];
-            TmemLd16(dcol + pr * Cs + 16 * h, raw);
+          for (int it = whalf; it < kItems; it += 4) {
+            uint32_t d0, b0, c0, d1 = 0, b1 = 0, c1 = 0;
+            target(it, &d0, &b0, &c0);
+            const bool two = it + 2 < kItems;
+            uint32_t r0[16], r1[16];
+            if (two) {
+              target(it + 2, &d1, &b1, &c1);
+              TmemLd16x2(c0, r0, c1, r1);
+            } else {
+              TmemLd16(c0, r0);
+            }
             if (exists) {
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                StAsync16(dst + 64 * h + 16 * e, __uint_as_float(raw[4 * e]), __uint_as_float(raw[4 * e + 1]),
-                          __uint_as_float(raw[4 * e + 2]), __uint_as_float(raw[4 * e + 3]), rbar);
+                StAsync16(d0 + 16 * e, __uint_as_float(r0[4 * e]), __uint_as_float(r0[4 * e + 1]), __uint_as_float(r0[4 * e + 2]),
+                          __uint_as_float(r0[4 * e + 3]), b0);
+              if (two) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  StAsync16(d1 + 16 * e, __uint_as_float(r1[4 * e]), __uint_as_float(r1[4 * e + 1]), __uint_as_float(r1[4 * e + 2]),
+                            __uint_as_float(r1[4 * e + 3]), b1);
+              }
             }
           }
         }
